@@ -1,0 +1,44 @@
+"""Reader for vb200 setup blobs (include/vb200_blob.h) and the catalogue of the
+blobs shipped in setups/ (generated from the reference by tools/make_setups.py)."""
+import os
+import struct
+import zlib
+import numpy as np
+
+MAGIC = 0x42323056
+_DT = {0: np.float32, 1: np.int32, 2: np.uint8, 3: np.float64, 4: np.uint32}
+SETUP_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "setups")
+
+# name -> (channels, rate, quality, managed nominal bitrate)
+CATALOGUE = {
+    "q4_44k_2ch": (2, 44100, 0.4, 0),      # BASELINE configs[0], [1]
+    "q5_44k_2ch": (2, 44100, 0.5, 0),      # configs[2]
+    "q8_48k_6ch": (6, 48000, 0.8, 0),      # configs[3]: 5.1, residue type 2 + LFE residue type 1
+    "q10_48k_2ch": (2, 48000, 1.0, 0),     # configs[4a]
+    "abr128_44k_2ch": (2, 44100, 0.4, 128000),  # configs[4b]: managed, 15 packet blobs
+    "q2_44k_2ch": (2, 44100, 0.2, 0),      # aoTuV M4/M5/M8 + noise normalisation live
+    "q4_48k_6ch": (6, 48000, 0.4, 0),      # 5.1 with 4 coupling steps
+    "q4_44k_1ch": (1, 44100, 0.4, 0),      # mono, no coupling
+}
+
+
+def parse(blob):
+    magic, version, nsec, total = struct.unpack_from("<IIII", blob, 0)
+    if magic != MAGIC or total != len(blob):
+        raise ValueError("not a vb200 setup blob")
+    pos, out = 16, {}
+    for _ in range(nsec):
+        name = blob[pos:pos + 24].split(b"\0")[0].decode()
+        dtype, count = struct.unpack_from("<II", blob, pos + 24)
+        pos += 32
+        dt = np.dtype(_DT[dtype])
+        nbytes = count * dt.itemsize
+        out[name] = np.frombuffer(blob, dtype=dt, count=count, offset=pos).copy()
+        pos += (nbytes + 7) & ~7
+    return out
+
+
+def load(name):
+    """Raw bytes of a shipped setup blob."""
+    with open(os.path.join(SETUP_DIR, name + ".vb2s.z"), "rb") as f:
+        return zlib.decompress(f.read())

@@ -1,0 +1,205 @@
+/* K1 -- window + forward MDCT + real FFT + dB spectra, one CTA per ch-block.
+ *
+ * Replaces, for every channel of every block (mapping0.c:783-902, 933-951):
+ *   _postnoise_detection   psy.c:619-648      (on the un-windowed PCM)
+ *   _vorbis_apply_window   window.c:2137-2261
+ *   mdct_forward           mdct.c:1799-1869   out[k]=(4/n) sum x[t] cos(pi/(2n)(2t+1+n/2)(2k+1))
+ *   drft_forward           smallft.c:6770     + the |X|^2 -> dB loop mapping0.c:848-888
+ *   logmdct                mapping0.c:933-951
+ *
+ * B200 mapping: the block is staged once in shared memory with float4 loads, both
+ * transforms run out of shared memory (MDCT as an n/4-point complex FFT with
+ * pre/post twiddles, the real FFT as an n/2-point complex FFT + split), and the
+ * three result vectors leave with coalesced stores.  HBM traffic = the algorithmic
+ * minimum: n*4 bytes in, 3*N2*4 bytes out (20480 / 2560 B).
+ * Not a port of the reference's butterflies: Stockham autosort radix-2 stages
+ * with twiddles precomputed in double (setup.cu).
+ */
+#include "vb200_internal.h"
+#include "dev_util.cuh"
+
+namespace {
+
+/* M-point complex FFT, forward (exp(-i...)), data in `a`, scratch `b`; root[k]=exp(-2*pi*i*k*rstride/...) table
+   holds exp(-2*pi*i*k/Mroot) for k<Mroot/2 and we need exp(-2*pi*i*k/M): index k*(Mroot/M).  Returns the
+   buffer that holds the result. */
+template <int M, int THREADS>
+__device__ __forceinline__ float2 *cta_fft(float2 *a, float2 *b, const float2 *__restrict__ root, int rootM) {
+  const int tid = threadIdx.x;
+  const int rs = rootM / M;
+#pragma unroll 1
+  for (int Ns = 1; Ns < M; Ns <<= 1) {
+    for (int j = tid; j < M / 2; j += THREADS) {
+      int k = j & (Ns - 1);
+      float2 w = __ldg(&root[k * (M / (2 * Ns)) * rs]);
+      float2 u = a[j];
+      float2 v = a[j + M / 2];
+      float2 t;
+      t.x = __fsub_rn(__fmul_rn(v.x, w.x), __fmul_rn(v.y, w.y));
+      t.y = __fadd_rn(__fmul_rn(v.x, w.y), __fmul_rn(v.y, w.x));
+      int o = ((j - k) << 1) + k;
+      b[o] = make_float2(u.x + t.x, u.y + t.y);
+      b[o + Ns] = make_float2(u.x - t.x, u.y - t.y);
+    }
+    __syncthreads();
+    float2 *tmp = a; a = b; b = tmp;
+  }
+  return a;
+}
+
+template <int N, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_transform(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm, const long long *__restrict__ pcm_off,
+            const int *__restrict__ lWv, const int *__restrict__ nWv,
+            const int *__restrict__ block_mode, const int *__restrict__ lW_block_mode,
+            float *__restrict__ gmdct, float *__restrict__ logfft, float *__restrict__ logmdct,
+            float *__restrict__ local_ampmax, float *__restrict__ poste) {
+  constexpr int N2 = N / 2, N4 = N / 4;
+  __shared__ __align__(16) float x[N];
+  __shared__ __align__(16) float2 bufA[N2];
+  __shared__ __align__(16) float2 bufB[N2];
+  __shared__ double red[2][THREADS / 32];
+  __shared__ float redf[THREADS / 32];
+
+  const int item = blockIdx.x, tid = threadIdx.x;
+  const float *src = pcm + (pcm_off ? pcm_off[item] : (long long)item * N);
+
+  /* ---- stage the block ---- */
+  if ((((uintptr_t)src) & 15) == 0) {
+    for (int i = tid; i < N / 4; i += THREADS) reinterpret_cast<float4 *>(x)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+  } else {
+    for (int i = tid; i < N; i += THREADS) x[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  /* ---- aoTuV M2 post-echo detector on the un-windowed PCM (psy.c:619-648) ---- */
+  if (poste) {
+    float ret = -1.f;
+    const int mode = block_mode[item], lwm = lW_block_mode[item];
+    if (mode == 2 && lwm == 0 && N >= 2048) {   /* uniform per CTA */
+      const int sn = N >> 2, mn = sn + sn, en = sn + (N >> 1);
+      double up = 0., un = 0.;
+      for (int i = sn + tid; i < mn; i += THREADS) up += (double)fabsf(x[i]);
+      for (int i = mn + tid; i < en; i += THREADS) un += (double)fabsf(x[i]);
+      up = warp_sum_d(up); un = warp_sum_d(un);
+      if ((tid & 31) == 0) { red[0][tid >> 5] = up; red[1][tid >> 5] = un; }
+      __syncthreads();
+      if (tid == 0) {
+        double upt = 0., unt = 0.;
+        for (int w = 0; w < THREADS / 32; w++) { upt += red[0][w]; unt += red[1][w]; }
+        if (!(unt / sn > 0.01)) {
+          upt *= upt; unt *= unt; unt *= 15;
+          if (upt > unt) { ret = (float)(upt - unt); if (ret < 0.1) ret = -1.0f; }
+        }
+        poste[item] = ret;
+      }
+    } else if (tid == 0) poste[item] = ret;
+  }
+
+  /* ---- window (window.c:2137-2261) ---- */
+  {
+    const int lW = W ? lWv[item] : 0, nW = W ? nWv[item] : 0;
+    const int ln = S->bs[lW], rn = S->bs[nW];
+    const float *wl = S->win[lW], *wr = S->win[nW];
+    const int leftbegin = N / 4 - ln / 4, leftend = leftbegin + ln / 2;
+    const int rightbegin = N / 2 + N / 4 - rn / 4, rightend = rightbegin + rn / 2;
+    for (int i = tid; i < N; i += THREADS) {
+      float v = x[i];
+      if (i < leftbegin) v = 0.f;
+      else if (i < leftend) v = __fmul_rn(v, __ldg(wl + (i - leftbegin)));
+      else if (i >= rightend) v = 0.f;
+      else if (i >= rightbegin) v = __fmul_rn(v, __ldg(wr + (rn / 2 - 1 - (i - rightbegin))));
+      x[i] = v;
+    }
+  }
+  __syncthreads();
+
+  /* ---- MDCT: fold to N2 reals, pre-twiddle to N4 complex, FFT, post-twiddle ---- */
+  {
+    const float2 *tw = S->mdct_tw[W];
+    for (int m = tid; m < N4; m += THREADS) {
+      /* u[i] = -x[3N2/2-1-i]-x[3N2/2+i]  (i<N2/2);  x[i-N2/2]-x[3N2/2-1-i]  (i>=N2/2) */
+      const int i0 = 2 * m, i1 = N2 - 1 - 2 * m;
+      float u0, u1;
+      if (i0 < N2 / 2) u0 = -x[3 * N2 / 2 - 1 - i0] - x[3 * N2 / 2 + i0];
+      else u0 = x[i0 - N2 / 2] - x[3 * N2 / 2 - 1 - i0];
+      if (i1 < N2 / 2) u1 = -x[3 * N2 / 2 - 1 - i1] - x[3 * N2 / 2 + i1];
+      else u1 = x[i1 - N2 / 2] - x[3 * N2 / 2 - 1 - i1];
+      float2 t = __ldg(tw + m);
+      bufA[m] = make_float2(u0 * t.x - u1 * t.y, u0 * t.y + u1 * t.x);
+    }
+    __syncthreads();
+    float2 *Z = cta_fft<N4, THREADS>(bufA, bufB, S->fft_root[W], N2);
+    const float scale = 4.f / N;
+    float *gm = gmdct + (size_t)item * N2, *lm = logmdct + (size_t)item * N2;
+    float2 *Y = (Z == bufA) ? bufB : bufA;   /* stage the interleaved result for coalesced stores */
+    float *out = reinterpret_cast<float *>(Y);
+    for (int k = tid; k < N4; k += THREADS) {
+      float2 t = __ldg(tw + k), z = Z[k];
+      float yr = z.x * t.x - z.y * t.y, yi = z.x * t.y + z.y * t.x;
+      out[2 * k] = yr * scale;
+      out[N2 - 1 - 2 * k] = -yi * scale;
+    }
+    __syncthreads();
+    for (int i = tid; i < N2; i += THREADS) {
+      float v = out[i];
+      gm[i] = v;
+      lm[i] = todB_p345(v);
+    }
+    __syncthreads();
+  }
+
+  /* ---- real FFT of the same windowed block via an N2-point complex FFT ---- */
+  {
+    for (int m = tid; m < N2; m += THREADS) bufA[m] = make_float2(x[2 * m], x[2 * m + 1]);
+    __syncthreads();
+    float2 *Z = cta_fft<N2, THREADS>(bufA, bufB, S->fft_root[W], N2);
+    const float2 *rt = S->rfft_tw[W];
+    const float scale = 4.f / N;
+    const float scale_dB = todB_p345(scale);
+    float *lf = logfft + (size_t)item * N2;
+    float mx = -3.0e38f;
+    for (int k = tid; k < N2; k += THREADS) {
+      float v;
+      if (k == 0) {
+        float re0 = Z[0].x + Z[0].y;          /* X[0] = sum x[t] */
+        v = (float)((double)__fadd_rn(scale_dB, todB_raw(re0)) + .345);
+      } else {
+        float2 a = Z[k], b = Z[N2 - k];
+        /* X[k] = (a+conj(b))/2 - i*w*(a-conj(b))/2,  w = exp(-2*pi*i*k/N) */
+        float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
+        float orr = 0.5f * (a.x - b.x), oi = 0.5f * (a.y + b.y);
+        float2 w = __ldg(rt + k);
+        /* -i*w*(orr + i*oi) = (w.y*orr + w.x*oi) + i*(w.y*oi - w.x*orr) */
+        float xr = er + (w.y * orr + w.x * oi);
+        float xi = ei + (w.y * oi - w.x * orr);
+        float p = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));
+        v = (float)((double)__fadd_rn(scale_dB, __fmul_rn(.5f, todB_raw(p))) + .345);
+      }
+      lf[k] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max_f(mx);
+    if ((tid & 31) == 0) redf[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      float m = redf[0];
+      for (int w = 1; w < THREADS / 32; w++) m = fmaxf(m, redf[w]);
+      if (m > 0.f) m = 0.f;
+      local_ampmax[item] = m;
+    }
+  }
+}
+
+}  // namespace
+
+int vb200_launch_transform(const vb200_setup *s, cudaStream_t st, int W, int items,
+                           const float *pcm, const long long *pcm_off, const int *lW, const int *nW,
+                           const int *block_mode, const int *lW_block_mode,
+                           float *gmdct, float *logfft, float *logmdct, float *local_ampmax, float *poste) {
+  if (items <= 0) return VB200_OK;
+  if (W) k_transform<2048, 256><<<items, 256, 0, st>>>(s->d, 1, pcm, pcm_off, lW, nW, block_mode, lW_block_mode, gmdct, logfft, logmdct, local_ampmax, poste);
+  else   k_transform<256, 64><<<items, 64, 0, st>>>(s->d, 0, pcm, pcm_off, lW, nW, block_mode, lW_block_mode, gmdct, logfft, logmdct, local_ampmax, poste);
+  LAUNCH_CHECK();
+  return VB200_OK;
+}

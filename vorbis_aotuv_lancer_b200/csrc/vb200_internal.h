@@ -1,0 +1,132 @@
+/* Internal device/host structures of libvorbis_b200 (not part of the C ABI). */
+#ifndef VB200_INTERNAL_H
+#define VB200_INTERNAL_H
+#include <stdint.h>
+#include <stddef.h>
+#include "vorbis_b200.h"
+#include "vb200_blob.h"
+
+#define VB200_P_BANDS 17
+#define VB200_P_LEVELS 8
+#define VB200_EHMER 58            /* EHMER_MAX+2: two fenceposts + 56 curve points (psy.c:336-344) */
+#define VB200_COMPAND_LEVELS 40
+#define VB200_MAX_PSY 4
+#define VB200_MAX_FLOORS 4
+#define VB200_MAX_RESIDUES 6
+#define VB200_MAX_MAPS 2
+#define VB200_MAX_COUPLING 8
+#define VB200_MAX_BOOKS 128
+#define VB200_MAX_SUBMAPS 4
+
+/* ---- device-resident tables (App. F of SURVEY.md) ---- */
+struct DevPsy {
+  int n, blockflag, firstoc, shiftoc, eighth, total_octave_lines, rate;
+  int m3n[3];
+  int tonecomp_endp, min_nn_lp, tonefix_end, n25p, n33p, n75p;
+  int noisewindowfixed, normal_p, normal_start, normal_partition, partition;
+  float m_val, tonecomp_thres, ath_adjatt, ath_maxatt, tone_masteratt[3];
+  float tone_abs_limit, max_curve_dB, noisemaxsupp;
+  double normal_thresh;
+  const float *ath;          /* [n] */
+  const int   *octave;       /* [n] */
+  const int   *bark;         /* [n] packed ((lo-1)<<16)+(hi-1) */
+  const float *tonecurves;   /* [17][8][58] */
+  const float *noiseoffset;  /* [3][n] */
+  const float *ntfix;        /* [n] */
+  float compand[VB200_COMPAND_LEVELS], compand_hi[VB200_COMPAND_LEVELS];
+};
+
+struct DevFloor {
+  int type, posts, n, quant_q, mult, info_n;
+  float maxover, maxunder, maxerr, twofitweight, twofitatten;
+  int postlist[VB200_MAX_POSTS], sorted[VB200_MAX_POSTS], forward[VB200_MAX_POSTS], reverse[VB200_MAX_POSTS];
+  int lonb[VB200_MAX_POSTS], hinb[VB200_MAX_POSTS];
+};
+
+struct DevResidue {
+  int type, begin, end, grouping, partitions, partvals, groupbook, stages, phrase_dim;
+  int secondstages[64], classmetric1[64], classmetric2[64];
+  int partbooks[64*8];
+};
+
+struct DevBook {
+  int dim, entries, quantvals, minval, delta;
+  int used;                     /* number of entries with a codeword */
+  const uint8_t  *len;          /* [entries] codeword lengths (0 = unused) */
+  const uint32_t *code;         /* [entries] */
+  const int      *used_list;    /* [used] entry indices in ascending order */
+  const int      *used_vals;    /* [used][8] lattice value of each used entry (res0.c:343-370 enumeration) */
+};
+
+struct DevMap {
+  int submaps, coupling_steps;
+  int chmux[VB200_MAX_CHANNELS];
+  int floorsubmap[16], residuesubmap[16];
+  int mag[VB200_MAX_COUPLING], ang[VB200_MAX_COUPLING];
+};
+
+struct DevSetup {
+  int channels, rate, bs[2], modebits, managed, lowpassr[2];
+  int psys, floors, residues, books, maps, modes;
+  int mode_blockflag[8], mode_mapping[8];
+  float ampmax_att_per_sec;
+  int pointlimit[2][VB200_PACKETBLOBS], prepointamp[VB200_PACKETBLOBS], postpointamp[VB200_PACKETBLOBS];
+  int sliding_lowpass[2][VB200_PACKETBLOBS];
+  DevPsy psy[VB200_MAX_PSY];
+  DevFloor flr[VB200_MAX_FLOORS];
+  DevResidue res[VB200_MAX_RESIDUES];
+  DevMap map[VB200_MAX_MAPS];
+  const DevBook *book;          /* [books] (device) */
+  const float *win[2];          /* half windows, bs/2 each */
+  /* transform tables per W: computed in double on the host at setup time */
+  const float2 *mdct_tw[2];     /* [n/4]  exp(-i*pi*(8m+1)/(8*N2)) */
+  const float2 *fft_root[2];    /* [n/4]  exp(-2*pi*i*k/(n/2)), k<n/4 : roots for the n/2-point FFT */
+  const float2 *rfft_tw[2];     /* [n/2]  exp(-2*pi*i*k/n) */
+};
+
+/* ---- host-side object behind vb200_setup ---- */
+struct HostBook {
+  int dim, entries, quantvals, minval, delta, maptype;
+  const uint8_t *len; const uint32_t *code;   /* point into the owned blob copy */
+};
+struct HostFloor {
+  int partitions;
+  int partclass[31], class_dim[16], class_subs[16], class_book[16], class_subbook[16*8];
+};
+
+struct vb200_setup {
+  int device;                 /* -1: host-only (no tables uploaded) */
+  unsigned char *blob; size_t blob_bytes;
+  DevSetup h;                 /* host copy (pointers are device pointers) */
+  DevSetup *d;                /* device copy */
+  HostBook book[VB200_MAX_BOOKS];
+  HostFloor hflr[VB200_MAX_FLOORS];
+  const unsigned char *hdr[3]; long hdrlen[3];
+  int bi_i32[4]; double bi_f64[2];
+  void *stream;               /* cudaStream_t */
+  void **allocs; int nallocs, capallocs;
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+void vb200_set_error(const char *fmt, ...);
+void vb200_count_launch(int n);
+const void *vb200_blob_find(const unsigned char *blob, size_t bytes, const char *name, uint32_t *dtype, uint32_t *count);
+#ifdef __cplusplus
+}
+#endif
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define CUDA_TRY(expr) do{ cudaError_t e_=(expr); if(e_!=cudaSuccess){ \
+  vb200_set_error("%s:%d %s: %s",__FILE__,__LINE__,#expr,cudaGetErrorString(e_)); return VB200_EFAULT; } }while(0)
+#define LAUNCH_CHECK() do{ vb200_count_launch(1); CUDA_TRY(cudaGetLastError()); }while(0)
+
+/* stage launchers on device pointers (used by both the stage calls and the batched path) */
+int vb200_launch_transform(const vb200_setup *s, cudaStream_t st, int W, int items,
+                           const float *pcm, const long long *pcm_off, const int *lW, const int *nW,
+                           const int *block_mode, const int *lW_block_mode,
+                           float *gmdct, float *logfft, float *logmdct, float *local_ampmax, float *poste);
+#endif
+#endif
