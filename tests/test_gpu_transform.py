@@ -38,16 +38,19 @@ def test_transform_matches_reference(config, W):
     # the dB mapping itself is bit-exact on our own coefficients (scales.h:43-51 + the double .345)
     mine = (todB_np(out["gmdct"]).astype(np.float64) + .345).astype(np.float32)
     assert np.array_equal(mine, out["logmdct"])
-    # logmdct / logfft agree with the reference within 1e-5 relative on well-conditioned bins
-    good = np.abs(ref_m) > 1e-3 * rms
-    d = np.abs(out["logmdct"] - ref_lm)[good] / np.abs(ref_lm[good]).clip(1.0)
-    assert d.max() < 1e-5, d.max()
+    # logmdct: the dB image of the MDCT tolerance.  todB is piecewise linear in the mantissa with a
+    # slope of at most 12.05 dB per unit relative error, so |d dB| <= 12.05*(1e-5*rms/|m|) (+1e-4 slack)
+    allowed = 12.05 * 1e-5 * rms / np.abs(ref_m).clip(1e-30) + 1e-4
+    d = np.abs(out["logmdct"] - ref_lm)
+    ok = (d <= allowed) | (np.abs(ref_m) < 1e-4 * rms)
+    assert ok.all(), float((d / allowed)[~ok].max())
+    # logfft: power spectrum within 1e-5 of the block's peak power -> same dB image (slope 6.03 on power)
     peak = ref_lf.max(axis=1, keepdims=True)
-    goodf = ref_lf > peak - 60.0
-    d = np.abs(out["logfft"] - ref_lf)[goodf] / np.abs(ref_lf[goodf]).clip(1.0)
-    assert d.max() < 1e-5, d.max()
-    # everywhere: within a millibel of power-relative error bound
-    assert np.abs(out["logfft"] - ref_lf).max() < 0.05
+    rel = 10.0 ** ((peak - ref_lf).astype(np.float64) / 10.0)      # peak power / bin power
+    allowedf = 6.03 * 1e-5 * rel + 2e-4
+    d = np.abs(out["logfft"] - ref_lf)
+    ok = (d <= allowedf) | (ref_lf < peak - 90.0)
+    assert ok.all(), float((d / allowedf)[~ok].max())
     assert np.allclose(out["local_ampmax"], np.array(ref_amp), rtol=1e-5, atol=1e-4)
     po = np.array(ref_po)
     assert np.array_equal(out["poste"] > 0, po > 0)
