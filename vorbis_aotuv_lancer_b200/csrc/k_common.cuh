@@ -1,0 +1,30 @@
+/* Shared device-side descriptors. */
+#ifndef VB200_K_COMMON_CUH
+#define VB200_K_COMMON_CUH
+#include <cuda_runtime.h>
+
+/* How a ch-block finds `lastmdct`, the previous block's logmdct as aoTuV keeps it in
+   private_state.mblock (psy.c:4462-4501).  The reference copies / 8x-expands / 8:1 min-pools the
+   previous block's logmdct into a state buffer; here the previous block's logmdct is still in HBM, so
+   the consumer applies the resampling rule on the fly and the state buffer never round-trips. */
+enum { LAST_COPY = 0, LAST_EXPAND8 = 1, LAST_MINPOOL8 = 2, LAST_ZERO = 3 };
+struct LastRef {
+  const float *base;        /* buffer the offsets index */
+  const long long *off;     /* [items] element offset, or NULL: item*stride */
+  const int *rule;          /* [items] LAST_*, or NULL: LAST_COPY */
+  long long stride;
+  __device__ __forceinline__ float at(int item, int i) const {
+    const float *p = base + (off ? off[item] : (long long)item * stride);
+    const int r = rule ? rule[item] : LAST_COPY;
+    if (r == LAST_COPY) return __ldg(p + i);
+    if (r == LAST_EXPAND8) return __ldg(p + (i >> 3));
+    if (r == LAST_MINPOOL8) {
+      float m = __ldg(p + i * 8);
+#pragma unroll
+      for (int j = 1; j < 8; j++) { float v = __ldg(p + i * 8 + j); if (m > v) m = v; }
+      return m;
+    }
+    return 0.f;
+  }
+};
+#endif

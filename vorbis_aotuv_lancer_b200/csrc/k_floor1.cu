@@ -1,0 +1,308 @@
+/* K5 -- floor-1: fit (K5a) and post quantisation + integer floor render (K5b), one warp per
+ * ch-block.
+ *
+ * Replaces floor1_fit (floor1.c:597-750: accumulate_fit :427, fit_line :477, inspect_error :537),
+ * floor1_interpolate_fit (:752) and the non-emitting parts of floor1_encode (:774-974).
+ *
+ * B200 mapping.  The greedy split is a data-dependent loop of at most posts-2 steps, so again a
+ * small CTA (one warp, ~6 KB of shared memory) per ch-block and many resident CTAs per SM.
+ * Inside a step the error inspection of a candidate line runs across the warp: the integer line is
+ * evaluated in closed form per bin (base slope + accumulated carries) instead of being stepped,
+ * and the early-exit tests become a warp vote.  Integer sums are exact in any order; the
+ * least-squares solve stays in double on one lane in the reference's summation order, because
+ * the rounded intercepts decide the posts.  HBM traffic: logmdct + logmask in, posts out (K5a);
+ * posts in, ilogmask + coded values out (K5b).
+ */
+#include "vb200_internal.h"
+#include "dev_util.cuh"
+
+namespace {
+
+__device__ __forceinline__ int dbq(float x) {      /* vorbis_dBquant, floor1.c:285-298 */
+  int i = (int)__fadd_rn(__fmul_rn(x, 7.3142857f), 1023.5f);
+  return i > 1023 ? 1023 : (i < 0 ? 0 : i);
+}
+
+/* integer line (x0,y0)-(x1,y1) at x, as render_line0 / inspect_error step it (floor1.c:397-425) */
+__device__ __forceinline__ int line_at(int x0, int x1, int y0, int y1, int x) {
+  const int dy = y1 - y0, adx = x1 - x0, base = dy / adx;
+  const int rem = abs(dy) - abs(base * adx), k = x - x0;
+  const int carry = (rem * k) / adx;
+  return y0 + base * k + (dy < 0 ? -carry : carry);
+}
+/* render_point, floor1.c:260-283 */
+__device__ __forceinline__ int point_at(int x0, int x1, int y0, int y1, int x) {
+  y0 &= 0x7fff; y1 &= 0x7fff;
+  const int dy = y1 - y0, adx = x1 - x0;
+  const int off = (abs(dy) * (x - x0)) / adx;
+  return dy < 0 ? y0 - off : y0 + off;
+}
+
+struct Seg { int x0, x1; int s[2][6]; };   /* s[class] = sum x, y, xx, yy, xy, count */
+
+template <int N>
+struct FitSmem {
+  unsigned short q[N];
+  unsigned char loud[N];
+  Seg seg[VB200_MAX_POSTS];
+  int A[VB200_MAX_POSTS], B[VB200_MAX_POSTS], lo[VB200_MAX_POSTS], hi[VB200_MAX_POSTS], memo[VB200_MAX_POSTS];
+  int y[4];
+};
+
+/* fit_line, floor1.c:477-535 (lane 0) */
+__device__ int fit_line(const Seg *a, int cnt, int *y0, int *y1, float weight) {
+  double xb = 0, yb = 0, x2b = 0, y2b = 0, xyb = 0, bn = 0;
+  const int x0 = a[0].x0, x1 = a[cnt - 1].x1;
+  for (int i = 0; i < cnt; i++) {
+    const int an = a[i].s[0][5], bnn = a[i].s[1][5];
+    const double w = (double)__fdiv_rn(__fmul_rn((float)(bnn + an), weight), (float)(an + 1)) + 1.;
+    xb += (double)a[i].s[1][0] + (double)a[i].s[0][0] * w;
+    yb += (double)a[i].s[1][1] + (double)a[i].s[0][1] * w;
+    x2b += (double)a[i].s[1][2] + (double)a[i].s[0][2] * w;
+    y2b += (double)a[i].s[1][3] + (double)a[i].s[0][3] * w;
+    xyb += (double)a[i].s[1][4] + (double)a[i].s[0][4] * w;
+    bn += (double)bnn + (double)an * w;
+  }
+  if (*y0 >= 0) { xb += x0; yb += *y0; x2b += x0 * x0; y2b += *y0 * *y0; xyb += *y0 * x0; bn++; }
+  if (*y1 >= 0) { xb += x1; yb += *y1; x2b += x1 * x1; y2b += *y1 * *y1; xyb += *y1 * x1; bn++; }
+  const double den = bn * x2b - xb * xb;
+  if (den > 0.) {
+    const double ic = (yb * x2b - xyb * xb) / den, sl = (bn * xyb - xb * yb) / den;
+    int v0 = (int)rint(ic + sl * x0), v1 = (int)rint(ic + sl * x1);
+    if (v0 > 1023) v0 = 1023;
+    if (v1 > 1023) v1 = 1023;
+    if (v0 < 0) v0 = 0;
+    if (v1 < 0) v1 = 0;
+    *y0 = v0; *y1 = v1;
+    return 0;
+  }
+  *y0 = 0; *y1 = 0;
+  return 1;
+}
+
+__device__ __forceinline__ int pick(const int *A, const int *B, int i) {
+  if (A[i] < 0) return B[i];
+  if (B[i] < 0) return A[i];
+  return (A[i] + B[i]) >> 1;
+}
+
+template <int N>
+__global__ void __launch_bounds__(32)
+k_floor_fit(const DevSetup *__restrict__ S, int floor_index, const float *__restrict__ logmdct, const float *__restrict__ logmask,
+            int mdct_stride, int mask_stride, const int *__restrict__ gate, int *__restrict__ posts_out, int *__restrict__ fitted) {
+  __shared__ FitSmem<N> sm;
+  const int item = blockIdx.x, lane = threadIdx.x;
+  const DevFloor &F = S->flr[floor_index];
+  const int n = F.n, posts = F.posts;
+  int *out = posts_out + (size_t)item * VB200_MAX_POSTS;
+  if (gate && !gate[item]) { if (lane == 0) fitted[item] = 0; return; }
+  const float *lm = logmdct + (size_t)item * mdct_stride, *mk = logmask + (size_t)item * mask_stride;
+
+  for (int i = lane; i < n; i += 32) {
+    const float m = __ldg(mk + i);
+    sm.q[i] = (unsigned short)dbq(m);
+    sm.loud[i] = (__fadd_rn(__ldg(lm + i), F.twofitatten) >= m) ? 1 : 0;
+  }
+  __syncwarp();
+  /* accumulate_fit: one lane per post interval, integer sums */
+  int mine = 0;
+  for (int j = lane; j < posts - 1; j += 32) {
+    const int x0 = F.sorted[j], x1 = F.sorted[j + 1], xe = x1 >= n ? n - 1 : x1;
+    int s[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+    for (int i = x0; i <= xe; i++) {
+      const int q = sm.q[i];
+      if (q) {
+        int *t = s[sm.loud[i] ? 0 : 1];
+        t[0] += i; t[1] += q; t[2] += i * i; t[3] += q * q; t[4] += i * q; t[5]++;
+      }
+    }
+    Seg &g = sm.seg[j];
+    g.x0 = x0; g.x1 = x1;
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+      for (int k = 0; k < 6; k++) g.s[c][k] = s[c][k];
+    mine += s[0][5];
+  }
+  const int any = warp_sum_i(mine);
+  if (!any) { if (lane == 0) fitted[item] = 0; return; }
+  for (int i = lane; i < posts; i += 32) { sm.A[i] = -200; sm.B[i] = -200; sm.lo[i] = 0; sm.hi[i] = 1; sm.memo[i] = -1; }
+  __syncwarp();
+  if (lane == 0) {
+    int y0 = -200, y1 = -200;
+    fit_line(sm.seg, posts - 1, &y0, &y1, F.twofitweight);
+    sm.A[0] = sm.B[0] = y0; sm.A[1] = sm.B[1] = y1;
+  }
+  __syncwarp();
+
+  for (int i = 2; i < posts; i++) {
+    const int sp = F.reverse[i], ln = sm.lo[sp], hn = sm.hi[sp];
+    if (sm.memo[ln] == hn) continue;            /* uniform across the warp */
+    __syncwarp();
+    if (lane == 0) sm.memo[ln] = hn;
+    const int lsp = F.reverse[ln], hsp = F.reverse[hn];
+    const int lx = F.postlist[ln], hx = F.postlist[hn];
+    const int ly = pick(sm.A, sm.B, ln), hy = pick(sm.A, sm.B, hn);
+    /* inspect_error across the warp */
+    int viol = 0, mse = 0;
+    for (int x = lx + lane; x < hx; x += 32) {
+      const int y = line_at(lx, hx, ly, hy, x), v = sm.q[x];
+      mse += (y - v) * (y - v);
+      if (sm.loud[x] && (x == lx || v)) {
+        if (__fadd_rn((float)y, F.maxover) < (float)v) viol = 1;
+        if (__fsub_rn((float)y, F.maxunder) > (float)v) viol = 1;
+      }
+    }
+    viol = __any_sync(FULLMASK, viol);
+    mse = warp_sum_i(mse);
+    int bad;
+    {
+      const int cnt = hx - lx;
+      if (viol) bad = 1;
+      else if (__fdiv_rn(__fmul_rn(F.maxover, F.maxover), (float)cnt) > F.maxerr) bad = 0;
+      else if (__fdiv_rn(__fmul_rn(F.maxunder, F.maxunder), (float)cnt) > F.maxerr) bad = 0;
+      else bad = ((float)(mse / cnt) > F.maxerr) ? 1 : 0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (bad) {
+        int ly0 = -200, ly1 = -200, hy0 = -200, hy1 = -200;
+        const int r0 = fit_line(sm.seg + lsp, sp - lsp, &ly0, &ly1, F.twofitweight);
+        const int r1 = fit_line(sm.seg + sp, hsp - sp, &hy0, &hy1, F.twofitweight);
+        if (r0) { ly0 = ly; ly1 = hy0; }
+        if (r1) { hy0 = ly1; hy1 = hy; }
+        if (r0 && r1) { sm.A[i] = -200; sm.B[i] = -200; }
+        else {
+          sm.B[ln] = ly0; if (ln == 0) sm.A[ln] = ly0;
+          sm.A[i] = ly1; sm.B[i] = hy0;
+          sm.A[hn] = hy1; if (hn == 1) sm.B[hn] = hy1;
+          if (ly1 >= 0 || hy0 >= 0) {
+            for (int j = sp - 1; j >= 0 && sm.hi[j] == hn; j--) sm.hi[j] = i;
+            for (int j = sp + 1; j < posts && sm.lo[j] == ln; j++) sm.lo[j] = i;
+          }
+        }
+      } else { sm.A[i] = -200; sm.B[i] = -200; }
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  if (lane == 0) {
+    out[0] = pick(sm.A, sm.B, 0);
+    out[1] = pick(sm.A, sm.B, 1);
+    for (int i = 2; i < posts; i++) {
+      const int ln = F.lonb[i - 2], hn = F.hinb[i - 2];
+      const int pred = point_at(F.postlist[ln], F.postlist[hn], out[ln], out[hn], F.postlist[i]);
+      const int vx = pick(sm.A, sm.B, i);
+      out[i] = (vx >= 0 && pred != vx) ? vx : (pred | 0x8000);
+    }
+    fitted[item] = 1;
+  }
+}
+
+/* floor1_interpolate_fit (floor1.c:752-771) for the managed-mode blob ladder: out = blend(A,B,del) */
+__global__ void k_floor_interp(const DevSetup *__restrict__ S, int floor_index, const int *__restrict__ A, const int *__restrict__ B,
+                               const int *__restrict__ fa, const int *__restrict__ fb, int del, int *__restrict__ out, int *__restrict__ fo, int items) {
+  const int item = blockIdx.x * blockDim.y + threadIdx.y, i = threadIdx.x;
+  if (item >= items) return;
+  const int posts = S->flr[floor_index].posts;
+  const int ok = fa[item] && fb[item];
+  if (i == 0) fo[item] = ok;
+  if (!ok) return;
+  for (int k = i; k < posts; k += blockDim.x) {
+    const int a = A[(size_t)item * VB200_MAX_POSTS + k], b = B[(size_t)item * VB200_MAX_POSTS + k];
+    int v = ((65536 - del) * (a & 0x7fff) + del * (b & 0x7fff) + 32768) >> 16;
+    if ((a & 0x8000) && (b & 0x8000)) v |= 0x8000;
+    out[(size_t)item * VB200_MAX_POSTS + k] = v;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(32)
+k_floor_encode(const DevSetup *__restrict__ S, int floor_index, int *__restrict__ posts_io, const int *__restrict__ fitted,
+               int *__restrict__ vals_out, int *__restrict__ ilogmask, int *__restrict__ nonzero) {
+  __shared__ int post[VB200_MAX_POSTS];
+  __shared__ int segx[VB200_MAX_POSTS], segy[VB200_MAX_POSTS];
+  __shared__ int nseg;
+  const int item = blockIdx.x, lane = threadIdx.x;
+  const DevFloor &F = S->flr[floor_index];
+  const int posts = F.posts;
+  int *ilog = ilogmask + (size_t)item * N;
+  if (!fitted[item]) {
+    for (int i = lane; i < N; i += 32) ilog[i] = 0;
+    if (lane == 0) nonzero[item] = 0;
+    return;
+  }
+  int *pio = posts_io + (size_t)item * VB200_MAX_POSTS, *vals = vals_out + (size_t)item * VB200_MAX_POSTS;
+  for (int i = lane; i < posts; i += 32) {
+    const int p = pio[i];
+    int v = p & 0x7fff;
+    switch (F.mult) { case 1: v >>= 2; break; case 2: v >>= 3; break; case 3: v /= 12; break; case 4: v >>= 4; break; }
+    post[i] = v | (p & 0x8000);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    vals[0] = post[0]; vals[1] = post[1];
+    for (int i = 2; i < posts; i++) {
+      const int ln = F.lonb[i - 2], hn = F.hinb[i - 2];
+      const int pred = point_at(F.postlist[ln], F.postlist[hn], post[ln], post[hn], F.postlist[i]);
+      if ((post[i] & 0x8000) || pred == post[i]) { post[i] = pred | 0x8000; vals[i] = 0; }
+      else {
+        const int room = (F.quant_q - pred < pred) ? F.quant_q - pred : pred;
+        int d = post[i] - pred;
+        if (d < 0) d = (d < -room) ? room - d - 1 : -1 - (d << 1);
+        else d = (d >= room) ? d + room : d << 1;
+        vals[i] = d;
+        post[ln] &= 0x7fff; post[hn] &= 0x7fff;
+      }
+    }
+    /* the posts that take part in the rendered curve, in x order */
+    int k = 0;
+    segx[0] = 0; segy[0] = post[0] * F.mult; k = 1;
+    for (int j = 1; j < posts; j++) {
+      const int cur = F.forward[j], hy = post[cur] & 0x7fff;
+      if (hy == post[cur]) { segx[k] = F.postlist[cur]; segy[k] = hy * F.mult; k++; }
+    }
+    nseg = k;
+    nonzero[item] = 1;
+  }
+  __syncwarp();
+  for (int i = lane; i < posts; i += 32) pio[i] = post[i];
+  const int ns = nseg;
+  for (int s = 0; s + 1 < ns; s++) {
+    const int lx = segx[s], hx = segx[s + 1], ly = segy[s], hy = segy[s + 1];
+    const int lim = N < hx ? N : hx;
+    for (int x = lx + lane; x < lim; x += 32) ilog[x] = line_at(lx, hx, ly, hy, x);
+  }
+  { const int hx = ns > 1 ? segx[ns - 1] : 0, ly = segy[ns - 1]; for (int x = hx + lane; x < N; x += 32) ilog[x] = ly; }
+}
+
+}  // namespace
+
+int vb200_launch_floor_fit(const vb200_setup *s, cudaStream_t st, int W, int items, int floor_index,
+                           const float *logmdct, const float *logmask, int mdct_stride, int mask_stride,
+                           const int *gate, int *posts, int *fitted) {
+  if (items <= 0) return VB200_OK;
+  if (s->h.flr[floor_index].type != 1 || s->h.flr[floor_index].n != s->h.bs[W] / 2) { vb200_set_error("floor %d is not a floor-1 of this block size", floor_index); return VB200_EINVAL; }
+  if (W) k_floor_fit<1024><<<items, 32, 0, st>>>(s->d, floor_index, logmdct, logmask, mdct_stride, mask_stride, gate, posts, fitted);
+  else   k_floor_fit<128><<<items, 32, 0, st>>>(s->d, floor_index, logmdct, logmask, mdct_stride, mask_stride, gate, posts, fitted);
+  LAUNCH_CHECK();
+  return VB200_OK;
+}
+
+int vb200_launch_floor_interp(const vb200_setup *s, cudaStream_t st, int items, int floor_index, const int *A, const int *B,
+                              const int *fa, const int *fb, int del, int *out, int *fo) {
+  if (items <= 0) return VB200_OK;
+  dim3 blk(32, 4);
+  k_floor_interp<<<(items + 3) / 4, blk, 0, st>>>(s->d, floor_index, A, B, fa, fb, del, out, fo, items);
+  LAUNCH_CHECK();
+  return VB200_OK;
+}
+
+int vb200_launch_floor_encode(const vb200_setup *s, cudaStream_t st, int W, int items, int floor_index,
+                              int *posts, const int *fitted, int *vals, int *ilogmask, int *nonzero) {
+  if (items <= 0) return VB200_OK;
+  if (W) k_floor_encode<1024><<<items, 32, 0, st>>>(s->d, floor_index, posts, fitted, vals, ilogmask, nonzero);
+  else   k_floor_encode<128><<<items, 32, 0, st>>>(s->d, floor_index, posts, fitted, vals, ilogmask, nonzero);
+  LAUNCH_CHECK();
+  return VB200_OK;
+}

@@ -1,0 +1,237 @@
+/* K4 -- offset & mix: noise + tone -> masking curve, aoTuV M1/M3/M4.
+ *
+ * Replaces _vp_offset_and_mix (psy.c:4274-4502) and set_m3p (psy.c:4148-4272).
+ *
+ * B200 mapping.  For long-size blocks the stage is purely elementwise: float4-friendly
+ * coalesced loads of noise/tone/logmdct/mdct, one pass, coalesced stores -- HBM bound.
+ * Impulse blocks carry aoTuV's M3 state: `tempmdct` is a true recurrence along a run of
+ * consecutive impulse blocks of one channel, so a CTA owns a whole *chain*
+ * of items and keeps tempmdct in shared memory across them; chains are independent.  In
+ * managed-bitrate mode the three offset selections (1, 2, 0 in the reference's call order,
+ * mapping0.c:1044-1149) run back to back in the same CTA, including the "nominal fit exists"
+ * gate of mapping0.c:1097, which is a simple any-bin predicate (floor1.c:441-448).
+ */
+#include "vb200_internal.h"
+#include "dev_util.cuh"
+
+namespace {
+
+struct M3 { int on, keep; float rate, rate_low, center, tone_rate; };
+
+__device__ __forceinline__ int dbq(float x) {      /* vorbis_dBquant, floor1.c:285-298 */
+  int i = (int)__fadd_rn(__fmul_rn(x, 7.3142857f), 1023.5f);
+  return i > 1023 ? 1023 : (i < 0 ? 0 : i);
+}
+
+template <int N, int T>
+__global__ void __launch_bounds__(T)
+k_mix(const DevSetup *__restrict__ S, const int *__restrict__ chain_start, const int *__restrict__ chain_len,
+      const int *__restrict__ psyv, const int *__restrict__ params, const float *__restrict__ low_compandv,
+      const float *__restrict__ noise, const float *__restrict__ tone, const float *__restrict__ logmdct,
+      float *__restrict__ mdct, LastRef last, float *__restrict__ temp_state, const long long *__restrict__ temp_off,
+      float *__restrict__ npeak, int npeak_stride, float *__restrict__ logmask, int nsel, int mask_stride,
+      float *__restrict__ last_out, int *__restrict__ fit_gate, float twofitatten) {
+  __shared__ float temp[N > 256 ? 1 : 256];
+  __shared__ int pflag[64];
+  __shared__ int gate;
+  const int tid = threadIdx.x;
+  const int c0 = chain_start ? chain_start[blockIdx.x] : blockIdx.x;
+  const int clen = chain_len ? chain_len[blockIdx.x] : 1;
+  constexpr bool SHORT = (N <= 256);
+
+  for (int ci = 0; ci < clen; ci++) {
+    const int item = c0 + ci;
+    const DevPsy &P = S->psy[psyv[item]];
+    const int *pr = params + item * 8;
+    const int managed = pr[1], end_block = pr[2], block_mode = pr[3], nW = pr[4], lW_block_mode = pr[5], lW_no = pr[6], impadnum = pr[7];
+    const int hs = P.rate < 26000 ? 0 : 1;
+    const int part = P.partition;
+    const float *nz = noise + (size_t)item * N, *tn = tone + (size_t)item * N, *lm = logmdct + (size_t)item * N;
+    float *md = mdct + (size_t)item * N;
+    float *np = npeak + (size_t)item * npeak_stride;
+    float *tstate = (SHORT && temp_state) ? temp_state + (temp_off ? temp_off[item] : (long long)item * 256) : nullptr;
+
+    if (SHORT && ci == 0 && tstate) { for (int i = tid; i < N; i += T) temp[i] = tstate[i]; }
+    if (tid == 0) gate = 1;
+    __syncthreads();
+
+    for (int si = 0; si < nsel; si++) {
+      /* VBR: the single selection pr[0]; managed: 1, 2, 0 */
+      const int sel = (nsel == 1) ? pr[0] : (si == 0 ? 1 : (si == 1 ? 2 : 0));
+      if (si > 0 && !gate) break;       /* mapping0.c:1097: no nominal fit -> no hi/lo curves */
+      const float toneatt = P.tone_masteratt[sel];
+      float low_compand = low_compandv[item];
+      if (low_compand < 0.f || toneatt < 25.f) low_compand = 0.f;
+      else low_compand = (float)((double)low_compand * ((double)toneatt - 25.));
+
+      /* ---- set_m3p ---- */
+      M3 m3; m3.on = 0; m3.keep = 0; m3.rate = m3.rate_low = m3.center = m3.tone_rate = 0.f;
+      bool m3_go = false;
+      if (hs) {
+        if (!managed || sel == 2) { m3.keep = 1; m3_go = true; }
+        else if (sel != 0) m3_go = true;
+        if (block_mode) m3_go = false;
+      }
+      if (SHORT && m3_go && (N == 128 || N == 256)) {
+        const int *bfn = (N == 128) ? S->freq_bfn128 : S->freq_bfn256;
+        const double drop = (N == 128) ? 5. : 10.;
+        if (N == 128) {
+          const int count = (toneatt < 3.f) ? 2 : 3;
+          if (!lW_block_mode) {
+            if (lW_no < 8) { m3.rate = (float)(0.7 - (double)((float)(lW_no - 1) / 17.f)); m3.center = (float)(lW_no * count); m3.tone_rate = (float)(8 - lW_no); }
+            else { m3.rate = (float)0.3; m3.center = 25.f; m3.tone_rate = 0.f; if ((lW_no * count) < 24) m3.center = (float)(lW_no * count); }
+          } else { m3.rate = (float)0.7; m3.center = 0.f; m3.tone_rate = 8.f; }
+        } else {
+          const int count = 6;
+          if (!lW_block_mode) {
+            if (lW_no < 4) { m3.rate = (float)(0.4 - (double)((float)(lW_no - 1) / 11.f)); m3.center = (float)(lW_no * count + 12); m3.tone_rate = (float)(8 - lW_no * 2); }
+            else { m3.rate = (float)0.2; m3.center = 30.f; m3.tone_rate = 0.f; }
+          } else { m3.rate = (float)0.6; m3.center = 12.f; m3.tone_rate = 8.f; }
+        }
+        if (m3.keep) {
+          if (!lW_block_mode) { for (int i = tid; i < N; i += T) temp[i] = (float)((double)temp[i] - drop); }
+          else { for (int i = tid; i < N; i += T) temp[i] = (float)((double)last.at(item, i) - drop); }
+        }
+        m3.rate_low = 0.f;
+        m3.on = 1;
+        if (impadnum) m3.rate = (float)((double)m3.rate * ((double)impadnum * (N == 128 ? 0.125 : 0.0625)));
+        __syncthreads();
+        if (m3.keep && tid == 0) {      /* cross-bin spread: order dependent, serial (psy.c:4215-4222) */
+          for (int i = 0; i < N; i++) {
+            const int b = bfn[i];
+            const float cell = 75.f / (float)b, l = lm[i];
+            for (int j = 1; j < b; j++) {
+              const float fb = __fsub_rn(l, __fmul_rn(cell, (float)j));
+              if (temp[i + j] < fb) temp[i + j] = (float)((double)temp[i + j] + (drop / (double)(float)bfn[i + j]));
+            }
+          }
+        }
+        if (managed && sel == 0 && m3.on) m3.rate = (float)((double)m3.rate * 0.2);
+      }
+      if (tid < 64) pflag[tid] = 0;
+      __syncthreads();
+
+      /* ---- M4 set-up ---- */
+      int m4_start = P.normal_start, m4_end = P.tonecomp_endp, m4_endblock = end_block + P.normal_partition;
+      if (m4_endblock > N) m4_endblock = N;
+      if (!hs) m4_end = m4_endblock;
+      else if (P.normal_thresh > 1.) m4_start = 9999;
+      const float m4_thres = P.tonecomp_thres;
+      const float *noff = P.noiseoffset + sel * N;
+      float *mk = logmask + (size_t)item * mask_stride + (size_t)si * N;
+      int local_gate = 0;
+
+      for (int i = tid; i < N; i += T) {
+        float val = __fadd_rn(__ldg(nz + i), __ldg(noff + i));
+        float tval = __fadd_rn(__ldg(tn + i), toneatt);
+        const float l = __ldg(lm + i);
+        if (i <= m4_start) tval = __fsub_rn(tval, low_compand);
+        if (val > P.noisemaxsupp) val = P.noisemaxsupp;
+        if (SHORT && m3.on && val > tval) {                                       /* aoTuV M3 */
+          const float la = last.at(item, i);
+          if (val > la && l > __fadd_rn(temp[i], m3.center)) {
+            int toneac = 0;
+            if (m3.keep) temp[i] = l;
+            float rate = (l > la) ? m3.rate : m3.rate_low;
+            if (!impadnum && i < P.tonecomp_endp && __fsub_rn(val, la) > 20.f) {
+              const float dBsub = __fsub_rn(l, la);
+              if (dBsub > 25.f) {
+                toneac = 1;
+                if (tval > -100.f && __fsub_rn(l, tval) < 48.f) {
+                  float tr = m3.tone_rate;
+                  if (dBsub < 35.f) tr = __fmul_rn(tr, __fmul_rn(__fsub_rn(35.f, dBsub), .1f));
+                  tval = __fsub_rn(tval, tr);
+                  if (tval < -100.f) tval = -100.f;
+                  if (__fsub_rn(l, tval) > 48.f) tval = __fsub_rn(l, 48.f);
+                }
+              }
+            }
+            float mainth;
+            if (i > P.m3n[0]) mainth = 30.f;
+            else if (i > P.m3n[1]) mainth = 20.f;
+            else if (i > P.m3n[2]) { mainth = 10.f; rate = __fmul_rn(rate, .5f); }
+            else { mainth = 10.f; rate = __fmul_rn(rate, .3f); }
+            float valmask;
+            const float dv = __fsub_rn(val, tval);
+            if (dv > mainth) valmask = __fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(dv, mainth), .1f), mainth), rate);
+            else valmask = __fmul_rn(dv, rate);
+            if (__fsub_rn(val, valmask) > la) val = __fsub_rn(val, valmask); else val = la;
+            if (toneac) { const float t = __fsub_rn(val, fmaxf(la, -140.f)); if (t > 20.f) val = __fsub_rn(val, __fmul_rn(__fsub_rn(t, 20.f), .2f)); }
+            atomicOr(&pflag[i / part], toneac ? 3 : 1);
+          }
+        }
+        float out;                                                                /* aoTuV M4 */
+        if (val > tval) out = val;
+        else {
+          if (i > m4_start && i < m4_end && l < tval) {
+            if (l < val) tval = __fsub_rn(tval, __fmul_rn(__fsub_rn(tval, val), m4_thres)); else tval = l;
+          }
+          out = tval;
+        }
+        mk[i] = out;
+        if (sel == 1) {                                                           /* aoTuV M1 */
+          const float coeffi = (float)-17.2;
+          const float v = __fsub_rn(val, l);
+          float de;
+          if (v > coeffi) { de = (float)(1.0 - ((double)__fsub_rn(v, coeffi) * 0.005 * (double)P.m_val)); if (de < 0.f) de = (float)0.0001; }
+          else de = (float)(1.0 - ((double)__fsub_rn(v, coeffi) * 0.0003 * (double)P.m_val));
+          md[i] = __fmul_rn(md[i], de);
+          if (nsel > 1 && dbq(out) && __fadd_rn(l, twofitatten) >= out) local_gate = 1;
+        }
+      }
+      if (nsel > 1 && si == 0) {
+        if (tid == 0) gate = 0;
+        __syncthreads();
+        if (local_gate) gate = 1;
+      }
+      __syncthreads();
+      /* npeak exceptions for M8 (psy.c:4396-4398): any tone hit -> -1, else a hit clears a positive value */
+      if (SHORT && m3.on) {
+        for (int k = tid; k < N / part; k += T) {
+          const int fl = pflag[k];
+          if (fl & 2) np[k] = -1.f;
+          else if (fl & 1) { if (np[k] > 0.f) np[k] = 0.f; }
+        }
+      }
+      /* lastmdct as the reference leaves it (psy.c:4462-4501) -- only materialised on request */
+      if (last_out && m3.keep) {
+        float *lo_ = last_out + (size_t)item * 2048;
+        if (block_mode <= 1) {
+          if (nW) { for (int i = tid; i < N * 8; i += T) lo_[i] = __ldg(lm + (i >> 3)); }
+          else { for (int i = tid; i < N; i += T) lo_[i] = __ldg(lm + i); }
+        } else if (block_mode == 2 && !nW) {
+          for (int i = tid; i < (N >> 3); i += T) {
+            float mn = __ldg(lm + i * 8);
+            for (int j = 1; j < 8; j++) { const float v = __ldg(lm + i * 8 + j); if (mn > v) mn = v; }
+            lo_[i] = mn;
+          }
+        } else { for (int i = tid; i < N; i += T) lo_[i] = __ldg(lm + i); }
+      }
+      __syncthreads();
+    }
+    if (fit_gate && tid == 0) fit_gate[item] = gate;
+    if (SHORT && tstate) {
+      /* keep the chain's tempmdct in its slot (the next chain link / the stream state reads it) */
+      float *dst = temp_state + (temp_off ? temp_off[item] : (long long)item * 256);
+      for (int i = tid; i < N; i += T) dst[i] = temp[i];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int vb200_launch_mix(const vb200_setup *s, cudaStream_t st, int W, int nchains, const int *chain_start, const int *chain_len,
+                     const int *psy, const int *params, const float *low_compand,
+                     const float *noise, const float *tone, const float *logmdct, float *mdct, LastRef last,
+                     float *temp_state, const long long *temp_off, float *npeak, int npeak_stride,
+                     float *logmask, int nsel, int mask_stride, float *last_out, int *fit_gate, int floor_index) {
+  if (nchains <= 0) return VB200_OK;
+  const float atten = s->h.flr[floor_index].twofitatten;
+  if (W) k_mix<1024, 256><<<nchains, 256, 0, st>>>(s->d, chain_start, chain_len, psy, params, low_compand, noise, tone, logmdct, mdct, last,
+                                                   temp_state, temp_off, npeak, npeak_stride, logmask, nsel, mask_stride, last_out, fit_gate, atten);
+  else   k_mix<128, 64><<<nchains, 64, 0, st>>>(s->d, chain_start, chain_len, psy, params, low_compand, noise, tone, logmdct, mdct, last,
+                                                temp_state, temp_off, npeak, npeak_stride, logmask, nsel, mask_stride, last_out, fit_gate, atten);
+  LAUNCH_CHECK();
+  return VB200_OK;
+}

@@ -1,0 +1,267 @@
+/* K2 -- noise masking, one small CTA per ch-block.
+ *
+ * Replaces _vp_noisemask (psy.c:3770-4074): two bark-window regressions
+ * (bark_noise_hybridmp, psy.c:3480-3638), the aoTuV M7 tone-peak correction (ntfix,
+ * psy.c:3645-3768), the noise compander, M2 post-echo cut, M8 (npeak) and M9 (epeak).
+ *
+ * B200 mapping.  The regression is built on five float32 prefix sums whose left-to-right
+ * summation order is part of the result, so each of them is an
+ * inherently serial 1024-step chain.  The kernel therefore (a) computes the per-bin terms in
+ * parallel, (b) lets five lanes walk the five chains out of shared memory, (c) evaluates the
+ * per-bin window fits in parallel again -- and keeps the CTA tiny (64 threads, ~29 KB of
+ * shared memory) so that 7-8 CTAs are resident per SM and the serial chains of different
+ * ch-blocks overlap.  HBM traffic is the algorithmic minimum: logmdct (+lastmdct for M9) in,
+ * noise + epeak + npeak out.
+ */
+#include "vb200_internal.h"
+#include "dev_util.cuh"
+#include "k_common.cuh"
+
+namespace {
+
+template <int N>
+struct NoiseSmem {
+  float sums[5][N + 1];   /* N, X, XX, Y, XY prefix sums; +1 keeps the five chain lanes on different banks */
+  float work[N];
+  float noise[N];
+  float held[3];          /* A, B, D of the last fitted bin, reused above the last full window */
+  float tmp[256], inm[256];
+};
+
+/* one regression pass over all bins (the parallel part of bark_noise_hybridmp) */
+template <int N, int T>
+__device__ __forceinline__ void fit_pass(NoiseSmem<N> &sm, const int *__restrict__ bark, int fixed, int pass,
+                                         int b1, int b2, float offset) {
+  const int tid = threadIdx.x;
+  /* bins below b2 have their own window; publish the fit of bin b2-1 for the bins above */
+  for (int i = tid; i < b2; i += T) {
+    int lo, hi;
+    if (pass == 0) { int b = __ldg(bark + i); lo = b >> 16; hi = b & 0xffff; }
+    else { hi = i + fixed / 2; lo = hi - fixed; }
+    float tN, tX, tXX, tY, tXY;
+    if (i < b1) {
+      tN = __fadd_rn(sm.sums[0][hi], sm.sums[0][-lo]); tX = __fsub_rn(sm.sums[1][hi], sm.sums[1][-lo]);
+      tXX = __fadd_rn(sm.sums[2][hi], sm.sums[2][-lo]); tY = __fadd_rn(sm.sums[3][hi], sm.sums[3][-lo]);
+      tXY = __fsub_rn(sm.sums[4][hi], sm.sums[4][-lo]);
+    } else {
+      tN = __fsub_rn(sm.sums[0][hi], sm.sums[0][lo]); tX = __fsub_rn(sm.sums[1][hi], sm.sums[1][lo]);
+      tXX = __fsub_rn(sm.sums[2][hi], sm.sums[2][lo]); tY = __fsub_rn(sm.sums[3][hi], sm.sums[3][lo]);
+      tXY = __fsub_rn(sm.sums[4][hi], sm.sums[4][lo]);
+    }
+    float A = __fsub_rn(__fmul_rn(tY, tXX), __fmul_rn(tX, tXY));
+    float B = __fsub_rn(__fmul_rn(tN, tXY), __fmul_rn(tX, tY));
+    float D = __fsub_rn(__fmul_rn(tN, tXX), __fmul_rn(tX, tX));
+    if (i == b2 - 1) { sm.held[0] = A; sm.held[1] = B; sm.held[2] = D; }
+    float R = __fdiv_rn(__fadd_rn(A, __fmul_rn((float)i, B)), D);
+    if (pass == 0) { if (R < 0.f) R = 0.f; sm.noise[i] = __fsub_rn(R, offset); }
+    else { float v = __fsub_rn(R, offset); if (v < sm.noise[i]) sm.noise[i] = v; }
+  }
+  __syncthreads();
+  {
+    const float A = sm.held[0], B = sm.held[1], D = sm.held[2];
+    for (int i = b2 + tid; i < N; i += T) {
+      float R = __fdiv_rn(__fadd_rn(A, __fmul_rn((float)i, B)), D);
+      if (pass == 0) { if (R < 0.f) R = 0.f; sm.noise[i] = __fsub_rn(R, offset); }
+      else { float v = __fsub_rn(R, offset); if (v < sm.noise[i]) sm.noise[i] = v; }
+    }
+  }
+  __syncthreads();
+}
+
+/* f (shared or global) -> sm.noise;  both regression passes of one bark_noise_hybridmp call */
+template <int N, int T, typename F>
+__device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f, float offset, int fixed) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N; i += T) {
+    float y = __fadd_rn(f(i), offset);
+    if (y < 1.f) y = 1.f;
+    float w = __fmul_rn(y, y);
+    if (i == 0) {
+      w = __fmul_rn(w, .5f);
+      sm.sums[0][0] = w; sm.sums[1][0] = w; sm.sums[2][0] = 0.f; sm.sums[3][0] = __fmul_rn(w, y); sm.sums[4][0] = 0.f;
+    } else {
+      float x = (float)i, wx = __fmul_rn(w, x);
+      sm.sums[0][i] = w; sm.sums[1][i] = wx; sm.sums[2][i] = __fmul_rn(wx, x);
+      sm.sums[3][i] = __fmul_rn(w, y); sm.sums[4][i] = __fmul_rn(wx, y);
+    }
+  }
+  if (tid == 0) { sm.held[0] = 0.f; sm.held[1] = 0.f; sm.held[2] = 1.f; }
+  __syncthreads();
+  if (tid < 5) {                       /* the five serial float32 chains */
+    float *r = sm.sums[tid];
+    float acc = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < N; i += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = r[i + k];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { acc = __fadd_rn(acc, v[k]); v[k] = acc; }
+#pragma unroll
+      for (int k = 0; k < 8; k++) r[i + k] = v[k];
+    }
+  }
+  __syncthreads();
+  fit_pass<N, T>(sm, P.bark, fixed, 0, P.nf_b1[0], P.nf_b2[0], offset);
+  if (fixed > 0) fit_pass<N, T>(sm, P.bark, fixed, 1, P.nf_b1[1], P.nf_b2[1], offset);
+}
+
+/* aoTuV M7 (psy.c:3645-3768) on sm.work; short blocks: peak-driven, transition blocks: 8-bin groups.
+   Data-dependent and tiny: lane 0 walks it. */
+template <int N>
+__device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restrict__ spec, int block_mode) {
+  int nx = P.tonefix_end;
+  if (!nx) return;
+  const float *off1 = P.noiseoffset + N;
+  const float limit = fabsf(__ldg(off1));
+  float *noise = sm.work;
+  for (int i = 0; i < 256; i++) { sm.tmp[i] = 0.f; sm.inm[i] = 0.f; }
+  if (block_mode <= 1) {
+    const int up = 3, un = 4;
+    int nxp = nx + un;
+    const float tol = (N == 256) ? 15.f : 9.f, strength = .6f;
+    if (nxp > N) { nx = N; nxp = N - un; }
+    for (int i = 0; i < nxp; i++) {
+      float s = spec[i];
+      sm.inm[i] = (s < -70.f) ? (float)(-70. + (double)__fadd_rn(s, 70.f) * .1) : s;
+    }
+    for (int i = un; i < nx; i++) {
+      if (!(spec[i] > spec[i - 1] && spec[i] > spec[i + 1])) continue;
+      int ps = i - 1, pe = i + 1;
+      for (int j = ps; j > i - up; j--) { if (spec[j + 1] < spec[j]) break; ps = j; }
+      for (int j = pe; j < i + un; j++) { if (spec[j - 1] < spec[j]) break; pe = j; }
+      float ss = fmaxf(__fsub_rn(sm.inm[i], sm.inm[ps]), __fsub_rn(sm.inm[i], sm.inm[pe]));
+      if (ss > tol) {
+        if (spec[i] > noise[i]) { ss = __fsub_rn(ss, tol); ss = __fmul_rn(ss, strength); }
+        for (int j = ps; j <= pe; j++) { float t = fmaxf(ss, sm.tmp[j]); if (t < 0.f) t = 0.f; sm.tmp[j] = t; }
+      }
+      i = pe;
+    }
+    for (int i = un - 1; i < nx; i++) {
+      float cap = fminf(__ldg(P.ntfix + i), __fadd_rn(__ldg(off1 + i), limit));
+      float t = sm.tmp[i];
+      if (t > cap) t = cap;
+      noise[i] = __fsub_rn(noise[i], t);
+    }
+  } else if (block_mode == 2) {
+    int k = 0;
+    for (int i = 0; i < nx; i += 8, k++) {
+      double a = 0;
+      for (int j = 0; j < 8; j++) a += (double)noise[i + j];
+      sm.tmp[k] = (float)(a / 8);
+    }
+    const int groups = nx / 8;
+    for (int i = 3; i < groups; i++) {
+      if (!(sm.tmp[i] > sm.tmp[i - 1] && sm.tmp[i] > sm.tmp[i + 1])) continue;
+      float base; int a;
+      if (sm.tmp[i - 1] > sm.tmp[i - 2]) { base = sm.tmp[i - 2]; a = i - 3; } else { base = sm.tmp[i - 1]; a = i - 2; }
+      const int b = i + 3;
+      float th = __fsub_rn(sm.tmp[i], base);
+      if (th > 2.f) {
+        float cap = fminf(__ldg(P.ntfix + i * 8), __fadd_rn(__ldg(off1 + i * 8), limit));
+        th = fminf(__fsub_rn(th, 2.f), cap);
+        for (int j = a * 8; j <= b * 8; j++) noise[j] = __fsub_rn(noise[j], th);
+      }
+    }
+  }
+}
+
+template <int N, int T>
+__global__ void __launch_bounds__(T)
+k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const int *__restrict__ block_mode,
+            const float *__restrict__ lowcomp, const float *__restrict__ postev,
+            const float *__restrict__ logmdct, LastRef last,
+            float *__restrict__ noise_out, float *__restrict__ epeak_out, float *__restrict__ npeak_out, int npeak_stride) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  NoiseSmem<N> &sm = *reinterpret_cast<NoiseSmem<N> *>(smraw);
+  const int item = blockIdx.x, tid = threadIdx.x;
+  const DevPsy &P = S->psy[psyv[item]];
+  const float *lm = logmdct + (size_t)item * N;
+  const int mode = block_mode[item];
+  const float level = lowcomp[item], poste = postev[item];
+  const int part = P.partition;
+
+  noise_fit<N, T>(sm, P, [&](int i) { return __ldg(lm + i); }, 140.f, -1);
+  for (int i = tid; i < N; i += T) sm.work[i] = __fsub_rn(__ldg(lm + i), sm.noise[i]);
+  __syncthreads();
+  noise_fit<N, T>(sm, P, [&](int i) { return sm.work[i]; }, 0.f, P.noisewindowfixed);
+  for (int i = tid; i < N; i += T) sm.work[i] = __fsub_rn(__ldg(lm + i), sm.work[i]);
+  __syncthreads();
+  if (mode <= 2 && P.tonefix_end) {
+    if (tid == 0) tone_fix<N>(sm, P, lm, mode);
+    __syncthreads();
+  }
+
+  /* compander (psy.c:3878-4012); epeak staged in sums[0] for M9 */
+  float *ep = sm.sums[0];
+  for (int i = tid; i < N; i += T) {
+    int dB = (int)((double)sm.noise[i] + .5);
+    if (dB >= VB200_COMPAND_LEVELS) dB = VB200_COMPAND_LEVELS - 1;
+    if (dB < 0) dB = 0;
+    const float w = sm.work[i], c = P.compand[dB];
+    ep[i] = __fadd_rn(w, (float)S->stn_compand[dB]);
+    float v = __fadd_rn(w, c);
+    if (level > 0.f && i < P.n33p) v = __fsub_rn(v, __fmul_rn(__fsub_rn(c, P.compand_hi[dB]), level));
+    sm.noise[i] = v;
+  }
+  __syncthreads();
+
+  /* per-partition work: M2 post-echo cut then M8 npeak (psy.c:4025-4063); one lane per partition */
+  const int nparts = N / part;
+  const float *off1 = P.noiseoffset + N;
+  for (int k = tid; k < nparts; k += T) {
+    const int i = k * part;
+    float np = 0.f;
+    if (i < P.min_nn_lp) {
+      if (poste > 0.f) {
+        float t = fminf(fminf(poste, 30.f), __fadd_rn(__ldg(off1 + i), 30.f));
+        if (t > 0.f) { np = -1.f; for (int j = 0; j < part; j++) sm.noise[i + j] = __fsub_rn(sm.noise[i + j], t); }
+      }
+      const float nt = 4.f;
+      const float o = __fadd_rn(__ldg(off1 + i + part - 1), 6.f);
+      if (o > 0.f && !(np < -0.5f)) {
+        float me = 0.f, av = 0.f;
+        for (int j = 0; j < part; j++) {
+          const float l = __ldg(lm + i + j);
+          const float t = __fsub_rn(l, sm.noise[i + j]);
+          if (me < t) me = t;
+          av = __fadd_rn(av, l);
+        }
+        if (!(av < (float)(-95 * part)) && me < nt) np = __fdiv_rn(fminf(o, __fsub_rn(nt, me)), nt);
+      }
+    }
+    npeak_out[(size_t)item * npeak_stride + k] = np;
+  }
+  __syncthreads();
+
+  /* M9 (psy.c:4065-4073) + stores */
+  float *no = noise_out + (size_t)item * N, *eo = epeak_out + (size_t)item * N;
+  for (int i = tid; i < N; i += T) {
+    float e = 0.f;
+    if (mode > 1 && i < P.tonecomp_endp) {
+      const float l = __ldg(lm + i);
+      if (__fsub_rn(l, ep[i]) >= 12.f) { const float mi = __fsub_rn(l, last.at(item, i)); if (mi >= 1.f) e = mi; }
+    }
+    eo[i] = e;
+    no[i] = sm.noise[i];
+  }
+}
+
+}  // namespace
+
+int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
+                           const int *block_mode, const float *lowcomp, const float *poste,
+                           const float *logmdct, LastRef last, float *noise, float *epeak, float *npeak, int npeak_stride) {
+  if (items <= 0) return VB200_OK;
+  if (W) {
+    constexpr int N = 1024, T = 64;
+    static bool attr = false;
+    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(k_noisemask<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NoiseSmem<N>))); attr = true; }
+    k_noisemask<N, T><<<items, T, sizeof(NoiseSmem<N>), st>>>(s->d, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
+  } else {
+    constexpr int N = 128, T = 32;
+    k_noisemask<N, T><<<items, T, sizeof(NoiseSmem<N>), st>>>(s->d, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
+  }
+  LAUNCH_CHECK();
+  return VB200_OK;
+}

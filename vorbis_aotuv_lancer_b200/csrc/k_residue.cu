@@ -1,0 +1,262 @@
+/* K7 -- residue partition classification (K7a) and cascade lattice VQ search (K7b).
+ *
+ * Replaces res1_class/_01class (res0.c:735,406-468), res2_class/_2class (:759,473-526) and
+ * res1_forward/res2_forward -> _01forward -> _encodepart -> local_book_besterror
+ * (:715,773-799,528-640,384-404,316-378).  Codeword emission (vorbis_book_encode,
+ * codebook.c:402-410) is not done here: the kernel returns the (book,entry) symbol list in the
+ * reference's emission order and the bit packer consumes it.
+ *
+ * B200 mapping.  Partitions are independent; the cascade (stage s quantises what stage s-1 left)
+ * is serial per partition.  One CTA per block and submap, four warps, each warp owning every
+ * fourth partition in shared memory.  Inside a stage the dim-sized vectors of the partition map to
+ * lanes; the lattice index is arithmetic, and when it lands on an entry without a codeword the
+ * whole warp searches the book's compacted used-entry table (first minimum wins, as the
+ * reference's linear scan).  Entries land in a shared-memory table; a warp scan over the per-
+ * (stage, partition, row) symbol counts then turns the table into the emission-ordered list with
+ * coalesced stores.  HBM traffic: the quantised residue in, ~2 KB of symbols out.
+ */
+#include "vb200_internal.h"
+#include "dev_util.cuh"
+
+namespace {
+
+/* ------------------------------------------------------------------ K7a */
+__global__ void __launch_bounds__(64)
+k_residue_class(const DevSetup *__restrict__ S, int resnum, int n, int ch, const int *__restrict__ chlist, int tot_ch,
+                const int *__restrict__ in, const int *__restrict__ nonzero, int *__restrict__ partword, int *__restrict__ classified) {
+  const int blk = blockIdx.x, tid = threadIdx.x;
+  const DevResidue &R = S->res[resnum];
+  const int partvals = (R.end - R.begin) / R.grouping;
+  const int *base = in + (size_t)blk * tot_ch * n;
+  const int *nz = nonzero + (size_t)blk * tot_ch;
+  int *pw = partword + (size_t)blk * ch * partvals;
+  int used = 0;
+  for (int k = 0; k < ch; k++) if (nz[chlist[k]]) used++;
+  if (tid == 0) classified[blk] = used ? (R.type == 2 ? 1 : used) : 0;
+  if (!used) return;
+  if (R.type == 2) {
+    const int per = (R.grouping + ch - 1) / ch;   /* positions per channel per partition (res0.c:498-503) */
+    for (int p = tid; p < partvals; p += blockDim.x) {
+      int l = R.begin / ch + p * per, mag = 0, ang = 0;
+      for (int j = 0; j < R.grouping; j += ch, l++) {
+        const int a = abs(__ldg(base + (size_t)chlist[0] * n + l));
+        if (a > mag) mag = a;
+        for (int k = 1; k < ch; k++) { const int b = abs(__ldg(base + (size_t)chlist[k] * n + l)); if (b > ang) ang = b; }
+      }
+      int c = 0;
+      for (; c < R.partitions - 1; c++) if (mag <= R.classmetric1[c] && ang <= R.classmetric2[c]) break;
+      pw[p] = c;
+    }
+  } else {
+    const float scale = (float)(100. / (double)R.grouping);
+    int row = 0;
+    for (int k = 0; k < ch; k++) {
+      if (!nz[chlist[k]]) continue;
+      const int *v = base + (size_t)chlist[k] * n + R.begin;
+      for (int p = tid; p < partvals; p += blockDim.x) {
+        int mx = 0, ent = 0;
+        for (int t = 0; t < R.grouping; t++) { const int a = abs(__ldg(v + p * R.grouping + t)); if (a > mx) mx = a; ent += a; }
+        ent = (int)__fmul_rn((float)ent, scale);
+        int c = 0;
+        for (; c < R.partitions - 1; c++) if (mx <= R.classmetric1[c] && (R.classmetric2[c] < 0 || ent < R.classmetric2[c])) break;
+        pw[row * partvals + p] = c;
+      }
+      row++;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ K7b */
+constexpr int RF_WARPS = 4;
+constexpr int RF_MAXG = 64;     /* largest partition size handled (grouping) */
+
+struct RfShared {
+  int vec[RF_WARPS][RF_MAXG];
+  int red_d[RF_WARPS], red_i[RF_WARPS];
+};
+
+__global__ void __launch_bounds__(RF_WARPS * 32)
+k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, const int *__restrict__ chlist, int tot_ch,
+                  int *__restrict__ in, const int *__restrict__ nonzero, const int *__restrict__ partword,
+                  int maxvec, int *__restrict__ syms, int max_syms, int *__restrict__ nsyms) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ RfShared sh;
+  const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const DevResidue &R = S->res[resnum];
+  const DevBook *books = S->book;
+  const int partvals = (R.end - R.begin) / R.grouping, G = R.grouping, stages = R.stages;
+  int *base = in + (size_t)blk * tot_ch * n;
+  const int *nz = nonzero + (size_t)blk * tot_ch;
+  int used = 0;
+  for (int k = 0; k < ch; k++) if (nz[chlist[k]]) used++;
+  if (!used) { if (tid == 0) nsyms[blk] = 0; return; }
+  const int rows = (R.type == 2) ? 1 : used;
+  const int *pw = partword + (size_t)blk * ch * partvals;
+  /* dynamic shared memory: entry table [stages][partvals][rows][maxvec] (int16) + scan offsets + row->channel map */
+  short *ent = reinterpret_cast<short *>(dyn);
+  const size_t ent_elems = (size_t)stages * partvals * rows * maxvec;
+  int *offs = reinterpret_cast<int *>(dyn + ((ent_elems * 2 + 15) & ~(size_t)15));   /* [stages*partvals*rows + 1] */
+  __shared__ int rowch[VB200_MAX_CHANNELS];
+  if (tid == 0) { int r = 0; for (int k = 0; k < ch; k++) if (R.type == 2 || nz[chlist[k]]) rowch[r++] = chlist[k]; }
+  __syncthreads();
+
+  /* ---- pass 1: cascade VQ per (partition,row), warps stride over them ---- */
+  for (int pr = warp; pr < partvals * rows; pr += RF_WARPS) {
+    const int p = pr / rows, row = pr % rows;
+    const int cls = pw[row * partvals + p];
+    int *v = sh.vec[warp];
+    const int off = p * G + R.begin;
+    /* stage the partition: res2 reads the channel-interleaved vector work[j*ch+c]=in[c][j] (res0.c:782-787) */
+    for (int t = lane; t < G; t += 32) {
+      if (R.type == 2) { const int w = off + t; v[t] = base[(size_t)chlist[w % ch] * n + w / ch]; }
+      else v[t] = base[(size_t)rowch[row] * n + off + t];
+    }
+    __syncwarp();
+    for (int s = 0; s < stages; s++) {
+      if (!(R.secondstages[cls] & (1 << s))) continue;
+      const int bk = R.partbooks[cls * 8 + s];
+      if (bk < 0) continue;
+      const DevBook &B = books[bk];
+      const int dim = B.dim, nvec = G / dim, qv = B.quantvals, ze = qv >> 1;
+      short *e_out = ent + (((size_t)s * partvals + p) * rows + row) * maxvec;
+      for (int t0 = 0; t0 < nvec; t0 += 32) {
+        const int t = t0 + lane;
+        bool fb = false;
+        int index = 0;
+        if (t < nvec) {
+          int *a = v + t * dim;
+          int pt[8];
+          for (int i = 0, o = dim; i < dim; i++) {
+            --o;
+            const int x = (B.delta != 1) ? (a[o] - B.minval + (B.delta >> 1)) / B.delta : a[o] - B.minval;
+            const int m = (x < ze) ? ((ze - x) << 1) - 1 : ((x - ze) << 1);
+            index = index * qv + (m < 0 ? 0 : (m >= qv ? qv - 1 : m));
+            pt[o] = x * B.delta + B.minval;
+          }
+          if (__ldg(B.len + index) == 0) fb = true;
+          else { for (int i = 0; i < dim; i++) a[i] -= pt[i]; e_out[t] = (short)index; }
+        }
+        /* entries without a codeword: warp-wide exhaustive search over the used entries */
+        unsigned fm = __ballot_sync(FULLMASK, fb);
+        while (fm) {
+          const int src = __ffs(fm) - 1; fm &= fm - 1;
+          const int tv = t0 + src;
+          int *a = v + tv * dim;
+          int bestd = 0x7fffffff, besti = 0x7fffffff;
+          for (int u = lane; u < B.used; u += 32) {
+            const int *ev = B.used_vals + (size_t)u * 8;
+            int d = 0;
+            for (int j = 0; j < dim; j++) { const int df = __ldg(ev + j) - a[j]; d += df * df; }
+            if (d < bestd) { bestd = d; besti = u; }      /* u ascending per lane: first minimum kept */
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const int od = __shfl_xor_sync(FULLMASK, bestd, o), oi = __shfl_xor_sync(FULLMASK, besti, o);
+            if (od < bestd || (od == bestd && oi < besti)) { bestd = od; besti = oi; }
+          }
+          __syncwarp();
+          if (besti != 0x7fffffff) {
+            if (lane < dim) a[lane] -= __ldg(B.used_vals + (size_t)besti * 8 + lane);
+            if (lane == 0) e_out[tv] = (short)__ldg(B.used_list + besti);
+          } else if (lane == 0) e_out[tv] = -1;
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+    }
+    /* res1 leaves the cascade residual in place (res2 worked on a private interleaved copy) */
+    if (R.type != 2) for (int t = lane; t < G; t += 32) base[(size_t)rowch[row] * n + off + t] = v[t];
+    __syncwarp();
+  }
+  __syncthreads();
+
+  /* ---- pass 2: emission order.  Count symbols per (stage, partition, row), scan, scatter. ---- */
+  const int pd = R.phrase_dim;
+  const int nslots = stages * partvals * rows;
+  const int phrase_entries = books[R.groupbook].entries;
+  if (warp == 0) {
+    int carry = 0;
+    for (int b0 = 0; b0 < nslots; b0 += 32) {
+      const int idx = b0 + lane;
+      int cnt = 0;
+      if (idx < nslots) {
+        const int s = idx / (partvals * rows), rem = idx % (partvals * rows), p = rem / rows, row = rem % rows;
+        const int cls = pw[row * partvals + p];
+        if (R.secondstages[cls] & (1 << s)) { const int bk = R.partbooks[cls * 8 + s]; if (bk >= 0) cnt = G / books[bk].dim; }
+        if (s == 0 && (p % pd) == 0 && row == 0) {
+          /* the phrase words of this partition group (one per row) precede its residual symbols */
+          for (int r2 = 0; r2 < rows; r2++) {
+            int val = pw[r2 * partvals + p];
+            for (int k = 1; k < pd; k++) { val *= R.partitions; if (p + k < partvals) val += pw[r2 * partvals + p + k]; }
+            if (val < phrase_entries) cnt += 1 << 16;      /* high half counts phrase symbols */
+          }
+        }
+      }
+      const int tot = (cnt & 0xffff) + (cnt >> 16);
+      int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += y; }
+      if (idx < nslots) offs[idx] = carry + incl - tot;
+      carry += __shfl_sync(FULLMASK, incl, 31);
+    }
+    if (lane == 0) { offs[nslots] = carry; nsyms[blk] = carry < max_syms ? carry : max_syms; }
+  }
+  __syncthreads();
+  int *out = syms + (size_t)blk * max_syms * 2;
+  for (int idx = warp; idx < nslots; idx += RF_WARPS) {
+    const int s = idx / (partvals * rows), rem = idx % (partvals * rows), p = rem / rows, row = rem % rows;
+    int o = offs[idx];
+    if (s == 0 && (p % pd) == 0 && row == 0) {
+      for (int r2 = 0; r2 < rows; r2++) {
+        int val = pw[r2 * partvals + p];
+        for (int k = 1; k < pd; k++) { val *= R.partitions; if (p + k < partvals) val += pw[r2 * partvals + p + k]; }
+        if (val < phrase_entries) { if (lane == 0 && o < max_syms) { out[o * 2] = R.groupbook; out[o * 2 + 1] = val; } o++; }
+      }
+    }
+    const int cls = pw[row * partvals + p];
+    if (!(R.secondstages[cls] & (1 << s))) continue;
+    const int bk = R.partbooks[cls * 8 + s];
+    if (bk < 0) continue;
+    const int nvec = G / books[bk].dim;
+    const short *e_in = ent + (((size_t)s * partvals + p) * rows + row) * maxvec;
+    for (int t = lane; t < nvec; t += 32) if (o + t < max_syms) { out[(o + t) * 2] = bk; out[(o + t) * 2 + 1] = e_in[t]; }
+  }
+}
+
+}  // namespace
+
+int vb200_launch_residue_class(const vb200_setup *s, cudaStream_t st, int W, int blocks, int resnum, int ch, const int *chlist,
+                               int tot_ch, const int *in, const int *nonzero, int *partword, int *classified) {
+  if (blocks <= 0) return VB200_OK;
+  const int n = s->h.bs[W] / 2;
+  k_residue_class<<<blocks, 64, 0, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, classified);
+  LAUNCH_CHECK();
+  return VB200_OK;
+}
+
+int vb200_residue_maxvec(const vb200_setup *s, int resnum) {
+  const DevResidue &R = s->h.res[resnum];
+  int mindim = 1 << 30;
+  for (int c = 0; c < R.partitions; c++)
+    for (int k = 0; k < 8; k++) { const int b = R.partbooks[c * 8 + k]; if (b >= 0 && s->book[b].dim < mindim) mindim = s->book[b].dim; }
+  if (mindim == (1 << 30)) return 1;
+  return R.grouping / mindim;
+}
+
+int vb200_launch_residue_forward(const vb200_setup *s, cudaStream_t st, int W, int blocks, int resnum, int ch, const int *chlist,
+                                 int tot_ch, int *in, const int *nonzero, const int *partword, int *syms, int max_syms, int *nsyms) {
+  if (blocks <= 0) return VB200_OK;
+  const int n = s->h.bs[W] / 2;
+  const DevResidue &R = s->h.res[resnum];
+  if (R.grouping > RF_MAXG) { vb200_set_error("residue %d: partition size %d not built", resnum, R.grouping); return VB200_EIMPL; }
+  const int partvals = (R.end - R.begin) / R.grouping;
+  const int rows = R.type == 2 ? 1 : ch;
+  const int maxvec = vb200_residue_maxvec(s, resnum);
+  const size_t ent_bytes = ((size_t)R.stages * partvals * rows * maxvec * 2 + 15) & ~(size_t)15;
+  const size_t dyn = ent_bytes + sizeof(int) * ((size_t)R.stages * partvals * rows + 1);
+  if (dyn > 200 * 1024) { vb200_set_error("residue %d: symbol table does not fit shared memory", resnum); return VB200_EIMPL; }
+  CUDA_TRY(cudaFuncSetAttribute(k_residue_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  k_residue_forward<<<blocks, RF_WARPS * 32, dyn, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, maxvec, syms, max_syms, nsyms);
+  LAUNCH_CHECK();
+  return VB200_OK;
+}

@@ -184,6 +184,58 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
     const void *c1 = L.getk("psy%d.compand_hi", k, VB200_F32, VB200_COMPAND_LEVELS);
     if (c0) memcpy(p.compand, c0, sizeof(p.compand));
     if (c1) memcpy(p.compand_hi, c1, sizeof(p.compand_hi));
+    if (!L.ok) break;
+    /* static structure of the noise regression windows (bark_noise_hybridmp, psy.c:3540-3637): the
+       first bin whose window no longer mirrors below 0 (b1) and the first bin that has no full
+       window and re-uses the previous fit (b2), for the bark pass and the fixed-width pass */
+    {
+      const int *bark = (const int *)L.getk("psy%d.bark", k, VB200_I32, p.n);
+      const int n = p.n, fixed = p.noisewindowfixed;
+      for (int pass = 0; pass < 2; pass++) {
+        int i = 0;
+        for (; i < n; i++) {
+          int lo, hi;
+          if (pass == 0) { lo = bark[i] >> 16; hi = bark[i] & 0xffff; } else { hi = i + fixed / 2; lo = hi - fixed; }
+          if (!(hi < n && lo < 0 && (pass == 1 || -lo < n))) break;
+        }
+        p.nf_b1[pass] = i;
+        for (; i < n; i++) {
+          int lo, hi;
+          if (pass == 0) { lo = bark[i] >> 16; hi = bark[i] & 0xffff; } else { hi = i + fixed / 2; lo = hi - fixed; }
+          if (!(hi < n && lo >= 0 && (pass == 1 || lo < n))) break;
+        }
+        p.nf_b2[pass] = i;
+      }
+    }
+    /* static structure of max_seeds (psy.c:936-1070): which seed span feeds which run of bins */
+    {
+      const int *oct = (const int *)L.getk("psy%d.octave", k, VB200_I32, p.n);
+      const int n = p.n;
+      int4 *g = (int4 *)malloc(sizeof(int4) * (n + 1));
+      int ng = 0, lin = 0, pos = oct[0] - p.firstoc - (p.eighth >> 1);
+      bool bad = pos < 0;
+      while (!bad && lin + 1 < n) {
+        int p0 = pos, end = ((oct[lin] + oct[lin + 1]) >> 1) - p.firstoc, l0 = lin;
+        while (pos + 1 <= end) pos++;
+        end = pos + p.firstoc;
+        for (; lin < n && oct[lin] <= end; lin++) {}
+        if (lin == l0 || pos >= p.total_octave_lines) { bad = true; break; }
+        g[ng++] = make_int4(p0, pos, l0, lin);
+      }
+      if (bad) { vb200_set_error("psy %d: octave table outside the built path", k); L.ok = false; free(g); break; }
+      p.n_tone_groups = ng; p.tone_tail = lin;
+      p.tone_groups = (const int4 *)L.up(g, sizeof(int4) * (ng ? ng : 1));
+      free(g);
+    }
+  }
+  {
+    const void *t;
+    if ((t = L.get("aotuv.stn_compand", VB200_I32, VB200_COMPAND_LEVELS))) memcpy(h.stn_compand, t, sizeof(h.stn_compand));
+    if ((t = L.get("aotuv.freq_bfn128", VB200_I32, 128))) memcpy(h.freq_bfn128, t, sizeof(h.freq_bfn128));
+    if ((t = L.get("aotuv.freq_bfn256", VB200_I32, 256))) memcpy(h.freq_bfn256, t, sizeof(h.freq_bfn256));
+    if ((t = L.get("aotuv.stereo_th", VB200_F64, 9))) memcpy(h.stereo_th, t, sizeof(h.stereo_th));
+    if ((t = L.get("aotuv.stereo_thx", VB200_F64, 9))) memcpy(h.stereo_thx, t, sizeof(h.stereo_thx));
+    if ((t = L.get("fromdB", VB200_F32, 256))) memcpy(h.fromdB, t, sizeof(h.fromdB));
   }
 
   for (int k = 0; k < h.floors && L.ok; k++) {

@@ -34,6 +34,10 @@ struct DevPsy {
   const float *noiseoffset;  /* [3][n] */
   const float *ntfix;        /* [n] */
   float compand[VB200_COMPAND_LEVELS], compand_hi[VB200_COMPAND_LEVELS];
+  /* derived at setup time (static properties of the tables) */
+  int nf_b1[2], nf_b2[2];    /* noise regression: first bin of the interior / held window class, per pass */
+  const int4 *tone_groups;   /* max_seeds: (seed pos0, pos1, bin0, bin1) per group */
+  int n_tone_groups, tone_tail;
 };
 
 struct DevFloor {
@@ -72,6 +76,10 @@ struct DevSetup {
   float ampmax_att_per_sec;
   int pointlimit[2][VB200_PACKETBLOBS], prepointamp[VB200_PACKETBLOBS], postpointamp[VB200_PACKETBLOBS];
   int sliding_lowpass[2][VB200_PACKETBLOBS];
+  int stn_compand[VB200_COMPAND_LEVELS];
+  int freq_bfn128[128], freq_bfn256[256];
+  double stereo_th[9], stereo_thx[9];
+  float fromdB[256];
   DevPsy psy[VB200_MAX_PSY];
   DevFloor flr[VB200_MAX_FLOORS];
   DevResidue res[VB200_MAX_RESIDUES];
@@ -119,6 +127,7 @@ const void *vb200_blob_find(const unsigned char *blob, size_t bytes, const char 
 
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
+#include "k_common.cuh"
 #define CUDA_TRY(expr) do{ cudaError_t e_=(expr); if(e_!=cudaSuccess){ \
   vb200_set_error("%s:%d %s: %s",__FILE__,__LINE__,#expr,cudaGetErrorString(e_)); return VB200_EFAULT; } }while(0)
 #define LAUNCH_CHECK() do{ vb200_count_launch(1); CUDA_TRY(cudaGetLastError()); }while(0)
@@ -128,5 +137,29 @@ int vb200_launch_transform(const vb200_setup *s, cudaStream_t st, int W, int ite
                            const float *pcm, const long long *pcm_off, const int *lW, const int *nW,
                            const int *block_mode, const int *lW_block_mode,
                            float *gmdct, float *logfft, float *logmdct, float *local_ampmax, float *poste);
+int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
+                           const int *block_mode, const float *lowcomp, const float *poste,
+                           const float *logmdct, LastRef last, float *noise, float *epeak, float *npeak, int npeak_stride);
+int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
+                          const float *logfft, const float *global_ampmax, const float *local_ampmax, float *tone);
+int vb200_launch_mix(const vb200_setup *s, cudaStream_t st, int W, int nchains, const int *chain_start, const int *chain_len,
+                     const int *psy, const int *params, const float *low_compand,
+                     const float *noise, const float *tone, const float *logmdct, float *mdct, LastRef last,
+                     float *temp_state, const long long *temp_off, float *npeak, int npeak_stride,
+                     float *logmask, int nsel, int mask_stride, float *last_out, int *fit_gate, int floor_index);
+int vb200_launch_floor_fit(const vb200_setup *s, cudaStream_t st, int W, int items, int floor_index,
+                           const float *logmdct, const float *logmask, int mdct_stride, int mask_stride,
+                           const int *gate, int *posts, int *fitted);
+int vb200_launch_floor_interp(const vb200_setup *s, cudaStream_t st, int items, int floor_index, const int *A, const int *B,
+                              const int *fa, const int *fb, int del, int *out, int *fo);
+int vb200_launch_floor_encode(const vb200_setup *s, cudaStream_t st, int W, int items, int floor_index,
+                              int *posts, const int *fitted, int *vals, int *ilogmask, int *nonzero);
+int vb200_launch_couple(const vb200_setup *s, cudaStream_t st, int W, int blocks, const int *psy, int blobno,
+                        const float *mdct, const float *epeak, float *npeak, int npeak_stride, int *iwork, int *nonzero);
+int vb200_launch_residue_class(const vb200_setup *s, cudaStream_t st, int W, int blocks, int resnum, int ch, const int *chlist,
+                               int tot_ch, const int *in, const int *nonzero, int *partword, int *classified);
+int vb200_residue_maxvec(const vb200_setup *s, int resnum);
+int vb200_launch_residue_forward(const vb200_setup *s, cudaStream_t st, int W, int blocks, int resnum, int ch, const int *chlist,
+                                 int tot_ch, int *in, const int *nonzero, const int *partword, int *syms, int max_syms, int *nsyms);
 #endif
 #endif

@@ -56,9 +56,17 @@ class Setup:
     def n2(self, W):
         return self.blocksizes[W] // 2
 
-    def partition(self, psy):
-        t = self.tables["psy%d.i32" % psy]
-        return int(t[19]) if t[17] else 16
+    def partition(self, W):
+        for k in range(int(self.tables["cfg.i32"][8])):
+            t = self.tables["psy%d.i32" % k]
+            if t[1] == W:
+                return int(t[19]) if t[17] else 16
+        return 16
+
+    def residue(self, resnum):
+        t = self.tables["res%d.i32" % resnum]
+        return dict(type=int(t[0]), begin=int(t[1]), end=int(t[2]), grouping=int(t[3]),
+                    partvals=(int(t[2]) - int(t[1])) // int(t[3]))
 
     def header(self, i):
         d, n = C.POINTER(C.c_ubyte)(), C.c_long()
@@ -82,3 +90,100 @@ def forward_transform(s, W, pcm, lW, nW, block_mode, lW_block_mode):
                                   _p(out["gmdct"]), _p(out["logfft"]), _p(out["logmdct"]),
                                   _p(out["local_ampmax"]), _p(out["poste"])), "vb200_stage_transform")
     return out
+
+
+# ------------------------------------------------------------------ K2
+def _vp_noisemask(s, W, psy, noise_compand_level, logmdct, lastmdct, poste, block_mode):
+    """psy.c:3770-4074, batched: -> (noise, epeak, npeak)."""
+    logmdct, lastmdct = _f(logmdct), _f(lastmdct)
+    items, N2 = logmdct.shape
+    nps = N2 // s.partition(W)
+    noise, epeak, npeak = np.empty((items, N2), np.float32), np.empty((items, N2), np.float32), np.empty((items, nps), np.float32)
+    psy, bm, lc, po = _i(psy), _i(block_mode), _f(noise_compand_level), _f(poste)
+    check(L.vb200_stage_noisemask(s.h, W, items, _p(psy), _p(bm), _p(lc), _p(po), _p(logmdct), _p(lastmdct),
+                                  _p(noise), _p(epeak), _p(npeak)), "vb200_stage_noisemask")
+    return noise, epeak, npeak
+
+
+# ------------------------------------------------------------------ K3
+def _vp_tonemask(s, W, psy, logfft, global_specmax, local_specmax):
+    """psy.c:4076-4142, batched: -> tone."""
+    logfft = _f(logfft)
+    items, N2 = logfft.shape
+    tone = np.empty((items, N2), np.float32)
+    psy, g, l = _i(psy), _f(global_specmax), _f(local_specmax)
+    check(L.vb200_stage_tonemask(s.h, W, items, _p(psy), _p(logfft), _p(g), _p(l), _p(tone)), "vb200_stage_tonemask")
+    return tone
+
+
+# ------------------------------------------------------------------ K4
+def _vp_offset_and_mix(s, W, psy, noise, tone, params, low_compand, mdct, logmdct, lastmdct, tempmdct, npeak):
+    """psy.c:4274-4502, batched.  params [items,8] = offset_select, bit_managed, end_block, block_mode,
+    nW_modenumber, lW_block_mode, lW_no, impadnum.  -> (logmask, mdct, lastmdct, tempmdct, npeak)."""
+    noise, tone, logmdct = _f(noise), _f(tone), _f(logmdct)
+    mdct, last, temp, npk = np.array(mdct, np.float32), np.array(lastmdct, np.float32), np.array(tempmdct, np.float32), np.array(npeak, np.float32)
+    items, N2 = noise.shape
+    assert last.shape == (items, 2048) and temp.shape == (items, 256)
+    mask = np.empty((items, N2), np.float32)
+    psy, par, lc = _i(psy), _i(params), _f(low_compand)
+    check(L.vb200_stage_offset_and_mix(s.h, W, items, _p(psy), _p(par), _p(lc), _p(noise), _p(tone), _p(logmdct),
+                                       _p(mdct), _p(last), _p(temp), _p(npk), _p(mask)), "vb200_stage_offset_and_mix")
+    return mask, mdct, last, temp, npk
+
+
+# ------------------------------------------------------------------ K5
+def floor1_fit(s, W, floor_index, logmdct, logmask):
+    """floor1.c:597-750, batched: -> (posts [items,65], fitted [items]); fitted==0 is the reference's NULL."""
+    logmdct, logmask = _f(logmdct), _f(logmask)
+    items = logmdct.shape[0]
+    posts, fitted = np.zeros((items, MAX_POSTS), np.int32), np.zeros(items, np.int32)
+    check(L.vb200_stage_floor1_fit(s.h, W, items, floor_index, _p(logmdct), _p(logmask), _p(posts), _p(fitted)),
+          "vb200_stage_floor1_fit")
+    return posts, fitted
+
+
+def floor1_encode(s, W, floor_index, posts, fitted):
+    """floor1.c:774-974 minus bit emission, batched: -> (posts mutated, vals, ilogmask, nonzero)."""
+    posts, fitted = np.array(posts, np.int32), _i(fitted)
+    items = posts.shape[0]
+    N2 = s.n2(W)
+    vals, ilog, nz = np.zeros((items, MAX_POSTS), np.int32), np.zeros((items, N2), np.int32), np.zeros(items, np.int32)
+    check(L.vb200_stage_floor1_encode(s.h, W, items, floor_index, _p(posts), _p(fitted), _p(vals), _p(ilog), _p(nz)),
+          "vb200_stage_floor1_encode")
+    return posts, vals, ilog, nz
+
+
+# ------------------------------------------------------------------ K6
+def _vp_couple_quantize_normalize(s, W, psy, blobno, mdct, enpeak, nepeak, iwork, nonzero):
+    """psy.c:4858-5142, batched over blocks: mdct/enpeak [blocks,ch,N2], nepeak [blocks,ch,N2/partition],
+    iwork [blocks,ch,N2] (ilogmask in), nonzero [blocks,ch] -> (iwork, nonzero, nepeak)."""
+    mdct, enpeak = _f(mdct), _f(enpeak)
+    npk, iw, nz = np.array(nepeak, np.float32), np.array(iwork, np.int32), np.array(nonzero, np.int32)
+    blocks = mdct.shape[0]
+    psy = _i(psy)
+    check(L.vb200_stage_couple(s.h, W, blocks, _p(psy), int(blobno), _p(mdct), _p(enpeak), _p(npk), _p(iw), _p(nz)),
+          "vb200_stage_couple")
+    return iw, nz, npk
+
+
+# ------------------------------------------------------------------ K7
+def residue_class(s, W, resnum, rows, nonzero):
+    """->class of the residue backend (res0.c:735-768), batched: rows [blocks,ch,N2], nonzero [blocks,ch]
+    -> (partword [blocks,ch,partvals], classified [blocks] = number of valid partword rows, 0 == NULL)."""
+    rows, nz = _i(rows), _i(nonzero)
+    blocks, ch, _ = rows.shape
+    pv = s.residue(resnum)["partvals"]
+    pw, cl = np.zeros((blocks, ch, pv), np.int32), np.zeros(blocks, np.int32)
+    check(L.vb200_stage_residue_class(s.h, W, blocks, resnum, ch, _p(rows), _p(nz), _p(pw), _p(cl)), "vb200_stage_residue_class")
+    return pw, cl
+
+
+def residue_forward(s, W, resnum, rows, nonzero, partword, max_syms=16384):
+    """->forward of the residue backend (res0.c:715-799): VQ search, batched.
+    -> (syms [blocks] list of [n,2] (book,entry) in emission order, rows after the cascade)."""
+    rows, nz, pw = np.array(rows, np.int32), _i(nonzero), _i(partword)
+    blocks, ch, _ = rows.shape
+    syms, ns = np.zeros((blocks, max_syms, 2), np.int32), np.zeros(blocks, np.int32)
+    check(L.vb200_stage_residue_forward(s.h, W, blocks, resnum, ch, _p(rows), _p(nz), _p(pw), _p(syms), max_syms, _p(ns)),
+          "vb200_stage_residue_forward")
+    return [syms[b, :ns[b]].copy() for b in range(blocks)], rows
