@@ -14,7 +14,10 @@ struct LastRef {
   const int *rule;          /* [items] LAST_*, or NULL: LAST_COPY */
   long long stride;
   __device__ __forceinline__ float at(int item, int i) const {
-    const float *p = base + (off ? off[item] : (long long)item * stride);
+    /* base==NULL: off[] holds absolute device addresses (previous block / stream state live in
+       different allocations) */
+    const float *p = base ? base + (off ? off[item] : (long long)item * stride)
+                          : reinterpret_cast<const float *>(static_cast<uintptr_t>(off[item]));
     const int r = rule ? rule[item] : LAST_COPY;
     if (r == LAST_COPY) return __ldg(p + i);
     if (r == LAST_EXPAND8) return __ldg(p + (i >> 3));

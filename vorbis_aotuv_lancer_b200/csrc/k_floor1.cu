@@ -88,11 +88,11 @@ __device__ __forceinline__ int pick(const int *A, const int *B, int i) {
 
 template <int N>
 __global__ void __launch_bounds__(32)
-k_floor_fit(const DevSetup *__restrict__ S, int floor_index, const float *__restrict__ logmdct, const float *__restrict__ logmask,
+k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, const float *__restrict__ logmdct, const float *__restrict__ logmask,
             int mdct_stride, int mask_stride, const int *__restrict__ gate, int *__restrict__ posts_out, int *__restrict__ fitted) {
   __shared__ FitSmem<N> sm;
   const int item = blockIdx.x, lane = threadIdx.x;
-  const DevFloor &F = S->flr[floor_index];
+  const DevFloor &F = S->flr[floor_index >= 0 ? floor_index : S->floor_of_ch[W][item % ch]];
   const int n = F.n, posts = F.posts;
   int *out = posts_out + (size_t)item * VB200_MAX_POSTS;
   if (gate && !gate[item]) { if (lane == 0) fitted[item] = 0; return; }
@@ -200,11 +200,11 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, const float *__rest
 }
 
 /* floor1_interpolate_fit (floor1.c:752-771) for the managed-mode blob ladder: out = blend(A,B,del) */
-__global__ void k_floor_interp(const DevSetup *__restrict__ S, int floor_index, const int *__restrict__ A, const int *__restrict__ B,
+__global__ void k_floor_interp(const DevSetup *__restrict__ S, int floor_index, int W, int ch, const int *__restrict__ A, const int *__restrict__ B,
                                const int *__restrict__ fa, const int *__restrict__ fb, int del, int *__restrict__ out, int *__restrict__ fo, int items) {
   const int item = blockIdx.x * blockDim.y + threadIdx.y, i = threadIdx.x;
   if (item >= items) return;
-  const int posts = S->flr[floor_index].posts;
+  const int posts = S->flr[floor_index >= 0 ? floor_index : S->floor_of_ch[W][item % ch]].posts;
   const int ok = fa[item] && fb[item];
   if (i == 0) fo[item] = ok;
   if (!ok) return;
@@ -218,13 +218,13 @@ __global__ void k_floor_interp(const DevSetup *__restrict__ S, int floor_index, 
 
 template <int N>
 __global__ void __launch_bounds__(32)
-k_floor_encode(const DevSetup *__restrict__ S, int floor_index, int *__restrict__ posts_io, const int *__restrict__ fitted,
+k_floor_encode(const DevSetup *__restrict__ S, int floor_index, int W, int ch, int *__restrict__ posts_io, const int *__restrict__ fitted,
                int *__restrict__ vals_out, int *__restrict__ ilogmask, int *__restrict__ nonzero) {
   __shared__ int post[VB200_MAX_POSTS];
   __shared__ int segx[VB200_MAX_POSTS], segy[VB200_MAX_POSTS];
   __shared__ int nseg;
   const int item = blockIdx.x, lane = threadIdx.x;
-  const DevFloor &F = S->flr[floor_index];
+  const DevFloor &F = S->flr[floor_index >= 0 ? floor_index : S->floor_of_ch[W][item % ch]];
   const int posts = F.posts;
   int *ilog = ilogmask + (size_t)item * N;
   if (!fitted[item]) {
@@ -282,18 +282,19 @@ int vb200_launch_floor_fit(const vb200_setup *s, cudaStream_t st, int W, int ite
                            const float *logmdct, const float *logmask, int mdct_stride, int mask_stride,
                            const int *gate, int *posts, int *fitted) {
   if (items <= 0) return VB200_OK;
-  if (s->h.flr[floor_index].type != 1 || s->h.flr[floor_index].n != s->h.bs[W] / 2) { vb200_set_error("floor %d is not a floor-1 of this block size", floor_index); return VB200_EINVAL; }
-  if (W) k_floor_fit<1024><<<items, 32, 0, st>>>(s->d, floor_index, logmdct, logmask, mdct_stride, mask_stride, gate, posts, fitted);
-  else   k_floor_fit<128><<<items, 32, 0, st>>>(s->d, floor_index, logmdct, logmask, mdct_stride, mask_stride, gate, posts, fitted);
+  /* look->n = postlist[1] may be smaller than N2 (the 5.1 LFE floor covers 10 bins) */
+  if (floor_index >= 0 && (s->h.flr[floor_index].type != 1 || s->h.flr[floor_index].n > s->h.bs[W] / 2 || s->h.flr[floor_index].posts < 2)) { vb200_set_error("floor %d is not a floor-1 of this block size", floor_index); return VB200_EINVAL; }
+  if (W) k_floor_fit<1024><<<items, 32, 0, st>>>(s->d, floor_index, W, s->h.channels, logmdct, logmask, mdct_stride, mask_stride, gate, posts, fitted);
+  else   k_floor_fit<128><<<items, 32, 0, st>>>(s->d, floor_index, W, s->h.channels, logmdct, logmask, mdct_stride, mask_stride, gate, posts, fitted);
   LAUNCH_CHECK();
   return VB200_OK;
 }
 
-int vb200_launch_floor_interp(const vb200_setup *s, cudaStream_t st, int items, int floor_index, const int *A, const int *B,
+int vb200_launch_floor_interp(const vb200_setup *s, cudaStream_t st, int W, int items, int floor_index, const int *A, const int *B,
                               const int *fa, const int *fb, int del, int *out, int *fo) {
   if (items <= 0) return VB200_OK;
   dim3 blk(32, 4);
-  k_floor_interp<<<(items + 3) / 4, blk, 0, st>>>(s->d, floor_index, A, B, fa, fb, del, out, fo, items);
+  k_floor_interp<<<(items + 3) / 4, blk, 0, st>>>(s->d, floor_index, W, s->h.channels, A, B, fa, fb, del, out, fo, items);
   LAUNCH_CHECK();
   return VB200_OK;
 }
@@ -301,8 +302,8 @@ int vb200_launch_floor_interp(const vb200_setup *s, cudaStream_t st, int items, 
 int vb200_launch_floor_encode(const vb200_setup *s, cudaStream_t st, int W, int items, int floor_index,
                               int *posts, const int *fitted, int *vals, int *ilogmask, int *nonzero) {
   if (items <= 0) return VB200_OK;
-  if (W) k_floor_encode<1024><<<items, 32, 0, st>>>(s->d, floor_index, posts, fitted, vals, ilogmask, nonzero);
-  else   k_floor_encode<128><<<items, 32, 0, st>>>(s->d, floor_index, posts, fitted, vals, ilogmask, nonzero);
+  if (W) k_floor_encode<1024><<<items, 32, 0, st>>>(s->d, floor_index, W, s->h.channels, posts, fitted, vals, ilogmask, nonzero);
+  else   k_floor_encode<128><<<items, 32, 0, st>>>(s->d, floor_index, W, s->h.channels, posts, fitted, vals, ilogmask, nonzero);
   LAUNCH_CHECK();
   return VB200_OK;
 }

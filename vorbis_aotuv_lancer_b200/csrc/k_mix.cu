@@ -25,12 +25,12 @@ __device__ __forceinline__ int dbq(float x) {      /* vorbis_dBquant, floor1.c:2
 
 template <int N, int T>
 __global__ void __launch_bounds__(T)
-k_mix(const DevSetup *__restrict__ S, const int *__restrict__ chain_start, const int *__restrict__ chain_len,
+k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start, const int *__restrict__ chain_len, const int *__restrict__ chain_items,
       const int *__restrict__ psyv, const int *__restrict__ params, const float *__restrict__ low_compandv,
       const float *__restrict__ noise, const float *__restrict__ tone, const float *__restrict__ logmdct,
       float *__restrict__ mdct, LastRef last, float *__restrict__ temp_state, const long long *__restrict__ temp_off,
       float *__restrict__ npeak, int npeak_stride, float *__restrict__ logmask, int nsel, int mask_stride,
-      float *__restrict__ last_out, int *__restrict__ fit_gate, float twofitatten) {
+      float *__restrict__ last_out, int *__restrict__ fit_gate, int floor_index, int ch) {
   __shared__ float temp[N > 256 ? 1 : 256];
   __shared__ int pflag[64];
   __shared__ int gate;
@@ -40,7 +40,7 @@ k_mix(const DevSetup *__restrict__ S, const int *__restrict__ chain_start, const
   constexpr bool SHORT = (N <= 256);
 
   for (int ci = 0; ci < clen; ci++) {
-    const int item = c0 + ci;
+    const int item = chain_items ? chain_items[c0 + ci] : c0 + ci;
     const DevPsy &P = S->psy[psyv[item]];
     const int *pr = params + item * 8;
     const int managed = pr[1], end_block = pr[2], block_mode = pr[3], nW = pr[4], lW_block_mode = pr[5], lW_no = pr[6], impadnum = pr[7];
@@ -176,7 +176,7 @@ k_mix(const DevSetup *__restrict__ S, const int *__restrict__ chain_start, const
           if (v > coeffi) { de = (float)(1.0 - ((double)__fsub_rn(v, coeffi) * 0.005 * (double)P.m_val)); if (de < 0.f) de = (float)0.0001; }
           else de = (float)(1.0 - ((double)__fsub_rn(v, coeffi) * 0.0003 * (double)P.m_val));
           md[i] = __fmul_rn(md[i], de);
-          if (nsel > 1 && dbq(out) && __fadd_rn(l, twofitatten) >= out) local_gate = 1;
+          if (nsel > 1 && dbq(out) && __fadd_rn(l, S->flr[floor_index >= 0 ? floor_index : S->floor_of_ch[W][item % ch]].twofitatten) >= out) local_gate = 1;
         }
       }
       if (nsel > 1 && si == 0) {
@@ -221,17 +221,16 @@ k_mix(const DevSetup *__restrict__ S, const int *__restrict__ chain_start, const
 
 }  // namespace
 
-int vb200_launch_mix(const vb200_setup *s, cudaStream_t st, int W, int nchains, const int *chain_start, const int *chain_len,
+int vb200_launch_mix(const vb200_setup *s, cudaStream_t st, int W, int nchains, const int *chain_start, const int *chain_len, const int *chain_items,
                      const int *psy, const int *params, const float *low_compand,
                      const float *noise, const float *tone, const float *logmdct, float *mdct, LastRef last,
                      float *temp_state, const long long *temp_off, float *npeak, int npeak_stride,
                      float *logmask, int nsel, int mask_stride, float *last_out, int *fit_gate, int floor_index) {
   if (nchains <= 0) return VB200_OK;
-  const float atten = s->h.flr[floor_index].twofitatten;
-  if (W) k_mix<1024, 256><<<nchains, 256, 0, st>>>(s->d, chain_start, chain_len, psy, params, low_compand, noise, tone, logmdct, mdct, last,
-                                                   temp_state, temp_off, npeak, npeak_stride, logmask, nsel, mask_stride, last_out, fit_gate, atten);
-  else   k_mix<128, 64><<<nchains, 64, 0, st>>>(s->d, chain_start, chain_len, psy, params, low_compand, noise, tone, logmdct, mdct, last,
-                                                temp_state, temp_off, npeak, npeak_stride, logmask, nsel, mask_stride, last_out, fit_gate, atten);
+  if (W) k_mix<1024, 256><<<nchains, 256, 0, st>>>(s->d, W, chain_start, chain_len, chain_items, psy, params, low_compand, noise, tone, logmdct, mdct, last,
+                                                   temp_state, temp_off, npeak, npeak_stride, logmask, nsel, mask_stride, last_out, fit_gate, floor_index, s->h.channels);
+  else   k_mix<128, 64><<<nchains, 64, 0, st>>>(s->d, W, chain_start, chain_len, chain_items, psy, params, low_compand, noise, tone, logmdct, mdct, last,
+                                                temp_state, temp_off, npeak, npeak_stride, logmask, nsel, mask_stride, last_out, fit_gate, floor_index, s->h.channels);
   LAUNCH_CHECK();
   return VB200_OK;
 }

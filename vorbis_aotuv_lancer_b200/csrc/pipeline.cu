@@ -1,0 +1,768 @@
+/* The batched whole path: vb200_stream / vb200_batch.
+ *
+ * Replaces `vorbis_analysis` -> `_mapping_P[0]->forward` (analysis.c:29-63,
+ * mapping0.c:738-1322), `vorbis_bitrate_addblock` (bitrate.c:73-227) and
+ * `vorbis_bitrate_flushpacket` (bitrate.c:229-252) for many blocks of many independent
+ * streams per call.
+ *
+ * Data layout in HBM.  Blocks are split by size class (W); inside a class every per-bin
+ * vector is a dense [block][channel][N2] array (one cudaMalloc'd arena per batch, carved once),
+ * so that every kernel reads and writes unit-stride rows.  Cross-block state:
+ *   lastmdct  -- never materialised: a consumer gets the address of the previous block's
+ *                logmdct row (or of the stream's saved state) plus a resampling rule;
+ *   tempmdct  -- lives in the per-stream state slot; runs of consecutive impulse blocks form
+ *                chains that one CTA walks in order;
+ *   ampmax / lowcomp -- a per-stream scan kernel between K1 and K2/K3;
+ *   lW_block_mode, lW_no, impadnum -- pure functions of the block-type sequence: host.
+ * The host then emits the codewords (emit.cu) and runs the bitrate manager.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include "vb200_internal.h"
+#include "dev_util.cuh"
+#include "emit.h"
+
+#define PIPE_MAX_STREAM_SLOTS 4096
+#define PIPE_SYMS_PER_ITEM_LONG 1536   /* worst case q10: 64 partitions x 16 vectors x 3 stages / 2 ch */
+#define PIPE_SYMS_PER_ITEM_SHORT 256
+
+/* ------------------------------------------------------------------ per-setup stream state pool */
+struct StatePool {
+  float *last;    /* [slots][ch][2048]  private_state.mblock  */
+  float *temp;    /* [slots][ch][256]   private_state.tblock  */
+  float *scal;    /* [slots][2+ch]      g->ampmax, vbi->ampmax, lownoise_compand_level[ch] */
+  unsigned char used[PIPE_MAX_STREAM_SLOTS];
+};
+
+struct vb200_stream {
+  vb200_setup *s;
+  int slot;
+  int lW_block_mode, lW_no, impadnum;      /* codec_internal.h:89-91 */
+  bool started;
+  /* lastmdct source for the next block: in the state slot until a batch leaves a newer one there */
+  /* bitrate manager (bitrate.h:26-38) */
+  int managed;
+  long avg_reservoir, minmax_reservoir, avg_bitsper, min_bitsper, max_bitsper, short_per_long;
+  double avgfloat;
+  int64_t sequence;
+};
+
+static StatePool *pool_of(vb200_setup *s);
+
+/* ------------------------------------------------------------------ small kernels */
+namespace {
+
+struct ScanBlock { int W, first_item, block_mode, lW_block_mode, psy; };
+
+/* per-stream sequential pass between K1 and K2/K3: the ampmax max-plus recurrence
+   (block.c:649-651, psy.c:4504-4515, mapping0.c:887-888,1184) and lb_loudnoise_fix (psy.c:5152-5180) */
+__global__ void k_stream_scan(const DevSetup *__restrict__ S, int nstreams, const int *__restrict__ slot,
+                              const int *__restrict__ blk_start, const ScanBlock *__restrict__ blks,
+                              float *__restrict__ scal, const float *const *__restrict__ local_ampmax,
+                              float *const *__restrict__ global_ampmax, const float *const *__restrict__ logmdct,
+                              float *const *__restrict__ lowcomp) {
+  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= nstreams) return;
+  const int ch = S->channels;
+  float *st = scal + (size_t)slot[sidx] * (2 + VB200_MAX_CHANNELS);
+  float g = st[0], vbi = st[1];
+  for (int b = blk_start[sidx]; b < blk_start[sidx + 1]; b++) {
+    const ScanBlock B = blks[b];
+    const int N2 = S->bs[B.W] / 2;
+    if (vbi > g) g = vbi;
+    {
+      const float secs = __fdiv_rn((float)N2, (float)S->rate);
+      g = __fadd_rn(g, __fmul_rn(secs, S->ampmax_att_per_sec));
+      if (g < -9999.f) g = -9999.f;
+    }
+    float gl = g;
+    for (int c = 0; c < ch; c++) { const float la = local_ampmax[B.W][B.first_item + c]; if (la > gl) gl = la; }
+    for (int c = 0; c < ch; c++) global_ampmax[B.W][B.first_item + c] = gl;
+    vbi = gl;
+    const DevPsy &P = S->psy[B.psy];
+    for (int c = 0; c < ch; c++) {
+      float lv = st[2 + c];
+      if (P.m_val < 0.5f) lv = -1.f;
+      else if (P.normal_thresh > .45) lv = -1.f;
+      else if ((B.block_mode == 2 && B.lW_block_mode == 3) || (B.block_mode == 3 && B.lW_block_mode == 2)) {
+        const float *lm = logmdct[B.W] + (size_t)(B.first_item + c) * N2;
+        double acc = 0;
+        for (int i = P.n25p; i < P.n75p; i++) { const float v = lm[i]; acc += (v > -130.f) ? (double)v : -130.; }
+        acc /= P.n;
+        if (acc > -40.) lv = -1.f;
+        else if (acc < -50.) lv = 1.f;
+        else lv = (float)(1. - ((acc + 50) / 10));
+      }
+      st[2 + c] = lv;
+      lowcomp[B.W][B.first_item + c] = lv;
+    }
+  }
+  st[0] = g; st[1] = vbi;
+}
+
+/* end of batch: leave lastmdct in the stream's state slot exactly as the reference leaves
+   private_state.mblock (psy.c:4462-4501) */
+__global__ void k_save_last(int n, const float *const *__restrict__ src, const int *__restrict__ rule,
+                            const int *__restrict__ srcN, float *const *__restrict__ dst) {
+  const int j = blockIdx.x;
+  if (j >= n) return;
+  const float *s = src[j]; float *d = dst[j];
+  const int r = rule[j], N = srcN[j];
+  if (r == LAST_COPY) { for (int i = threadIdx.x; i < N; i += blockDim.x) d[i] = s[i]; }
+  else if (r == LAST_EXPAND8) { for (int i = threadIdx.x; i < N * 8; i += blockDim.x) d[i] = s[i >> 3]; }
+  else if (r == LAST_MINPOOL8) {
+    for (int i = threadIdx.x; i < (N >> 3); i += blockDim.x) {
+      float m = s[i * 8];
+      for (int k = 1; k < 8; k++) { const float v = s[i * 8 + k]; if (m > v) m = v; }
+      d[i] = m;
+    }
+  }
+}
+
+__global__ void k_copy_i32(const int *__restrict__ src, int *__restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void k_copy_f32(const float *__restrict__ src, float *__restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------------ arena */
+struct Arena {
+  unsigned char *base = nullptr; size_t cap = 0, top = 0;
+  template <typename T> T *take(size_t n) {
+    top = (top + 255) & ~(size_t)255;
+    T *p = reinterpret_cast<T *>(base + top);
+    top += n * sizeof(T);
+    return top <= cap ? p : nullptr;
+  }
+};
+
+struct ClassBufs {           /* one size class (W) */
+  int cap_items = 0, cap_blocks = 0, N2 = 0, nps = 0;
+  float *gmdct, *logfft, *logmdct, *noise, *tone, *epeak, *logmask, *npeak, *local_ampmax, *global_ampmax, *lowcomp, *poste;
+  float *npeak_work;
+  int *posts[3], *fitted[3], *posts_k, *fitted_k, *vals, *iwork, *nonzero, *fit_gate;
+  int *psy_item, *psy_blk, *block_mode, *lW_block_mode, *lW, *nW, *params;
+  long long *pcm_off, *last_addr; int *last_rule;
+  int *chain_start, *chain_len, *chain_items; long long *temp_off;
+  int *partword, *classified, *syms, *nsyms;
+  int max_syms;
+};
+
+struct HostBlock { int stream, W, lW, nW, blocktype, block_mode, psy, idx; int64_t granulepos; int eof; int hist[3]; };
+
+struct vb200_batch {
+  vb200_setup *s;
+  int max_blocks;
+  Arena dev, pin;
+  ClassBufs c[2];
+  float *d_pcm; size_t pcm_cap;
+  ScanBlock *d_scan; int *d_scan_start, *d_slot; float **d_ptrs;
+  const float **d_save_src; float **d_save_dst; int *d_save_rule, *d_save_N; int *d_chl;
+  /* host staging (pinned) mirrors of the descriptor arrays are carved from `pin` per run */
+  std::vector<HostBlock> hb;
+  /* results */
+  BitWriter bw;
+  std::vector<size_t> pk_off, pk_bytes; std::vector<int64_t> pk_gp; std::vector<int> pk_eos, pk_stream;
+  /* timing */
+  cudaEvent_t ev[16]; int nev; const char *evname[16]; float ev_ms[16]; float total_ms;
+  /* host copies for vb200_batch_get */
+  int n_items[2], n_blocks[2];
+};
+
+/* ------------------------------------------------------------------ streams */
+static StatePool *g_pools[64]; static vb200_setup *g_pool_owner[64]; static int g_npools = 0;
+
+static StatePool *pool_of(vb200_setup *s) {
+  for (int i = 0; i < g_npools; i++) if (g_pool_owner[i] == s) return g_pools[i];
+  if (g_npools >= 64) return nullptr;
+  StatePool *p = (StatePool *)calloc(1, sizeof(StatePool));
+  const size_t ch = s->h.channels;
+  if (cudaMalloc(&p->last, sizeof(float) * PIPE_MAX_STREAM_SLOTS * ch * 2048) != cudaSuccess ||
+      cudaMalloc(&p->temp, sizeof(float) * PIPE_MAX_STREAM_SLOTS * ch * 256) != cudaSuccess ||
+      cudaMalloc(&p->scal, sizeof(float) * PIPE_MAX_STREAM_SLOTS * (2 + VB200_MAX_CHANNELS)) != cudaSuccess) { free(p); return nullptr; }
+  g_pool_owner[g_npools] = s; g_pools[g_npools++] = p;
+  return p;
+}
+
+extern "C" int vb200_stream_create(vb200_setup *s, vb200_stream **out) {
+  if (!s || !out) { vb200_set_error("vb200_stream_create: bad arguments"); return VB200_EINVAL; }
+  if (s->device < 0 || !s->d) { vb200_set_error("vb200_stream_create: setup has no CUDA device (no CPU fallback)"); return VB200_EFAULT; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  StatePool *p = pool_of(s);
+  if (!p) { vb200_set_error("vb200_stream_create: state pool allocation failed"); return VB200_EFAULT; }
+  int slot = -1;
+  for (int i = 0; i < PIPE_MAX_STREAM_SLOTS; i++) if (!p->used[i]) { slot = i; break; }
+  if (slot < 0) { vb200_set_error("vb200_stream_create: more than %d live streams per setup", PIPE_MAX_STREAM_SLOTS); return VB200_EIMPL; }
+  p->used[slot] = 1;
+  const size_t ch = s->h.channels;
+  cudaStream_t st = (cudaStream_t)s->stream;
+  /* everything calloc-zero, ampmax -9999 (block.c:93,196,314-317; psy.c:128) */
+  CUDA_TRY(cudaMemsetAsync(p->last + (size_t)slot * ch * 2048, 0, sizeof(float) * ch * 2048, st));
+  CUDA_TRY(cudaMemsetAsync(p->temp + (size_t)slot * ch * 256, 0, sizeof(float) * ch * 256, st));
+  float init[2 + VB200_MAX_CHANNELS]; init[0] = -9999.f; init[1] = -9999.f;
+  for (int c = 0; c < VB200_MAX_CHANNELS; c++) init[2 + c] = 0.f;
+  CUDA_TRY(cudaMemcpyAsync(p->scal + (size_t)slot * (2 + VB200_MAX_CHANNELS), init, sizeof(init), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  vb200_stream *x = new vb200_stream();
+  memset(x, 0, sizeof(*x));
+  x->s = s; x->slot = slot;
+  /* vorbis_bitrate_init, bitrate.c:28-61 */
+  if (s->bi_i32[3] > 0) {
+    const long rate = s->h.rate; const int half = s->h.bs[0] >> 1;
+    x->short_per_long = s->h.bs[1] / s->h.bs[0];
+    x->managed = 1;
+    x->avg_bitsper = (long)rint(1. * s->bi_i32[0] * half / rate);
+    x->min_bitsper = (long)rint(1. * s->bi_i32[1] * half / rate);
+    x->max_bitsper = (long)rint(1. * s->bi_i32[2] * half / rate);
+    x->avgfloat = VB200_PACKETBLOBS / 2;
+    const long fill = (long)(s->bi_i32[3] * s->bi_f64[0]);
+    x->minmax_reservoir = fill; x->avg_reservoir = fill;
+  }
+  *out = x;
+  return VB200_OK;
+}
+
+extern "C" void vb200_stream_destroy(vb200_stream *x) {
+  if (!x) return;
+  StatePool *p = pool_of(x->s);
+  if (p) p->used[x->slot] = 0;
+  delete x;
+}
+
+/* ------------------------------------------------------------------ batch */
+static bool carve_class(vb200_batch *b, int W, int cap_blocks) {
+  const vb200_setup *s = b->s;
+  ClassBufs &c = b->c[W];
+  const int ch = s->h.channels, N2 = s->h.bs[W] / 2;
+  int part = 16;
+  for (int k = 0; k < s->h.psys; k++) if (s->h.psy[k].blockflag == W) part = s->h.psy[k].partition;
+  c.cap_blocks = cap_blocks; c.cap_items = cap_blocks * ch; c.N2 = N2; c.nps = N2 / part;
+  const size_t I = c.cap_items, V = I * N2;
+  const int nsel = s->h.managed ? 3 : 1;
+  Arena &a = b->dev;
+  c.gmdct = a.take<float>(V); c.logfft = a.take<float>(V); c.logmdct = a.take<float>(V); c.noise = a.take<float>(V);
+  c.tone = a.take<float>(V); c.epeak = a.take<float>(V); c.logmask = a.take<float>(V * nsel);
+  c.npeak = a.take<float>(I * c.nps); c.npeak_work = a.take<float>(I * c.nps);
+  c.local_ampmax = a.take<float>(I); c.global_ampmax = a.take<float>(I); c.lowcomp = a.take<float>(I); c.poste = a.take<float>(I);
+  for (int k = 0; k < 3; k++) { c.posts[k] = a.take<int>(I * VB200_MAX_POSTS); c.fitted[k] = a.take<int>(I); }
+  c.posts_k = a.take<int>(I * VB200_MAX_POSTS); c.fitted_k = a.take<int>(I);
+  c.vals = a.take<int>(I * VB200_MAX_POSTS); c.iwork = a.take<int>(V); c.nonzero = a.take<int>(I); c.fit_gate = a.take<int>(I);
+  c.psy_item = a.take<int>(I); c.psy_blk = a.take<int>(cap_blocks); c.block_mode = a.take<int>(I); c.lW_block_mode = a.take<int>(I);
+  c.lW = a.take<int>(I); c.nW = a.take<int>(I); c.params = a.take<int>(I * 8);
+  c.pcm_off = a.take<long long>(I); c.last_addr = a.take<long long>(I); c.last_rule = a.take<int>(I);
+  c.chain_start = a.take<int>(I); c.chain_len = a.take<int>(I); c.chain_items = a.take<int>(I); c.temp_off = a.take<long long>(I);
+  int maxpv = 1;
+  for (int r = 0; r < s->h.residues; r++) { const DevResidue &R = s->h.res[r]; const int pv = (R.end - R.begin) / R.grouping; if (pv > maxpv) maxpv = pv; }
+  c.partword = a.take<int>((size_t)cap_blocks * VB200_MAX_SUBMAPS * ch * maxpv);
+  c.classified = a.take<int>((size_t)cap_blocks * VB200_MAX_SUBMAPS);
+  c.max_syms = (W ? PIPE_SYMS_PER_ITEM_LONG : PIPE_SYMS_PER_ITEM_SHORT) * ch;
+  c.syms = a.take<int>((size_t)cap_blocks * VB200_MAX_SUBMAPS * c.max_syms * 2);
+  c.nsyms = a.take<int>((size_t)cap_blocks * VB200_MAX_SUBMAPS);
+  return c.nsyms != nullptr;
+}
+
+static size_t class_bytes(const vb200_setup *s, int W, int cap_blocks) {
+  const size_t ch = s->h.channels, N2 = s->h.bs[W] / 2, I = (size_t)cap_blocks * ch, V = I * N2;
+  const size_t nsel = s->h.managed ? 3 : 1;
+  size_t maxpv = 1;
+  for (int r = 0; r < s->h.residues; r++) { const DevResidue &R = s->h.res[r]; const size_t pv = (R.end - R.begin) / R.grouping; if (pv > maxpv) maxpv = pv; }
+  const size_t max_syms = (size_t)(W ? PIPE_SYMS_PER_ITEM_LONG : PIPE_SYMS_PER_ITEM_SHORT) * ch;
+  size_t b = 4 * (V * (7 + nsel) + I * (N2 / 8) * 2 + I * 8 + I * VB200_MAX_POSTS * 5 + I * 32 + cap_blocks * 8)
+           + 8 * I * 4 + 4 * ((size_t)cap_blocks * VB200_MAX_SUBMAPS * (ch * maxpv + 2 + max_syms * 2));
+  return b + 64 * 256;
+}
+
+extern "C" int vb200_batch_create(vb200_setup *s, int max_blocks, vb200_batch **out) {
+  if (!s || !out || max_blocks < 1) { vb200_set_error("vb200_batch_create: bad arguments"); return VB200_EINVAL; }
+  if (s->device < 0 || !s->d) { vb200_set_error("vb200_batch_create: setup has no CUDA device (no CPU fallback)"); return VB200_EFAULT; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  vb200_batch *b = new vb200_batch();
+  b->s = s; b->max_blocks = max_blocks; b->d_pcm = nullptr; b->pcm_cap = 0; b->nev = 0; b->total_ms = 0;
+  const size_t bytes = class_bytes(s, 0, max_blocks) + class_bytes(s, 1, max_blocks) + sizeof(ScanBlock) * (size_t)max_blocks
+                     + (size_t)PIPE_MAX_STREAM_SLOTS * (8 + VB200_MAX_CHANNELS * 24) + 65536;
+  if (cudaMalloc(&b->dev.base, bytes) != cudaSuccess) { cudaGetLastError(); vb200_set_error("vb200_batch_create: cannot allocate %zu bytes of HBM", bytes); delete b; return VB200_EFAULT; }
+  b->dev.cap = bytes;
+  b->d_scan = b->dev.take<ScanBlock>(max_blocks); b->d_scan_start = b->dev.take<int>(PIPE_MAX_STREAM_SLOTS + 1); b->d_slot = b->dev.take<int>(PIPE_MAX_STREAM_SLOTS);
+  b->d_ptrs = b->dev.take<float *>(8);
+  b->d_save_src = b->dev.take<const float *>((size_t)PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS); b->d_save_dst = b->dev.take<float *>((size_t)PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS);
+  b->d_save_rule = b->dev.take<int>((size_t)PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS); b->d_save_N = b->dev.take<int>((size_t)PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS);
+  b->d_chl = b->dev.take<int>(2 * VB200_MAX_SUBMAPS * VB200_MAX_CHANNELS);
+  if (!b->d_chl || !carve_class(b, 0, max_blocks) || !carve_class(b, 1, max_blocks)) { vb200_set_error("vb200_batch_create: arena sizing bug"); cudaFree(b->dev.base); delete b; return VB200_EFAULT; }
+  /* pinned staging for descriptors and results */
+  const size_t ch = s->h.channels;
+  const size_t pin_bytes = (size_t)max_blocks * ch * (64 * 4 + VB200_MAX_POSTS * 4 + 16) * 2 + (size_t)max_blocks * VB200_MAX_SUBMAPS * (b->c[1].max_syms * 8 + 16) * 2 + (1 << 20);
+  if (cudaMallocHost(&b->pin.base, pin_bytes) != cudaSuccess) { cudaGetLastError(); vb200_set_error("vb200_batch_create: cannot allocate pinned staging"); cudaFree(b->dev.base); delete b; return VB200_EFAULT; }
+  b->pin.cap = pin_bytes;
+  for (int i = 0; i < 16; i++) cudaEventCreate(&b->ev[i]);
+  *out = b;
+  return VB200_OK;
+}
+
+extern "C" void vb200_batch_destroy(vb200_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->s->device);
+  for (int i = 0; i < 16; i++) cudaEventDestroy(b->ev[i]);
+  if (b->d_pcm) cudaFree(b->d_pcm);
+  cudaFree(b->dev.base);
+  cudaFreeHost(b->pin.base);
+  delete b;
+}
+
+/* ------------------------------------------------------------------ bitrate manager (host) */
+/* vorbis_bitrate_addblock, bitrate.c:73-227, restated over the 15 blob sizes of one block.
+   Returns the chosen blob and the final byte size (after truncation / zero padding). */
+static int bitrate_choose(vb200_stream *x, const vb200_setup *s, int W, const long *blob_bytes, long *final_bytes) {
+  const long reservoir_bits = s->bi_i32[3]; const double bias = s->bi_f64[0], slew_damp = s->bi_f64[1];
+  int choice = (int)rint(x->avgfloat);
+  long this_bits = blob_bytes[choice] * 8;
+  const long min_target = W ? x->min_bitsper * x->short_per_long : x->min_bitsper;
+  const long max_target = W ? x->max_bitsper * x->short_per_long : x->max_bitsper;
+  const int samples = s->h.bs[W] >> 1;
+  const long desired_fill = (long)(reservoir_bits * bias);
+  const long rate = s->h.rate;
+  if (x->avg_bitsper > 0) {
+    double slew = 0.;
+    const long avg_target = W ? x->avg_bitsper * x->short_per_long : x->avg_bitsper;
+    const double slewlimit = 15. / slew_damp;
+    if (x->avg_reservoir + (this_bits - avg_target) > desired_fill) {
+      while (choice > 0 && this_bits > avg_target && x->avg_reservoir + (this_bits - avg_target) > desired_fill) { choice--; this_bits = blob_bytes[choice] * 8; }
+    } else if (x->avg_reservoir + (this_bits - avg_target) < desired_fill) {
+      while (choice + 1 < VB200_PACKETBLOBS && this_bits < avg_target && x->avg_reservoir + (this_bits - avg_target) < desired_fill) { choice++; this_bits = blob_bytes[choice] * 8; }
+    }
+    slew = rint(choice - x->avgfloat) / samples * rate;
+    if (slew < -slewlimit) slew = -slewlimit;
+    if (slew > slewlimit) slew = slewlimit;
+    choice = (int)rint(x->avgfloat += slew / rate * samples);
+    this_bits = blob_bytes[choice] * 8;
+  }
+  if (x->min_bitsper > 0 && this_bits < min_target) {
+    while (x->minmax_reservoir - (min_target - this_bits) < 0) { choice++; if (choice >= VB200_PACKETBLOBS) break; this_bits = blob_bytes[choice] * 8; }
+  }
+  if (x->max_bitsper > 0 && this_bits > max_target) {
+    while (x->minmax_reservoir + (this_bits - max_target) > reservoir_bits) { choice--; if (choice < 0) break; this_bits = blob_bytes[choice] * 8; }
+  }
+  long fb;
+  if (choice < 0) {
+    const long maxsize = (max_target + (reservoir_bits - x->minmax_reservoir)) / 8;
+    choice = 0;
+    fb = blob_bytes[0];
+    if (fb > maxsize) fb = maxsize;             /* oggpack_writetrunc */
+  } else {
+    long minsize = (min_target - x->minmax_reservoir + 7) / 8;
+    if (choice >= VB200_PACKETBLOBS) choice = VB200_PACKETBLOBS - 1;
+    fb = blob_bytes[choice];
+    if (minsize > fb) fb = minsize;             /* zero padding */
+  }
+  this_bits = fb * 8;
+  if (x->min_bitsper > 0 || x->max_bitsper > 0) {
+    if (max_target > 0 && this_bits > max_target) x->minmax_reservoir += (this_bits - max_target);
+    else if (min_target > 0 && this_bits < min_target) x->minmax_reservoir += (this_bits - min_target);
+    else if (x->minmax_reservoir > desired_fill) {
+      if (max_target > 0) { x->minmax_reservoir += (this_bits - max_target); if (x->minmax_reservoir < desired_fill) x->minmax_reservoir = desired_fill; }
+      else x->minmax_reservoir = desired_fill;
+    } else {
+      if (min_target > 0) { x->minmax_reservoir += (this_bits - min_target); if (x->minmax_reservoir > desired_fill) x->minmax_reservoir = desired_fill; }
+      else x->minmax_reservoir = desired_fill;
+    }
+  }
+  if (x->avg_bitsper > 0) {
+    const long avg_target = W ? x->avg_bitsper * x->short_per_long : x->avg_bitsper;
+    x->avg_reservoir += this_bits - avg_target;
+  }
+  *final_bytes = fb;
+  return choice;
+}
+
+/* ------------------------------------------------------------------ the run */
+#define EV(name) do{ if (b->nev < 16) { b->evname[b->nev] = name; cudaEventRecord(b->ev[b->nev++], st); } }while(0)
+#define RUN(x) do{ int r_ = (x); if (r_) return r_; }while(0)
+
+extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstreams,
+                               const vb200_block *blocks, int nblocks,
+                               const float *pcm, size_t pcm_elems, int pcm_on_device) {
+  if (!b || !streams || !blocks || !pcm || nstreams < 1 || nblocks < 0) { vb200_set_error("vb200_batch_run: bad arguments"); return VB200_EINVAL; }
+  if (nstreams > PIPE_MAX_STREAM_SLOTS) { vb200_set_error("vb200_batch_run: too many streams"); return VB200_EINVAL; }
+  if (nblocks > b->max_blocks) { vb200_set_error("vb200_batch_run: %d blocks > batch capacity %d", nblocks, b->max_blocks); return VB200_EINVAL; }
+  vb200_setup *s = b->s;
+  CUDA_TRY(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)s->stream;
+  StatePool *pool = pool_of(s);
+  const int ch = s->h.channels, managed = s->h.managed;
+  const int nsel = managed ? 3 : 1;
+  b->nev = 0;
+  b->pk_off.clear(); b->pk_bytes.clear(); b->pk_gp.clear(); b->pk_eos.clear(); b->pk_stream.clear();
+  b->bw.reset();
+  if (nblocks == 0) return VB200_OK;
+
+  /* ---- host pre-pass over the block descriptors ---- */
+  b->hb.resize(nblocks);
+  int nb[2] = {0, 0};
+  std::vector<int> last_of_stream(nstreams, -1);
+  b->pin.top = 0;
+  struct HostClass { int *psy_item, *psy_blk, *block_mode, *lW_block_mode, *lW, *nW, *params; long long *pcm_off, *last_addr; int *last_rule;
+                     int *chain_start, *chain_len, *chain_items; long long *temp_off; int nchains, nchain_items; } hc[2];
+  for (int W = 0; W < 2; W++) {
+    const size_t I = (size_t)nblocks * ch;
+    hc[W].psy_item = b->pin.take<int>(I); hc[W].psy_blk = b->pin.take<int>(nblocks); hc[W].block_mode = b->pin.take<int>(I);
+    hc[W].lW_block_mode = b->pin.take<int>(I); hc[W].lW = b->pin.take<int>(I); hc[W].nW = b->pin.take<int>(I); hc[W].params = b->pin.take<int>(I * 8);
+    hc[W].pcm_off = b->pin.take<long long>(I); hc[W].last_addr = b->pin.take<long long>(I); hc[W].last_rule = b->pin.take<int>(I);
+    hc[W].chain_start = b->pin.take<int>(I); hc[W].chain_len = b->pin.take<int>(I); hc[W].chain_items = b->pin.take<int>(I); hc[W].temp_off = b->pin.take<long long>(I);
+    hc[W].nchains = 0; hc[W].nchain_items = 0;
+    if (!hc[W].temp_off) { vb200_set_error("vb200_batch_run: pinned staging too small"); return VB200_EFAULT; }
+  }
+  ScanBlock *h_scan = b->pin.take<ScanBlock>(nblocks);
+  int *h_scan_start = b->pin.take<int>(nstreams + 1), *h_slot = b->pin.take<int>(nstreams);
+  /* stream-major ordering for the scan kernel */
+  std::vector<std::vector<int>> per_stream(nstreams);
+  for (int i = 0; i < nblocks; i++) {
+    const vb200_block &q = blocks[i];
+    if (q.stream < 0 || q.stream >= nstreams || (q.W != 0 && q.W != 1)) { vb200_set_error("vb200_batch_run: block %d malformed", i); return VB200_EINVAL; }
+    per_stream[q.stream].push_back(i);
+  }
+  const int flr_of_end[2] = { s->h.flr[s->h.floor_of_ch[0][0]].info_n, s->h.flr[s->h.floor_of_ch[1][0]].info_n };
+  const bool hs = s->h.rate >= 26000;
+  for (int i = 0; i < nblocks; i++) {
+    const vb200_block &q = blocks[i];
+    vb200_stream *x = streams[q.stream];
+    HostBlock &h = b->hb[i];
+    const int W = q.W;
+    h.stream = q.stream; h.W = W; h.lW = (int)q.lW; h.nW = (int)q.nW; h.blocktype = q.blocktype;
+    h.block_mode = q.blocktype | (W << 1); h.psy = q.blocktype + (W ? 2 : 0);
+    h.granulepos = q.granulepos; h.eof = q.eofflag;
+    h.idx = nb[W]++;
+    h.hist[0] = x->lW_block_mode; h.hist[1] = x->lW_no; h.hist[2] = x->impadnum;
+    HostClass &c = hc[W];
+    ClassBufs &dc = b->c[W];
+    c.psy_blk[h.idx] = h.psy;
+    /* where this block finds lastmdct */
+    const int prev = last_of_stream[q.stream];
+    for (int k = 0; k < ch; k++) {
+      const int it = h.idx * ch + k;
+      c.psy_item[it] = h.psy; c.block_mode[it] = h.block_mode; c.lW_block_mode[it] = x->lW_block_mode;
+      c.lW[it] = h.lW; c.nW[it] = h.nW;
+      int *pr = c.params + (size_t)it * 8;
+      pr[0] = 1; pr[1] = managed; pr[2] = flr_of_end[W]; pr[3] = h.block_mode; pr[4] = h.nW; pr[5] = x->lW_block_mode; pr[6] = x->lW_no; pr[7] = x->impadnum;
+      c.pcm_off[it] = q.pcm_offset + (long long)k * q.pcm_stride;
+      if (!hs) { c.last_addr[it] = (long long)(uintptr_t)(pool->last + ((size_t)x->slot * ch + k) * 2048); c.last_rule[it] = LAST_ZERO; }
+      else if (prev < 0) { c.last_addr[it] = (long long)(uintptr_t)(pool->last + ((size_t)x->slot * ch + k) * 2048); c.last_rule[it] = LAST_COPY; }
+      else {
+        const HostBlock &p = b->hb[prev];
+        const ClassBufs &pc = b->c[p.W];
+        c.last_addr[it] = (long long)(uintptr_t)(pc.logmdct + ((size_t)p.idx * ch + k) * pc.N2);
+        c.last_rule[it] = (p.block_mode <= 1) ? (W ? LAST_EXPAND8 : LAST_COPY) : ((p.block_mode == 2 && !W) ? LAST_MINPOOL8 : LAST_COPY);
+      }
+      c.temp_off[it] = ((long long)x->slot * ch + k) * 256;
+    }
+    last_of_stream[q.stream] = i;
+    /* aoTuV history, mapping0.c:1297-1305 -- once per packet blob */
+    for (int rep = 0; rep < (managed ? VB200_PACKETBLOBS : 1); rep++) {
+      if (h.block_mode >= 2) x->impadnum = 0;
+      if (!x->lW_block_mode && h.block_mode == 1) x->impadnum = 1;
+      else if (x->impadnum && x->impadnum < 8) x->impadnum++;
+      if (x->lW_block_mode == h.block_mode) x->lW_no++; else x->lW_no = 1;
+      x->lW_block_mode = h.block_mode;
+    }
+    (void)dc;
+  }
+  /* chains for K4: runs of consecutive impulse blocks of one stream, per channel; everything else is its own chain */
+  for (int sidx = 0; sidx < nstreams; sidx++) {
+    const std::vector<int> &lst = per_stream[sidx];
+    for (int k = 0; k < ch; k++) {
+      size_t j = 0;
+      while (j < lst.size()) {
+        const HostBlock &h = b->hb[lst[j]];
+        HostClass &c = hc[h.W];
+        const int start = c.nchain_items;
+        c.chain_items[c.nchain_items++] = h.idx * ch + k;
+        size_t e = j + 1;
+        if (h.W == 0 && h.block_mode == 0)
+          while (e < lst.size() && b->hb[lst[e]].W == 0 && b->hb[lst[e]].block_mode == 0) { c.chain_items[c.nchain_items++] = b->hb[lst[e]].idx * ch + k; e++; }
+        c.chain_start[c.nchains] = start; c.chain_len[c.nchains] = c.nchain_items - start; c.nchains++;
+        j = e;
+      }
+    }
+  }
+  {
+    int pos = 0;
+    for (int sidx = 0; sidx < nstreams; sidx++) {
+      h_scan_start[sidx] = pos; h_slot[sidx] = streams[sidx]->slot;
+      for (int bi : per_stream[sidx]) {
+        const HostBlock &h = b->hb[bi];
+        h_scan[pos].W = h.W; h_scan[pos].first_item = h.idx * ch; h_scan[pos].block_mode = h.block_mode; h_scan[pos].lW_block_mode = h.hist[0]; h_scan[pos].psy = h.psy;
+        pos++;
+      }
+    }
+    h_scan_start[nstreams] = pos;
+  }
+  b->n_blocks[0] = nb[0]; b->n_blocks[1] = nb[1]; b->n_items[0] = nb[0] * ch; b->n_items[1] = nb[1] * ch;
+
+  /* ---- uploads ---- */
+  EV("h2d");
+  const float *d_pcm = pcm;
+  if (!pcm_on_device) {
+    if (b->pcm_cap < pcm_elems) {
+      if (b->d_pcm) cudaFree(b->d_pcm);
+      b->d_pcm = nullptr; b->pcm_cap = 0;
+      CUDA_TRY(cudaMalloc(&b->d_pcm, pcm_elems * sizeof(float)));
+      b->pcm_cap = pcm_elems;
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->d_pcm, pcm, pcm_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+    d_pcm = b->d_pcm;
+  }
+#define UP(dst, src, n) CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(*(src)) * (size_t)(n), cudaMemcpyHostToDevice, st))
+  for (int W = 0; W < 2; W++) {
+    const int I = nb[W] * ch;
+    if (!I) continue;
+    ClassBufs &c = b->c[W]; HostClass &h = hc[W];
+    UP(c.psy_item, h.psy_item, I); UP(c.psy_blk, h.psy_blk, nb[W]); UP(c.block_mode, h.block_mode, I); UP(c.lW_block_mode, h.lW_block_mode, I);
+    UP(c.lW, h.lW, I); UP(c.nW, h.nW, I); UP(c.params, h.params, I * 8); UP(c.pcm_off, h.pcm_off, I);
+    UP(c.last_addr, h.last_addr, I); UP(c.last_rule, h.last_rule, I);
+    UP(c.chain_start, h.chain_start, h.nchains); UP(c.chain_len, h.chain_len, h.nchains); UP(c.chain_items, h.chain_items, h.nchain_items);
+    UP(c.temp_off, h.temp_off, I);
+  }
+  ScanBlock *d_scan = b->d_scan; int *d_scan_start = b->d_scan_start, *d_slot = b->d_slot; float **d_ptrs = b->d_ptrs;
+  {
+    UP(d_scan, h_scan, nblocks); UP(d_scan_start, h_scan_start, nstreams + 1); UP(d_slot, h_slot, nstreams);
+    float **h_ptrs = b->pin.take<float *>(8);
+    h_ptrs[0] = b->c[0].local_ampmax; h_ptrs[1] = b->c[1].local_ampmax; h_ptrs[2] = b->c[0].global_ampmax; h_ptrs[3] = b->c[1].global_ampmax;
+    h_ptrs[4] = b->c[0].logmdct; h_ptrs[5] = b->c[1].logmdct; h_ptrs[6] = b->c[0].lowcomp; h_ptrs[7] = b->c[1].lowcomp;
+    UP(d_ptrs, h_ptrs, 8);
+  }
+
+  /* ---- K1: window + MDCT + FFT/dB ---- */
+  EV("K1 transform");
+  for (int W = 0; W < 2; W++) {
+    ClassBufs &c = b->c[W];
+    RUN(vb200_launch_transform(s, st, W, nb[W] * ch, d_pcm, c.pcm_off, c.lW, c.nW, c.block_mode, c.lW_block_mode,
+                               c.gmdct, c.logfft, c.logmdct, c.local_ampmax, c.poste));
+  }
+  EV("scan ampmax");
+  k_stream_scan<<<(nstreams + 63) / 64, 64, 0, st>>>(s->d, nstreams, d_slot, d_scan_start, d_scan, pool->scal,
+                                                    (const float *const *)d_ptrs, (float *const *)(d_ptrs + 2),
+                                                    (const float *const *)(d_ptrs + 4), (float *const *)(d_ptrs + 6));
+  LAUNCH_CHECK();
+  /* ---- K2 / K3 ---- */
+  EV("K2 noisemask");
+  for (int W = 0; W < 2; W++) {
+    ClassBufs &c = b->c[W];
+    LastRef last{nullptr, c.last_addr, c.last_rule, 0};
+    RUN(vb200_launch_noisemask(s, st, W, nb[W] * ch, c.psy_item, c.block_mode, c.lowcomp, c.poste, c.logmdct, last, c.noise, c.epeak, c.npeak, c.nps));
+  }
+  EV("K3 tonemask");
+  for (int W = 0; W < 2; W++) {
+    ClassBufs &c = b->c[W];
+    RUN(vb200_launch_tonemask(s, st, W, nb[W] * ch, c.psy_item, c.logfft, c.global_ampmax, c.local_ampmax, c.tone));
+  }
+  /* ---- K4 ---- */
+  EV("K4 offset_and_mix");
+  for (int W = 0; W < 2; W++) {
+    ClassBufs &c = b->c[W];
+    if (!nb[W]) continue;
+    LastRef last{nullptr, c.last_addr, c.last_rule, 0};
+    RUN(vb200_launch_mix(s, st, W, hc[W].nchains, c.chain_start, c.chain_len, c.chain_items, c.psy_item, c.params, c.lowcomp,
+                         c.noise, c.tone, c.logmdct, c.gmdct, last, pool->temp, c.temp_off, c.npeak, c.nps,
+                         c.logmask, nsel, c.N2 * nsel, nullptr, managed ? c.fit_gate : nullptr, -1));
+  }
+  /* ---- K5a ---- */
+  EV("K5 floor fit");
+  for (int W = 0; W < 2; W++) {
+    ClassBufs &c = b->c[W];
+    const int I = nb[W] * ch;
+    if (!I) continue;
+    /* nominal curve: blob PACKETBLOBS/2 */
+    RUN(vb200_launch_floor_fit(s, st, W, I, -1, c.logmdct, c.logmask, c.N2, c.N2 * nsel, nullptr, c.posts[1], c.fitted[1]));
+    if (managed) {
+      RUN(vb200_launch_floor_fit(s, st, W, I, -1, c.logmdct, c.logmask + c.N2, c.N2, c.N2 * nsel, c.fitted[1], c.posts[2], c.fitted[2]));
+      RUN(vb200_launch_floor_fit(s, st, W, I, -1, c.logmdct, c.logmask + 2 * c.N2, c.N2, c.N2 * nsel, c.fitted[1], c.posts[0], c.fitted[0]));
+    }
+  }
+  /* stream state for the next batch: lastmdct of every stream's last block, tempmdct is already in place */
+  {
+    int n = 0;
+    const float **h_src = b->pin.take<const float *>((size_t)nstreams * ch); float **h_dst = b->pin.take<float *>((size_t)nstreams * ch);
+    int *h_rule = b->pin.take<int>((size_t)nstreams * ch), *h_N = b->pin.take<int>((size_t)nstreams * ch);
+    for (int sidx = 0; sidx < nstreams && hs; sidx++) {
+      if (last_of_stream[sidx] < 0) continue;
+      const HostBlock &h = b->hb[last_of_stream[sidx]];
+      const ClassBufs &c = b->c[h.W];
+      for (int k = 0; k < ch; k++) {
+        h_src[n] = c.logmdct + ((size_t)h.idx * ch + k) * c.N2;
+        h_dst[n] = pool->last + ((size_t)streams[sidx]->slot * ch + k) * 2048;
+        h_rule[n] = (h.block_mode <= 1) ? (h.nW ? LAST_EXPAND8 : LAST_COPY) : ((h.block_mode == 2 && !h.nW) ? LAST_MINPOOL8 : LAST_COPY);
+        h_N[n] = c.N2; n++;
+      }
+    }
+    if (n) {
+      const float **d_src = b->d_save_src; float **d_dst = b->d_save_dst; int *d_rule = b->d_save_rule, *d_N = b->d_save_N;
+      UP(d_src, h_src, n); UP(d_dst, h_dst, n); UP(d_rule, h_rule, n); UP(d_N, h_N, n);
+      k_save_last<<<n, 128, 0, st>>>(n, d_src, d_rule, d_N, d_dst);
+      LAUNCH_CHECK();
+    }
+  }
+
+  /* ---- per packet blob: K5b, K6, K7 and the D2H of what the host emits ---- */
+  const int k_lo = managed ? 0 : VB200_PACKETBLOBS / 2, k_hi = managed ? VB200_PACKETBLOBS - 1 : VB200_PACKETBLOBS / 2;
+  const int nblobs = k_hi - k_lo + 1;
+  /* host result staging: per blob, per class */
+  struct HostRes { int *vals, *nonzero, *nsyms, *syms; } hr[2];
+  std::vector<std::vector<unsigned char>> blob_bytes_store;   /* managed: packets of all blobs */
+  std::vector<long> blob_sizes((size_t)nblocks * VB200_PACKETBLOBS, 0);
+  std::vector<BitWriter *> blob_bw;
+  for (int W = 0; W < 2; W++) {
+    const size_t I = (size_t)nb[W] * ch;
+    const DevMap &M = s->h.map[s->h.mode_mapping[W]];
+    hr[W].vals = b->pin.take<int>(I * VB200_MAX_POSTS + 1); hr[W].nonzero = b->pin.take<int>(I + 1);
+    hr[W].nsyms = b->pin.take<int>((size_t)nb[W] * M.submaps + 1);
+    hr[W].syms = b->pin.take<int>((size_t)nb[W] * M.submaps * b->c[W].max_syms * 2 + 1);
+    if (!hr[W].syms) { vb200_set_error("vb200_batch_run: pinned staging too small for results"); return VB200_EFAULT; }
+  }
+  /* chlist per (W, submap) on device */
+  int *d_chlist[2][VB200_MAX_SUBMAPS]; int nch_sub[2][VB200_MAX_SUBMAPS];
+  {
+    int *h_cl = b->pin.take<int>(2 * VB200_MAX_SUBMAPS * VB200_MAX_CHANNELS);
+    int *d_cl = b->d_chl;
+    for (int W = 0; W < 2; W++) {
+      const DevMap &M = s->h.map[s->h.mode_mapping[W]];
+      for (int sm = 0; sm < M.submaps; sm++) {
+        int n = 0;
+        for (int k = 0; k < ch; k++) if (M.chmux[k] == sm) h_cl[(W * VB200_MAX_SUBMAPS + sm) * VB200_MAX_CHANNELS + n++] = k;
+        nch_sub[W][sm] = n;
+        d_chlist[W][sm] = d_cl + (W * VB200_MAX_SUBMAPS + sm) * VB200_MAX_CHANNELS;
+      }
+    }
+    UP(d_cl, h_cl, 2 * VB200_MAX_SUBMAPS * VB200_MAX_CHANNELS);
+  }
+
+  std::vector<BitWriter> bws(managed ? VB200_PACKETBLOBS : 0);
+  std::vector<std::vector<size_t>> boff(managed ? VB200_PACKETBLOBS : 0);
+  for (int k = k_lo; k <= k_hi; k++) {
+    EV(k == k_lo ? "K5b floor encode" : "blob");
+    for (int W = 0; W < 2; W++) {
+      ClassBufs &c = b->c[W];
+      const int I = nb[W] * ch;
+      if (!I) continue;
+      const DevMap &M = s->h.map[s->h.mode_mapping[W]];
+      /* posts of blob k (mapping0.c:1090-1181) into posts_k (floor1_encode mutates them) */
+      const int H = VB200_PACKETBLOBS / 2;
+      if (!managed || k == H) { k_copy_i32<<<148, 256, 0, st>>>(c.posts[1], c.posts_k, (size_t)I * VB200_MAX_POSTS); k_copy_i32<<<8, 256, 0, st>>>(c.fitted[1], c.fitted_k, I); vb200_count_launch(2); }
+      else if (k == 0) { k_copy_i32<<<148, 256, 0, st>>>(c.posts[0], c.posts_k, (size_t)I * VB200_MAX_POSTS); k_copy_i32<<<8, 256, 0, st>>>(c.fitted[0], c.fitted_k, I); vb200_count_launch(2); }
+      else if (k == VB200_PACKETBLOBS - 1) { k_copy_i32<<<148, 256, 0, st>>>(c.posts[2], c.posts_k, (size_t)I * VB200_MAX_POSTS); k_copy_i32<<<8, 256, 0, st>>>(c.fitted[2], c.fitted_k, I); vb200_count_launch(2); }
+      else if (k < H) RUN(vb200_launch_floor_interp(s, st, W, I, -1, c.posts[0], c.posts[1], c.fitted[0], c.fitted[1], k * 65536 / H, c.posts_k, c.fitted_k));
+      else RUN(vb200_launch_floor_interp(s, st, W, I, -1, c.posts[1], c.posts[2], c.fitted[1], c.fitted[2], (k - H) * 65536 / H, c.posts_k, c.fitted_k));
+      RUN(vb200_launch_floor_encode(s, st, W, I, -1, c.posts_k, c.fitted_k, c.vals, c.iwork, c.nonzero));
+      CUDA_TRY(cudaMemcpyAsync(hr[W].vals, c.vals, sizeof(int) * (size_t)I * VB200_MAX_POSTS, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(hr[W].nonzero, c.nonzero, sizeof(int) * (size_t)I, cudaMemcpyDeviceToHost, st));
+      if (k == k_lo) EV("K6 couple");
+      RUN(vb200_launch_couple(s, st, W, nb[W], c.psy_blk, k, c.gmdct, c.epeak, c.npeak, c.nps, c.iwork, c.nonzero));
+      if (k == k_lo) EV("K7 residue");
+      for (int sm = 0; sm < M.submaps; sm++) {
+        const int resnum = M.residuesubmap[sm];
+        const DevResidue &R = s->h.res[resnum];
+        const int pv = (R.end - R.begin) / R.grouping;
+        int *pw = c.partword + (size_t)sm * c.cap_blocks * ch * pv;    /* [submap][block][ch][pv] with this residue's pv */
+        int *cl = c.classified + (size_t)sm * c.cap_blocks;
+        int *sy = c.syms + (size_t)sm * c.cap_blocks * c.max_syms * 2;
+        int *ns = c.nsyms + (size_t)sm * c.cap_blocks;
+        RUN(vb200_launch_residue_class(s, st, W, nb[W], resnum, nch_sub[W][sm], d_chlist[W][sm], ch, c.iwork, c.nonzero, pw, cl));
+        RUN(vb200_launch_residue_forward(s, st, W, nb[W], resnum, nch_sub[W][sm], d_chlist[W][sm], ch, c.iwork, c.nonzero, pw, sy, c.max_syms, ns));
+        CUDA_TRY(cudaMemcpyAsync(hr[W].nsyms + (size_t)sm * nb[W], ns, sizeof(int) * (size_t)nb[W], cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(hr[W].syms + (size_t)sm * nb[W] * c.max_syms * 2, sy, sizeof(int) * (size_t)nb[W] * c.max_syms * 2, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    if (k == k_lo) EV("d2h+emit");
+    CUDA_TRY(cudaStreamSynchronize(st));
+    /* ---- host emission of blob k for every block (mapping0.c:1204-1295 order) ---- */
+    BitWriter &w = managed ? bws[k] : b->bw;
+    for (int i = 0; i < nblocks; i++) {
+      const HostBlock &h = b->hb[i];
+      const int W = h.W;
+      const DevMap &M = s->h.map[s->h.mode_mapping[W]];
+      const size_t start = w.begin_packet();
+      vb200_emit_header(s, w, W, h.lW, h.nW);
+      for (int c2 = 0; c2 < ch; c2++) {
+        const size_t it = (size_t)h.idx * ch + c2;
+        vb200_emit_floor(s, w, s->h.floor_of_ch[W][c2], hr[W].nonzero[it], hr[W].vals + it * VB200_MAX_POSTS);
+      }
+      for (int sm = 0; sm < M.submaps; sm++) {
+        const int n = hr[W].nsyms[(size_t)sm * nb[W] + h.idx];
+        vb200_emit_syms(s, w, hr[W].syms + ((size_t)sm * nb[W] + h.idx) * b->c[W].max_syms * 2, n);
+      }
+      if (managed) { boff[k].push_back(start); blob_sizes[(size_t)i * VB200_PACKETBLOBS + k] = (long)w.bytes_since(start); }
+      else {
+        b->pk_off.push_back(start); b->pk_bytes.push_back(w.bytes_since(start));
+        b->pk_gp.push_back(h.granulepos); b->pk_eos.push_back(h.eof); b->pk_stream.push_back(h.stream);
+      }
+    }
+  }
+  if (managed) {
+    /* bitrate.c: choose one blob per block, in stream order (blocks arrive in stream order) */
+    for (int i = 0; i < nblocks; i++) {
+      const HostBlock &h = b->hb[i];
+      long fb = 0;
+      const int choice = bitrate_choose(streams[h.stream], s, h.W, &blob_sizes[(size_t)i * VB200_PACKETBLOBS], &fb);
+      const size_t start = b->bw.begin_packet();
+      const unsigned char *src = bws[choice].buf + boff[choice][i];
+      const long have = blob_sizes[(size_t)i * VB200_PACKETBLOBS + choice];
+      for (long t = 0; t < fb; t++) b->bw.put(t < have ? src[t] : 0, 8);
+      b->pk_off.push_back(start); b->pk_bytes.push_back((size_t)fb);
+      b->pk_gp.push_back(h.granulepos); b->pk_eos.push_back(h.eof); b->pk_stream.push_back(h.stream);
+    }
+  }
+  EV("end");
+  CUDA_TRY(cudaStreamSynchronize(st));
+  b->total_ms = 0;
+  for (int i = 0; i + 1 < b->nev; i++) { cudaEventElapsedTime(&b->ev_ms[i], b->ev[i], b->ev[i + 1]); }
+  if (b->nev > 1) cudaEventElapsedTime(&b->total_ms, b->ev[0], b->ev[b->nev - 1]);
+  (void)nblobs;
+  return VB200_OK;
+}
+
+extern "C" int vb200_batch_packet(vb200_batch *b, int i, const unsigned char **data, long *bytes,
+                                  int64_t *granulepos, int *eos, int *stream) {
+  if (!b || i < 0 || i >= (int)b->pk_off.size()) return VB200_EINVAL;
+  if (data) *data = b->bw.buf + b->pk_off[i];
+  if (bytes) *bytes = (long)b->pk_bytes[i];
+  if (granulepos) *granulepos = b->pk_gp[i];
+  if (eos) *eos = b->pk_eos[i];
+  if (stream) *stream = b->pk_stream[i];
+  return VB200_OK;
+}
+
+extern "C" float vb200_batch_kernel_ms(vb200_batch *b) { return b ? b->total_ms : 0.f; }
+
+extern "C" int vb200_batch_kernel_times(vb200_batch *b, const char **names, float *ms, int cap) {
+  if (!b) return 0;
+  int n = 0;
+  for (int i = 0; i + 1 < b->nev && n < cap; i++, n++) { names[n] = b->evname[i]; ms[n] = b->ev_ms[i]; }
+  return n;
+}
+
+extern "C" int vb200_batch_get(vb200_batch *b, int what, int block, int chn, void *out, int count) {
+  if (!b || !out || block < 0 || block >= (int)b->hb.size() || chn < 0 || chn >= b->s->h.channels) return VB200_EINVAL;
+  const HostBlock &h = b->hb[block];
+  const ClassBufs &c = b->c[h.W];
+  const size_t it = (size_t)h.idx * b->s->h.channels + chn;
+  const void *src = nullptr; size_t n = c.N2, esz = 4;
+  switch (what) {
+    case VB200_GET_GMDCT: src = c.gmdct + it * c.N2; break;
+    case VB200_GET_LOGFFT: src = c.logfft + it * c.N2; break;
+    case VB200_GET_LOGMDCT: src = c.logmdct + it * c.N2; break;
+    case VB200_GET_NOISE: src = c.noise + it * c.N2; break;
+    case VB200_GET_TONE: src = c.tone + it * c.N2; break;
+    case VB200_GET_LOGMASK: src = c.logmask + it * c.N2 * (b->s->h.managed ? 3 : 1); break;
+    case VB200_GET_EPEAK: src = c.epeak + it * c.N2; break;
+    case VB200_GET_IWORK: src = c.iwork + it * c.N2; break;
+    case VB200_GET_ILOGMASK: src = c.iwork + it * c.N2; break;
+    case VB200_GET_POSTS: src = c.posts[1] + it * VB200_MAX_POSTS; n = VB200_MAX_POSTS; break;
+    default: return VB200_EINVAL;
+  }
+  if ((size_t)count < n) n = count;
+  if (cudaMemcpy(out, src, n * esz, cudaMemcpyDeviceToHost) != cudaSuccess) { vb200_set_error("vb200_batch_get: copy failed"); return VB200_EFAULT; }
+  return (int)n;
+}

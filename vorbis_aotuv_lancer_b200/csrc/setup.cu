@@ -289,6 +289,11 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
     copy_i(m.ang, L.getk("map%d.coupling_ang", k, VB200_I32, m.coupling_steps ? m.coupling_steps : 1), m.coupling_steps);
   }
 
+  for (int w = 0; w < 2 && L.ok; w++) {
+    const DevMap &m = h.map[h.mode_mapping[w]];
+    for (int c = 0; c < h.channels; c++) h.floor_of_ch[w][c] = m.floorsubmap[m.chmux[c]];
+  }
+
   /* codebooks: lattice parameters + the compacted used-entry list with the value each used entry
      decodes to, enumerated the way the exhaustive fallback of res0.c:343-370 walks them */
   DevBook *hb = (DevBook *)calloc(h.books ? h.books : 1, sizeof(DevBook));

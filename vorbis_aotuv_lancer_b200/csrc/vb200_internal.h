@@ -80,6 +80,7 @@ struct DevSetup {
   int freq_bfn128[128], freq_bfn256[256];
   double stereo_th[9], stereo_thx[9];
   float fromdB[256];
+  int floor_of_ch[2][VB200_MAX_CHANNELS];   /* floorsubmap[chmuxlist[c]] of the mapping of mode W */
   DevPsy psy[VB200_MAX_PSY];
   DevFloor flr[VB200_MAX_FLOORS];
   DevResidue res[VB200_MAX_RESIDUES];
@@ -142,7 +143,7 @@ int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int ite
                            const float *logmdct, LastRef last, float *noise, float *epeak, float *npeak, int npeak_stride);
 int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
                           const float *logfft, const float *global_ampmax, const float *local_ampmax, float *tone);
-int vb200_launch_mix(const vb200_setup *s, cudaStream_t st, int W, int nchains, const int *chain_start, const int *chain_len,
+int vb200_launch_mix(const vb200_setup *s, cudaStream_t st, int W, int nchains, const int *chain_start, const int *chain_len, const int *chain_items,
                      const int *psy, const int *params, const float *low_compand,
                      const float *noise, const float *tone, const float *logmdct, float *mdct, LastRef last,
                      float *temp_state, const long long *temp_off, float *npeak, int npeak_stride,
@@ -150,7 +151,7 @@ int vb200_launch_mix(const vb200_setup *s, cudaStream_t st, int W, int nchains, 
 int vb200_launch_floor_fit(const vb200_setup *s, cudaStream_t st, int W, int items, int floor_index,
                            const float *logmdct, const float *logmask, int mdct_stride, int mask_stride,
                            const int *gate, int *posts, int *fitted);
-int vb200_launch_floor_interp(const vb200_setup *s, cudaStream_t st, int items, int floor_index, const int *A, const int *B,
+int vb200_launch_floor_interp(const vb200_setup *s, cudaStream_t st, int W, int items, int floor_index, const int *A, const int *B,
                               const int *fa, const int *fb, int del, int *out, int *fo);
 int vb200_launch_floor_encode(const vb200_setup *s, cudaStream_t st, int W, int items, int floor_index,
                               int *posts, const int *fitted, int *vals, int *ilogmask, int *nonzero);

@@ -187,3 +187,96 @@ def residue_forward(s, W, resnum, rows, nonzero, partword, max_syms=16384):
     check(L.vb200_stage_residue_forward(s.h, W, blocks, resnum, ch, _p(rows), _p(nz), _p(pw), _p(syms), max_syms, _p(ns)),
           "vb200_stage_residue_forward")
     return [syms[b, :ns[b]].copy() for b in range(blocks)], rows
+
+
+# ------------------------------------------------------------------ whole path
+class Block(C.Structure):
+    """vb200_block (include/vorbis_b200.h): the vorbis_block fields mapping0_forward reads."""
+    _fields_ = [("stream", C.c_int32), ("W", C.c_int32), ("lW", C.c_int32), ("nW", C.c_int32),
+                ("blocktype", C.c_int32), ("eofflag", C.c_int32), ("granulepos", C.c_int64),
+                ("pcm_offset", C.c_int64), ("pcm_stride", C.c_int64)]
+
+
+class Stream:
+    """vb200_stream: per-stream aoTuV history, ampmax feedback and bitrate-manager state."""
+
+    def __init__(self, setup):
+        self.setup = setup
+        h = C.c_void_p()
+        check(L.vb200_stream_create(setup.h, C.byref(h)), "vb200_stream_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            L.vb200_stream_destroy(self.h)
+            self.h = None
+
+
+class Batch:
+    """vb200_batch: `vorbis_analysis` + `vorbis_bitrate_addblock` + `vorbis_bitrate_flushpacket`
+    for many blocks of many streams per call."""
+
+    def __init__(self, setup, max_blocks):
+        self.setup = setup
+        h = C.c_void_p()
+        check(L.vb200_batch_create(setup.h, int(max_blocks), C.byref(h)), "vb200_batch_create")
+        self.h = h
+        self.n = 0
+
+    def close(self):
+        if self.h:
+            L.vb200_batch_destroy(self.h)
+            self.h = None
+
+    def run(self, streams, blocks, pcm, pcm_on_device=False, pcm_elems=None):
+        """blocks: ctypes array of Block (stream order within each stream); pcm: float32 numpy array
+        (host) or an integer device address with pcm_elems."""
+        sh = (C.c_void_p * len(streams))(*[s.h for s in streams])
+        if pcm_on_device:
+            ptr, n = C.c_void_p(int(pcm)), int(pcm_elems)
+        else:
+            pcm = _f(pcm)
+            ptr, n = _p(pcm), pcm.size
+        check(L.vb200_batch_run(self.h, sh, len(streams), blocks, len(blocks), ptr, C.c_size_t(n), int(pcm_on_device)),
+              "vb200_batch_run")
+        self.n = len(blocks)
+
+    def packets(self):
+        """[(bytes, granulepos, eos, stream)] of the last run, in block order."""
+        out = []
+        d, nb, gp, eos, st = C.POINTER(C.c_ubyte)(), C.c_long(), C.c_int64(), C.c_int(), C.c_int()
+        for i in range(self.n):
+            check(L.vb200_batch_packet(self.h, i, C.byref(d), C.byref(nb), C.byref(gp), C.byref(eos), C.byref(st)))
+            out.append((C.string_at(d, nb.value), gp.value, eos.value, st.value))
+        return out
+
+    def packet_bytes(self):
+        nb = C.c_long()
+        tot = 0
+        for i in range(self.n):
+            L.vb200_batch_packet(self.h, i, None, C.byref(nb), None, None, None)
+            tot += nb.value
+        return tot
+
+    def kernel_ms(self):
+        return float(L.vb200_batch_kernel_ms(self.h))
+
+    def kernel_times(self):
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        n = L.vb200_batch_kernel_times(self.h, names, ms, 16)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+    def get(self, what, block, ch, count, dtype=np.float32):
+        out = np.zeros(count, dtype)
+        n = check(L.vb200_batch_get(self.h, int(what), int(block), int(ch), _p(out), int(count)), "vb200_batch_get")
+        return out[:n]
+
+
+def blocks_array(descs):
+    """descs: iterable of dicts/tuples (stream, W, lW, nW, blocktype, eofflag, granulepos, pcm_offset, pcm_stride)."""
+    arr = (Block * len(descs))()
+    for i, d in enumerate(descs):
+        (arr[i].stream, arr[i].W, arr[i].lW, arr[i].nW, arr[i].blocktype, arr[i].eofflag, arr[i].granulepos,
+         arr[i].pcm_offset, arr[i].pcm_stride) = [int(x) for x in d]
+    return arr
