@@ -167,6 +167,20 @@ typedef struct {
   int64_t  pcm_stride;   /* element distance between channels */
 } vb200_block;
 
+/* Host-side segmentation of a whole stream into analysis blocks (works without a GPU).  Replaces,
+ * for offline encoding, vorbis_analysis_buffer/_wrote (block.c:411-553, incl. the LPC head/tail
+ * extrapolation of lpc.c), _ve_envelope_search/_ve_envelope_mark (envelope.c:569-706) and the
+ * window sequencing of vorbis_analysis_blockout (block.c:557-812).  The returned blocks index the
+ * returned timeline buffer ([channels][total], lead-in + PCM + tail), which is what vb200_batch_run
+ * takes as `pcm`.  chunk = the vorbis_analysis_wrote granularity to mirror (<=0: 1024). */
+typedef struct vb200_segments vb200_segments;
+int  vb200_segment_stream(const vb200_setup *s, const float *pcm, long nsamples, long stride, int chunk,
+                          int stream_index, vb200_segments **out);
+void vb200_segments_free(vb200_segments *g);
+int  vb200_segments_count(const vb200_segments *g);
+const vb200_block *vb200_segments_blocks(const vb200_segments *g);
+const float *vb200_segments_pcm(const vb200_segments *g, long *elems);
+
 /* Per-stream state: replaces the aoTuV fields of private_state (codec_internal.h:85-92), the
  * ampmax feedback of block.c:649-651 and bitrate_manager_state (bitrate.h:26-38). */
 int  vb200_stream_create(vb200_setup *s, vb200_stream **out);
