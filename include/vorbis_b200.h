@@ -195,6 +195,9 @@ void vb200_batch_destroy(vb200_batch *b);
 int  vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstreams,
                      const vb200_block *blocks, int nblocks,
                      const float *pcm, size_t pcm_elems, int pcm_on_device);
+/* Debug/verification switch: 1 = emit codewords on the host from the device's symbol lists (the
+ * reference-order implementation in emit.cu), 0 (default) = pack bits on the device (K8). */
+int  vb200_batch_set_host_emit(vb200_batch *b, int on);
 /* Replaces `vorbis_bitrate_flushpacket` (bitrate.c:229-252): packet i of the last run, in block
  * order.  Memory is owned by the batch until the next run. */
 int  vb200_batch_packet(vb200_batch *b, int i, const unsigned char **data, long *bytes,

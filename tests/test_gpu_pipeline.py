@@ -67,4 +67,13 @@ def test_stream_matches_reference(config, seconds):
     assert abs(gbytes - rbytes) / rbytes < 0.005
     assert frac > 0.80
     assert snr > 30.0
-    st.close(); bt.close(); s.close()
+    # the device bit packer (K8) and the host reference-order emitter must agree byte for byte
+    from vorbis_aotuv_lancer_b200.lib import L
+    st2 = ops.Stream(s)
+    L.vb200_batch_set_host_emit(bt.h, 1)
+    bt.run([st2], (ops.Block * half)(*blocks[:half]), pcm)
+    pk2 = bt.packets()
+    bt.run([st2], (ops.Block * (len(blocks) - half))(*blocks[half:]), pcm)
+    pk2 += bt.packets()
+    assert [a[0] for a in pk2] == [a[0] for a in pk]
+    st.close(); st2.close(); bt.close(); s.close()

@@ -36,7 +36,11 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
   __shared__ int gate;
   const int tid = threadIdx.x;
   const int c0 = chain_start ? chain_start[blockIdx.x] : blockIdx.x;
-  const int clen = chain_len ? chain_len[blockIdx.x] : 1;
+  /* chain_len: low bits = links; bit 30 = do not load tempmdct from the state slot, bit 29 = do not store it
+     back (only a chain that starts / ends the stream's part of this batch touches the per-stream state) */
+  const int clen_raw = chain_len ? chain_len[blockIdx.x] : 1;
+  const int clen = clen_raw & 0xffffff;
+  const bool t_load = !(clen_raw & (1 << 30)), t_save = !(clen_raw & (1 << 29));
   constexpr bool SHORT = (N <= 256);
 
   for (int ci = 0; ci < clen; ci++) {
@@ -51,7 +55,7 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
     float *np = npeak + (size_t)item * npeak_stride;
     float *tstate = (SHORT && temp_state) ? temp_state + (temp_off ? temp_off[item] : (long long)item * 256) : nullptr;
 
-    if (SHORT && ci == 0 && tstate) { for (int i = tid; i < N; i += T) temp[i] = tstate[i]; }
+    if (SHORT && ci == 0 && tstate && t_load) { for (int i = tid; i < N; i += T) temp[i] = tstate[i]; }
     if (tid == 0) gate = 1;
     __syncthreads();
 
@@ -210,8 +214,8 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
       __syncthreads();
     }
     if (fit_gate && tid == 0) fit_gate[item] = gate;
-    if (SHORT && tstate) {
-      /* keep the chain's tempmdct in its slot (the next chain link / the stream state reads it) */
+    if (SHORT && tstate && t_save && ci == clen - 1) {
+      /* leave the chain's tempmdct in the stream's state slot for the next batch */
       float *dst = temp_state + (temp_off ? temp_off[item] : (long long)item * 256);
       for (int i = tid; i < N; i += T) dst[i] = temp[i];
     }

@@ -150,7 +150,7 @@ struct ClassBufs {           /* one size class (W) */
   int *psy_item, *psy_blk, *block_mode, *lW_block_mode, *lW, *nW, *params;
   long long *pcm_off, *last_addr; int *last_rule;
   int *chain_start, *chain_len, *chain_items; long long *temp_off;
-  int *partword, *classified, *syms, *nsyms;
+  int *partword, *classified, *syms, *nsyms, *floor_nz;
   int max_syms;
 };
 
@@ -168,6 +168,10 @@ struct vb200_batch {
   std::vector<HostBlock> hb;
   /* results */
   BitWriter bw;
+  const unsigned char *pk_base;
+  int host_emit, host_emit_ready;
+  unsigned char *d_pool, *h_pool; size_t pool_cap; unsigned long long *d_pool_top, *h_pool_top;
+  long long *d_pk_off, *h_pk_off; int *d_pk_bytes, *h_pk_bytes;
   std::vector<size_t> pk_off, pk_bytes; std::vector<int64_t> pk_gp; std::vector<int> pk_eos, pk_stream;
   /* timing */
   cudaEvent_t ev[16]; int nev; const char *evname[16]; float ev_ms[16]; float total_ms;
@@ -259,11 +263,13 @@ static bool carve_class(vb200_batch *b, int W, int cap_blocks) {
   c.chain_start = a.take<int>(I); c.chain_len = a.take<int>(I); c.chain_items = a.take<int>(I); c.temp_off = a.take<long long>(I);
   int maxpv = 1;
   for (int r = 0; r < s->h.residues; r++) { const DevResidue &R = s->h.res[r]; const int pv = (R.end - R.begin) / R.grouping; if (pv > maxpv) maxpv = pv; }
-  c.partword = a.take<int>((size_t)cap_blocks * VB200_MAX_SUBMAPS * ch * maxpv);
-  c.classified = a.take<int>((size_t)cap_blocks * VB200_MAX_SUBMAPS);
+  const int nsub = s->h.map[s->h.mode_mapping[W]].submaps;
+  c.partword = a.take<int>((size_t)cap_blocks * nsub * ch * maxpv);
+  c.classified = a.take<int>((size_t)cap_blocks * nsub);
   c.max_syms = (W ? PIPE_SYMS_PER_ITEM_LONG : PIPE_SYMS_PER_ITEM_SHORT) * ch;
-  c.syms = a.take<int>((size_t)cap_blocks * VB200_MAX_SUBMAPS * c.max_syms * 2);
-  c.nsyms = a.take<int>((size_t)cap_blocks * VB200_MAX_SUBMAPS);
+  c.syms = a.take<int>((size_t)cap_blocks * nsub * c.max_syms * 2);
+  c.nsyms = a.take<int>((size_t)cap_blocks * nsub);
+  c.floor_nz = a.take<int>(I);
   return c.nsyms != nullptr;
 }
 
@@ -274,7 +280,7 @@ static size_t class_bytes(const vb200_setup *s, int W, int cap_blocks) {
   for (int r = 0; r < s->h.residues; r++) { const DevResidue &R = s->h.res[r]; const size_t pv = (R.end - R.begin) / R.grouping; if (pv > maxpv) maxpv = pv; }
   const size_t max_syms = (size_t)(W ? PIPE_SYMS_PER_ITEM_LONG : PIPE_SYMS_PER_ITEM_SHORT) * ch;
   size_t b = 4 * (V * (7 + nsel) + I * (N2 / 8) * 2 + I * 8 + I * VB200_MAX_POSTS * 5 + I * 32 + cap_blocks * 8)
-           + 8 * I * 4 + 4 * ((size_t)cap_blocks * VB200_MAX_SUBMAPS * (ch * maxpv + 2 + max_syms * 2));
+           + 8 * I * 4 + 4 * ((size_t)cap_blocks * s->h.map[s->h.mode_mapping[W]].submaps * (ch * maxpv + 2 + max_syms * 2));
   return b + 64 * 256;
 }
 
@@ -296,9 +302,22 @@ extern "C" int vb200_batch_create(vb200_setup *s, int max_blocks, vb200_batch **
   if (!b->d_chl || !carve_class(b, 0, max_blocks) || !carve_class(b, 1, max_blocks)) { vb200_set_error("vb200_batch_create: arena sizing bug"); cudaFree(b->dev.base); delete b; return VB200_EFAULT; }
   /* pinned staging for descriptors and results */
   const size_t ch = s->h.channels;
-  const size_t pin_bytes = (size_t)max_blocks * ch * (64 * 4 + VB200_MAX_POSTS * 4 + 16) * 2 + (size_t)max_blocks * VB200_MAX_SUBMAPS * (b->c[1].max_syms * 8 + 16) * 2 + (1 << 20);
+  /* descriptors only; the (large) symbol staging of the host-emission debug path is added on demand */
+  const size_t pin_bytes = (size_t)max_blocks * ch * (64 * 4) * 2 + (size_t)PIPE_MAX_STREAM_SLOTS * 64 + (1 << 20);
   if (cudaMallocHost(&b->pin.base, pin_bytes) != cudaSuccess) { cudaGetLastError(); vb200_set_error("vb200_batch_create: cannot allocate pinned staging"); cudaFree(b->dev.base); delete b; return VB200_EFAULT; }
   b->pin.cap = pin_bytes;
+  {
+    const int nbl = s->h.managed ? VB200_PACKETBLOBS : 1;
+    b->pool_cap = (size_t)max_blocks * 3072 * nbl + (1 << 16);
+    b->host_emit = 0; b->host_emit_ready = 0; b->pk_base = nullptr;
+    const size_t nent = (size_t)nbl * 2 * max_blocks;
+    if (cudaMalloc(&b->d_pool, b->pool_cap) != cudaSuccess || cudaMalloc(&b->d_pool_top, 8) != cudaSuccess ||
+        cudaMalloc(&b->d_pk_off, sizeof(long long) * nent) != cudaSuccess || cudaMalloc(&b->d_pk_bytes, sizeof(int) * nent) != cudaSuccess ||
+        cudaMallocHost(&b->h_pool, b->pool_cap) != cudaSuccess || cudaMallocHost(&b->h_pool_top, 8) != cudaSuccess ||
+        cudaMallocHost(&b->h_pk_off, sizeof(long long) * nent) != cudaSuccess || cudaMallocHost(&b->h_pk_bytes, sizeof(int) * nent) != cudaSuccess) {
+      cudaGetLastError(); vb200_set_error("vb200_batch_create: cannot allocate the packet pool"); return VB200_EFAULT;
+    }
+  }
   for (int i = 0; i < 16; i++) cudaEventCreate(&b->ev[i]);
   *out = b;
   return VB200_OK;
@@ -311,6 +330,8 @@ extern "C" void vb200_batch_destroy(vb200_batch *b) {
   if (b->d_pcm) cudaFree(b->d_pcm);
   cudaFree(b->dev.base);
   cudaFreeHost(b->pin.base);
+  cudaFree(b->d_pool); cudaFree(b->d_pool_top); cudaFree(b->d_pk_off); cudaFree(b->d_pk_bytes);
+  cudaFreeHost(b->h_pool); cudaFreeHost(b->h_pool_top); cudaFreeHost(b->h_pk_off); cudaFreeHost(b->h_pk_bytes);
   delete b;
 }
 
@@ -483,7 +504,11 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
         size_t e = j + 1;
         if (h.W == 0 && h.block_mode == 0)
           while (e < lst.size() && b->hb[lst[e]].W == 0 && b->hb[lst[e]].block_mode == 0) { c.chain_items[c.nchain_items++] = b->hb[lst[e]].idx * ch + k; e++; }
-        c.chain_start[c.nchains] = start; c.chain_len[c.nchains] = c.nchain_items - start; c.nchains++;
+        /* only the chain holding the stream's first block may read tempmdct from the state slot, and only
+           the one holding its last block leaves it there */
+        c.chain_start[c.nchains] = start;
+        c.chain_len[c.nchains] = (c.nchain_items - start) | (j == 0 ? 0 : (1 << 30)) | (e == lst.size() ? 0 : (1 << 29));
+        c.nchains++;
         j = e;
       }
     }
@@ -606,21 +631,23 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
     }
   }
 
-  /* ---- per packet blob: K5b, K6, K7 and the D2H of what the host emits ---- */
+  /* ---- per packet blob: K5b, K6, K7, then the bit packer (device) or the symbol D2H (host emission) ---- */
   const int k_lo = managed ? 0 : VB200_PACKETBLOBS / 2, k_hi = managed ? VB200_PACKETBLOBS - 1 : VB200_PACKETBLOBS / 2;
   const int nblobs = k_hi - k_lo + 1;
-  /* host result staging: per blob, per class */
-  struct HostRes { int *vals, *nonzero, *nsyms, *syms; } hr[2];
-  std::vector<std::vector<unsigned char>> blob_bytes_store;   /* managed: packets of all blobs */
+  const bool host_emit = b->host_emit != 0;
+  struct HostRes { int *vals, *nonzero, *nsyms, *syms; } hr[2] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
   std::vector<long> blob_sizes((size_t)nblocks * VB200_PACKETBLOBS, 0);
-  std::vector<BitWriter *> blob_bw;
-  for (int W = 0; W < 2; W++) {
-    const size_t I = (size_t)nb[W] * ch;
-    const DevMap &M = s->h.map[s->h.mode_mapping[W]];
-    hr[W].vals = b->pin.take<int>(I * VB200_MAX_POSTS + 1); hr[W].nonzero = b->pin.take<int>(I + 1);
-    hr[W].nsyms = b->pin.take<int>((size_t)nb[W] * M.submaps + 1);
-    hr[W].syms = b->pin.take<int>((size_t)nb[W] * M.submaps * b->c[W].max_syms * 2 + 1);
-    if (!hr[W].syms) { vb200_set_error("vb200_batch_run: pinned staging too small for results"); return VB200_EFAULT; }
+  if (host_emit) {
+    for (int W = 0; W < 2; W++) {
+      const size_t I = (size_t)nb[W] * ch;
+      const DevMap &M = s->h.map[s->h.mode_mapping[W]];
+      hr[W].vals = b->pin.take<int>(I * VB200_MAX_POSTS + 1); hr[W].nonzero = b->pin.take<int>(I + 1);
+      hr[W].nsyms = b->pin.take<int>((size_t)nb[W] * M.submaps + 1);
+      hr[W].syms = b->pin.take<int>((size_t)nb[W] * M.submaps * b->c[W].max_syms * 2 + 1);
+      if (!hr[W].syms) { vb200_set_error("vb200_batch_run: pinned staging too small for host emission (use a smaller batch)"); return VB200_EFAULT; }
+    }
+  } else {
+    CUDA_TRY(cudaMemsetAsync(b->d_pool_top, 0, sizeof(unsigned long long), st));
   }
   /* chlist per (W, submap) on device */
   int *d_chlist[2][VB200_MAX_SUBMAPS]; int nch_sub[2][VB200_MAX_SUBMAPS];
@@ -639,8 +666,8 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
     UP(d_cl, h_cl, 2 * VB200_MAX_SUBMAPS * VB200_MAX_CHANNELS);
   }
 
-  std::vector<BitWriter> bws(managed ? VB200_PACKETBLOBS : 0);
-  std::vector<std::vector<size_t>> boff(managed ? VB200_PACKETBLOBS : 0);
+  std::vector<BitWriter> bws((managed && host_emit) ? VB200_PACKETBLOBS : 0);
+  std::vector<std::vector<size_t>> boff((managed && host_emit) ? VB200_PACKETBLOBS : 0);
   for (int k = k_lo; k <= k_hi; k++) {
     EV(k == k_lo ? "K5b floor encode" : "blob");
     for (int W = 0; W < 2; W++) {
@@ -655,9 +682,13 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
       else if (k == VB200_PACKETBLOBS - 1) { k_copy_i32<<<148, 256, 0, st>>>(c.posts[2], c.posts_k, (size_t)I * VB200_MAX_POSTS); k_copy_i32<<<8, 256, 0, st>>>(c.fitted[2], c.fitted_k, I); vb200_count_launch(2); }
       else if (k < H) RUN(vb200_launch_floor_interp(s, st, W, I, -1, c.posts[0], c.posts[1], c.fitted[0], c.fitted[1], k * 65536 / H, c.posts_k, c.fitted_k));
       else RUN(vb200_launch_floor_interp(s, st, W, I, -1, c.posts[1], c.posts[2], c.fitted[1], c.fitted[2], (k - H) * 65536 / H, c.posts_k, c.fitted_k));
-      RUN(vb200_launch_floor_encode(s, st, W, I, -1, c.posts_k, c.fitted_k, c.vals, c.iwork, c.nonzero));
-      CUDA_TRY(cudaMemcpyAsync(hr[W].vals, c.vals, sizeof(int) * (size_t)I * VB200_MAX_POSTS, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaMemcpyAsync(hr[W].nonzero, c.nonzero, sizeof(int) * (size_t)I, cudaMemcpyDeviceToHost, st));
+      /* floor1_encode's return value (the pre-coupling nonzero flag) is what the packet carries */
+      RUN(vb200_launch_floor_encode(s, st, W, I, -1, c.posts_k, c.fitted_k, c.vals, c.iwork, c.floor_nz));
+      k_copy_i32<<<8, 256, 0, st>>>(c.floor_nz, c.nonzero, I); vb200_count_launch(1);
+      if (host_emit) {
+        CUDA_TRY(cudaMemcpyAsync(hr[W].vals, c.vals, sizeof(int) * (size_t)I * VB200_MAX_POSTS, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(hr[W].nonzero, c.floor_nz, sizeof(int) * (size_t)I, cudaMemcpyDeviceToHost, st));
+      }
       if (k == k_lo) EV("K6 couple");
       RUN(vb200_launch_couple(s, st, W, nb[W], c.psy_blk, k, c.gmdct, c.epeak, c.npeak, c.nps, c.iwork, c.nonzero));
       if (k == k_lo) EV("K7 residue");
@@ -671,10 +702,19 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
         int *ns = c.nsyms + (size_t)sm * c.cap_blocks;
         RUN(vb200_launch_residue_class(s, st, W, nb[W], resnum, nch_sub[W][sm], d_chlist[W][sm], ch, c.iwork, c.nonzero, pw, cl));
         RUN(vb200_launch_residue_forward(s, st, W, nb[W], resnum, nch_sub[W][sm], d_chlist[W][sm], ch, c.iwork, c.nonzero, pw, sy, c.max_syms, ns));
-        CUDA_TRY(cudaMemcpyAsync(hr[W].nsyms + (size_t)sm * nb[W], ns, sizeof(int) * (size_t)nb[W], cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(hr[W].syms + (size_t)sm * nb[W] * c.max_syms * 2, sy, sizeof(int) * (size_t)nb[W] * c.max_syms * 2, cudaMemcpyDeviceToHost, st));
+        if (host_emit) {
+          CUDA_TRY(cudaMemcpyAsync(hr[W].nsyms + (size_t)sm * nb[W], ns, sizeof(int) * (size_t)nb[W], cudaMemcpyDeviceToHost, st));
+          CUDA_TRY(cudaMemcpyAsync(hr[W].syms + (size_t)sm * nb[W] * c.max_syms * 2, sy, sizeof(int) * (size_t)nb[W] * c.max_syms * 2, cudaMemcpyDeviceToHost, st));
+        }
+      }
+      if (!host_emit) {
+        if (k == k_lo) EV("K8 bitpack");
+        RUN(vb200_launch_pack(s, st, W, nb[W], c.lW, c.nW, c.vals, c.floor_nz, M.submaps, c.syms, c.nsyms, c.cap_blocks, c.max_syms,
+                              b->d_pool, b->pool_cap, b->d_pool_top,
+                              b->d_pk_off + ((size_t)(k - k_lo) * 2 + W) * b->max_blocks, b->d_pk_bytes + ((size_t)(k - k_lo) * 2 + W) * b->max_blocks));
       }
     }
+    if (!host_emit) continue;
     if (k == k_lo) EV("d2h+emit");
     CUDA_TRY(cudaStreamSynchronize(st));
     /* ---- host emission of blob k for every block (mapping0.c:1204-1295 order) ---- */
@@ -700,6 +740,38 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
       }
     }
   }
+  b->pk_base = nullptr;
+  if (!host_emit) {
+    /* the only D2H of the path: packet offsets/sizes, then the packet pool itself */
+    EV("d2h packets");
+    const size_t nent = (size_t)nblobs * 2 * b->max_blocks;
+    CUDA_TRY(cudaMemcpyAsync(b->h_pool_top, b->d_pool_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    for (int kk = 0; kk < nblobs; kk++) for (int W = 0; W < 2; W++) if (nb[W]) {
+      const size_t o = ((size_t)kk * 2 + W) * b->max_blocks;
+      CUDA_TRY(cudaMemcpyAsync(b->h_pk_off + o, b->d_pk_off + o, sizeof(long long) * nb[W], cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(b->h_pk_bytes + o, b->d_pk_bytes + o, sizeof(int) * nb[W], cudaMemcpyDeviceToHost, st));
+    }
+    (void)nent;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const unsigned long long top = *b->h_pool_top;
+    if (top > b->pool_cap) { vb200_set_error("vb200_batch_run: packet pool overflow (%llu > %llu bytes)", top, (unsigned long long)b->pool_cap); return VB200_EFAULT; }
+    CUDA_TRY(cudaMemcpyAsync(b->h_pool, b->d_pool, top, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < nblocks; i++) {
+      const HostBlock &h = b->hb[i];
+      for (int kk = 0; kk < nblobs; kk++) {
+        const size_t o = ((size_t)kk * 2 + h.W) * b->max_blocks + h.idx;
+        if (b->h_pk_off[o] < 0) { vb200_set_error("vb200_batch_run: packet of block %d does not fit the packer's image", i); return VB200_EFAULT; }
+        blob_sizes[(size_t)i * VB200_PACKETBLOBS + k_lo + kk] = b->h_pk_bytes[o];
+      }
+      if (!managed) {
+        const size_t o = (size_t)h.W * b->max_blocks + h.idx;
+        b->pk_off.push_back((size_t)b->h_pk_off[o]); b->pk_bytes.push_back((size_t)b->h_pk_bytes[o]);
+        b->pk_gp.push_back(h.granulepos); b->pk_eos.push_back(h.eof); b->pk_stream.push_back(h.stream);
+      }
+    }
+    if (!managed) b->pk_base = b->h_pool;
+  }
   if (managed) {
     /* bitrate.c: choose one blob per block, in stream order (blocks arrive in stream order) */
     for (int i = 0; i < nblocks; i++) {
@@ -707,26 +779,47 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
       long fb = 0;
       const int choice = bitrate_choose(streams[h.stream], s, h.W, &blob_sizes[(size_t)i * VB200_PACKETBLOBS], &fb);
       const size_t start = b->bw.begin_packet();
-      const unsigned char *src = bws[choice].buf + boff[choice][i];
+      const unsigned char *src = host_emit ? bws[choice].buf + boff[choice][i]
+                                           : b->h_pool + b->h_pk_off[((size_t)choice * 2 + h.W) * b->max_blocks + h.idx];
       const long have = blob_sizes[(size_t)i * VB200_PACKETBLOBS + choice];
       for (long t = 0; t < fb; t++) b->bw.put(t < have ? src[t] : 0, 8);
       b->pk_off.push_back(start); b->pk_bytes.push_back((size_t)fb);
       b->pk_gp.push_back(h.granulepos); b->pk_eos.push_back(h.eof); b->pk_stream.push_back(h.stream);
     }
   }
+  if (!b->pk_base) b->pk_base = b->bw.buf;
   EV("end");
   CUDA_TRY(cudaStreamSynchronize(st));
   b->total_ms = 0;
   for (int i = 0; i + 1 < b->nev; i++) { cudaEventElapsedTime(&b->ev_ms[i], b->ev[i], b->ev[i + 1]); }
   if (b->nev > 1) cudaEventElapsedTime(&b->total_ms, b->ev[0], b->ev[b->nev - 1]);
-  (void)nblobs;
+  return VB200_OK;
+}
+
+extern "C" int vb200_batch_set_host_emit(vb200_batch *b, int on) {
+  if (!b) return VB200_EINVAL;
+  if (on && !b->host_emit_ready) {
+    /* grow the pinned staging so that it can also hold vals + symbols of a whole batch */
+    const vb200_setup *s = b->s;
+    const size_t ch = s->h.channels;
+    size_t extra = 0;
+    for (int W = 0; W < 2; W++) {
+      const size_t nsub = s->h.map[s->h.mode_mapping[W]].submaps;
+      extra += (size_t)b->max_blocks * (ch * (VB200_MAX_POSTS + 2) * 4 + nsub * ((size_t)b->c[W].max_syms * 8 + 8)) + 4096;
+    }
+    unsigned char *nb = nullptr;
+    if (cudaMallocHost(&nb, b->pin.cap + extra) != cudaSuccess) { cudaGetLastError(); vb200_set_error("vb200_batch_set_host_emit: cannot allocate %zu bytes of pinned staging", b->pin.cap + extra); return VB200_EFAULT; }
+    cudaFreeHost(b->pin.base);
+    b->pin.base = nb; b->pin.cap += extra; b->host_emit_ready = 1;
+  }
+  b->host_emit = on;
   return VB200_OK;
 }
 
 extern "C" int vb200_batch_packet(vb200_batch *b, int i, const unsigned char **data, long *bytes,
                                   int64_t *granulepos, int *eos, int *stream) {
   if (!b || i < 0 || i >= (int)b->pk_off.size()) return VB200_EINVAL;
-  if (data) *data = b->bw.buf + b->pk_off[i];
+  if (data) *data = b->pk_base + b->pk_off[i];
   if (bytes) *bytes = (long)b->pk_bytes[i];
   if (granulepos) *granulepos = b->pk_gp[i];
   if (eos) *eos = b->pk_eos[i];

@@ -261,6 +261,12 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
     copy_i(s->hflr[k].class_subs, L.getk("flr%d.class_subs", k, VB200_I32, 16), 16);
     copy_i(s->hflr[k].class_book, L.getk("flr%d.class_book", k, VB200_I32, 16), 16);
     copy_i(s->hflr[k].class_subbook, L.getk("flr%d.class_subbook", k, VB200_I32, 128), 128);
+    fl.partitions = s->hflr[k].partitions;
+    memcpy(fl.partclass, s->hflr[k].partclass, sizeof(fl.partclass));
+    memcpy(fl.class_dim, s->hflr[k].class_dim, sizeof(fl.class_dim));
+    memcpy(fl.class_subs, s->hflr[k].class_subs, sizeof(fl.class_subs));
+    memcpy(fl.class_book, s->hflr[k].class_book, sizeof(fl.class_book));
+    memcpy(fl.class_subbook, s->hflr[k].class_subbook, sizeof(fl.class_subbook));
   }
 
   for (int k = 0; k < h.residues && L.ok; k++) {

@@ -45,6 +45,8 @@ struct DevFloor {
   float maxover, maxunder, maxerr, twofitweight, twofitatten;
   int postlist[VB200_MAX_POSTS], sorted[VB200_MAX_POSTS], forward[VB200_MAX_POSTS], reverse[VB200_MAX_POSTS];
   int lonb[VB200_MAX_POSTS], hinb[VB200_MAX_POSTS];
+  /* emission tables (vorbis_info_floor1, backends.h:60-70) for the device bit packer */
+  int partitions, partclass[31], class_dim[16], class_subs[16], class_book[16], class_subbook[16 * 8];
 };
 
 struct DevResidue {
@@ -160,6 +162,10 @@ int vb200_launch_couple(const vb200_setup *s, cudaStream_t st, int W, int blocks
 int vb200_launch_residue_class(const vb200_setup *s, cudaStream_t st, int W, int blocks, int resnum, int ch, const int *chlist,
                                int tot_ch, const int *in, const int *nonzero, int *partword, int *classified);
 int vb200_residue_maxvec(const vb200_setup *s, int resnum);
+int vb200_launch_pack(const vb200_setup *s, cudaStream_t st, int W, int blocks, const int *lW, const int *nW,
+                      const int *vals, const int *floor_nonzero, int submaps, const int *syms, const int *nsyms,
+                      int cap_blocks, int max_syms, unsigned char *pool, unsigned long long pool_cap,
+                      unsigned long long *pool_top, long long *pk_off, int *pk_bytes);
 int vb200_launch_residue_forward(const vb200_setup *s, cudaStream_t st, int W, int blocks, int resnum, int ch, const int *chlist,
                                  int tot_ch, int *in, const int *nonzero, const int *partword, int *syms, int max_syms, int *nsyms);
 #endif
