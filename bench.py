@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native aoTuV/Vorbis per-block analysis path.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference's own CPU path, host cores)
+
+Metric (BASELINE.json): encoded audio-seconds per wall-second at q4 44.1 kHz stereo.
+Workload: S independent 60 s synthetic streams (SURVEY.md section 8d signal), all of their blocks batched
+per step.  A step = one pass of the hot path over that batch.
+  value : inputs (the segmented PCM timeline + block descriptors) already resident in HBM when the
+          timed region starts; the region ends when the packets are back on the host.
+  e2e   : the public call (Encoder.encode) from HOST PCM: host segmentation (envelope / block-size
+          decision), H2D of the PCM, all kernels incl. bit packing, D2H of the packets.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIG = "q4_44k_2ch"
+# algorithmic HBM bytes per ch-block (long N2=1024 / short N2=128), SURVEY.md section 8(d)
+ALGO_BYTES = {
+    "K1 transform": (20480, 2560), "K2 noisemask": (16512, 2112), "K3 tonemask": (8192, 1024),
+    "K4 offset_and_mix": (32768, 4096), "K5 floor fit": (8308, 1076), "K5b floor encode": (4212, 564),
+    "K6 couple": (16512, 2112), "K7 residue": (6200, 800), "K8 bitpack": (2400, 400),
+}
+
+
+def clocks_sampler(stop, out, gpu):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+            out.append([x.strip() for x in r])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    sm = [float(s[0]) for s in samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+    mx = [float(s[1]) for s in samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+    reasons = set()
+    for s in samples:
+        if len(s) >= 6:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons)}
+
+
+def synth_streams(L, nstreams, seconds, channels, rate, first_index, threads=8):
+    from concurrent.futures import ThreadPoolExecutor
+    n = int(rate * seconds)
+
+    def one(i):
+        a = np.empty((channels, n), np.float32)
+        seed = L.vb200_splitmix64(C.c_uint64(88172645463325252 + first_index + i))
+        L.vb200_synth_pcm(C.c_uint64(seed), channels, C.c_long(rate), C.c_long(n), a.ctypes.data_as(C.c_void_p), C.c_long(n))
+        return a
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return list(ex.map(one, range(nstreams)))
+
+
+# ------------------------------------------------------------------ reference arm / cpu baseline
+def _ref_worker(args):
+    flavour, channels, rate, quality, seconds, seed_index, reps = args
+    from oracle import reflib
+    from vorbis_aotuv_lancer_b200.lib import L
+    pcm = synth_streams(L, 1, seconds, channels, rate, seed_index, threads=1)[0]
+    R = reflib.RefLib(flavour)
+    t0 = time.perf_counter()
+    nbytes = 0
+    for _ in range(reps):
+        h = R.open(channels, rate, quality, 0)
+        R.write(h, pcm)
+        nbytes += sum(len(p[0]) for p in R.packets(h))
+        R.close(h)
+    return time.perf_counter() - t0, nbytes
+
+
+def reference_throughput(cores, seconds, reps, flavour="sse"):
+    """The UNMODIFIED reference (oracle/_ref, Lancer SSE path, -O3 -ffast-math) one stream per core."""
+    import multiprocessing as mp
+    from vorbis_aotuv_lancer_b200 import blob as vblob
+    ch, rate, q, _ = vblob.CATALOGUE[CONFIG]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_ref_worker, [(flavour, ch, rate, q, 0.5, i, 1) for i in range(cores)])      # warm the workers
+        t0 = time.perf_counter()
+        res = pool.map(_ref_worker, [(flavour, ch, rate, q, seconds, i, reps) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    return cores * reps * seconds / wall, wall, max(r[0] for r in res)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import reflib
+    if not reflib.available("sse"):
+        reflib.build()
+    cores = os.cpu_count() or 1
+    seconds = 60.0
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, wall, _ = reference_throughput(cores, seconds, 1)
+        if i >= args.warmup:
+            vals.append((v, wall))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([w for _, w in vals]) * 1e3)
+    sample = "%d processes x one 60 s q4 44.1 kHz stereo stream each (reference build oracle/_ref, Lancer SSE, -O3 -ffast-math)" % cores
+    out = {"impl": "reference", "metric": "encoded audio-sec/sec @q4 44.1k stereo", "value": value, "unit": "audio-s/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "q4 44.1 kHz stereo, 60 s synthetic streams, one per host core", "quality": 0.4},
+           "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample},
+           "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from vorbis_aotuv_lancer_b200 import ops, encoder
+    from vorbis_aotuv_lancer_b200.lib import L
+    from vorbis_aotuv_lancer_b200 import blob as vblob
+
+    ch, rate, q, _ = vblob.CATALOGUE[CONFIG]
+    S, T = args.streams, args.seconds
+    setup = ops.Setup(CONFIG, device=local)
+    pcms = synth_streams(L, S, T, ch, rate, rank * S)
+    blocks_per_stream = int(T * rate / 700) + 64
+    enc = encoder.Encoder(setup, S * blocks_per_stream, threads=min(32, os.cpu_count() or 8))
+    blocks, timeline, counts = enc.segment(pcms)
+    nblocks = len(blocks)
+    nlong = int(np.frombuffer(blocks, dtype=encoder.BLOCK_DTYPE)["W"].sum())
+    nshort = nblocks - nlong
+    d_timeline = torch.from_numpy(timeline).cuda()
+    audio = S * T
+    total_steps = args.warmup + args.steps
+    streams = [[ops.Stream(setup) for _ in range(S)] for _ in range(2 * total_steps)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxtime(t):
+        if world > 1:
+            x = torch.tensor([t], device="cuda", dtype=torch.float64)
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
+            return float(x.item())
+        return t
+
+    # ---- device-resident value ----
+    for i in range(args.warmup):
+        enc.batch.run(streams[i], blocks, d_timeline.data_ptr(), pcm_on_device=True, pcm_elems=timeline.size)
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
+    kt = {}
+    barrier()
+    L.vb200_launch_count_reset()
+    th.start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        enc.batch.run(streams[args.warmup + i], blocks, d_timeline.data_ptr(), pcm_on_device=True, pcm_elems=timeline.size)
+        for name, ms in enc.batch.kernel_times():
+            kt[name] = kt.get(name, 0.0) + ms
+    barrier()
+    t_dev = maxtime(time.perf_counter() - t0)
+    launches = L.vb200_launch_count()
+    stop.set()
+    th.join()
+    tab = encoder.table(enc.batch)
+    packet_bytes = tab["total"]
+
+    # ---- e2e: host PCM -> packets through the public call ----
+    for i in range(min(args.warmup, 1)):
+        enc.encode(pcms, streams[total_steps + i])
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for i in range(e2e_steps):
+        enc.encode(pcms, streams[total_steps + 1 + i])
+    barrier()
+    t_e2e = maxtime(time.perf_counter() - t0)
+
+    if rank == 0:
+        ms_step = t_dev / args.steps * 1e3
+        value = world * audio * args.steps / t_dev
+        e2e_value = world * audio * e2e_steps / t_e2e
+        # roofline of the dominant kernel
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+        stage_ms = {k: v / args.steps for k, v in kt.items()}
+        kern = {k: v for k, v in stage_ms.items() if k in ALGO_BYTES}
+        top = max(kern, key=kern.get)
+        algo = (nlong * ALGO_BYTES[top][0] + nshort * ALGO_BYTES[top][1]) * ch
+        achieved = algo / (kern[top] * 1e-3) / 1e9
+        whole = sum((nlong * v[0] + nshort * v[1]) * ch for v in ALGO_BYTES.values())
+        whole_gbs = whole / (sum(kern.values()) * 1e-3) / 1e9
+        cores = os.cpu_count() or 1
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                from oracle import reflib
+                if reflib.available("sse"):
+                    v, wall, _ = reference_throughput(cores, 60.0, 1)
+                    cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference",
+                           "sample": "%d processes x one 60 s q4 44.1 kHz stereo stream each, reference build oracle/_ref "
+                                     "(Lancer SSE, -O3 -ffast-math), %.1f s wall" % (cores, wall)}
+            except Exception as e:  # the baseline is reported, never required
+                cpu = {"value": None, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
+        out = {"metric": "encoded audio-sec/sec @q4 44.1k stereo", "value": value, "unit": "audio-s/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "%d independent %g s q4 44.1 kHz stereo synthetic streams per GPU, all %d blocks "
+                                      "(%d long, %d short) batched per step" % (S, T, nblocks, nlong, nshort),
+                          "quality": 0.4, "streams_per_gpu": S, "seconds_per_stream": T, "parallelism": "streams sharded i mod G, no collective",
+                          "l2": "inputs larger than L2 (PCM timeline %.0f MB, per-stage vectors %.0f MB)" % (timeline.nbytes / 1e6, (nlong * 1024 + nshort * 128) * ch * 4 / 1e6)},
+               "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(timeline.nbytes), "d2h_bytes_per_step": int(packet_bytes),
+                       "steps": e2e_steps, "includes": "host segmentation (envelope detector), H2D PCM, all kernels, bit packing, D2H packets"},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "kernel_ms": kern[top],
+                            "all_kernels": {"algorithmic_GBps": whole_gbs, "frac": whole_gbs / peak, "ms": sum(kern.values())}},
+               "stage_ms": stage_ms, "clocks": summarize_clocks(samples), "cpu_baseline": cpu,
+               "packet_bytes_per_step": int(packet_bytes), "kbps": packet_bytes * 8 / audio / 1000.0}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=64)
+    ap.add_argument("--seconds", type=float, default=60.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

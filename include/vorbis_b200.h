@@ -202,6 +202,9 @@ int  vb200_batch_set_host_emit(vb200_batch *b, int on);
  * order.  Memory is owned by the batch until the next run. */
 int  vb200_batch_packet(vb200_batch *b, int i, const unsigned char **data, long *bytes,
                         int64_t *granulepos, int *eos, int *stream);
+/* All packets of the last run at once: returns their number; arrays stay owned by the batch. */
+int  vb200_batch_packet_table(vb200_batch *b, const unsigned char **base, const size_t **off, const size_t **bytes,
+                              const int64_t **granulepos, const int **eos, const int **stream);
 /* device time (ms) of the kernels of the last run, measured with CUDA events on the batch's stream */
 float vb200_batch_kernel_ms(vb200_batch *b);
 /* per-kernel device time of the last run: name[i], ms[i]; returns the number of kernels */

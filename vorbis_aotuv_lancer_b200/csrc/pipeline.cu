@@ -827,6 +827,18 @@ extern "C" int vb200_batch_packet(vb200_batch *b, int i, const unsigned char **d
   return VB200_OK;
 }
 
+extern "C" int vb200_batch_packet_table(vb200_batch *b, const unsigned char **base, const size_t **off, const size_t **bytes,
+                                        const int64_t **granulepos, const int **eos, const int **stream) {
+  if (!b) return VB200_EINVAL;
+  if (base) *base = b->pk_base;
+  if (off) *off = b->pk_off.data();
+  if (bytes) *bytes = b->pk_bytes.data();
+  if (granulepos) *granulepos = b->pk_gp.data();
+  if (eos) *eos = b->pk_eos.data();
+  if (stream) *stream = b->pk_stream.data();
+  return (int)b->pk_off.size();
+}
+
 extern "C" float vb200_batch_kernel_ms(vb200_batch *b) { return b ? b->total_ms : 0.f; }
 
 extern "C" int vb200_batch_kernel_times(vb200_batch *b, const char **names, float *ms, int cap) {
