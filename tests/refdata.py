@@ -41,3 +41,24 @@ def capture(config, seconds=3.0, lo=0, hi=1 << 30, flavour="c", seed=0):
 def by_size(cap, W):
     """seqs of the captured blocks with size flag W, in order."""
     return [s for s in sorted(cap["blocks"]) if "TAP_BLOCK" in cap["blocks"][s] and cap["blocks"][s]["TAP_BLOCK"][0]["data"][0] == W]
+
+
+GOLDEN_DIR = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden")
+
+
+def load_golden(config):
+    """The committed reference vectors of tests/golden (tools/make_golden.py) in capture() layout."""
+    import os
+    z = np.load(os.path.join(GOLDEN_DIR, config + ".npz"))
+    blocks = {}
+    for key in z.files:
+        if key == "seqs" or key.endswith("/a"):
+            continue
+        seq, tag, k = key.split("/")
+        a = z[key + "/a"]
+        blocks.setdefault(int(seq), {}).setdefault(tag, {})[int(k)] = dict(tag=tag, seq=int(seq), a0=int(a[0]), a1=int(a[1]), a2=int(a[2]), a3=int(a[3]), data=z[key])
+    for seq in blocks:
+        for tag in blocks[seq]:
+            d = blocks[seq][tag]
+            blocks[seq][tag] = [d[i] for i in sorted(d)]
+    return dict(blocks=blocks)
