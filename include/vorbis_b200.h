@@ -181,6 +181,20 @@ int  vb200_segments_count(const vb200_segments *g);
 const vb200_block *vb200_segments_blocks(const vb200_segments *g);
 const float *vb200_segments_pcm(const vb200_segments *g, long *elems);
 
+/* The same segmentation for many streams at once, with the detector's heavy half (128-point MDCT +
+ * band energies every 64 samples; envelope.c:101-217) as CUDA kernels.  The timeline of all streams is
+ * uploaded once and stays in HBM: pass vb200_segmenter_device_pcm() to vb200_batch_run with
+ * pcm_on_device = 1.  Blocks are stream-major; block.stream = index into pcm[]. */
+typedef struct vb200_segmenter vb200_segmenter;
+int  vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out);
+void vb200_segmenter_destroy(vb200_segmenter *g);
+int  vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float *const *pcm, const long *nsamples,
+                         const long *stride, int chunk, int threads);
+int  vb200_segmenter_count(const vb200_segmenter *g);
+const vb200_block *vb200_segmenter_blocks(const vb200_segmenter *g);
+const float *vb200_segmenter_device_pcm(const vb200_segmenter *g, size_t *elems);
+const float *vb200_segmenter_host_pcm(const vb200_segmenter *g);
+
 /* Per-stream state: replaces the aoTuV fields of private_state (codec_internal.h:85-92), the
  * ampmax feedback of block.c:649-651 and bitrate_manager_state (bitrate.h:26-38). */
 int  vb200_stream_create(vb200_setup *s, vb200_stream **out);

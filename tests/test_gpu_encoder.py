@@ -1,0 +1,56 @@
+"""The public call (Encoder.encode): GPU-assisted segmentation must equal the host segmenter (and through
+tests/test_segment.py the reference's blockout) exactly, and the stream must decode."""
+import numpy as np
+import pytest
+
+from tests import refdata
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("config,seconds", [("q4_44k_2ch", 4.0), ("q8_48k_6ch", 1.5), ("q4_44k_1ch", 0.4)])
+def test_gpu_segmenter_equals_host_segmenter(config, seconds):
+    from vorbis_aotuv_lancer_b200 import blob as vblob, encoder, ops, segment
+    ch, rate, _, _ = vblob.CATALOGUE[config]
+    s = ops.Setup(config)
+    pcms = [refdata.synth(ch, rate, seconds, seed=11 + i) for i in range(3)] + [refdata.synth(ch, rate, 0.05, seed=5)]
+    g = encoder.Segmenter(s)
+    blocks, dptr, elems = g.run(pcms, threads=4)
+    tl = g.host_timeline(elems)
+    pos, base = 0, 0
+    for i, p in enumerate(pcms):
+        hb, ht = segment.segment_stream(s, p, stream_index=i)
+        for k in range(len(hb)):
+            a, b = blocks[pos + k], hb[k]
+            assert (a.stream, a.W, a.lW, a.nW, a.blocktype, a.eofflag, a.granulepos, a.pcm_offset - base, a.pcm_stride) == \
+                   (b.stream, b.W, b.lW, b.nW, b.blocktype, b.eofflag, b.granulepos, b.pcm_offset, b.pcm_stride), (i, k)
+        assert np.array_equal(tl[base:base + ht.size], ht)
+        pos += len(hb)
+        base += ht.size
+    assert pos == len(blocks)
+    g.close(); s.close()
+
+
+def test_encode_decodes_and_matches_reference_bitrate():
+    from oracle import reflib
+    from vorbis_aotuv_lancer_b200 import encoder, ops
+    if not reflib.available("c"):
+        pytest.skip("oracle/_ref not present")
+    cap = refdata.capture("q4_44k_2ch", 6.0)
+    s = ops.Setup("q4_44k_2ch")
+    enc = encoder.Encoder(s, 4096, threads=4)
+    tab = enc.encode([cap["pcm"], cap["pcm"][:, :44100]])
+    pk = encoder.packets_of(tab, 0)
+    ref = cap["packets"]
+    assert len(pk) == len(ref)
+    gb, rb = sum(len(p[0]) for p in pk), sum(len(p[0]) for p in ref)
+    assert abs(gb - rb) / rb < 0.005
+    R = reflib.RefLib("c")
+    dec, _ = R.decode(cap["headers"], pk, cap["pcm"].shape[1] + 8192)
+    decr, _ = R.decode(cap["headers"], ref, cap["pcm"].shape[1] + 8192)
+    m = min(dec.shape[1], decr.shape[1])
+    err = (dec[:, :m] - decr[:, :m]).astype(np.float64)
+    snr = 10 * np.log10((decr[:, :m].astype(np.float64) ** 2).sum() / (err ** 2).sum())
+    assert snr > 30, snr
+    assert len(encoder.packets_of(tab, 1)) > 20
+    enc.close(); s.close()

@@ -58,49 +58,93 @@ namespace {
 struct ScanBlock { int W, first_item, block_mode, lW_block_mode, psy; };
 
 /* per-stream sequential pass between K1 and K2/K3: the ampmax max-plus recurrence
-   (block.c:649-651, psy.c:4504-4515, mapping0.c:887-888,1184) and lb_loudnoise_fix (psy.c:5152-5180) */
-__global__ void k_stream_scan(const DevSetup *__restrict__ S, int nstreams, const int *__restrict__ slot,
-                              const int *__restrict__ blk_start, const ScanBlock *__restrict__ blks,
-                              float *__restrict__ scal, const float *const *__restrict__ local_ampmax,
-                              float *const *__restrict__ global_ampmax, const float *const *__restrict__ logmdct,
-                              float *const *__restrict__ lowcomp) {
-  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+   (block.c:649-651, psy.c:4504-4515, mapping0.c:887-888,1184) and lb_loudnoise_fix (psy.c:5152-5180).
+   One warp per stream: lanes fetch 32 blocks' inputs in parallel (and evaluate the rare loud-noise
+   mean for their own block), then the recurrence itself is replayed in block order through shuffles --
+   the float adds of the decay must happen one after the other to round like the reference. */
+__global__ void __launch_bounds__(128)
+k_stream_scan(const DevSetup *__restrict__ S, int nstreams, const int *__restrict__ slot,
+              const int *__restrict__ blk_start, const ScanBlock *__restrict__ blks,
+              float *__restrict__ scal, const float *const *__restrict__ local_ampmax,
+              float *const *__restrict__ global_ampmax, const float *const *__restrict__ logmdct,
+              float *const *__restrict__ lowcomp) {
+  const int lane = threadIdx.x & 31;
+  const int sidx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (sidx >= nstreams) return;
   const int ch = S->channels;
   float *st = scal + (size_t)slot[sidx] * (2 + VB200_MAX_CHANNELS);
   float g = st[0], vbi = st[1];
-  for (int b = blk_start[sidx]; b < blk_start[sidx + 1]; b++) {
-    const ScanBlock B = blks[b];
+  float lv[VB200_MAX_CHANNELS];
+#pragma unroll
+  for (int c = 0; c < VB200_MAX_CHANNELS; c++) lv[c] = (c < ch) ? st[2 + c] : 0.f;
+  const int b_end = blk_start[sidx + 1];
+  for (int b0 = blk_start[sidx]; b0 < b_end; b0 += 32) {
+    const int b = b0 + lane;
+    const bool have = b < b_end;
+    ScanBlock B; B.W = 0; B.first_item = 0; B.block_mode = 0; B.lW_block_mode = 0; B.psy = 0;
+    if (have) B = blks[b];
     const int N2 = S->bs[B.W] / 2;
-    if (vbi > g) g = vbi;
-    {
-      const float secs = __fdiv_rn((float)N2, (float)S->rate);
-      g = __fadd_rn(g, __fmul_rn(secs, S->ampmax_att_per_sec));
-      if (g < -9999.f) g = -9999.f;
-    }
-    float gl = g;
-    for (int c = 0; c < ch; c++) { const float la = local_ampmax[B.W][B.first_item + c]; if (la > gl) gl = la; }
-    for (int c = 0; c < ch; c++) global_ampmax[B.W][B.first_item + c] = gl;
-    vbi = gl;
-    const DevPsy &P = S->psy[B.psy];
-    for (int c = 0; c < ch; c++) {
-      float lv = st[2 + c];
-      if (P.m_val < 0.5f) lv = -1.f;
-      else if (P.normal_thresh > .45) lv = -1.f;
-      else if ((B.block_mode == 2 && B.lW_block_mode == 3) || (B.block_mode == 3 && B.lW_block_mode == 2)) {
-        const float *lm = logmdct[B.W] + (size_t)(B.first_item + c) * N2;
-        double acc = 0;
-        for (int i = P.n25p; i < P.n75p; i++) { const float v = lm[i]; acc += (v > -130.f) ? (double)v : -130.; }
-        acc /= P.n;
-        if (acc > -40.) lv = -1.f;
-        else if (acc < -50.) lv = 1.f;
-        else lv = (float)(1. - ((acc + 50) / 10));
+    float lmax = -3.0e38f;                 /* max over the block's channels of local_ampmax */
+    float decay = 0.f;
+    /* per-channel loud-noise decision of this lane's block: 0 carry, 1 force -1, 2 new value in nv[] */
+    int kind[VB200_MAX_CHANNELS]; float nv[VB200_MAX_CHANNELS];
+#pragma unroll
+    for (int c = 0; c < VB200_MAX_CHANNELS; c++) { kind[c] = 0; nv[c] = 0.f; }
+    if (have) {
+      for (int c = 0; c < ch; c++) { const float la = local_ampmax[B.W][B.first_item + c]; if (la > lmax) lmax = la; }
+      decay = __fmul_rn(__fdiv_rn((float)N2, (float)S->rate), S->ampmax_att_per_sec);
+      const DevPsy &P = S->psy[B.psy];
+      const bool off = (P.m_val < 0.5f) || (P.normal_thresh > .45);
+      const bool recompute = (B.block_mode == 2 && B.lW_block_mode == 3) || (B.block_mode == 3 && B.lW_block_mode == 2);
+#pragma unroll
+      for (int c = 0; c < VB200_MAX_CHANNELS; c++) {
+        if (c >= ch) continue;
+        if (off) kind[c] = 1;
+        else if (recompute) {
+          const float *lm = logmdct[B.W] + (size_t)(B.first_item + c) * N2;
+          double acc = 0;
+          for (int i = P.n25p; i < P.n75p; i++) { const float v = lm[i]; acc += (v > -130.f) ? (double)v : -130.; }
+          acc /= P.n;
+          kind[c] = 2;
+          nv[c] = (acc > -40.) ? -1.f : ((acc < -50.) ? 1.f : (float)(1. - ((acc + 50) / 10)));
+        }
       }
-      st[2 + c] = lv;
-      lowcomp[B.W][B.first_item + c] = lv;
+    }
+    float my_gl = 0.f;
+    float my_lv[VB200_MAX_CHANNELS];
+#pragma unroll
+    for (int c = 0; c < VB200_MAX_CHANNELS; c++) my_lv[c] = 0.f;
+    const int cnt = min(32, b_end - b0);
+    for (int t = 0; t < cnt; t++) {
+      const float lm_t = __shfl_sync(FULLMASK, lmax, t), d_t = __shfl_sync(FULLMASK, decay, t);
+      if (vbi > g) g = vbi;
+      g = __fadd_rn(g, d_t);
+      if (g < -9999.f) g = -9999.f;
+      float gl = g;
+      if (lm_t > gl) gl = lm_t;
+      vbi = gl;
+      if (lane == t) my_gl = gl;
+#pragma unroll
+      for (int c = 0; c < VB200_MAX_CHANNELS; c++) {
+        const int k_t = __shfl_sync(FULLMASK, kind[c], t);
+        const float n_t = __shfl_sync(FULLMASK, nv[c], t);
+        if (k_t == 1) lv[c] = -1.f; else if (k_t == 2) lv[c] = n_t;
+        if (lane == t) my_lv[c] = lv[c];
+      }
+    }
+    if (have) {
+#pragma unroll
+      for (int c = 0; c < VB200_MAX_CHANNELS; c++) {
+        if (c >= ch) continue;
+        global_ampmax[B.W][B.first_item + c] = my_gl;
+        lowcomp[B.W][B.first_item + c] = my_lv[c];
+      }
     }
   }
-  st[0] = g; st[1] = vbi;
+  if (lane == 0) {
+    st[0] = g; st[1] = vbi;
+    for (int c = 0; c < ch; c++) st[2 + c] = lv[c];
+  }
 }
 
 /* end of batch: leave lastmdct in the stream's state slot exactly as the reference leaves
@@ -568,7 +612,7 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
                                c.gmdct, c.logfft, c.logmdct, c.local_ampmax, c.poste));
   }
   EV("scan ampmax");
-  k_stream_scan<<<(nstreams + 63) / 64, 64, 0, st>>>(s->d, nstreams, d_slot, d_scan_start, d_scan, pool->scal,
+  k_stream_scan<<<(nstreams + 3) / 4, 128, 0, st>>>(s->d, nstreams, d_slot, d_scan_start, d_scan, pool->scal,
                                                     (const float *const *)d_ptrs, (float *const *)(d_ptrs + 2),
                                                     (const float *const *)(d_ptrs + 4), (float *const *)(d_ptrs + 6));
   LAUNCH_CHECK();

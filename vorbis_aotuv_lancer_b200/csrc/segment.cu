@@ -1,4 +1,4 @@
-/* Host-side stream segmentation: PCM of a whole stream -> the list of analysis blocks.
+/* Stream segmentation: PCM of whole streams -> the list of analysis blocks.
  *
  * Replaces, for offline (whole-stream) encoding, the block layer that north_star keeps on the
  * host: vorbis_analysis_buffer/_wrote (block.c:411-553: pre-amplitude, LPC extrapolation of the
@@ -7,16 +7,24 @@
  * impulse blocks) and the window sequencing of vorbis_analysis_blockout (block.c:557-812).
  *
  * Not a port: the reference streams through a sliding buffer that it shifts after every block;
- * here the whole stream sits on one absolute timeline (1024 extrapolated samples of lead-in, the
- * PCM, 3 long blocks of extrapolated tail), the detector runs once over every 64-sample step,
- * and blocks are descriptors that point into that timeline -- nothing is copied per block, and
- * the timeline is exactly the buffer the GPU path reads.
+ * here a whole stream sits on one absolute timeline (1024 extrapolated samples of lead-in, the
+ * PCM, 3 long blocks of extrapolated tail), and blocks are descriptors that point into that
+ * timeline -- nothing is copied per block, and the timeline is exactly the buffer the GPU path
+ * reads.  Two drivers share the code:
+ *   vb200_segment_stream   -- host only (works without a GPU);
+ *   vb200_segmenter_*      -- many streams at once; the detector's heavy half (a 128-point MDCT and
+ *                             12 band energies every 64 samples) runs as CUDA
+ *                             kernels on the timeline that is uploaded ONCE and then handed to
+ *                             vb200_batch_run in place; the host keeps the LPC fits and the window
+ *                             sequencing.  Both drivers produce identical blocks.
  */
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 #include "vb200_internal.h"
+#include "dev_util.cuh"
 
 namespace {
 
@@ -27,9 +35,14 @@ constexpr int VE_N = 128, VE_STEP = 64;
 const int kBandBegin[VE_BANDS] = {2, 4, 6, 9, 13, 17, 22, 12, 8, 3, 2, 1};
 const int kBandEnd[VE_BANDS] = {4, 5, 6, 8, 8, 8, 8, 4, 4, 3, 2, 4};
 
-inline float todB_h(float x) {
+__host__ __device__ inline float todB_hd(float x) {
+#ifdef __CUDA_ARCH__
+  const uint32_t i = __float_as_uint(x) & 0x7fffffffu;
+  return __fadd_rn(__fmul_rn(__uint2float_rn(i), 7.17711438e-7f), -764.6161886f);
+#else
   union { uint32_t i; float f; } u; u.f = x; u.i &= 0x7fffffffu;
   return (float)(u.i * 7.17711438e-7f - 764.6161886f);
+#endif
 }
 
 /* Levinson-Durbin from the autocorrelation (lpc.c:60-130) */
@@ -65,14 +78,17 @@ void lpc_predict(const float *coeff, const float *prime, int m, float *data, lon
   }
 }
 
+/* tables of the detector, built once (envelope.c:42-82); the 128-point MDCT is kept as its 64x128
+   matrix in double so that host and device evaluate the very same sums */
 struct Detector {
   float win[VE_N];
   float bandwin[VE_BANDS][8], bandtotal[VE_BANDS];
-  double cs[VE_N / 2][VE_N];       /* the 128-point MDCT as a matrix (64 x 128), built once */
+  double cs[VE_N / 2][VE_N];
   Detector() {
     for (int i = 0; i < VE_N; i++) { const float t = (float)sin(i / (VE_N - 1.) * M_PI); win[i] = t * t; }
     for (int j = 0; j < VE_BANDS; j++) {
       const int n = kBandEnd[j]; float tot = 0;
+      for (int i = 0; i < 8; i++) bandwin[j][i] = 0.f;
       for (int i = 0; i < n; i++) { bandwin[j][i] = (float)sin((i + .5) / n * M_PI); tot += bandwin[j][i]; }
       bandtotal[j] = (float)(1. / tot);
     }
@@ -82,104 +98,130 @@ struct Detector {
 };
 const Detector &detector() { static Detector d; return d; }
 
-struct FilterState { float ampbuf[VE_AMP]; int ampptr; float nearDC[VE_NEARDC]; float nearDC_acc, nearDC_partialacc; int nearptr; };
+/* ---- the detector step, split into its four parts (envelope.c:101-217) ---- */
+struct NearDC { float ring[VE_NEARDC]; float acc, partial; int ptr; };
+struct BandFilter { float ampbuf[VE_AMP]; int ampptr; };
 
-/* one detector step on 128 samples of one channel (envelope.c:101-217) */
-int ve_amp(const Detector &D, const float *data, FilterState *nearst, FilterState *filters, int stretch_state,
-           float minV, float stretch_penalty, const float *pre_th, const float *post_th) {
-  float vec[VE_N];
-  int ret = 0;
-  const int stretch = stretch_state / 2 > VE_MINSTRETCH ? stretch_state / 2 : VE_MINSTRETCH;
-  float penalty = stretch_penalty - (stretch_state / 2 - VE_MINSTRETCH);
-  if (penalty < 0.f) penalty = 0.f;
-  if (penalty > stretch_penalty) penalty = stretch_penalty;
-  {
-    float w[VE_N];
-    for (int i = 0; i < VE_N; i++) w[i] = data[i] * D.win[i];
-    for (int k = 0; k < VE_N / 2; k++) { double a = 0; for (int t = 0; t < VE_N; t++) a += D.cs[k][t] * w[t]; vec[k] = (float)a; }
-  }
+/* (1) windowed 128-point MDCT, first `nout` coefficients */
+inline void ve_mdct(const Detector &D, const float *data, float *vec, int nout) {
+  float w[VE_N];
+  for (int i = 0; i < VE_N; i++) w[i] = data[i] * D.win[i];
+  for (int k = 0; k < nout; k++) { double a = 0; for (int t = 0; t < VE_N; t++) a += D.cs[k][t] * w[t]; vec[k] = (float)a; }
+}
+__host__ __device__ inline float ve_neartemp(float v0, float v1, float v2) {
+  return (float)((double)(v0 * v0) + .7 * (double)v1 * (double)v1 + .2 * (double)v2 * (double)v2);
+}
+/* (2) near-DC running sum with its periodic refresh -> decay */
+__host__ __device__ inline float ve_neardc(NearDC *s, float temp) {
   float decay;
-  {
-    const float temp = (float)(vec[0] * vec[0] + .7 * vec[1] * vec[1] + .2 * vec[2] * vec[2]);
-    const int ptr = nearst->nearptr;
-    if (ptr == 0) { decay = nearst->nearDC_acc = nearst->nearDC_partialacc + temp; nearst->nearDC_partialacc = temp; }
-    else { decay = nearst->nearDC_acc += temp; nearst->nearDC_partialacc += temp; }
-    nearst->nearDC_acc -= nearst->nearDC[ptr];
-    nearst->nearDC[ptr] = temp;
-    decay = (float)(decay * (1. / (VE_NEARDC + 1)));
-    nearst->nearptr++;
-    if (nearst->nearptr >= VE_NEARDC) nearst->nearptr = 0;
-    decay = (float)(todB_h(decay) * .5 - 15.f);
-  }
+  const int ptr = s->ptr;
+  if (ptr == 0) { decay = s->acc = s->partial + temp; s->partial = temp; }
+  else { decay = s->acc += temp; s->partial += temp; }
+  s->acc -= s->ring[ptr];
+  s->ring[ptr] = temp;
+  decay = (float)((double)decay * (1. / (VE_NEARDC + 1)));
+  s->ptr++;
+  if (s->ptr >= VE_NEARDC) s->ptr = 0;
+  return (float)((double)todB_hd(decay) * .5 - (double)15.f);
+}
+/* (3) spread/limit the spectrum and take the 12 band amplitudes */
+inline void ve_bands(const Detector &D, const float *vec, float decay, float minV, float *acc_out) {
+  float v2[VE_N / 4];
   for (int i = 0; i < VE_N / 2; i += 2) {
     float val = vec[i] * vec[i] + vec[i + 1] * vec[i + 1];
-    val = todB_h(val) * .5f;
+    val = todB_hd(val) * .5f;
     if (val < decay) val = decay;
     if (val < minV) val = minV;
-    vec[i >> 1] = val;
-    decay = (float)(decay - 8.);
+    v2[i >> 1] = val;
+    decay = (float)((double)decay - 8.);
   }
   for (int j = 0; j < VE_BANDS; j++) {
     float acc = 0.f;
-    for (int i = 0; i < kBandEnd[j]; i++) acc += vec[i + kBandBegin[j]] * D.bandwin[j][i];
-    acc *= D.bandtotal[j];
-    FilterState &f = filters[j];
-    const int cur = f.ampptr;
-    int p = cur - 1; if (p < 0) p += VE_AMP;
-    const float postmax = acc > f.ampbuf[p] ? acc : f.ampbuf[p], postmin = acc < f.ampbuf[p] ? acc : f.ampbuf[p];
-    float premax = -99999.f, premin = 99999.f;
-    for (int i = 0; i < stretch; i++) {
-      p--; if (p < 0) p += VE_AMP;
-      if (f.ampbuf[p] > premax) premax = f.ampbuf[p];
-      if (f.ampbuf[p] < premin) premin = f.ampbuf[p];
-    }
-    const float valmin = postmin - premin, valmax = postmax - premax;
-    f.ampbuf[cur] = acc;
-    f.ampptr++; if (f.ampptr >= VE_AMP) f.ampptr = 0;
-    if (valmax > pre_th[j] + penalty) ret |= 1 | 4;
-    if (valmin < post_th[j] - penalty) ret |= 2;
+    for (int i = 0; i < kBandEnd[j]; i++) acc += v2[i + kBandBegin[j]] * D.bandwin[j][i];
+    acc_out[j] = acc * D.bandtotal[j];
   }
+}
+/* (4) pre/post-echo trigger of one band */
+__host__ __device__ inline int ve_trigger(BandFilter *f, float acc, int stretch, float penalty, float pre_th, float post_th) {
+  const int cur = f->ampptr;
+  int p = cur - 1; if (p < 0) p += VE_AMP;
+  const float postmax = acc > f->ampbuf[p] ? acc : f->ampbuf[p], postmin = acc < f->ampbuf[p] ? acc : f->ampbuf[p];
+  float premax = -99999.f, premin = 99999.f;
+  for (int i = 0; i < stretch; i++) {
+    p--; if (p < 0) p += VE_AMP;
+    if (f->ampbuf[p] > premax) premax = f->ampbuf[p];
+    if (f->ampbuf[p] < premin) premin = f->ampbuf[p];
+  }
+  const float valmin = postmin - premin, valmax = postmax - premax;
+  f->ampbuf[cur] = acc;
+  f->ampptr++; if (f->ampptr >= VE_AMP) f->ampptr = 0;
+  int ret = 0;
+  if (valmax > pre_th + penalty) ret |= 1 | 4;
+  if (valmin < post_th - penalty) ret |= 2;
   return ret;
 }
+__host__ __device__ inline void ve_stretch_params(int stretch_state, float stretch_penalty, int *stretch, float *penalty) {
+  *stretch = stretch_state / 2 > VE_MINSTRETCH ? stretch_state / 2 : VE_MINSTRETCH;
+  float p = stretch_penalty - (float)(stretch_state / 2 - VE_MINSTRETCH);
+  if (p < 0.f) p = 0.f;
+  if (p > stretch_penalty) p = stretch_penalty;
+  *penalty = p;
+}
 
-}  // namespace
+struct EnvParams { float stretch_penalty, minenergy, pre_amp; float pre_th[VE_BANDS], post_th[VE_BANDS]; };
 
-struct vb200_segments {
-  int channels; long total;                  /* timeline length per channel */
-  std::vector<float> pcm;                    /* [channels][total] */
-  std::vector<vb200_block> blocks;
-};
-
-/* Segment one whole stream.  pcm: planar [channels][nsamples] (stride between channels),
-   chunk: the granularity the caller would have fed vorbis_analysis_wrote with (it decides how much
-   signal the head extrapolation sees, block.c:545-548; the reference's examples use 1024). */
-extern "C" int vb200_segment_stream(const vb200_setup *s, const float *pcm, long nsamples, long stride, int chunk,
-                                    int stream_index, vb200_segments **out) {
-  if (!s || !pcm || !out || nsamples < 0) { vb200_set_error("vb200_segment_stream: bad arguments"); return VB200_EINVAL; }
+bool env_params(const vb200_setup *s, EnvParams *e) {
   uint32_t cnt = 0;
   const float *gf = (const float *)vb200_blob_find(s->blob, s->blob_bytes, "psyg.f32", nullptr, &cnt);
-  if (!gf || cnt < 4 + 2 * VE_BANDS) { vb200_set_error("vb200_segment_stream: setup blob lacks the envelope parameters"); return VB200_EINVAL; }
-  const float stretch_penalty = gf[1], minenergy = gf[2], pre_amp = gf[3];
-  const float *pre_th = gf + 4, *post_th = gf + 4 + VE_BANDS;
-  const int ch = s->h.channels, bs0 = s->h.bs[0], bs1 = s->h.bs[1];
-  const long lead = bs1 / 2, tail = 3L * bs1;
-  if (chunk <= 0) chunk = 1024;
-  vb200_segments *g = new vb200_segments();
-  g->channels = ch; g->total = lead + nsamples + tail;
-  g->pcm.assign((size_t)ch * g->total, 0.f);
-  const long T = g->total;
-  /* timeline: lead-in | pre-amplified PCM | tail */
-  for (int c = 0; c < ch; c++) { float *d = &g->pcm[(size_t)c * T + lead]; const float *q = pcm + (size_t)c * stride; for (long i = 0; i < nsamples; i++) d[i] = q[i] * pre_amp; }
-  /* head: reverse LPC extrapolation over the lead-in, from the signal that had arrived when the
-     reference first had more than one long block (block.c:438-471,545-548) */
-  {
+  if (!gf || cnt < 4 + 2 * VE_BANDS) return false;
+  e->stretch_penalty = gf[1]; e->minenergy = gf[2]; e->pre_amp = gf[3];
+  for (int i = 0; i < VE_BANDS; i++) { e->pre_th[i] = gf[4 + i]; e->post_th[i] = gf[4 + VE_BANDS + i]; }
+  return true;
+}
+
+/* One stream on its timeline: LPC head/tail, detector state, window sequencing. */
+struct StreamSeg {
+  const vb200_setup *s; EnvParams env;
+  int ch, bs0, bs1, stream_index;
+  long lead, nsamples, T, eof_abs;
+  float *pcm;                       /* [ch][T], owned by the caller */
+  std::vector<unsigned char> mark;
+  std::vector<NearDC> near; std::vector<BandFilter> filt;
+  int stretch = 0;
+  long next_step = 0, ve_current = 0;
+  int lW = 0, W = 0;
+  long centerW, cursor, curmark = 0;
+  int64_t granulepos = 0;
+  bool finished = false;
+  std::vector<vb200_block> blocks;
+  long pcm_base = 0;               /* offset of this stream's timeline inside the batch buffer */
+
+  void init(const vb200_setup *s_, const EnvParams &e, long nsamples_, float *timeline, int index) {
+    s = s_; env = e; ch = s->h.channels; bs0 = s->h.bs[0]; bs1 = s->h.bs[1]; stream_index = index;
+    lead = bs1 / 2; nsamples = nsamples_; T = lead + nsamples + 3L * bs1; eof_abs = lead + nsamples; pcm = timeline;
+    mark.assign((size_t)(T / VE_STEP) + VE_WIN + VE_POST + 4, 0);
+    near.assign(ch, NearDC()); filt.assign((size_t)ch * VE_BANDS, BandFilter());
+    memset(near.data(), 0, sizeof(NearDC) * near.size()); memset(filt.data(), 0, sizeof(BandFilter) * filt.size());
+    centerW = lead; cursor = bs1 / 2;
+  }
+  static long timeline_len(const vb200_setup *s, long nsamples) { return s->h.bs[1] / 2 + nsamples + 3L * s->h.bs[1]; }
+
+  /* timeline: lead-in | pre-amplified PCM | tail; head = reverse LPC extrapolation from the signal that
+     had arrived when the reference first had more than one long block (block.c:438-471,545-548) */
+  void fill_and_head(const float *src, long stride, int chunk) {
+    for (int c = 0; c < ch; c++) {
+      float *d = pcm + (size_t)c * T; const float *q = src + (size_t)c * stride;
+      for (long i = 0; i < lead; i++) d[i] = 0.f;
+      for (long i = 0; i < nsamples; i++) d[lead + i] = q[i] * env.pre_amp;
+      for (long i = eof_abs; i < T; i++) d[i] = 0.f;
+    }
     long seen = 0;
     while (seen < nsamples && !(seen > bs1)) seen += (nsamples - seen < chunk ? nsamples - seen : chunk);
-    const long cur = lead + seen;                 /* pcm_current at that moment; centerW == lead */
+    const long cur = lead + seen;
     if (cur - lead > 32) {
       std::vector<float> work(cur); float lpc[16];
       for (int c = 0; c < ch; c++) {
-        float *d = &g->pcm[(size_t)c * T];
+        float *d = pcm + (size_t)c * T;
         for (long j = 0; j < cur; j++) work[j] = d[cur - j - 1];
         lpc_from_data(work.data(), lpc, (int)(cur - lead), 16);
         lpc_predict(lpc, work.data() + cur - lead - 16, 16, work.data() + cur - lead, lead);
@@ -187,43 +229,86 @@ extern "C" int vb200_segment_stream(const vb200_setup *s, const float *pcm, long
       }
     }
   }
-  const long eof_abs = lead + nsamples;           /* first sample past the real signal */
-  const Detector &D = detector();
-  std::vector<unsigned char> mark((size_t)(T / VE_STEP) + VE_WIN + VE_POST + 4, 0);
-  std::vector<FilterState> filt((size_t)VE_BANDS * ch);
-  memset(filt.data(), 0, sizeof(FilterState) * filt.size());
-  int stretch = 0;
-  long next_step = 0, ve_current = 0;
-  /* block sequencing state (block.c:557-812) on the absolute timeline */
-  int lW = 0, W = 0;
-  long centerW = lead, cursor = bs1 / 2, curmark = 0;
-  int64_t granulepos = 0;
-  const int bsz[2] = {bs0, bs1};
-  bool finished = false;
+  /* tail: forward LPC extrapolation of 3 long blocks (block.c:497-537) from the signal still held in the
+     reference's sliding buffer, i.e. back to centerW - blocksize[1]/2 */
+  void tail() {
+    float lpc[32];
+    const long held = eof_abs - (centerW - lead);
+    for (int c = 0; c < ch; c++) {
+      float *d = pcm + (size_t)c * T;
+      if (held > 64) {
+        long n = held; if (n > bs1) n = bs1;
+        lpc_from_data(d + eof_abs - n, lpc, (int)n, 32);
+        lpc_predict(lpc, d + eof_abs - 32, 32, d + eof_abs, T - eof_abs);
+      }
+    }
+  }
+  long steps_complete(long avail) const { const long l = avail / VE_STEP - VE_WIN; return l > 0 ? l : 0; }
 
-  /* everything the reference can do once `avail` samples of the timeline exist */
-  auto advance = [&](long avail, bool eof) {
-    /* detector over every 64-sample step that is complete (envelope.c:569-616) */
-    const long last = avail / VE_STEP - VE_WIN;
+  void apply_ret(long j, int ret) {
+    mark[j + VE_POST] = 0;
+    if (ret & 1) { mark[j] = 1; mark[j + 1] = 1; }
+    if (ret & 2) { mark[j] = 1; if (j > 0) mark[j - 1] = 1; }
+    if (ret & 4) stretch = -1;
+  }
+  /* detector over every complete 64-sample step (envelope.c:569-616), host evaluation */
+  void detect_host(long avail) {
+    const Detector &D = detector();
+    const long last = steps_complete(avail);
     for (long j = next_step; j < last; j++) {
       int ret = 0;
       stretch++;
       if (stretch > VE_MAXSTRETCH * 2) stretch = VE_MAXSTRETCH * 2;
-      for (int c = 0; c < ch; c++)
-        ret |= ve_amp(D, &g->pcm[(size_t)c * T + VE_STEP * j], &filt[(size_t)c * VE_BANDS], &filt[(size_t)c * VE_BANDS], stretch,
-                      minenergy, stretch_penalty, pre_th, post_th);
-      mark[j + VE_POST] = 0;
-      if (ret & 1) { mark[j] = 1; mark[j + 1] = 1; }
-      if (ret & 2) { mark[j] = 1; if (j > 0) mark[j - 1] = 1; }
-      if (ret & 4) stretch = -1;
+      int st; float pen;
+      ve_stretch_params(stretch, env.stretch_penalty, &st, &pen);
+      for (int c = 0; c < ch; c++) {
+        float vec[VE_N / 2], acc[VE_BANDS];
+        ve_mdct(D, pcm + (size_t)c * T + VE_STEP * j, vec, VE_N / 2);
+        const float decay = ve_neardc(&near[c], ve_neartemp(vec[0], vec[1], vec[2]));
+        ve_bands(D, vec, decay, env.minenergy, acc);
+        for (int b = 0; b < VE_BANDS; b++) ret |= ve_trigger(&filt[(size_t)c * VE_BANDS + b], acc[b], st, pen, env.pre_th[b], env.post_th[b]);
+      }
+      apply_ret(j, ret);
     }
     if (last > next_step) next_step = last;
     if (last > 0) ve_current = last * VE_STEP;
+  }
+  /* the detector ran elsewhere (device) for steps [0,last): adopt its marks and its final state */
+  void adopt(long last, const unsigned char *marks, int stretch_final, const float *acc_tail /*[ch][17][12]*/,
+             const float *temp_tail /*[ch][45]*/) {
+    for (long j = 0; j < last + VE_POST && j < (long)mark.size(); j++) mark[j] = marks[j];
+    stretch = stretch_final;
+    for (int c = 0; c < ch; c++) {
+      for (int b = 0; b < VE_BANDS; b++) {
+        BandFilter &f = filt[(size_t)c * VE_BANDS + b];
+        for (int k = 0; k < VE_AMP; k++) f.ampbuf[k] = 0.f;
+        for (long sidx = last - VE_AMP; sidx < last; sidx++) if (sidx >= 0) f.ampbuf[sidx % VE_AMP] = acc_tail[((size_t)c * VE_AMP + (sidx - (last - VE_AMP))) * VE_BANDS + b];
+        f.ampptr = (int)(last % VE_AMP);
+      }
+      /* near-DC state: start from the last refresh step r0 that has a full cycle behind it (the state at
+         a refresh depends only on the 15 terms before it), then replay up to `last` */
+      NearDC &n = near[c];
+      memset(&n, 0, sizeof(n));
+      auto T_ = [&](long step) { return step >= 0 ? temp_tail[(size_t)c * 45 + (step - (last - 45))] : 0.f; };
+      const long r0 = last >= VE_NEARDC ? ((last - VE_NEARDC) / VE_NEARDC) * VE_NEARDC : 0;
+      if (r0 >= VE_NEARDC) {
+        for (int k = 0; k < VE_NEARDC; k++) n.ring[k] = T_(r0 - VE_NEARDC + k);
+        n.partial = T_(r0 - VE_NEARDC);
+        for (long u = r0 - VE_NEARDC + 1; u < r0; u++) n.partial += T_(u);
+      }
+      n.ptr = 0;
+      for (long sidx = r0; sidx < last; sidx++) (void)ve_neardc(&n, T_(sidx));
+    }
+    next_step = last;
+    if (last > 0) ve_current = last * VE_STEP;
+  }
+
+  /* window sequencing (block.c:557-812, envelope.c:617-706) on the absolute timeline */
+  void sequence(long avail, bool eof) {
+    const int bsz[2] = {bs0, bs1};
     while (!finished) {
       int nW;
       {
-        /* _ve_envelope_search (envelope.c:617-681): first marked step between the cursor and the
-           long-block horizon */
         long bp = -1;
         const long testW = centerW + bsz[W] / 4 + bs1 / 2 + bs0 / 4;
         long j = cursor;
@@ -237,48 +322,55 @@ extern "C" int vb200_segment_stream(const vb200_setup *s, const float *pcm, long
         else nW = (bs0 == bs1) ? 0 : (int)bp;
       }
       const long centerNext = centerW + bsz[W] / 4 + bsz[nW] / 4;
-      if (avail < centerNext + bsz[nW] / 2) return;      /* not enough data yet */
+      if (avail < centerNext + bsz[nW] / 2) return;
       vb200_block blk;
       memset(&blk, 0, sizeof(blk));
       blk.stream = stream_index; blk.W = W; blk.lW = lW; blk.nW = nW;
       if (W) blk.blocktype = (!lW || !nW) ? 0 : 1;
       else {
-        /* _ve_envelope_mark (envelope.c:683-706) */
         const long beginW = centerW - bs0 / 4 - bs0 / 4, endW = centerW + bs0 / 4 + bs0 / 4;
         int hit = (curmark >= beginW && curmark < endW);
         if (!hit) for (long i = beginW / VE_STEP; i < endW / VE_STEP; i++) if (i >= 0 && mark[i]) { hit = 1; break; }
         blk.blocktype = hit ? 0 : 1;
       }
       blk.granulepos = granulepos;
-      blk.pcm_offset = centerW - bsz[W] / 2;
+      blk.pcm_offset = pcm_base + centerW - bsz[W] / 2;
       blk.pcm_stride = T;
-      if (eof && centerW >= eof_abs) { blk.eofflag = 1; g->blocks.push_back(blk); finished = true; return; }
-      g->blocks.push_back(blk);
+      if (eof && centerW >= eof_abs) { blk.eofflag = 1; blocks.push_back(blk); finished = true; return; }
+      blocks.push_back(blk);
       const long movement = centerNext - centerW;
-      /* granule position: the padding past the end of the stream is not counted (block.c:793-803) */
       if (eof && centerNext >= eof_abs) granulepos += movement - (centerNext - eof_abs);
       else granulepos += movement;
       lW = W; W = nW; centerW = centerNext;
     }
-  };
-
-  /* phase 1: all real signal has arrived, end of stream not yet signalled */
-  advance(eof_abs, false);
-  /* phase 2: end of stream.  Forward LPC extrapolation of 3 long blocks (block.c:497-537) from the
-     signal still held in the reference's sliding buffer, i.e. back to centerW - blocksize[1]/2 */
-  {
-    float lpc[32];
-    const long held = eof_abs - (centerW - lead);        /* v->eofflag at vorbis_analysis_wrote(0) */
-    for (int c = 0; c < ch; c++) {
-      float *d = &g->pcm[(size_t)c * T];
-      if (held > 64) {
-        long n = held; if (n > bs1) n = bs1;
-        lpc_from_data(d + eof_abs - n, lpc, (int)n, 32);
-        lpc_predict(lpc, d + eof_abs - 32, 32, d + eof_abs, T - eof_abs);
-      }
-    }
   }
-  advance(T, true);
+};
+
+}  // namespace
+
+/* ================================================================ host-only driver */
+struct vb200_segments {
+  int channels; long total;
+  std::vector<float> pcm;
+  std::vector<vb200_block> blocks;
+};
+
+extern "C" int vb200_segment_stream(const vb200_setup *s, const float *pcm, long nsamples, long stride, int chunk,
+                                    int stream_index, vb200_segments **out) {
+  if (!s || !pcm || !out || nsamples < 0) { vb200_set_error("vb200_segment_stream: bad arguments"); return VB200_EINVAL; }
+  EnvParams env;
+  if (!env_params(s, &env)) { vb200_set_error("vb200_segment_stream: setup blob lacks the envelope parameters"); return VB200_EINVAL; }
+  if (chunk <= 0) chunk = 1024;
+  vb200_segments *g = new vb200_segments();
+  g->channels = s->h.channels; g->total = StreamSeg::timeline_len(s, nsamples);
+  g->pcm.assign((size_t)g->channels * g->total, 0.f);
+  StreamSeg q;
+  q.init(s, env, nsamples, g->pcm.data(), stream_index);
+  q.fill_and_head(pcm, stride, chunk);
+  q.detect_host(q.eof_abs); q.sequence(q.eof_abs, false);      /* all real signal arrived, no EOS yet */
+  q.tail();
+  q.detect_host(q.T); q.sequence(q.T, true);                    /* end of stream */
+  g->blocks.swap(q.blocks);
   *out = g;
   return VB200_OK;
 }
@@ -287,3 +379,317 @@ extern "C" void vb200_segments_free(vb200_segments *g) { delete g; }
 extern "C" int vb200_segments_count(const vb200_segments *g) { return g ? (int)g->blocks.size() : VB200_EINVAL; }
 extern "C" const vb200_block *vb200_segments_blocks(const vb200_segments *g) { return g ? g->blocks.data() : nullptr; }
 extern "C" const float *vb200_segments_pcm(const vb200_segments *g, long *elems) { if (!g) return nullptr; if (elems) *elems = (long)g->pcm.size(); return g->pcm.data(); }
+
+/* ================================================================ device half of the detector */
+namespace {
+
+struct EnvDev {            /* tables in HBM */
+  const double *cs;        /* [64][128] */
+  const float *win;        /* [128] */
+  float bandwin[VE_BANDS][8], bandtotal[VE_BANDS];
+  int bbegin[VE_BANDS], bend[VE_BANDS];
+  float minenergy, stretch_penalty, pre_th[VE_BANDS], post_th[VE_BANDS];
+};
+
+struct EnvStream { long long pcm_base; long long T; int nsteps; long long out_base; /* step-major output offset */ };
+
+constexpr int EV_TILE = 32;      /* steps per CTA */
+constexpr int EV_HALO = 30;      /* the near-DC sum of a step depends on at most the 30 previous steps */
+
+/* K0a: per (stream, channel, tile of steps): windowed 128-point MDCT -> near-DC decay -> spread/limit ->
+   12 band amplitudes.  Everything here is a pure function of the PCM, so tiles are independent. */
+__global__ void __launch_bounds__(64)
+k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams, int ch, const float *__restrict__ pcm,
+            float *__restrict__ acc_out /*[stream][ch][step][12]*/, float *__restrict__ temp_out /*[stream][ch][step]*/) {
+  __shared__ float x[(EV_TILE + EV_HALO) * VE_STEP + VE_STEP];
+  __shared__ float temps[EV_TILE + EV_HALO];
+  __shared__ float c3[(EV_TILE + EV_HALO) * 3];
+  __shared__ float decay[EV_TILE];
+  __shared__ float vec[VE_N / 2];
+  __shared__ float v2[VE_N / 4];
+  const EnvStream S = streams[blockIdx.z];
+  const int c = blockIdx.y, tid = threadIdx.x;
+  const int j0 = blockIdx.x * EV_TILE;
+  if (j0 >= S.nsteps) return;
+  const int jn = min(EV_TILE, S.nsteps - j0);
+  const int h0 = max(0, j0 - EV_HALO);                      /* first step whose samples we stage */
+  const float *src = pcm + S.pcm_base + (long long)c * S.T + (long long)h0 * VE_STEP;
+  const int nsamp = (j0 + jn - h0) * VE_STEP + VE_STEP;
+  for (int i = tid; i < nsamp; i += 64) x[i] = src[i];
+  __syncthreads();
+  /* near-DC terms of the halo + tile steps: only coefficients 0..2 are needed */
+  const int nh = j0 + jn - h0;
+  for (int w = tid; w < nh * 3; w += 64) {
+    const int sidx = w / 3, k = w % 3;
+    const float *d = x + sidx * VE_STEP;
+    const double *row = E->cs + k * VE_N;
+    double a = 0;
+    for (int t = 0; t < VE_N; t++) a += row[t] * (double)__fmul_rn(d[t], E->win[t]);
+    c3[w] = (float)a;
+  }
+  __syncthreads();
+  for (int sidx = tid; sidx < nh; sidx += 64) temps[sidx] = ve_neartemp(c3[sidx * 3], c3[sidx * 3 + 1], c3[sidx * 3 + 2]);
+  __syncthreads();
+  /* decay of every tile step: replay the refresh cycle it sits in (<= 44 float ops) */
+  for (int q = tid; q < jn; q += 64) {
+    const int j = j0 + q, ptr = j % VE_NEARDC, r = j - ptr;      /* r = last refresh step */
+    auto T_ = [&](int step) { return step >= 0 ? temps[step - h0] : 0.f; };
+    float partial = 0.f;
+    if (r >= VE_NEARDC) { partial = T_(r - VE_NEARDC); for (int u = r - VE_NEARDC + 1; u < r; u++) partial = __fadd_rn(partial, T_(u)); }
+    float acc = __fadd_rn(partial, T_(r));
+    float dec = acc;
+    acc = __fsub_rn(acc, r >= VE_NEARDC ? T_(r - VE_NEARDC) : 0.f);
+    for (int u = r + 1; u <= j; u++) {
+      acc = __fadd_rn(acc, T_(u)); dec = acc;
+      acc = __fsub_rn(acc, u >= VE_NEARDC ? T_(u - VE_NEARDC) : 0.f);
+    }
+    dec = (float)((double)dec * (1. / (VE_NEARDC + 1)));
+    decay[q] = (float)((double)todB_hd(dec) * .5 - (double)15.f);
+    temp_out[S.out_base * ch + (long long)c * S.nsteps + j] = T_(j);
+  }
+  __syncthreads();
+  for (int q = 0; q < jn; q++) {
+    const float *d = x + (j0 + q - h0) * VE_STEP;
+    {
+      double a = 0;
+      const double *row = E->cs + tid * VE_N;
+      for (int t = 0; t < VE_N; t++) a += row[t] * (double)__fmul_rn(d[t], E->win[t]);
+      vec[tid] = (float)a;
+    }
+    __syncthreads();
+    if (tid < VE_N / 4) {
+      const int i = tid * 2;
+      float val = __fadd_rn(__fmul_rn(vec[i], vec[i]), __fmul_rn(vec[i + 1], vec[i + 1]));
+      val = __fmul_rn(todB_hd(val), .5f);
+      float dec = decay[q];
+      for (int u = 0; u < tid; u++) dec = (float)((double)dec - 8.);
+      if (val < dec) val = dec;
+      if (val < E->minenergy) val = E->minenergy;
+      v2[tid] = val;
+    }
+    __syncthreads();
+    if (tid < VE_BANDS) {
+      float acc = 0.f;
+      for (int i = 0; i < E->bend[tid]; i++) acc = __fadd_rn(acc, __fmul_rn(v2[i + E->bbegin[tid]], E->bandwin[tid][i]));
+      acc_out[((S.out_base * ch + (long long)c * S.nsteps + (j0 + q)) * VE_BANDS) + tid] = __fmul_rn(acc, E->bandtotal[tid]);
+    }
+    __syncthreads();
+  }
+}
+
+/* K0b: the order-dependent half: trigger filters and the stretch counter, one warp per stream, lane =
+   (channel, band).  Writes the marks of steps [0,nsteps) (+2) and the final stretch. */
+__global__ void __launch_bounds__(32)
+k_env_trigger(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams, int ch, const float *__restrict__ acc_in,
+              unsigned char *__restrict__ marks, const long long *__restrict__ mark_base, int *__restrict__ stretch_out) {
+  __shared__ BandFilter f[VB200_MAX_CHANNELS * VE_BANDS];
+  const EnvStream S = streams[blockIdx.x];
+  const int lane = threadIdx.x, nf = ch * VE_BANDS;
+  for (int i = lane; i < nf; i += 32) { for (int k = 0; k < VE_AMP; k++) f[i].ampbuf[k] = 0.f; f[i].ampptr = 0; }
+  __syncwarp();
+  unsigned char *mk = marks + mark_base[blockIdx.x];
+  int stretch = 0;
+  for (int j = 0; j < S.nsteps; j++) {
+    stretch++;
+    if (stretch > VE_MAXSTRETCH * 2) stretch = VE_MAXSTRETCH * 2;
+    int st; float pen;
+    ve_stretch_params(stretch, E->stretch_penalty, &st, &pen);
+    int ret = 0;
+    for (int i = lane; i < nf; i += 32) {
+      const int c = i / VE_BANDS, b = i % VE_BANDS;
+      const float acc = acc_in[((S.out_base * ch + (long long)c * S.nsteps + j) * VE_BANDS) + b];
+      ret |= ve_trigger(&f[i], acc, st, pen, E->pre_th[b], E->post_th[b]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ret |= __shfl_xor_sync(FULLMASK, ret, o);
+    if (lane == 0) {
+      mk[j + VE_POST] = 0;
+      if (ret & 1) { mk[j] = 1; mk[j + 1] = 1; }
+      if (ret & 2) { mk[j] = 1; if (j > 0) mk[j - 1] = 1; }
+    }
+    if (ret & 4) stretch = -1;
+  }
+  if (lane == 0) stretch_out[blockIdx.x] = stretch;
+}
+
+/* the last 17 band amplitudes and 45 near-DC terms of every (stream, channel): what the host needs to
+   continue the detector over the extrapolated tail */
+__global__ void k_env_tail(const EnvStream *__restrict__ streams, int ch, const float *__restrict__ acc_in, const float *__restrict__ temp_in,
+                           float *__restrict__ acc_tail, float *__restrict__ temp_tail) {
+  const EnvStream S = streams[blockIdx.x];
+  const int c = blockIdx.y;
+  const long long o = S.out_base * ch + (long long)c * S.nsteps;
+  for (int i = threadIdx.x; i < VE_AMP * VE_BANDS; i += blockDim.x) {
+    const int k = i / VE_BANDS, b = i % VE_BANDS;
+    const int step = S.nsteps - VE_AMP + k;
+    acc_tail[((size_t)blockIdx.x * ch + c) * VE_AMP * VE_BANDS + i] = step >= 0 ? acc_in[(o + step) * VE_BANDS + b] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 45; i += blockDim.x) {
+    const int step = S.nsteps - 45 + i;
+    temp_tail[((size_t)blockIdx.x * ch + c) * 45 + i] = step >= 0 ? temp_in[o + step] : 0.f;
+  }
+}
+
+}  // namespace
+
+struct vb200_segmenter {
+  vb200_setup *s; EnvParams env;
+  EnvDev *d_env; double *d_cs; float *d_win;
+  float *h_pcm, *d_pcm; size_t pcm_cap;          /* pinned host timeline + device timeline */
+  float *d_acc, *d_temp; size_t step_cap;
+  unsigned char *d_marks, *h_marks; size_t mark_cap;
+  EnvStream *d_streams, *h_streams; long long *d_mark_base, *h_mark_base; int *d_stretch, *h_stretch;
+  float *d_acc_tail, *h_acc_tail, *d_temp_tail, *h_temp_tail; int stream_cap;
+  std::vector<vb200_block> blocks; size_t pcm_elems;
+};
+
+extern "C" int vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out) {
+  if (!s || !out) { vb200_set_error("vb200_segmenter_create: bad arguments"); return VB200_EINVAL; }
+  if (s->device < 0 || !s->d) { vb200_set_error("vb200_segmenter_create: setup has no CUDA device (no CPU fallback; use vb200_segment_stream on the host)"); return VB200_EFAULT; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  vb200_segmenter *g = new vb200_segmenter();
+  memset((void *)g, 0, sizeof(vb200_segmenter) - sizeof(std::vector<vb200_block>) - sizeof(size_t));
+  g->s = s;
+  if (!env_params(s, &g->env)) { delete g; vb200_set_error("vb200_segmenter_create: setup blob lacks the envelope parameters"); return VB200_EINVAL; }
+  const Detector &D = detector();
+  EnvDev e;
+  CUDA_TRY(cudaMalloc(&g->d_cs, sizeof(D.cs))); CUDA_TRY(cudaMalloc(&g->d_win, sizeof(D.win))); CUDA_TRY(cudaMalloc(&g->d_env, sizeof(EnvDev)));
+  CUDA_TRY(cudaMemcpy(g->d_cs, D.cs, sizeof(D.cs), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(g->d_win, D.win, sizeof(D.win), cudaMemcpyHostToDevice));
+  e.cs = g->d_cs; e.win = g->d_win;
+  memcpy(e.bandwin, D.bandwin, sizeof(e.bandwin)); memcpy(e.bandtotal, D.bandtotal, sizeof(e.bandtotal));
+  for (int i = 0; i < VE_BANDS; i++) { e.bbegin[i] = kBandBegin[i]; e.bend[i] = kBandEnd[i]; e.pre_th[i] = g->env.pre_th[i]; e.post_th[i] = g->env.post_th[i]; }
+  e.minenergy = g->env.minenergy; e.stretch_penalty = g->env.stretch_penalty;
+  CUDA_TRY(cudaMemcpy(g->d_env, &e, sizeof(e), cudaMemcpyHostToDevice));
+  *out = g;
+  return VB200_OK;
+}
+
+extern "C" void vb200_segmenter_destroy(vb200_segmenter *g) {
+  if (!g) return;
+  cudaSetDevice(g->s->device);
+  cudaFree(g->d_cs); cudaFree(g->d_win); cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
+  cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_marks); cudaFreeHost(g->h_marks);
+  cudaFree(g->d_streams); cudaFreeHost(g->h_streams); cudaFree(g->d_mark_base); cudaFreeHost(g->h_mark_base);
+  cudaFree(g->d_stretch); cudaFreeHost(g->h_stretch); cudaFree(g->d_acc_tail); cudaFreeHost(g->h_acc_tail);
+  cudaFree(g->d_temp_tail); cudaFreeHost(g->h_temp_tail);
+  delete g;
+}
+
+template <typename F> static void parallel_for(int n, int threads, F f) {
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = n;
+  if (threads <= 1) { for (int i = 0; i < n; i++) f(i); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++) th.emplace_back([=]() { for (int i = t; i < n; i += threads) f(i); });
+  for (auto &x : th) x.join();
+}
+
+#define SEG_ALLOC(ptr, bytes, host) do{ if (host) { CUDA_TRY(cudaMallocHost((void **)&(ptr), (bytes))); } else { CUDA_TRY(cudaMalloc((void **)&(ptr), (bytes))); } }while(0)
+
+/* Segment `nstreams` streams at once.  pcm[i]: planar [channels][nsamples[i]] with stride[i].
+   Afterwards the timeline of all streams sits in HBM (vb200_segmenter_device_pcm) and the blocks index it. */
+extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float *const *pcm, const long *nsamples,
+                                   const long *stride, int chunk, int threads) {
+  if (!g || nstreams < 1 || !pcm || !nsamples || !stride) { vb200_set_error("vb200_segmenter_run: bad arguments"); return VB200_EINVAL; }
+  vb200_setup *s = g->s;
+  CUDA_TRY(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)s->stream;
+  const int ch = s->h.channels;
+  if (chunk <= 0) chunk = 1024;
+  std::vector<StreamSeg> seg(nstreams);
+  std::vector<long long> base(nstreams + 1, 0), step_base(nstreams + 1, 0), mark_base(nstreams + 1, 0);
+  for (int i = 0; i < nstreams; i++) {
+    const long T = StreamSeg::timeline_len(s, nsamples[i]);
+    base[i + 1] = base[i] + (long long)T * ch;
+    const long steps = (s->h.bs[1] / 2 + nsamples[i]) / VE_STEP - VE_WIN;
+    step_base[i + 1] = step_base[i] + (steps > 0 ? steps : 0);
+    mark_base[i + 1] = mark_base[i] + ((T / VE_STEP + VE_WIN + VE_POST + 4 + 15) & ~15LL);
+  }
+  const size_t total = (size_t)base[nstreams];
+  if (g->pcm_cap < total) {
+    cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm); g->d_pcm = nullptr; g->h_pcm = nullptr; g->pcm_cap = 0;
+    SEG_ALLOC(g->h_pcm, total * sizeof(float), true); SEG_ALLOC(g->d_pcm, total * sizeof(float), false);
+    g->pcm_cap = total;
+  }
+  const size_t nstep_tot = (size_t)step_base[nstreams] * ch;
+  if (g->step_cap < nstep_tot) {
+    cudaFree(g->d_acc); cudaFree(g->d_temp); g->d_acc = g->d_temp = nullptr; g->step_cap = 0;
+    SEG_ALLOC(g->d_acc, (nstep_tot + 1) * VE_BANDS * sizeof(float), false); SEG_ALLOC(g->d_temp, (nstep_tot + 1) * sizeof(float), false);
+    g->step_cap = nstep_tot;
+  }
+  const size_t nmark = (size_t)mark_base[nstreams];
+  if (g->mark_cap < nmark) {
+    cudaFree(g->d_marks); cudaFreeHost(g->h_marks); g->mark_cap = 0;
+    SEG_ALLOC(g->d_marks, nmark, false); SEG_ALLOC(g->h_marks, nmark, true);
+    g->mark_cap = nmark;
+  }
+  if (g->stream_cap < nstreams) {
+    cudaFree(g->d_streams); cudaFreeHost(g->h_streams); cudaFree(g->d_mark_base); cudaFreeHost(g->h_mark_base);
+    cudaFree(g->d_stretch); cudaFreeHost(g->h_stretch); cudaFree(g->d_acc_tail); cudaFreeHost(g->h_acc_tail); cudaFree(g->d_temp_tail); cudaFreeHost(g->h_temp_tail);
+    g->stream_cap = 0;
+    SEG_ALLOC(g->d_streams, sizeof(EnvStream) * nstreams, false); SEG_ALLOC(g->h_streams, sizeof(EnvStream) * nstreams, true);
+    SEG_ALLOC(g->d_mark_base, sizeof(long long) * nstreams, false); SEG_ALLOC(g->h_mark_base, sizeof(long long) * nstreams, true);
+    SEG_ALLOC(g->d_stretch, sizeof(int) * nstreams, false); SEG_ALLOC(g->h_stretch, sizeof(int) * nstreams, true);
+    SEG_ALLOC(g->d_acc_tail, sizeof(float) * nstreams * ch * VE_AMP * VE_BANDS, false); SEG_ALLOC(g->h_acc_tail, sizeof(float) * nstreams * ch * VE_AMP * VE_BANDS, true);
+    SEG_ALLOC(g->d_temp_tail, sizeof(float) * nstreams * ch * 45, false); SEG_ALLOC(g->h_temp_tail, sizeof(float) * nstreams * ch * 45, true);
+    g->stream_cap = nstreams;
+  }
+  /* host: timelines (pre-amplified PCM + LPC head) straight into the pinned buffer */
+  parallel_for(nstreams, threads, [&](int i) {
+    seg[i].init(s, g->env, nsamples[i], g->h_pcm + base[i], i);
+    seg[i].pcm_base = (long)base[i];
+    seg[i].fill_and_head(pcm[i], stride[i], chunk);
+  });
+  int max_steps = 0;
+  for (int i = 0; i < nstreams; i++) {
+    EnvStream &e = g->h_streams[i];
+    e.pcm_base = base[i]; e.T = seg[i].T; e.nsteps = (int)seg[i].steps_complete(seg[i].eof_abs); e.out_base = step_base[i];
+    g->h_mark_base[i] = mark_base[i];
+    if (e.nsteps > max_steps) max_steps = e.nsteps;
+  }
+  /* one H2D of the whole timeline; the detector's heavy half on the device */
+  CUDA_TRY(cudaMemcpyAsync(g->d_pcm, g->h_pcm, total * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(g->d_streams, g->h_streams, sizeof(EnvStream) * nstreams, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(g->d_mark_base, g->h_mark_base, sizeof(long long) * nstreams, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(g->d_marks, 0, nmark, st));
+  if (max_steps > 0) {
+    dim3 grid((max_steps + EV_TILE - 1) / EV_TILE, ch, nstreams);
+    k_env_bands<<<grid, 64, 0, st>>>(g->d_env, g->d_streams, ch, g->d_pcm, g->d_acc, g->d_temp);
+    LAUNCH_CHECK();
+    k_env_trigger<<<nstreams, 32, 0, st>>>(g->d_env, g->d_streams, ch, g->d_acc, g->d_marks, g->d_mark_base, g->d_stretch);
+    LAUNCH_CHECK();
+    k_env_tail<<<dim3(nstreams, ch), 64, 0, st>>>(g->d_streams, ch, g->d_acc, g->d_temp, g->d_acc_tail, g->d_temp_tail);
+    LAUNCH_CHECK();
+  }
+  CUDA_TRY(cudaMemcpyAsync(g->h_marks, g->d_marks, nmark, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(g->h_stretch, g->d_stretch, sizeof(int) * nstreams, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(g->h_acc_tail, g->d_acc_tail, sizeof(float) * nstreams * ch * VE_AMP * VE_BANDS, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(g->h_temp_tail, g->d_temp_tail, sizeof(float) * nstreams * ch * 45, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  /* host: sequencing up to the end of the signal, LPC tail, detector over the tail, final sequencing */
+  parallel_for(nstreams, threads, [&](int i) {
+    StreamSeg &q = seg[i];
+    const long last = g->h_streams[i].nsteps;
+    if (last > 0) q.adopt(last, g->h_marks + mark_base[i], g->h_stretch[i], g->h_acc_tail + (size_t)i * ch * VE_AMP * VE_BANDS, g->h_temp_tail + (size_t)i * ch * 45);
+    q.sequence(q.eof_abs, false);
+    q.tail();
+    q.detect_host(q.T); q.sequence(q.T, true);
+  });
+  /* the extrapolated tails go up as well (small), then the blocks */
+  for (int i = 0; i < nstreams; i++)
+    for (int c = 0; c < ch; c++) {
+      const size_t o = (size_t)base[i] + (size_t)c * seg[i].T + seg[i].eof_abs;
+      CUDA_TRY(cudaMemcpyAsync(g->d_pcm + o, g->h_pcm + o, sizeof(float) * (seg[i].T - seg[i].eof_abs), cudaMemcpyHostToDevice, st));
+    }
+  g->blocks.clear();
+  for (int i = 0; i < nstreams; i++) g->blocks.insert(g->blocks.end(), seg[i].blocks.begin(), seg[i].blocks.end());
+  g->pcm_elems = total;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return VB200_OK;
+}
+
+extern "C" int vb200_segmenter_count(const vb200_segmenter *g) { return g ? (int)g->blocks.size() : VB200_EINVAL; }
+extern "C" const vb200_block *vb200_segmenter_blocks(const vb200_segmenter *g) { return g ? g->blocks.data() : nullptr; }
+extern "C" const float *vb200_segmenter_device_pcm(const vb200_segmenter *g, size_t *elems) { if (!g) return nullptr; if (elems) *elems = g->pcm_elems; return g->d_pcm; }
+extern "C" const float *vb200_segmenter_host_pcm(const vb200_segmenter *g) { return g ? g->h_pcm : nullptr; }

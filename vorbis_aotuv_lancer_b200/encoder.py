@@ -17,14 +17,54 @@ BLOCK_DTYPE = np.dtype([("stream", "<i4"), ("W", "<i4"), ("lW", "<i4"), ("nW", "
 assert BLOCK_DTYPE.itemsize == C.sizeof(ops.Block)
 
 
+L.vb200_segmenter_blocks.restype = C.POINTER(ops.Block)
+L.vb200_segmenter_device_pcm.restype = C.c_void_p
+L.vb200_segmenter_host_pcm.restype = C.POINTER(C.c_float)
+
+
+class Segmenter:
+    """vb200_segmenter: segmentation of many streams with the detector's heavy half on the GPU; leaves the
+    PCM timeline of all streams in HBM for Batch.run(pcm_on_device=True)."""
+
+    def __init__(self, setup):
+        self.setup = setup
+        h = C.c_void_p()
+        check(L.vb200_segmenter_create(setup.h, C.byref(h)), "vb200_segmenter_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            L.vb200_segmenter_destroy(self.h)
+            self.h = None
+
+    def run(self, pcms, chunk=1024, threads=8):
+        """pcms: list of float32 [channels, nsamples].  -> (Block array view, device address, elems)"""
+        pcms = [np.ascontiguousarray(p, np.float32) for p in pcms]
+        n = len(pcms)
+        ptrs = (C.c_void_p * n)(*[p.ctypes.data for p in pcms])
+        ns = (C.c_long * n)(*[p.shape[1] for p in pcms])
+        check(L.vb200_segmenter_run(self.h, n, ptrs, ns, ns, int(chunk), int(threads)), "vb200_segmenter_run")
+        nb = L.vb200_segmenter_count(self.h)
+        blocks = C.cast(L.vb200_segmenter_blocks(self.h), C.POINTER(ops.Block * nb)).contents
+        elems = C.c_size_t()
+        dptr = L.vb200_segmenter_device_pcm(self.h, C.byref(elems))
+        return blocks, dptr, elems.value
+
+    def host_timeline(self, elems):
+        return np.ctypeslib.as_array(L.vb200_segmenter_host_pcm(self.h), shape=(elems,))
+
+
 class Encoder:
     def __init__(self, setup, max_blocks, threads=8):
         self.setup = setup
         self.batch = ops.Batch(setup, max_blocks)
+        self.threads = threads
         self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.segmenter = Segmenter(setup)
 
     def close(self):
         self.batch.close()
+        self.segmenter.close()
         self.pool.shutdown()
 
     def segment(self, pcms):
@@ -46,12 +86,13 @@ class Encoder:
         return blocks, timeline, counts
 
     def encode(self, pcms, streams=None):
-        """-> (total packet bytes, packets per stream as produced by Batch.table())"""
-        blocks, timeline, counts = self.segment(pcms)
+        """Host PCM of many streams -> packet table.  Segmentation (detector on the GPU, LPC + window
+        sequencing on the host) uploads the PCM once; the analysis batch then reads it in place."""
+        blocks, dptr, elems = self.segmenter.run(pcms, threads=self.threads)
         own = streams is None
         if own:
             streams = [ops.Stream(self.setup) for _ in pcms]
-        self.batch.run(streams, blocks, timeline)
+        self.batch.run(streams, blocks, dptr, pcm_on_device=True, pcm_elems=elems)
         tab = table(self.batch)
         if own:
             for st in streams:
