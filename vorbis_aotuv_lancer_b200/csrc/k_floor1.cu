@@ -45,26 +45,28 @@ struct FitSmem {
   unsigned short q[N];
   unsigned char loud[N];
   Seg seg[VB200_MAX_POSTS];
+  double T[VB200_MAX_POSTS][6];
   int A[VB200_MAX_POSTS], B[VB200_MAX_POSTS], lo[VB200_MAX_POSTS], hi[VB200_MAX_POSTS], memo[VB200_MAX_POSTS];
-  int y[4];
 };
 
-/* fit_line, floor1.c:477-535 (lane 0) */
-__device__ int fit_line(const Seg *a, int cnt, int *y0, int *y1, float weight) {
-  double xb = 0, yb = 0, x2b = 0, y2b = 0, xyb = 0, bn = 0;
-  const int x0 = a[0].x0, x1 = a[cnt - 1].x1;
-  for (int i = 0; i < cnt; i++) {
-    const int an = a[i].s[0][5], bnn = a[i].s[1][5];
-    const double w = (double)__fdiv_rn(__fmul_rn((float)(bnn + an), weight), (float)(an + 1)) + 1.;
-    xb += (double)a[i].s[1][0] + (double)a[i].s[0][0] * w;
-    yb += (double)a[i].s[1][1] + (double)a[i].s[0][1] * w;
-    x2b += (double)a[i].s[1][2] + (double)a[i].s[0][2] * w;
-    y2b += (double)a[i].s[1][3] + (double)a[i].s[0][3] * w;
-    xyb += (double)a[i].s[1][4] + (double)a[i].s[0][4] * w;
-    bn += (double)bnn + (double)an * w;
-  }
+/* fit_line, floor1.c:477-535, split in three so that the warp shares it:
+   (a) per-segment weighted terms, one lane per segment, once per ch-block;
+   (b) the six running sums of a run of segments, one lane per sum, added in segment order exactly as
+       the reference accumulates them (the rounded intercepts decide the posts, so the order stays);
+   (c) pinned ends + the 2x2 solve. */
+__device__ __forceinline__ void fit_terms(const Seg &a, float weight, double *T) {
+  const int an = a.s[0][5], bnn = a.s[1][5];
+  const double w = (double)__fdiv_rn(__fmul_rn((float)(bnn + an), weight), (float)(an + 1)) + 1.;
+#pragma unroll
+  for (int k = 0; k < 5; k++) T[k] = (double)a.s[1][k] + (double)a.s[0][k] * w;
+  T[5] = (double)bnn + (double)an * w;
+}
+
+__device__ __forceinline__ int fit_solve(const double *sum, int x0, int x1, int *y0, int *y1) {
+  double xb = sum[0], yb = sum[1], x2b = sum[2], y2b = sum[3], xyb = sum[4], bn = sum[5];
   if (*y0 >= 0) { xb += x0; yb += *y0; x2b += x0 * x0; y2b += *y0 * *y0; xyb += *y0 * x0; bn++; }
   if (*y1 >= 0) { xb += x1; yb += *y1; x2b += x1 * x1; y2b += *y1 * *y1; xyb += *y1 * x1; bn++; }
+  (void)y2b;
   const double den = bn * x2b - xb * xb;
   if (den > 0.) {
     const double ic = (yb * x2b - xyb * xb) / den, sl = (bn * xyb - xb * yb) / den;
@@ -78,6 +80,19 @@ __device__ int fit_line(const Seg *a, int cnt, int *y0, int *y1, float weight) {
   }
   *y0 = 0; *y1 = 0;
   return 1;
+}
+
+/* lanes 0-5 sum run A = segments [a0,a0+na), lanes 6-11 run B = [b0,b0+nb); every lane returns with both
+   sets of six sums (broadcast), so lane 0 can solve both */
+__device__ __forceinline__ void fit_two(const double (*T)[6], int a0, int na, int b0, int nb, int lane, double *sa, double *sb) {
+  double acc = 0.;
+  const int k = lane < 6 ? lane : lane - 6;
+  if (lane < 12) {
+    const int s0 = lane < 6 ? a0 : b0, n = lane < 6 ? na : nb;
+    for (int i = 0; i < n; i++) acc += T[s0 + i][k];
+  }
+#pragma unroll
+  for (int q = 0; q < 6; q++) { sa[q] = __shfl_sync(FULLMASK, acc, q); sb[q] = __shfl_sync(FULLMASK, acc, 6 + q); }
 }
 
 __device__ __forceinline__ int pick(const int *A, const int *B, int i) {
@@ -122,16 +137,21 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     for (int c = 0; c < 2; c++)
 #pragma unroll
       for (int k = 0; k < 6; k++) g.s[c][k] = s[c][k];
+    fit_terms(g, F.twofitweight, sm.T[j]);
     mine += s[0][5];
   }
   const int any = warp_sum_i(mine);
   if (!any) { if (lane == 0) fitted[item] = 0; return; }
   for (int i = lane; i < posts; i += 32) { sm.A[i] = -200; sm.B[i] = -200; sm.lo[i] = 0; sm.hi[i] = 1; sm.memo[i] = -1; }
   __syncwarp();
-  if (lane == 0) {
-    int y0 = -200, y1 = -200;
-    fit_line(sm.seg, posts - 1, &y0, &y1, F.twofitweight);
-    sm.A[0] = sm.B[0] = y0; sm.A[1] = sm.B[1] = y1;
+  {
+    double sa[6], sb[6];
+    fit_two(sm.T, 0, posts - 1, 0, 0, lane, sa, sb);
+    if (lane == 0) {
+      int y0 = -200, y1 = -200;
+      fit_solve(sa, sm.seg[0].x0, sm.seg[posts - 2].x1, &y0, &y1);
+      sm.A[0] = sm.B[0] = y0; sm.A[1] = sm.B[1] = y1;
+    }
   }
   __syncwarp();
 
@@ -164,11 +184,13 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
       else bad = ((float)(mse / cnt) > F.maxerr) ? 1 : 0;
     }
     __syncwarp();
+    double sa[6], sb[6];
+    if (bad) fit_two(sm.T, lsp, sp - lsp, sp, hsp - sp, lane, sa, sb);      /* `bad` is warp-uniform */
     if (lane == 0) {
       if (bad) {
         int ly0 = -200, ly1 = -200, hy0 = -200, hy1 = -200;
-        const int r0 = fit_line(sm.seg + lsp, sp - lsp, &ly0, &ly1, F.twofitweight);
-        const int r1 = fit_line(sm.seg + sp, hsp - sp, &hy0, &hy1, F.twofitweight);
+        const int r0 = fit_solve(sa, sm.seg[lsp].x0, sm.seg[sp - 1].x1, &ly0, &ly1);
+        const int r1 = fit_solve(sb, sm.seg[sp].x0, sm.seg[hsp - 1].x1, &hy0, &hy1);
         if (r0) { ly0 = ly; ly1 = hy0; }
         if (r1) { hy0 = ly1; hy1 = hy; }
         if (r0 && r1) { sm.A[i] = -200; sm.B[i] = -200; }

@@ -100,14 +100,21 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
         m3.on = 1;
         if (impadnum) m3.rate = (float)((double)m3.rate * ((double)impadnum * (N == 128 ? 0.125 : 0.0625)));
         __syncthreads();
-        if (m3.keep && tid == 0) {      /* cross-bin spread: order dependent, serial (psy.c:4215-4222) */
-          for (int i = 0; i < N; i++) {
-            const int b = bfn[i];
-            const float cell = 75.f / (float)b, l = lm[i];
-            for (int j = 1; j < b; j++) {
-              const float fb = __fsub_rn(l, __fmul_rn(cell, (float)j));
-              if (temp[i + j] < fb) temp[i + j] = (float)((double)temp[i + j] + (drop / (double)(float)bfn[i + j]));
+        if (m3.keep) {
+          /* cross-bin spread (psy.c:4215-4222): bin i raises the bins i+1 .. i+bfn[i]-1.  The reference walks i
+             upwards; every target bin t is only ever touched through temp[t], so the updates of one target
+             form an independent chain in ascending i -- one thread per target, same order, no race */
+          for (int t = tid; t < N; t += T) {
+            float v = temp[t];
+            const double lift = drop / (double)(float)bfn[t];
+            for (int i = (t > 64 ? t - 64 : 0); i < t; i++) {
+              const int b = bfn[i], j = t - i;
+              if (j < b) {
+                const float fb = __fsub_rn(__ldg(lm + i), __fmul_rn(75.f / (float)b, (float)j));
+                if (v < fb) v = (float)((double)v + lift);
+              }
             }
+            temp[t] = v;
           }
         }
         if (managed && sel == 0 && m3.on) m3.rate = (float)((double)m3.rate * 0.2);

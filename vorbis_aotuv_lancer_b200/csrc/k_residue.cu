@@ -126,15 +126,24 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
         if (t < nvec) {
           int *a = v + t * dim;
           int pt[8];
+          bool on_lattice = true;          /* the input is exactly a lattice point inside the book's range */
           for (int i = 0, o = dim; i < dim; i++) {
             --o;
             const int x = (B.delta != 1) ? (a[o] - B.minval + (B.delta >> 1)) / B.delta : a[o] - B.minval;
             const int m = (x < ze) ? ((ze - x) << 1) - 1 : ((x - ze) << 1);
             index = index * qv + (m < 0 ? 0 : (m >= qv ? qv - 1 : m));
             pt[o] = x * B.delta + B.minval;
+            if (m < 0 || m >= qv || pt[o] != a[o]) on_lattice = false;
           }
-          if (__ldg(B.len + index) == 0) fb = true;
-          else { for (int i = 0; i < dim; i++) a[i] -= pt[i]; e_out[t] = (short)index; }
+          if (__ldg(B.len + index) == 0) {
+            if (B.nearest && on_lattice) {
+              /* the exhaustive search of res0.c:343-370 depends only on the lattice point: table lookup */
+              const int u = __ldg(B.nearest + index);
+              const int *ev = B.used_vals + (size_t)u * 8;
+              for (int i = 0; i < dim; i++) a[i] -= __ldg(ev + i);
+              e_out[t] = (short)__ldg(B.used_list + u);
+            } else fb = true;
+          } else { for (int i = 0; i < dim; i++) a[i] -= pt[i]; e_out[t] = (short)index; }
         }
         /* entries without a codeword: warp-wide exhaustive search over the used entries */
         unsigned fm = __ballot_sync(FULLMASK, fb);

@@ -22,6 +22,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <thread>
+#include <chrono>
+#include <stdio.h>
 #include <vector>
 #include "vb200_internal.h"
 #include "dev_util.cuh"
@@ -385,6 +387,7 @@ namespace {
 
 struct EnvDev {            /* tables in HBM */
   const double *cs;        /* [64][128] */
+  const double *cst;       /* [128][64] transposed */
   const float *win;        /* [128] */
   float bandwin[VE_BANDS][8], bandtotal[VE_BANDS];
   int bbegin[VE_BANDS], bend[VE_BANDS];
@@ -401,11 +404,11 @@ constexpr int EV_HALO = 30;      /* the near-DC sum of a step depends on at most
 __global__ void __launch_bounds__(64)
 k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams, int ch, const float *__restrict__ pcm,
             float *__restrict__ acc_out /*[stream][ch][step][12]*/, float *__restrict__ temp_out /*[stream][ch][step]*/) {
-  __shared__ float x[(EV_TILE + EV_HALO) * VE_STEP + VE_STEP];
+  __shared__ float x[(EV_TILE + EV_HALO + 4) * VE_STEP + VE_STEP];
   __shared__ float temps[EV_TILE + EV_HALO];
   __shared__ float c3[(EV_TILE + EV_HALO) * 3];
   __shared__ float decay[EV_TILE];
-  __shared__ float vec[VE_N / 2];
+  __shared__ float vec4[4][VE_N / 2];
   __shared__ float v2[VE_N / 4];
   const EnvStream S = streams[blockIdx.z];
   const int c = blockIdx.y, tid = threadIdx.x;
@@ -416,6 +419,7 @@ k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams,
   const float *src = pcm + S.pcm_base + (long long)c * S.T + (long long)h0 * VE_STEP;
   const int nsamp = (j0 + jn - h0) * VE_STEP + VE_STEP;
   for (int i = tid; i < nsamp; i += 64) x[i] = src[i];
+  for (int i = nsamp + tid; i < (EV_TILE + EV_HALO + 4) * VE_STEP + VE_STEP; i += 64) x[i] = 0.f;
   __syncthreads();
   /* near-DC terms of the halo + tile steps: only coefficients 0..2 are needed */
   const int nh = j0 + jn - h0;
@@ -448,32 +452,46 @@ k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams,
     temp_out[S.out_base * ch + (long long)c * S.nsteps + j] = T_(j);
   }
   __syncthreads();
-  for (int q = 0; q < jn; q++) {
-    const float *d = x + (j0 + q - h0) * VE_STEP;
+  /* the full 64-coefficient transform, four steps per pass so that one load of the (transposed) matrix row
+     element feeds four dot products; thread k owns coefficient k */
+  for (int q0 = 0; q0 < jn; q0 += 4) {
+    const int nq = min(4, jn - q0);
     {
-      double a = 0;
-      const double *row = E->cs + tid * VE_N;
-      for (int t = 0; t < VE_N; t++) a += row[t] * (double)__fmul_rn(d[t], E->win[t]);
-      vec[tid] = (float)a;
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      const float *d0 = x + (j0 + q0 - h0) * VE_STEP;
+      const double *col = E->cst + tid;                  /* cst[t][k]: consecutive k -> coalesced */
+      for (int t = 0; t < VE_N; t++) {
+        const double c = col[t * (VE_N / 2)];
+        const float wv = E->win[t];
+        a0 += c * (double)__fmul_rn(d0[t], wv);
+        a1 += c * (double)__fmul_rn(d0[t + VE_STEP], wv);
+        a2 += c * (double)__fmul_rn(d0[t + 2 * VE_STEP], wv);
+        a3 += c * (double)__fmul_rn(d0[t + 3 * VE_STEP], wv);
+      }
+      vec4[0][tid] = (float)a0; vec4[1][tid] = (float)a1; vec4[2][tid] = (float)a2; vec4[3][tid] = (float)a3;
     }
     __syncthreads();
-    if (tid < VE_N / 4) {
-      const int i = tid * 2;
-      float val = __fadd_rn(__fmul_rn(vec[i], vec[i]), __fmul_rn(vec[i + 1], vec[i + 1]));
-      val = __fmul_rn(todB_hd(val), .5f);
-      float dec = decay[q];
-      for (int u = 0; u < tid; u++) dec = (float)((double)dec - 8.);
-      if (val < dec) val = dec;
-      if (val < E->minenergy) val = E->minenergy;
-      v2[tid] = val;
+    for (int qq = 0; qq < nq; qq++) {
+      const float *vec = vec4[qq];
+      const int q = q0 + qq;
+      if (tid < VE_N / 4) {
+        const int i = tid * 2;
+        float val = __fadd_rn(__fmul_rn(vec[i], vec[i]), __fmul_rn(vec[i + 1], vec[i + 1]));
+        val = __fmul_rn(todB_hd(val), .5f);
+        float dec = decay[q];
+        for (int u = 0; u < tid; u++) dec = (float)((double)dec - 8.);
+        if (val < dec) val = dec;
+        if (val < E->minenergy) val = E->minenergy;
+        v2[tid] = val;
+      }
+      __syncthreads();
+      if (tid < VE_BANDS) {
+        float acc = 0.f;
+        for (int i = 0; i < E->bend[tid]; i++) acc = __fadd_rn(acc, __fmul_rn(v2[i + E->bbegin[tid]], E->bandwin[tid][i]));
+        acc_out[((S.out_base * ch + (long long)c * S.nsteps + (j0 + q)) * VE_BANDS) + tid] = __fmul_rn(acc, E->bandtotal[tid]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (tid < VE_BANDS) {
-      float acc = 0.f;
-      for (int i = 0; i < E->bend[tid]; i++) acc = __fadd_rn(acc, __fmul_rn(v2[i + E->bbegin[tid]], E->bandwin[tid][i]));
-      acc_out[((S.out_base * ch + (long long)c * S.nsteps + (j0 + q)) * VE_BANDS) + tid] = __fmul_rn(acc, E->bandtotal[tid]);
-    }
-    __syncthreads();
   }
 }
 
@@ -534,7 +552,7 @@ __global__ void k_env_tail(const EnvStream *__restrict__ streams, int ch, const 
 
 struct vb200_segmenter {
   vb200_setup *s; EnvParams env;
-  EnvDev *d_env; double *d_cs; float *d_win;
+  EnvDev *d_env; double *d_cs, *d_cst; float *d_win;
   float *h_pcm, *d_pcm; size_t pcm_cap;          /* pinned host timeline + device timeline */
   float *d_acc, *d_temp; size_t step_cap;
   unsigned char *d_marks, *h_marks; size_t mark_cap;
@@ -556,7 +574,13 @@ extern "C" int vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out) {
   CUDA_TRY(cudaMalloc(&g->d_cs, sizeof(D.cs))); CUDA_TRY(cudaMalloc(&g->d_win, sizeof(D.win))); CUDA_TRY(cudaMalloc(&g->d_env, sizeof(EnvDev)));
   CUDA_TRY(cudaMemcpy(g->d_cs, D.cs, sizeof(D.cs), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(g->d_win, D.win, sizeof(D.win), cudaMemcpyHostToDevice));
-  e.cs = g->d_cs; e.win = g->d_win;
+  {
+    std::vector<double> tr((size_t)VE_N * (VE_N / 2));
+    for (int k = 0; k < VE_N / 2; k++) for (int t = 0; t < VE_N; t++) tr[(size_t)t * (VE_N / 2) + k] = D.cs[k][t];
+    CUDA_TRY(cudaMalloc(&g->d_cst, tr.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(g->d_cst, tr.data(), tr.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  e.cs = g->d_cs; e.cst = g->d_cst; e.win = g->d_win;
   memcpy(e.bandwin, D.bandwin, sizeof(e.bandwin)); memcpy(e.bandtotal, D.bandtotal, sizeof(e.bandtotal));
   for (int i = 0; i < VE_BANDS; i++) { e.bbegin[i] = kBandBegin[i]; e.bend[i] = kBandEnd[i]; e.pre_th[i] = g->env.pre_th[i]; e.post_th[i] = g->env.post_th[i]; }
   e.minenergy = g->env.minenergy; e.stretch_penalty = g->env.stretch_penalty;
@@ -568,7 +592,7 @@ extern "C" int vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out) {
 extern "C" void vb200_segmenter_destroy(vb200_segmenter *g) {
   if (!g) return;
   cudaSetDevice(g->s->device);
-  cudaFree(g->d_cs); cudaFree(g->d_win); cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
+  cudaFree(g->d_cs); cudaFree(g->d_cst); cudaFree(g->d_win); cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
   cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_marks); cudaFreeHost(g->h_marks);
   cudaFree(g->d_streams); cudaFreeHost(g->h_streams); cudaFree(g->d_mark_base); cudaFreeHost(g->h_mark_base);
   cudaFree(g->d_stretch); cudaFreeHost(g->h_stretch); cudaFree(g->d_acc_tail); cudaFreeHost(g->h_acc_tail);
@@ -635,6 +659,9 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
     SEG_ALLOC(g->d_temp_tail, sizeof(float) * nstreams * ch * 45, false); SEG_ALLOC(g->h_temp_tail, sizeof(float) * nstreams * ch * 45, true);
     g->stream_cap = nstreams;
   }
+  const bool trace = getenv("VB200_TRACE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now(), t1, t2, t3, t4;
   /* host: timelines (pre-amplified PCM + LPC head) straight into the pinned buffer */
   parallel_for(nstreams, threads, [&](int i) {
     seg[i].init(s, g->env, nsamples[i], g->h_pcm + base[i], i);
@@ -648,6 +675,7 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
     g->h_mark_base[i] = mark_base[i];
     if (e.nsteps > max_steps) max_steps = e.nsteps;
   }
+  t1 = now();
   /* one H2D of the whole timeline; the detector's heavy half on the device */
   CUDA_TRY(cudaMemcpyAsync(g->d_pcm, g->h_pcm, total * sizeof(float), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(g->d_streams, g->h_streams, sizeof(EnvStream) * nstreams, cudaMemcpyHostToDevice, st));
@@ -666,6 +694,8 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
   CUDA_TRY(cudaMemcpyAsync(g->h_stretch, g->d_stretch, sizeof(int) * nstreams, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(g->h_acc_tail, g->d_acc_tail, sizeof(float) * nstreams * ch * VE_AMP * VE_BANDS, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(g->h_temp_tail, g->d_temp_tail, sizeof(float) * nstreams * ch * 45, cudaMemcpyDeviceToHost, st));
+  if (trace) { CUDA_TRY(cudaStreamSynchronize(st)); }
+  t2 = now();
   CUDA_TRY(cudaStreamSynchronize(st));
   /* host: sequencing up to the end of the signal, LPC tail, detector over the tail, final sequencing */
   parallel_for(nstreams, threads, [&](int i) {
@@ -676,6 +706,7 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
     q.tail();
     q.detect_host(q.T); q.sequence(q.T, true);
   });
+  t3 = now();
   /* the extrapolated tails go up as well (small), then the blocks */
   for (int i = 0; i < nstreams; i++)
     for (int c = 0; c < ch; c++) {
@@ -686,6 +717,8 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
   for (int i = 0; i < nstreams; i++) g->blocks.insert(g->blocks.end(), seg[i].blocks.begin(), seg[i].blocks.end());
   g->pcm_elems = total;
   CUDA_TRY(cudaStreamSynchronize(st));
+  t4 = now();
+  if (trace) fprintf(stderr, "[vb200 segmenter] fill+head %.1f ms | h2d+detector+d2h %.1f ms | sequencing+tail %.1f ms | tail h2d+collect %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3);
   return VB200_OK;
 }
 

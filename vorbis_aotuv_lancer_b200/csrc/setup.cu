@@ -224,6 +224,14 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
       }
       if (bad) { vb200_set_error("psy %d: octave table outside the built path", k); L.ok = false; free(g); break; }
       p.n_tone_groups = ng; p.tone_tail = lin;
+      {
+        int2 *runs = (int2 *)malloc(sizeof(int2) * n);
+        int nr = 0;
+        for (int i = 0; i < n;) { int e = i; while (e + 1 < n && oct[e + 1] == oct[i]) e++; runs[nr++] = make_int2(i, e); i = e + 1; }
+        p.n_tone_runs = nr;
+        p.tone_runs = (const int2 *)L.up(runs, sizeof(int2) * nr);
+        free(runs);
+      }
       p.tone_groups = (const int4 *)L.up(g, sizeof(int4) * (ng ? ng : 1));
       free(g);
     }
@@ -333,6 +341,28 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
       }
       d.used_list = (const int *)L.up(ul, sizeof(int) * (used ? used : 1));
       d.used_vals = (const int *)L.up(uv, sizeof(int) * 8 * (used ? used : 1));
+      if (used > 0 && used < b.entries && used < 32768) {
+        /* nearest used entry of every lattice point, first minimum in entry order (res0.c:349-361) */
+        short *nn = (short *)malloc(sizeof(short) * b.entries);
+        const int qv = b.quantvals, ze = qv >> 1;
+        for (int i = 0; i < b.entries; i++) {
+          int pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rem = i;
+          for (int j = 0; j < b.dim; j++) {             /* digit j of the index is the zig-zag code of component j */
+            const int m = rem % qv; rem /= qv;
+            const int v = (m & 1) ? ze - ((m + 1) >> 1) : ze + (m >> 1);
+            pt[j] = v * b.delta + b.minval;
+          }
+          int best = -1, bestu = 0;
+          for (int u2 = 0; u2 < used; u2++) {
+            int dd = 0;
+            for (int j = 0; j < b.dim; j++) { const int df = uv[u2 * 8 + j] - pt[j]; dd += df * df; }
+            if (best == -1 || dd < best) { best = dd; bestu = u2; }
+          }
+          nn[i] = (short)bestu;
+        }
+        d.nearest = (const short *)L.up(nn, sizeof(short) * b.entries);
+        free(nn);
+      }
       free(ul); free(uv);
     }
   }

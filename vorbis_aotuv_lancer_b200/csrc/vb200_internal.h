@@ -38,6 +38,8 @@ struct DevPsy {
   int nf_b1[2], nf_b2[2];    /* noise regression: first bin of the interior / held window class, per pass */
   const int4 *tone_groups;   /* max_seeds: (seed pos0, pos1, bin0, bin1) per group */
   int n_tone_groups, tone_tail;
+  const int2 *tone_runs;     /* seed_loop: (first bin, last bin) of every run of bins sharing an octave line */
+  int n_tone_runs;
 };
 
 struct DevFloor {
@@ -62,6 +64,9 @@ struct DevBook {
   const uint32_t *code;         /* [entries] */
   const int      *used_list;    /* [used] entry indices in ascending order */
   const int      *used_vals;    /* [used][8] lattice value of each used entry (res0.c:343-370 enumeration) */
+  const short    *nearest;      /* [entries] for books with unused entries: index into used_list of the used entry
+                                   nearest (first minimum) to lattice point i -- the exhaustive fallback of
+                                   res0.c:343-370 precomputed for inputs that sit exactly on the lattice */
 };
 
 struct DevMap {
