@@ -30,6 +30,21 @@ __device__ __forceinline__ int line_at(int x0, int x1, int y0, int y1, int x) {
   const int carry = (rem * k) / adx;
   return y0 + base * k + (dy < 0 ? -carry : carry);
 }
+/* the same line with its per-line constants hoisted (they are warp-uniform during error inspection) and the
+   per-bin division done as an exact reciprocal-multiply + correction: rem*k < 2^21 is exact in float */
+struct LineK { int x0, y0, base, rem, adx, neg; float radx; };
+__device__ __forceinline__ LineK line_setup(int x0, int x1, int y0, int y1) {
+  LineK L; const int dy = y1 - y0; L.x0 = x0; L.y0 = y0; L.adx = x1 - x0; L.base = dy / L.adx;
+  L.rem = abs(dy) - abs(L.base * L.adx); L.neg = dy < 0; L.radx = 1.0f / (float)L.adx;
+  return L;
+}
+__device__ __forceinline__ int line_eval(const LineK &L, int x) {
+  const int k = x - L.x0, num = L.rem * k;
+  int q = (int)((float)num * L.radx);
+  if (q * L.adx > num) q--;
+  if ((q + 1) * L.adx <= num) q++;
+  return L.y0 + L.base * k + (L.neg ? -q : q);
+}
 /* render_point, floor1.c:260-283 */
 __device__ __forceinline__ int point_at(int x0, int x1, int y0, int y1, int x) {
   y0 &= 0x7fff; y1 &= 0x7fff;
@@ -165,8 +180,9 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     const int ly = pick(sm.A, sm.B, ln), hy = pick(sm.A, sm.B, hn);
     /* inspect_error across the warp */
     int viol = 0, mse = 0;
+    const LineK LK = line_setup(lx, hx, ly, hy);
     for (int x = lx + lane; x < hx; x += 32) {
-      const int y = line_at(lx, hx, ly, hy, x), v = sm.q[x];
+      const int y = line_eval(LK, x), v = sm.q[x];
       mse += (y - v) * (y - v);
       if (sm.loud[x] && (x == lx || v)) {
         if (__fadd_rn((float)y, F.maxover) < (float)v) viol = 1;
@@ -186,11 +202,17 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     __syncwarp();
     double sa[6], sb[6];
     if (bad) fit_two(sm.T, lsp, sp - lsp, sp, hsp - sp, lane, sa, sb);      /* `bad` is warp-uniform */
+    int r0 = 0, r1 = 0, ly0 = -200, ly1 = -200, hy0 = -200, hy1 = -200;
+    if (bad) {
+      /* the two solves run side by side on lanes 0 and 6 */
+      int ya = -200, yb = -200, rr = 0;
+      if (lane == 0) rr = fit_solve(sa, sm.seg[lsp].x0, sm.seg[sp - 1].x1, &ya, &yb);
+      else if (lane == 6) rr = fit_solve(sb, sm.seg[sp].x0, sm.seg[hsp - 1].x1, &ya, &yb);
+      r0 = __shfl_sync(FULLMASK, rr, 0); ly0 = __shfl_sync(FULLMASK, ya, 0); ly1 = __shfl_sync(FULLMASK, yb, 0);
+      r1 = __shfl_sync(FULLMASK, rr, 6); hy0 = __shfl_sync(FULLMASK, ya, 6); hy1 = __shfl_sync(FULLMASK, yb, 6);
+    }
     if (lane == 0) {
       if (bad) {
-        int ly0 = -200, ly1 = -200, hy0 = -200, hy1 = -200;
-        const int r0 = fit_solve(sa, sm.seg[lsp].x0, sm.seg[sp - 1].x1, &ly0, &ly1);
-        const int r1 = fit_solve(sb, sm.seg[sp].x0, sm.seg[hsp - 1].x1, &hy0, &hy1);
         if (r0) { ly0 = ly; ly1 = hy0; }
         if (r1) { hy0 = ly1; hy1 = hy; }
         if (r0 && r1) { sm.A[i] = -200; sm.B[i] = -200; }

@@ -254,7 +254,7 @@ int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int ite
                            const float *logmdct, LastRef last, float *noise, float *epeak, float *npeak, int npeak_stride) {
   if (items <= 0) return VB200_OK;
   if (W) {
-    constexpr int N = 1024, T = 64;
+    constexpr int N = 1024, T = 256;
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(k_noisemask<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NoiseSmem<N>))); attr = true; }
     k_noisemask<N, T><<<items, T, sizeof(NoiseSmem<N>), st>>>(s->d, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);

@@ -20,8 +20,8 @@
 namespace {
 
 #define TM_NEGINF (-9999.f)
-constexpr int TM_ITEMS = 16;     /* ch-blocks per CTA */
-constexpr int TM_THREADS = 128;
+constexpr int TM_ITEMS = 8;      /* ch-blocks per CTA: one warp each for the cooperative phases, 8 lanes for the chase */
+constexpr int TM_THREADS = 256;
 constexpr int TM_WARPS = TM_THREADS / 32;
 constexpr int TM_QCAP = 64;      /* per-warp queue of curves to splat */
 
