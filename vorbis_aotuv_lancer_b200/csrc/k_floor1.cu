@@ -134,28 +134,36 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     sm.loud[i] = (__fadd_rn(__ldg(lm + i), F.twofitatten) >= m) ? 1 : 0;
   }
   __syncwarp();
-  /* accumulate_fit: one lane per post interval, integer sums */
+  /* accumulate_fit: the warp walks the post intervals together; a lane takes every 32nd bin of the interval
+     and the twelve integer sums are closed with the hardware warp reduction (integer sums are exact in any
+     order).  Branch-free: class a = loud bins, class b = the rest, both only where the quantised mask != 0. */
   int mine = 0;
-  for (int j = lane; j < posts - 1; j += 32) {
+  for (int j = 0; j < posts - 1; j++) {
     const int x0 = F.sorted[j], x1 = F.sorted[j + 1], xe = x1 >= n ? n - 1 : x1;
-    int s[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
-    for (int i = x0; i <= xe; i++) {
+    int ax = 0, ay = 0, ax2 = 0, ay2 = 0, axy = 0, an = 0, bx = 0, by = 0, bx2 = 0, by2 = 0, bxy = 0, bnn = 0;
+    for (int i = x0 + lane; i <= xe; i += 32) {
       const int q = sm.q[i];
-      if (q) {
-        int *t = s[sm.loud[i] ? 0 : 1];
-        t[0] += i; t[1] += q; t[2] += i * i; t[3] += q * q; t[4] += i * q; t[5]++;
-      }
+      const int on = q != 0, la = on & (int)sm.loud[i], lb = on & (la ^ 1);
+      const int ii = i * i, qq = q * q, iq = i * q;
+      ax += la * i; ay += la * q; ax2 += la * ii; ay2 += la * qq; axy += la * iq; an += la;
+      bx += lb * i; by += lb * q; bx2 += lb * ii; by2 += lb * qq; bxy += lb * iq; bnn += lb;
     }
-    Seg &g = sm.seg[j];
-    g.x0 = x0; g.x1 = x1;
-#pragma unroll
-    for (int c = 0; c < 2; c++)
-#pragma unroll
-      for (int k = 0; k < 6; k++) g.s[c][k] = s[c][k];
-    fit_terms(g, F.twofitweight, sm.T[j]);
-    mine += s[0][5];
+    ax = __reduce_add_sync(FULLMASK, ax); ay = __reduce_add_sync(FULLMASK, ay); ax2 = __reduce_add_sync(FULLMASK, ax2);
+    ay2 = __reduce_add_sync(FULLMASK, ay2); axy = __reduce_add_sync(FULLMASK, axy); an = __reduce_add_sync(FULLMASK, an);
+    bx = __reduce_add_sync(FULLMASK, bx); by = __reduce_add_sync(FULLMASK, by); bx2 = __reduce_add_sync(FULLMASK, bx2);
+    by2 = __reduce_add_sync(FULLMASK, by2); bxy = __reduce_add_sync(FULLMASK, bxy); bnn = __reduce_add_sync(FULLMASK, bnn);
+    if (lane == 0) {
+      Seg &g = sm.seg[j];
+      g.x0 = x0; g.x1 = x1;
+      g.s[0][0] = ax; g.s[0][1] = ay; g.s[0][2] = ax2; g.s[0][3] = ay2; g.s[0][4] = axy; g.s[0][5] = an;
+      g.s[1][0] = bx; g.s[1][1] = by; g.s[1][2] = bx2; g.s[1][3] = by2; g.s[1][4] = bxy; g.s[1][5] = bnn;
+      fit_terms(g, F.twofitweight, sm.T[j]);
+    }
+    mine += an;
   }
-  const int any = warp_sum_i(mine);
+  __syncwarp();
+  const int any = mine;
+
   if (!any) { if (lane == 0) fitted[item] = 0; return; }
   for (int i = lane; i < posts; i += 32) { sm.A[i] = -200; sm.B[i] = -200; sm.lo[i] = 0; sm.hi[i] = 1; sm.memo[i] = -1; }
   __syncwarp();

@@ -97,27 +97,40 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
   const size_t ent_elems = (size_t)stages * partvals * rows * maxvec;
   int *offs = reinterpret_cast<int *>(dyn + ((ent_elems * 2 + 15) & ~(size_t)15));   /* [stages*partvals*rows + 1] */
   __shared__ int rowch[VB200_MAX_CHANNELS];
+  __shared__ short tab_bk[64 * 8], tab_nvec[64 * 8];      /* per (class, stage): book and vectors per partition */
   if (tid == 0) { int r = 0; for (int k = 0; k < ch; k++) if (R.type == 2 || nz[chlist[k]]) rowch[r++] = chlist[k]; }
+  for (int i = tid; i < R.partitions * 8; i += RF_WARPS * 32) {
+    const int cls = i >> 3, st2 = i & 7;
+    int bk = -1, nv = 0;
+    if (st2 < stages && (R.secondstages[cls] & (1 << st2))) { bk = R.partbooks[i]; if (bk >= 0) nv = G / books[bk].dim; }
+    tab_bk[i] = (short)bk; tab_nvec[i] = (short)nv;
+  }
+  const int ch_shift = (ch & (ch - 1)) == 0 ? __ffs(ch) - 1 : -1;
+  const int pd_mask = (R.phrase_dim & (R.phrase_dim - 1)) == 0 ? R.phrase_dim - 1 : -1;
   __syncthreads();
 
   /* ---- pass 1: cascade VQ per (partition,row), warps stride over them ---- */
   for (int pr = warp; pr < partvals * rows; pr += RF_WARPS) {
-    const int p = pr / rows, row = pr % rows;
+    const int p = rows == 1 ? pr : pr / rows, row = rows == 1 ? 0 : pr % rows;
     const int cls = pw[row * partvals + p];
     int *v = sh.vec[warp];
     const int off = p * G + R.begin;
     /* stage the partition: res2 reads the channel-interleaved vector work[j*ch+c]=in[c][j] (res0.c:782-787) */
     for (int t = lane; t < G; t += 32) {
-      if (R.type == 2) { const int w = off + t; v[t] = base[(size_t)chlist[w % ch] * n + w / ch]; }
+      if (R.type == 2) {
+        const int w = off + t;
+        const int wc = ch_shift >= 0 ? (w & (ch - 1)) : w % ch, wj = ch_shift >= 0 ? (w >> ch_shift) : w / ch;
+        v[t] = base[(size_t)chlist[wc] * n + wj];
+      }
       else v[t] = base[(size_t)rowch[row] * n + off + t];
     }
     __syncwarp();
     for (int s = 0; s < stages; s++) {
-      if (!(R.secondstages[cls] & (1 << s))) continue;
-      const int bk = R.partbooks[cls * 8 + s];
+      const int bk = tab_bk[cls * 8 + s];
       if (bk < 0) continue;
       const DevBook &B = books[bk];
-      const int dim = B.dim, nvec = G / dim, qv = B.quantvals, ze = qv >> 1;
+      const int dim = B.dim, nvec = tab_nvec[cls * 8 + s], qv = B.quantvals, ze = qv >> 1;
+      const int bdelta = B.delta, bmin = B.minval;
       short *e_out = ent + (((size_t)s * partvals + p) * rows + row) * maxvec;
       for (int t0 = 0; t0 < nvec; t0 += 32) {
         const int t = t0 + lane;
@@ -129,10 +142,10 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
           bool on_lattice = true;          /* the input is exactly a lattice point inside the book's range */
           for (int i = 0, o = dim; i < dim; i++) {
             --o;
-            const int x = (B.delta != 1) ? (a[o] - B.minval + (B.delta >> 1)) / B.delta : a[o] - B.minval;
+            const int x = (bdelta != 1) ? (a[o] - bmin + (bdelta >> 1)) / bdelta : a[o] - bmin;
             const int m = (x < ze) ? ((ze - x) << 1) - 1 : ((x - ze) << 1);
             index = index * qv + (m < 0 ? 0 : (m >= qv ? qv - 1 : m));
-            pt[o] = x * B.delta + B.minval;
+            pt[o] = x * bdelta + bmin;
             if (m < 0 || m >= qv || pt[o] != a[o]) on_lattice = false;
           }
           if (__ldg(B.len + index) == 0) {
@@ -179,57 +192,56 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
   }
   __syncthreads();
 
-  /* ---- pass 2: emission order.  Count symbols per (stage, partition, row), scan, scatter. ---- */
+  /* ---- pass 2: emission order.  Count symbols per (stage, partition, row), scan, scatter.  Slots are walked
+     stage by stage so that no index has to be split by division. ---- */
   const int pd = R.phrase_dim;
-  const int nslots = stages * partvals * rows;
+  const int prow = partvals * rows;
+  const int nslots = stages * prow;
   const int phrase_entries = books[R.groupbook].entries;
+  auto phrase_val = [&](int r2, int p) {
+    int val = pw[r2 * partvals + p];
+    for (int k = 1; k < pd; k++) { val *= R.partitions; if (p + k < partvals) val += pw[r2 * partvals + p + k]; }
+    return val;
+  };
   if (warp == 0) {
     int carry = 0;
-    for (int b0 = 0; b0 < nslots; b0 += 32) {
-      const int idx = b0 + lane;
-      int cnt = 0;
-      if (idx < nslots) {
-        const int s = idx / (partvals * rows), rem = idx % (partvals * rows), p = rem / rows, row = rem % rows;
-        const int cls = pw[row * partvals + p];
-        if (R.secondstages[cls] & (1 << s)) { const int bk = R.partbooks[cls * 8 + s]; if (bk >= 0) cnt = G / books[bk].dim; }
-        if (s == 0 && (p % pd) == 0 && row == 0) {
-          /* the phrase words of this partition group (one per row) precede its residual symbols */
-          for (int r2 = 0; r2 < rows; r2++) {
-            int val = pw[r2 * partvals + p];
-            for (int k = 1; k < pd; k++) { val *= R.partitions; if (p + k < partvals) val += pw[r2 * partvals + p + k]; }
-            if (val < phrase_entries) cnt += 1 << 16;      /* high half counts phrase symbols */
-          }
+    for (int s = 0; s < stages; s++)
+      for (int b0 = 0; b0 < prow; b0 += 32) {
+        const int pr = b0 + lane;
+        int tot = 0;
+        if (pr < prow) {
+          const int p = rows == 1 ? pr : pr / rows, row = rows == 1 ? 0 : pr % rows;
+          tot = tab_nvec[pw[row * partvals + p] * 8 + s];
+          if (s == 0 && row == 0 && (pd_mask >= 0 ? (p & pd_mask) == 0 : (p % pd) == 0))
+            for (int r2 = 0; r2 < rows; r2++) if (phrase_val(r2, p) < phrase_entries) tot++;   /* phrase words lead the group */
         }
-      }
-      const int tot = (cnt & 0xffff) + (cnt >> 16);
-      int incl = tot;
+        int incl = tot;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += y; }
-      if (idx < nslots) offs[idx] = carry + incl - tot;
-      carry += __shfl_sync(FULLMASK, incl, 31);
-    }
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += y; }
+        if (pr < prow) offs[s * prow + pr] = carry + incl - tot;
+        carry += __shfl_sync(FULLMASK, incl, 31);
+      }
     if (lane == 0) { offs[nslots] = carry; nsyms[blk] = carry < max_syms ? carry : max_syms; }
   }
   __syncthreads();
   int *out = syms + (size_t)blk * max_syms * 2;
-  for (int idx = warp; idx < nslots; idx += RF_WARPS) {
-    const int s = idx / (partvals * rows), rem = idx % (partvals * rows), p = rem / rows, row = rem % rows;
-    int o = offs[idx];
-    if (s == 0 && (p % pd) == 0 && row == 0) {
-      for (int r2 = 0; r2 < rows; r2++) {
-        int val = pw[r2 * partvals + p];
-        for (int k = 1; k < pd; k++) { val *= R.partitions; if (p + k < partvals) val += pw[r2 * partvals + p + k]; }
-        if (val < phrase_entries) { if (lane == 0 && o < max_syms) { out[o * 2] = R.groupbook; out[o * 2 + 1] = val; } o++; }
+  for (int s = 0; s < stages; s++)
+    for (int pr = warp; pr < prow; pr += RF_WARPS) {
+      const int p = rows == 1 ? pr : pr / rows, row = rows == 1 ? 0 : pr % rows;
+      int o = offs[s * prow + pr];
+      if (s == 0 && row == 0 && (pd_mask >= 0 ? (p & pd_mask) == 0 : (p % pd) == 0)) {
+        for (int r2 = 0; r2 < rows; r2++) {
+          const int val = phrase_val(r2, p);
+          if (val < phrase_entries) { if (lane == 0 && o < max_syms) { out[o * 2] = R.groupbook; out[o * 2 + 1] = val; } o++; }
+        }
       }
+      const int cls = pw[row * partvals + p];
+      const int bk = tab_bk[cls * 8 + s];
+      if (bk < 0) continue;
+      const int nvec = tab_nvec[cls * 8 + s];
+      const short *e_in = ent + (((size_t)s * partvals + p) * rows + row) * maxvec;
+      for (int t = lane; t < nvec; t += 32) if (o + t < max_syms) { out[(o + t) * 2] = bk; out[(o + t) * 2 + 1] = e_in[t]; }
     }
-    const int cls = pw[row * partvals + p];
-    if (!(R.secondstages[cls] & (1 << s))) continue;
-    const int bk = R.partbooks[cls * 8 + s];
-    if (bk < 0) continue;
-    const int nvec = G / books[bk].dim;
-    const short *e_in = ent + (((size_t)s * partvals + p) * rows + row) * maxvec;
-    for (int t = lane; t < nvec; t += 32) if (o + t < max_syms) { out[(o + t) * 2] = bk; out[(o + t) * 2 + 1] = e_in[t]; }
-  }
 }
 
 }  // namespace
