@@ -194,6 +194,17 @@ int  vb200_segmenter_count(const vb200_segmenter *g);
 const vb200_block *vb200_segmenter_blocks(const vb200_segmenter *g);
 const float *vb200_segmenter_device_pcm(const vb200_segmenter *g, size_t *elems);
 const float *vb200_segmenter_host_pcm(const vb200_segmenter *g);
+/* 1 when the last run took the samples straight from the caller's page-locked buffers (every pcm[i] was
+   allocated with vb200_pinned_alloc / cudaHostAlloc / cudaHostRegister): the host timeline then holds only the
+   head and tail windows the host itself reads.  Pageable input is staged through the segmenter's own pinned
+   timeline (0).  Both give the same device timeline and the same blocks. */
+int  vb200_segmenter_direct(const vb200_segmenter *g);
+/* copy the device timeline of the last run back to host memory (tests, debugging) */
+int  vb200_segmenter_read_pcm(const vb200_segmenter *g, float *out, size_t elems);
+/* Page-locked host memory for PCM handed to vb200_segmenter_run (the buffer vorbis_analysis_buffer() returns,
+   block.c:421-436, would be allocated with this). */
+int  vb200_pinned_alloc(size_t bytes, void **out);
+void vb200_pinned_free(void *p);
 
 /* Per-stream state: replaces the aoTuV fields of private_state (codec_internal.h:85-92), the
  * ampmax feedback of block.c:649-651 and bitrate_manager_state (bitrate.h:26-38). */
@@ -209,6 +220,13 @@ void vb200_batch_destroy(vb200_batch *b);
 int  vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstreams,
                      const vb200_block *blocks, int nblocks,
                      const float *pcm, size_t pcm_elems, int pcm_on_device);
+/* The same in two halves, so that a caller can overlap the host side of the next batch (segmentation,
+ * H2D) with the kernels of this one: submit enqueues everything on the batch's own CUDA stream and
+ * returns; collect waits, fetches the packets and (managed mode) runs the bitrate manager. */
+int  vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int nstreams,
+                        const vb200_block *blocks, int nblocks,
+                        const float *pcm, size_t pcm_elems, int pcm_on_device);
+int  vb200_batch_collect(vb200_batch *b);
 /* Debug/verification switch: 1 = emit codewords on the host from the device's symbol lists (the
  * reference-order implementation in emit.cu), 0 (default) = pack bits on the device (K8). */
 int  vb200_batch_set_host_emit(vb200_batch *b, int on);

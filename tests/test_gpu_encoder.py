@@ -31,6 +31,32 @@ def test_gpu_segmenter_equals_host_segmenter(config, seconds):
     g.close(); s.close()
 
 
+@pytest.mark.parametrize("config,seconds", [("q4_44k_2ch", 4.0), ("q8_48k_6ch", 1.5), ("q4_44k_1ch", 0.4)])
+def test_pinned_input_goes_up_directly_and_gives_the_same_timeline(config, seconds):
+    """PCM in page-locked memory skips the staging copy; device timeline and blocks must not change."""
+    from vorbis_aotuv_lancer_b200 import blob as vblob, encoder, ops
+    ch, rate, _, _ = vblob.CATALOGUE[config]
+    s = ops.Setup(config)
+    pcms = [refdata.synth(ch, rate, seconds, seed=21 + i) for i in range(3)] + [refdata.synth(ch, rate, 0.05, seed=6),
+                                                                                 refdata.synth(ch, rate, 0.2, seed=7)]
+    pins = [encoder.PinnedArray(*p.shape) for p in pcms]
+    for a, p in zip(pins, pcms):
+        a.array[...] = p
+
+    def timeline(g, inputs):
+        blocks, dptr, elems = g.run(inputs, threads=4)
+        return np.frombuffer(blocks, dtype=encoder.BLOCK_DTYPE).copy(), g.device_timeline(elems)
+    g0, g1 = encoder.Segmenter(s), encoder.Segmenter(s)
+    b0, t0 = timeline(g0, pcms)
+    b1, t1 = timeline(g1, [a.array for a in pins])
+    assert not g0.direct and g1.direct
+    assert np.array_equal(b0, b1)
+    assert np.array_equal(t0, t1)
+    g0.close(); g1.close(); s.close()
+    for a in pins:
+        a.close()
+
+
 def test_encode_decodes_and_matches_reference_bitrate():
     from oracle import reflib
     from vorbis_aotuv_lancer_b200 import encoder, ops

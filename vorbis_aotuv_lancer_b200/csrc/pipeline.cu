@@ -214,6 +214,10 @@ struct vb200_batch {
   BitWriter bw;
   const unsigned char *pk_base;
   int host_emit, host_emit_ready;
+  cudaStream_t st;                 /* this batch's own stream: batches and segmenters overlap */
+  bool pending; int run_nblocks, run_nb[2];
+  std::vector<vb200_stream *> run_streams; std::vector<long> blob_sizes;
+  std::vector<BitWriter> bws; std::vector<std::vector<size_t>> boff;
   unsigned char *d_pool, *h_pool; size_t pool_cap; unsigned long long *d_pool_top, *h_pool_top;
   long long *d_pk_off, *h_pk_off; int *d_pk_bytes, *h_pk_bytes;
   std::vector<size_t> pk_off, pk_bytes; std::vector<int64_t> pk_gp; std::vector<int> pk_eos, pk_stream;
@@ -363,6 +367,8 @@ extern "C" int vb200_batch_create(vb200_setup *s, int max_blocks, vb200_batch **
     }
   }
   for (int i = 0; i < 16; i++) cudaEventCreate(&b->ev[i]);
+  b->pending = false;
+  if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess) { vb200_set_error("vb200_batch_create: cannot create a stream"); return VB200_EFAULT; }
   *out = b;
   return VB200_OK;
 }
@@ -371,6 +377,7 @@ extern "C" void vb200_batch_destroy(vb200_batch *b) {
   if (!b) return;
   cudaSetDevice(b->s->device);
   for (int i = 0; i < 16; i++) cudaEventDestroy(b->ev[i]);
+  cudaStreamDestroy(b->st);
   if (b->d_pcm) cudaFree(b->d_pcm);
   cudaFree(b->dev.base);
   cudaFreeHost(b->pin.base);
@@ -448,21 +455,25 @@ static int bitrate_choose(vb200_stream *x, const vb200_setup *s, int W, const lo
 #define EV(name) do{ if (b->nev < 16) { b->evname[b->nev] = name; cudaEventRecord(b->ev[b->nev++], st); } }while(0)
 #define RUN(x) do{ int r_ = (x); if (r_) return r_; }while(0)
 
-extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstreams,
-                               const vb200_block *blocks, int nblocks,
-                               const float *pcm, size_t pcm_elems, int pcm_on_device) {
-  if (!b || !streams || !blocks || !pcm || nstreams < 1 || nblocks < 0) { vb200_set_error("vb200_batch_run: bad arguments"); return VB200_EINVAL; }
+static int batch_finish(vb200_batch *b);
+
+extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int nstreams,
+                                  const vb200_block *blocks, int nblocks,
+                                  const float *pcm, size_t pcm_elems, int pcm_on_device) {
+  if (!b || !streams || !blocks || !pcm || nstreams < 1 || nblocks < 0) { vb200_set_error("vb200_batch_submit: bad arguments"); return VB200_EINVAL; }
   if (nstreams > PIPE_MAX_STREAM_SLOTS) { vb200_set_error("vb200_batch_run: too many streams"); return VB200_EINVAL; }
   if (nblocks > b->max_blocks) { vb200_set_error("vb200_batch_run: %d blocks > batch capacity %d", nblocks, b->max_blocks); return VB200_EINVAL; }
   vb200_setup *s = b->s;
   CUDA_TRY(cudaSetDevice(s->device));
-  cudaStream_t st = (cudaStream_t)s->stream;
+  cudaStream_t st = b->st;
+  if (b->pending) { vb200_set_error("vb200_batch_submit: the previous run has not been collected"); return VB200_EINVAL; }
   StatePool *pool = pool_of(s);
   const int ch = s->h.channels, managed = s->h.managed;
   const int nsel = managed ? 3 : 1;
   b->nev = 0;
   b->pk_off.clear(); b->pk_bytes.clear(); b->pk_gp.clear(); b->pk_eos.clear(); b->pk_stream.clear();
   b->bw.reset();
+  b->run_streams.assign(streams, streams + nstreams); b->run_nblocks = nblocks;
   if (nblocks == 0) return VB200_OK;
 
   /* ---- host pre-pass over the block descriptors ---- */
@@ -680,7 +691,8 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
   const int nblobs = k_hi - k_lo + 1;
   const bool host_emit = b->host_emit != 0;
   struct HostRes { int *vals, *nonzero, *nsyms, *syms; } hr[2] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
-  std::vector<long> blob_sizes((size_t)nblocks * VB200_PACKETBLOBS, 0);
+  std::vector<long> &blob_sizes = b->blob_sizes;
+  blob_sizes.assign((size_t)nblocks * VB200_PACKETBLOBS, 0);
   if (host_emit) {
     for (int W = 0; W < 2; W++) {
       const size_t I = (size_t)nb[W] * ch;
@@ -710,8 +722,9 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
     UP(d_cl, h_cl, 2 * VB200_MAX_SUBMAPS * VB200_MAX_CHANNELS);
   }
 
-  std::vector<BitWriter> bws((managed && host_emit) ? VB200_PACKETBLOBS : 0);
-  std::vector<std::vector<size_t>> boff((managed && host_emit) ? VB200_PACKETBLOBS : 0);
+  std::vector<BitWriter> &bws = b->bws; std::vector<std::vector<size_t>> &boff = b->boff;
+  bws.clear(); boff.clear();
+  if (managed && host_emit) { bws.resize(VB200_PACKETBLOBS); boff.resize(VB200_PACKETBLOBS); }
   for (int k = k_lo; k <= k_hi; k++) {
     EV(k == k_lo ? "K5b floor encode" : "blob");
     for (int W = 0; W < 2; W++) {
@@ -784,28 +797,47 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
       }
     }
   }
-  b->pk_base = nullptr;
+  b->run_nb[0] = nb[0]; b->run_nb[1] = nb[1];
   if (!host_emit) {
-    /* the only D2H of the path: packet offsets/sizes, then the packet pool itself */
+    /* first half of the only D2H of the path: packet offsets / sizes and the pool fill level */
     EV("d2h packets");
-    const size_t nent = (size_t)nblobs * 2 * b->max_blocks;
     CUDA_TRY(cudaMemcpyAsync(b->h_pool_top, b->d_pool_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     for (int kk = 0; kk < nblobs; kk++) for (int W = 0; W < 2; W++) if (nb[W]) {
       const size_t o = ((size_t)kk * 2 + W) * b->max_blocks;
       CUDA_TRY(cudaMemcpyAsync(b->h_pk_off + o, b->d_pk_off + o, sizeof(long long) * nb[W], cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaMemcpyAsync(b->h_pk_bytes + o, b->d_pk_bytes + o, sizeof(int) * nb[W], cudaMemcpyDeviceToHost, st));
     }
-    (void)nent;
+  }
+  b->pending = true;
+  if (host_emit) return batch_finish(b);
+  return VB200_OK;
+}
+
+/* second half: wait for the kernels, fetch the packets, run the bitrate manager */
+static int batch_finish(vb200_batch *b) {
+  vb200_setup *s = b->s;
+  CUDA_TRY(cudaSetDevice(s->device));
+  cudaStream_t st = b->st;
+  const int managed = s->h.managed, nblocks = b->run_nblocks;
+  const bool host_emit = b->host_emit != 0;
+  const int k_lo = managed ? 0 : VB200_PACKETBLOBS / 2, k_hi = managed ? VB200_PACKETBLOBS - 1 : VB200_PACKETBLOBS / 2;
+  const int nblobs = k_hi - k_lo + 1;
+  std::vector<long> &blob_sizes = b->blob_sizes;
+  std::vector<BitWriter> &bws = b->bws; std::vector<std::vector<size_t>> &boff = b->boff;
+  vb200_stream **streams = b->run_streams.data();
+  b->pending = false;
+  b->pk_base = nullptr;
+  if (!host_emit) {
     CUDA_TRY(cudaStreamSynchronize(st));
     const unsigned long long top = *b->h_pool_top;
-    if (top > b->pool_cap) { vb200_set_error("vb200_batch_run: packet pool overflow (%llu > %llu bytes)", top, (unsigned long long)b->pool_cap); return VB200_EFAULT; }
+    if (top > b->pool_cap) { vb200_set_error("vb200_batch_collect: packet pool overflow (%llu > %llu bytes)", top, (unsigned long long)b->pool_cap); return VB200_EFAULT; }
     CUDA_TRY(cudaMemcpyAsync(b->h_pool, b->d_pool, top, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int i = 0; i < nblocks; i++) {
       const HostBlock &h = b->hb[i];
       for (int kk = 0; kk < nblobs; kk++) {
         const size_t o = ((size_t)kk * 2 + h.W) * b->max_blocks + h.idx;
-        if (b->h_pk_off[o] < 0) { vb200_set_error("vb200_batch_run: packet of block %d does not fit the packer's image", i); return VB200_EFAULT; }
+        if (b->h_pk_off[o] < 0) { vb200_set_error("vb200_batch_collect: packet of block %d does not fit the packer's image", i); return VB200_EFAULT; }
         blob_sizes[(size_t)i * VB200_PACKETBLOBS + k_lo + kk] = b->h_pk_bytes[o];
       }
       if (!managed) {
@@ -838,6 +870,20 @@ extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstre
   for (int i = 0; i + 1 < b->nev; i++) { cudaEventElapsedTime(&b->ev_ms[i], b->ev[i], b->ev[i + 1]); }
   if (b->nev > 1) cudaEventElapsedTime(&b->total_ms, b->ev[0], b->ev[b->nev - 1]);
   return VB200_OK;
+}
+
+extern "C" int vb200_batch_collect(vb200_batch *b) {
+  if (!b) return VB200_EINVAL;
+  if (!b->pending) return VB200_OK;
+  return batch_finish(b);
+}
+
+extern "C" int vb200_batch_run(vb200_batch *b, vb200_stream **streams, int nstreams,
+                               const vb200_block *blocks, int nblocks,
+                               const float *pcm, size_t pcm_elems, int pcm_on_device) {
+  const int r = vb200_batch_submit(b, streams, nstreams, blocks, nblocks, pcm, pcm_elems, pcm_on_device);
+  if (r) return r;
+  return vb200_batch_collect(b);
 }
 
 extern "C" int vb200_batch_set_host_emit(vb200_batch *b, int on) {

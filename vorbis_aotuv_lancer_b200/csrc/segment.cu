@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <thread>
+#include <atomic>
 #include <chrono>
 #include <stdio.h>
 #include <vector>
@@ -210,11 +211,22 @@ struct StreamSeg {
 
   /* timeline: lead-in | pre-amplified PCM | tail; head = reverse LPC extrapolation from the signal that
      had arrived when the reference first had more than one long block (block.c:438-471,545-548) */
-  void fill_and_head(const float *src, long stride, int chunk) {
+  void fill_and_head(const float *src, long stride, int chunk, bool sparse = false) {
+    /* sparse: the body of the signal goes to the device straight from the caller's (pinned) memory and
+       only the two windows the host itself reads are staged: the head the LPC looks at and the tail the
+       end-of-stream extrapolation and the last detector steps look at */
+    long head_n = nsamples, tail_n = 0;
+    if (sparse) {
+      long sn = 0;
+      while (sn < nsamples && !(sn > bs1)) sn += (nsamples - sn < chunk ? nsamples - sn : chunk);
+      const long want_tail = bs1 + (VE_WIN + 4) * VE_STEP;
+      if (sn + want_tail < nsamples) { head_n = sn; tail_n = want_tail; }
+    }
     for (int c = 0; c < ch; c++) {
       float *d = pcm + (size_t)c * T; const float *q = src + (size_t)c * stride;
       for (long i = 0; i < lead; i++) d[i] = 0.f;
-      for (long i = 0; i < nsamples; i++) d[lead + i] = q[i] * env.pre_amp;
+      for (long i = 0; i < head_n; i++) d[lead + i] = q[i] * env.pre_amp;
+      for (long i = nsamples - tail_n; i < nsamples; i++) d[lead + i] = q[i] * env.pre_amp;
       for (long i = eof_abs; i < T; i++) d[i] = 0.f;
     }
     long seen = 0;
@@ -394,7 +406,7 @@ struct EnvDev {            /* tables in HBM */
   float minenergy, stretch_penalty, pre_th[VE_BANDS], post_th[VE_BANDS];
 };
 
-struct EnvStream { long long pcm_base; long long T; int nsteps; long long out_base; /* step-major output offset */ };
+struct EnvStream { long long pcm_base; long long T; int nsteps; long long out_base; /* step-major output offset */ long long eof; };
 
 constexpr int EV_TILE = 32;      /* steps per CTA */
 constexpr int EV_HALO = 30;      /* the near-DC sum of a step depends on at most the 30 previous steps */
@@ -495,39 +507,91 @@ k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams,
   }
 }
 
-/* K0b: the order-dependent half: trigger filters and the stretch counter, one warp per stream, lane =
-   (channel, band).  Writes the marks of steps [0,nsteps) (+2) and the final stretch. */
+/* K0b: the trigger of one band at step j reads the band's own amplitude history (a pure function of the PCM)
+   and the stretch counter, which is the only state carried from step to step.  The counter selects one of
+   11 (window, penalty) pairs, so the answer for all 11 is tabulated here, one thread per step, and the
+   serial walk below only looks its state up.  Word layout: bits 2v / 2v+1 = pre / post trigger of variant v
+   (window v+2 steps), OR-ed over channels and bands. */
+constexpr int EV_VARIANTS = VE_MAXSTRETCH - VE_MINSTRETCH + 1;
+__global__ void __launch_bounds__(128)
+k_env_flags(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams, int ch, const float *__restrict__ acc_in,
+            unsigned *__restrict__ flags /*[out_base + step]*/) {
+  const EnvStream S = streams[blockIdx.y];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= S.nsteps) return;
+  float pen[EV_VARIANTS];
+#pragma unroll
+  for (int v = 0; v < EV_VARIANTS; v++) { int st; ve_stretch_params(2 * (v + VE_MINSTRETCH), E->stretch_penalty, &st, &pen[v]); }
+  unsigned w = 0;
+  for (int c = 0; c < ch; c++)
+    for (int b = 0; b < VE_BANDS; b++) {
+      const float *a = acc_in + (S.out_base * ch + (long long)c * S.nsteps) * VE_BANDS + b;
+      auto A = [&](int step) { return step >= 0 ? a[(long long)step * VE_BANDS] : 0.f; };
+      const float cur = A(j), prev = A(j - 1);
+      const float postmax = cur > prev ? cur : prev, postmin = cur < prev ? cur : prev;
+      const float pre_th = E->pre_th[b], post_th = E->post_th[b];
+      float premax = -99999.f, premin = 99999.f;
+#pragma unroll
+      for (int i = 0; i < VE_MAXSTRETCH; i++) {
+        const float x = A(j - 2 - i);
+        if (x > premax) premax = x;
+        if (x < premin) premin = x;
+        if (i + 1 >= VE_MINSTRETCH) {
+          const int v = i + 1 - VE_MINSTRETCH;
+          const float valmin = __fsub_rn(postmin, premin), valmax = __fsub_rn(postmax, premax);
+          if (valmax > __fadd_rn(pre_th, pen[v])) w |= 1u << (2 * v);
+          if (valmin < __fsub_rn(post_th, pen[v])) w |= 2u << (2 * v);
+        }
+      }
+    }
+  flags[S.out_base + j] = w;
+}
+
+/* K0c: the order-dependent half: the stretch counter, one warp per stream, 32 steps fetched per pass.
+   Writes the marks of steps [0,nsteps] (the buffer is zeroed beforehand) and the final stretch. */
 __global__ void __launch_bounds__(32)
-k_env_trigger(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams, int ch, const float *__restrict__ acc_in,
+k_env_trigger(const EnvStream *__restrict__ streams, const unsigned *__restrict__ flags,
               unsigned char *__restrict__ marks, const long long *__restrict__ mark_base, int *__restrict__ stretch_out) {
-  __shared__ BandFilter f[VB200_MAX_CHANNELS * VE_BANDS];
   const EnvStream S = streams[blockIdx.x];
-  const int lane = threadIdx.x, nf = ch * VE_BANDS;
-  for (int i = lane; i < nf; i += 32) { for (int k = 0; k < VE_AMP; k++) f[i].ampbuf[k] = 0.f; f[i].ampptr = 0; }
-  __syncwarp();
+  const int lane = threadIdx.x;
   unsigned char *mk = marks + mark_base[blockIdx.x];
   int stretch = 0;
-  for (int j = 0; j < S.nsteps; j++) {
-    stretch++;
-    if (stretch > VE_MAXSTRETCH * 2) stretch = VE_MAXSTRETCH * 2;
-    int st; float pen;
-    ve_stretch_params(stretch, E->stretch_penalty, &st, &pen);
-    int ret = 0;
-    for (int i = lane; i < nf; i += 32) {
-      const int c = i / VE_BANDS, b = i % VE_BANDS;
-      const float acc = acc_in[((S.out_base * ch + (long long)c * S.nsteps + j) * VE_BANDS) + b];
-      ret |= ve_trigger(&f[i], acc, st, pen, E->pre_th[b], E->post_th[b]);
+  unsigned carry = 0;                                   /* a pre-echo hit at step j also marks j+1 */
+  for (int j0 = 0; j0 < S.nsteps; j0 += 32) {
+    const int n = min(32, S.nsteps - j0);
+    const unsigned w = lane < n ? flags[S.out_base + j0 + lane] : 0u;
+    unsigned pre = 0, post = 0;
+#pragma unroll 8
+    for (int k = 0; k < n; k++) {
+      const unsigned wk = __shfl_sync(FULLMASK, w, k);
+      stretch = min(stretch + 1, VE_MAXSTRETCH * 2);
+      const int v = max(stretch >> 1, VE_MINSTRETCH) - VE_MINSTRETCH;
+      const unsigned bits = (wk >> (2 * v)) & 3u;
+      pre |= (bits & 1u) << k; post |= (bits >> 1) << k;
+      if (bits & 1u) stretch = -1;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ret |= __shfl_xor_sync(FULLMASK, ret, o);
-    if (lane == 0) {
-      mk[j + VE_POST] = 0;
-      if (ret & 1) { mk[j] = 1; mk[j + 1] = 1; }
-      if (ret & 2) { mk[j] = 1; if (j > 0) mk[j - 1] = 1; }
-    }
-    if (ret & 4) stretch = -1;
+    const unsigned m = pre | post | (pre << 1) | (post >> 1) | carry;
+    if ((m >> lane) & 1u) mk[j0 + lane] = 1;
+    if (lane == 0 && (post & 1u) && j0 > 0) mk[j0 - 1] = 1;
+    carry = (pre >> (n - 1)) & 1u;
+    if (n < 32 && lane == 0 && carry) mk[j0 + n] = 1;
   }
-  if (lane == 0) stretch_out[blockIdx.x] = stretch;
+  if (lane == 0) {
+    if (carry && (S.nsteps & 31) == 0 && S.nsteps > 0) mk[S.nsteps] = 1;
+    stretch_out[blockIdx.x] = stretch;
+  }
+}
+
+/* direct upload: the caller's samples already sit at [lead, eof) of every channel row; zero the lead-in and
+   the tail and apply the setup's pre-amplitude in place */
+__global__ void k_timeline_finish(const EnvStream *__restrict__ streams, int ch, int lead, float pre_amp, float *__restrict__ pcm) {
+  const EnvStream S = streams[blockIdx.y / ch];
+  float *d = pcm + S.pcm_base + (long long)(blockIdx.y % ch) * S.T;
+  const bool scale = pre_amp != 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S.T; i += (long long)gridDim.x * blockDim.x) {
+    if (i < lead || i >= S.eof) d[i] = 0.f;
+    else if (scale) d[i] = __fmul_rn(d[i], pre_amp);
+  }
 }
 
 /* the last 17 band amplitudes and 45 near-DC terms of every (stream, channel): what the host needs to
@@ -554,10 +618,11 @@ struct vb200_segmenter {
   vb200_setup *s; EnvParams env;
   EnvDev *d_env; double *d_cs, *d_cst; float *d_win;
   float *h_pcm, *d_pcm; size_t pcm_cap;          /* pinned host timeline + device timeline */
-  float *d_acc, *d_temp; size_t step_cap;
+  float *d_acc, *d_temp; unsigned *d_flags; size_t step_cap;
   unsigned char *d_marks, *h_marks; size_t mark_cap;
   EnvStream *d_streams, *h_streams; long long *d_mark_base, *h_mark_base; int *d_stretch, *h_stretch;
   float *d_acc_tail, *h_acc_tail, *d_temp_tail, *h_temp_tail; int stream_cap;
+  cudaStream_t st; int direct;
   std::vector<vb200_block> blocks; size_t pcm_elems;
 };
 
@@ -585,6 +650,7 @@ extern "C" int vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out) {
   for (int i = 0; i < VE_BANDS; i++) { e.bbegin[i] = kBandBegin[i]; e.bend[i] = kBandEnd[i]; e.pre_th[i] = g->env.pre_th[i]; e.post_th[i] = g->env.post_th[i]; }
   e.minenergy = g->env.minenergy; e.stretch_penalty = g->env.stretch_penalty;
   CUDA_TRY(cudaMemcpy(g->d_env, &e, sizeof(e), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
   *out = g;
   return VB200_OK;
 }
@@ -592,8 +658,9 @@ extern "C" int vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out) {
 extern "C" void vb200_segmenter_destroy(vb200_segmenter *g) {
   if (!g) return;
   cudaSetDevice(g->s->device);
+  cudaStreamDestroy(g->st);
   cudaFree(g->d_cs); cudaFree(g->d_cst); cudaFree(g->d_win); cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
-  cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_marks); cudaFreeHost(g->h_marks);
+  cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_flags); cudaFree(g->d_marks); cudaFreeHost(g->h_marks);
   cudaFree(g->d_streams); cudaFreeHost(g->h_streams); cudaFree(g->d_mark_base); cudaFreeHost(g->h_mark_base);
   cudaFree(g->d_stretch); cudaFreeHost(g->h_stretch); cudaFree(g->d_acc_tail); cudaFreeHost(g->h_acc_tail);
   cudaFree(g->d_temp_tail); cudaFreeHost(g->h_temp_tail);
@@ -618,7 +685,7 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
   if (!g || nstreams < 1 || !pcm || !nsamples || !stride) { vb200_set_error("vb200_segmenter_run: bad arguments"); return VB200_EINVAL; }
   vb200_setup *s = g->s;
   CUDA_TRY(cudaSetDevice(s->device));
-  cudaStream_t st = (cudaStream_t)s->stream;
+  cudaStream_t st = g->st;
   const int ch = s->h.channels;
   if (chunk <= 0) chunk = 1024;
   std::vector<StreamSeg> seg(nstreams);
@@ -638,8 +705,9 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
   }
   const size_t nstep_tot = (size_t)step_base[nstreams] * ch;
   if (g->step_cap < nstep_tot) {
-    cudaFree(g->d_acc); cudaFree(g->d_temp); g->d_acc = g->d_temp = nullptr; g->step_cap = 0;
+    cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_flags); g->d_acc = g->d_temp = nullptr; g->d_flags = nullptr; g->step_cap = 0;
     SEG_ALLOC(g->d_acc, (nstep_tot + 1) * VE_BANDS * sizeof(float), false); SEG_ALLOC(g->d_temp, (nstep_tot + 1) * sizeof(float), false);
+    SEG_ALLOC(g->d_flags, ((size_t)step_base[nstreams] + 1) * sizeof(unsigned), false);
     g->step_cap = nstep_tot;
   }
   const size_t nmark = (size_t)mark_base[nstreams];
@@ -662,30 +730,76 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
   const bool trace = getenv("VB200_TRACE") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t0 = now(), t1, t2, t3, t4;
-  /* host: timelines (pre-amplified PCM + LPC head) straight into the pinned buffer */
-  parallel_for(nstreams, threads, [&](int i) {
-    seg[i].init(s, g->env, nsamples[i], g->h_pcm + base[i], i);
-    seg[i].pcm_base = (long)base[i];
-    seg[i].fill_and_head(pcm[i], stride[i], chunk);
-  });
+  /* inputs already in page-locked memory go up from where they are; otherwise they are staged through
+     the segmenter's own pinned timeline */
+  bool direct = getenv("VB200_SEG_STAGED") == nullptr;
+  for (int i = 0; direct && i < nstreams; i++) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, pcm[i]) != cudaSuccess) { (void)cudaGetLastError(); direct = false; }
+    else if (at.type != cudaMemoryTypeHost) direct = false;
+  }
+  g->direct = direct ? 1 : 0;
+  const int lead = s->h.bs[1] / 2;
   int max_steps = 0;
   for (int i = 0; i < nstreams; i++) {
     EnvStream &e = g->h_streams[i];
-    e.pcm_base = base[i]; e.T = seg[i].T; e.nsteps = (int)seg[i].steps_complete(seg[i].eof_abs); e.out_base = step_base[i];
+    const long T = StreamSeg::timeline_len(s, nsamples[i]), eof = lead + nsamples[i];
+    const long l = eof / VE_STEP - VE_WIN;
+    e.pcm_base = base[i]; e.T = T; e.nsteps = (int)(l > 0 ? l : 0); e.out_base = step_base[i]; e.eof = eof;
     g->h_mark_base[i] = mark_base[i];
     if (e.nsteps > max_steps) max_steps = e.nsteps;
   }
-  t1 = now();
-  /* one H2D of the whole timeline; the detector's heavy half on the device */
-  CUDA_TRY(cudaMemcpyAsync(g->d_pcm, g->h_pcm, total * sizeof(float), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(g->d_streams, g->h_streams, sizeof(EnvStream) * nstreams, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(g->d_mark_base, g->h_mark_base, sizeof(long long) * nstreams, cudaMemcpyHostToDevice, st));
+  /* host: timelines (pre-amplified PCM + LPC head) into the pinned buffer; staged mode sends every finished
+     stream to the device at once, so the H2D of stream i overlaps the fill of the streams after it */
+  {
+    std::vector<std::atomic<int>> done(nstreams);
+    for (int i = 0; i < nstreams; i++) done[i].store(0);
+    int nthr = threads < 1 ? 1 : (threads > nstreams ? nstreams : threads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthr; t++)
+      th.emplace_back([&, t]() {
+        for (int i = t; i < nstreams; i += nthr) {
+          seg[i].init(s, g->env, nsamples[i], g->h_pcm + base[i], i);
+          seg[i].pcm_base = (long)base[i];
+          seg[i].fill_and_head(pcm[i], stride[i], chunk, direct);
+          done[i].store(1, std::memory_order_release);
+        }
+      });
+    cudaError_t cerr = cudaSuccess;
+    if (direct) {
+      for (int i = 0; i < nstreams && cerr == cudaSuccess; i++)
+        if (nsamples[i] > 0)
+          cerr = cudaMemcpy2DAsync(g->d_pcm + base[i] + lead, sizeof(float) * g->h_streams[i].T, pcm[i], sizeof(float) * stride[i],
+                                   sizeof(float) * nsamples[i], ch, cudaMemcpyHostToDevice, st);
+      if (cerr == cudaSuccess) {
+        k_timeline_finish<<<dim3(64, nstreams * ch), 256, 0, st>>>(g->d_streams, ch, lead, g->env.pre_amp, g->d_pcm);
+        cerr = cudaGetLastError();
+      }
+    }
+    for (int i = 0; i < nstreams; i++) {
+      while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+      if (cerr != cudaSuccess) continue;
+      if (!direct)
+        cerr = cudaMemcpyAsync(g->d_pcm + base[i], g->h_pcm + base[i], (size_t)(base[i + 1] - base[i]) * sizeof(float), cudaMemcpyHostToDevice, st);
+      else
+        cerr = cudaMemcpy2DAsync(g->d_pcm + base[i], sizeof(float) * seg[i].T, g->h_pcm + base[i], sizeof(float) * seg[i].T,
+                                 sizeof(float) * lead, ch, cudaMemcpyHostToDevice, st);      /* the LPC head */
+    }
+    for (auto &x : th) x.join();
+    CUDA_TRY(cerr);
+  }
+  t1 = now();
+  /* the detector's heavy half on the device */
   CUDA_TRY(cudaMemsetAsync(g->d_marks, 0, nmark, st));
   if (max_steps > 0) {
     dim3 grid((max_steps + EV_TILE - 1) / EV_TILE, ch, nstreams);
     k_env_bands<<<grid, 64, 0, st>>>(g->d_env, g->d_streams, ch, g->d_pcm, g->d_acc, g->d_temp);
     LAUNCH_CHECK();
-    k_env_trigger<<<nstreams, 32, 0, st>>>(g->d_env, g->d_streams, ch, g->d_acc, g->d_marks, g->d_mark_base, g->d_stretch);
+    k_env_flags<<<dim3((max_steps + 127) / 128, nstreams), 128, 0, st>>>(g->d_env, g->d_streams, ch, g->d_acc, g->d_flags);
+    LAUNCH_CHECK();
+    k_env_trigger<<<nstreams, 32, 0, st>>>(g->d_streams, g->d_flags, g->d_marks, g->d_mark_base, g->d_stretch);
     LAUNCH_CHECK();
     k_env_tail<<<dim3(nstreams, ch), 64, 0, st>>>(g->d_streams, ch, g->d_acc, g->d_temp, g->d_acc_tail, g->d_temp_tail);
     LAUNCH_CHECK();
@@ -726,3 +840,16 @@ extern "C" int vb200_segmenter_count(const vb200_segmenter *g) { return g ? (int
 extern "C" const vb200_block *vb200_segmenter_blocks(const vb200_segmenter *g) { return g ? g->blocks.data() : nullptr; }
 extern "C" const float *vb200_segmenter_device_pcm(const vb200_segmenter *g, size_t *elems) { if (!g) return nullptr; if (elems) *elems = g->pcm_elems; return g->d_pcm; }
 extern "C" const float *vb200_segmenter_host_pcm(const vb200_segmenter *g) { return g ? g->h_pcm : nullptr; }
+extern "C" int vb200_segmenter_read_pcm(const vb200_segmenter *g, float *out, size_t elems) {
+  if (!g || !out || elems > g->pcm_elems) { vb200_set_error("vb200_segmenter_read_pcm: bad arguments"); return VB200_EINVAL; }
+  CUDA_TRY(cudaSetDevice(g->s->device));
+  CUDA_TRY(cudaMemcpy(out, g->d_pcm, elems * sizeof(float), cudaMemcpyDeviceToHost));
+  return VB200_OK;
+}
+extern "C" int vb200_pinned_alloc(size_t bytes, void **out) {
+  if (!out) { vb200_set_error("vb200_pinned_alloc: bad arguments"); return VB200_EINVAL; }
+  CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+  return VB200_OK;
+}
+extern "C" void vb200_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int vb200_segmenter_direct(const vb200_segmenter *g) { return g ? g->direct : VB200_EINVAL; }

@@ -4,6 +4,9 @@ Host side (north_star): stream segmentation (envelope / block-size decision, csr
 in managed mode, the bitrate manager; device side: everything mapping0_forward does, batched over
 all blocks of all streams (csrc/pipeline.cu), including the bit packing."""
 import ctypes as C
+import os
+import sys
+import time
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -20,6 +23,23 @@ assert BLOCK_DTYPE.itemsize == C.sizeof(ops.Block)
 L.vb200_segmenter_blocks.restype = C.POINTER(ops.Block)
 L.vb200_segmenter_device_pcm.restype = C.c_void_p
 L.vb200_segmenter_host_pcm.restype = C.POINTER(C.c_float)
+
+
+class PinnedArray:
+    """float32 [channels, nsamples] in page-locked host memory (vb200_pinned_alloc): PCM held in one of these goes
+    to the device straight from where it lies."""
+
+    def __init__(self, channels, nsamples):
+        p = C.c_void_p()
+        check(L.vb200_pinned_alloc(C.c_size_t(4 * channels * max(1, nsamples)), C.byref(p)), "vb200_pinned_alloc")
+        self.p = p
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(channels, nsamples))
+
+    def close(self):
+        if self.p:
+            self.array = None
+            L.vb200_pinned_free(self.p)
+            self.p = None
 
 
 class Segmenter:
@@ -50,25 +70,44 @@ class Segmenter:
         dptr = L.vb200_segmenter_device_pcm(self.h, C.byref(elems))
         return blocks, dptr, elems.value
 
+    @property
+    def direct(self):
+        return bool(L.vb200_segmenter_direct(self.h))
+
+    def device_timeline(self, elems):
+        out = np.empty(elems, np.float32)
+        check(L.vb200_segmenter_read_pcm(self.h, out.ctypes.data_as(C.c_void_p), C.c_size_t(elems)), "vb200_segmenter_read_pcm")
+        return out
+
     def host_timeline(self, elems):
         return np.ctypeslib.as_array(L.vb200_segmenter_host_pcm(self.h), shape=(elems,))
 
 
 class Encoder:
-    def __init__(self, setup, max_blocks, threads=8):
+    """PCM of many independent streams in, packets out.  The streams are processed in `chunks` groups, each with
+    its own segmenter and batch (own CUDA streams): while the kernels of group g run, the host segments group
+    g+1 and its PCM goes up -- the host stage and the device stage overlap."""
+
+    def __init__(self, setup, max_blocks, threads=8, chunks=4):
         self.setup = setup
-        self.batch = ops.Batch(setup, max_blocks)
         self.threads = threads
+        self.chunks = max(1, int(chunks))
+        per = (int(max_blocks) + self.chunks - 1) // self.chunks + 64
+        self.batches = [ops.Batch(setup, per) for _ in range(self.chunks)]
+        self.segmenters = [Segmenter(setup) for _ in range(self.chunks)]
+        self.batch = self.batches[0]
+        self.segmenter = self.segmenters[0]
         self.pool = ThreadPoolExecutor(max_workers=threads)
-        self.segmenter = Segmenter(setup)
 
     def close(self):
-        self.batch.close()
-        self.segmenter.close()
+        for b in self.batches:
+            b.close()
+        for g in self.segmenters:
+            g.close()
         self.pool.shutdown()
 
     def segment(self, pcms):
-        """pcms: list of float32 [channels, nsamples] -> (Block array, one timeline buffer, blocks per stream)."""
+        """Host-only segmentation: list of float32 [channels, nsamples] -> (Block array, one timeline buffer, counts)."""
         s = self.setup
         res = list(self.pool.map(lambda a: segment.segment_stream(s, a[1], stream_index=a[0]), enumerate(pcms)))
         n = sum(len(r[0]) for r in res)
@@ -86,18 +125,36 @@ class Encoder:
         return blocks, timeline, counts
 
     def encode(self, pcms, streams=None):
-        """Host PCM of many streams -> packet table.  Segmentation (detector on the GPU, LPC + window
-        sequencing on the host) uploads the PCM once; the analysis batch then reads it in place."""
-        blocks, dptr, elems = self.segmenter.run(pcms, threads=self.threads)
+        """Host PCM of many streams -> list of (packet table, first stream index), one per group."""
+        n = len(pcms)
         own = streams is None
         if own:
             streams = [ops.Stream(self.setup) for _ in pcms]
-        self.batch.run(streams, blocks, dptr, pcm_on_device=True, pcm_elems=elems)
-        tab = table(self.batch)
+        groups = [(g * n // self.chunks, (g + 1) * n // self.chunks) for g in range(self.chunks)]
+        groups = [(a, b) for a, b in groups if b > a]
+        trace = os.environ.get("VB200_TRACE")
+        t0 = time.perf_counter()
+        marks = []
+        for g, (a, b) in enumerate(groups):
+            blocks, dptr, elems = self.segmenters[g].run(pcms[a:b], threads=self.threads)
+            t1 = time.perf_counter()
+            self.batches[g].submit(streams[a:b], blocks, dptr, elems)
+            marks.append((t1 - t0, time.perf_counter() - t0))
+        out = []
+        for g, (a, b) in enumerate(groups):
+            self.batches[g].collect()
+            marks.append((time.perf_counter() - t0,))
+            out.append((table(self.batches[g]), a))
+        if trace:
+            print("[vb200 encode] ms since start: " + " ".join("/".join("%.1f" % (x * 1e3) for x in m) for m in marks), file=sys.stderr)
         if own:
             for st in streams:
                 st.close()
-        return tab
+        return out
+
+
+def total_bytes(tabs):
+    return sum(t["total"] for t, _ in tabs)
 
 
 def table(batch):
@@ -113,8 +170,17 @@ def table(batch):
                 stream=as_arr(st, C.c_int), total=int(b_.sum()))
 
 
-def packets_of(tab, stream):
-    """[(bytes, granulepos, eos)] of one stream from a packet table."""
+def packets_of(tabs, stream):
+    """[(bytes, granulepos, eos)] of one stream from the result of Encoder.encode (or a single table)."""
+    if isinstance(tabs, dict):
+        tabs = [(tabs, 0)]
+    tab = None
+    for t, first in sorted(tabs, key=lambda x: x[1]):
+        if first <= stream:
+            tab, rel = t, stream - first
+    if tab is None or not tab["n"]:
+        return []
+    stream = rel
     out = []
     for i in np.nonzero(tab["stream"] == stream)[0]:
         out.append((C.string_at(C.addressof(tab["base"].contents) + int(tab["off"][i]), int(tab["bytes"][i])),

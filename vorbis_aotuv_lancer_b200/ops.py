@@ -241,6 +241,16 @@ class Batch:
               "vb200_batch_run")
         self.n = len(blocks)
 
+    def submit(self, streams, blocks, pcm, pcm_elems):
+        """Asynchronous half of run() for device-resident PCM (vb200_batch_submit)."""
+        sh = (C.c_void_p * len(streams))(*[s.h for s in streams])
+        check(L.vb200_batch_submit(self.h, sh, len(streams), blocks, len(blocks), C.c_void_p(int(pcm)), C.c_size_t(int(pcm_elems)), 1),
+              "vb200_batch_submit")
+        self.n = len(blocks)
+
+    def collect(self):
+        check(L.vb200_batch_collect(self.h), "vb200_batch_collect")
+
     def packets(self):
         """[(bytes, granulepos, eos, stream)] of the last run, in block order."""
         out = []
