@@ -74,6 +74,15 @@ def synth_streams(L, nstreams, seconds, channels, rate, first_index, threads=8, 
         return list(ex.map(one, range(nstreams)))
 
 
+_REAL_STDOUT = None
+
+
+def emit(out):
+    f = _REAL_STDOUT or sys.stdout
+    f.write(json.dumps(out) + "\n")
+    f.flush()
+
+
 # ------------------------------------------------------------------ reference arm / cpu baseline
 def _ref_worker(args):
     flavour, channels, rate, quality, seconds, seed_index, reps = args
@@ -128,7 +137,7 @@ def run_reference(args):
            "config": {"workload": "q4 44.1 kHz stereo, 60 s synthetic streams, one per host core", "quality": 0.4},
            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample},
            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 # ------------------------------------------------------------------ our arm
@@ -228,7 +237,7 @@ def run_ours(args):
         whole_gbs = whole / (sum(kern.values()) * 1e-3) / 1e9
         cores = os.cpu_count() or 1
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
             try:
                 from oracle import reflib
                 if reflib.available("sse"):
@@ -253,7 +262,7 @@ def run_ours(args):
                             "all_kernels": {"algorithmic_GBps": whole_gbs, "frac": whole_gbs / peak, "ms": sum(kern.values())}},
                "stage_ms": stage_ms, "clocks": summarize_clocks(samples), "cpu_baseline": cpu,
                "packet_bytes_per_step": int(packet_bytes), "kbps": packet_bytes * 8 / audio / 1000.0}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -269,6 +278,12 @@ def main():
     ap.add_argument("--chunks", type=int, default=4, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries the one JSON line and nothing else: libraries that write to fd 1 (NCCL's version banner)
+    # are sent to stderr while the run lasts
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
