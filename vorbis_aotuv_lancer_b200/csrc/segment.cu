@@ -81,12 +81,13 @@ void lpc_predict(const float *coeff, const float *prime, int m, float *data, lon
   }
 }
 
-/* tables of the detector, built once (envelope.c:42-82); the 128-point MDCT is kept as its 64x128
-   matrix in double so that host and device evaluate the very same sums */
+/* tables of the detector, built once (envelope.c:42-82).  The 128-point MDCT is evaluated as fold (two
+   windowed products per point, summed in double) + 64x64 DCT-IV matrix in double with fused multiply-adds in
+   ascending order, so that host and device evaluate the very same sums */
 struct Detector {
   float win[VE_N];
   float bandwin[VE_BANDS][8], bandtotal[VE_BANDS];
-  double cs[VE_N / 2][VE_N];
+  double dct[VE_N / 2][VE_N / 2];      /* [k][n] */
   Detector() {
     for (int i = 0; i < VE_N; i++) { const float t = (float)sin(i / (VE_N - 1.) * M_PI); win[i] = t * t; }
     for (int j = 0; j < VE_BANDS; j++) {
@@ -96,7 +97,7 @@ struct Detector {
       bandtotal[j] = (float)(1. / tot);
     }
     for (int k = 0; k < VE_N / 2; k++)
-      for (int t = 0; t < VE_N; t++) cs[k][t] = (4.0 / VE_N) * cos(M_PI / (2.0 * VE_N) * (2 * t + 1 + VE_N / 2) * (2 * k + 1));
+      for (int n = 0; n < VE_N / 2; n++) dct[k][n] = (4.0 / VE_N) * cos(M_PI / (2.0 * VE_N) * (2 * n + 1) * (2 * k + 1));
   }
 };
 const Detector &detector() { static Detector d; return d; }
@@ -105,11 +106,30 @@ const Detector &detector() { static Detector d; return d; }
 struct NearDC { float ring[VE_NEARDC]; float acc, partial; int ptr; };
 struct BandFilter { float ampbuf[VE_AMP]; int ampptr; };
 
-/* (1) windowed 128-point MDCT, first `nout` coefficients */
+/* (1) windowed 128-point MDCT, first `nout` coefficients.  Fold: with M = 64, h = 32 and p[t] = data[t]*win[t]
+   (float), u[n] = -p[3h-1-n] - p[3h+n] for n < h, p[n-h] - p[3h-1-n] otherwise; X[k] = sum_n dct[k][n] u[n]. */
+__host__ __device__ inline double ve_fold(const float *data, const float *win, int n) {
+  constexpr int h = VE_N / 4;
+#ifdef __CUDA_ARCH__
+  if (n < h) return -(double)__fmul_rn(data[3 * h - 1 - n], win[3 * h - 1 - n]) - (double)__fmul_rn(data[3 * h + n], win[3 * h + n]);
+  return (double)__fmul_rn(data[n - h], win[n - h]) - (double)__fmul_rn(data[3 * h - 1 - n], win[3 * h - 1 - n]);
+#else
+  if (n < h) { const float a = data[3 * h - 1 - n] * win[3 * h - 1 - n], b = data[3 * h + n] * win[3 * h + n]; return -(double)a - (double)b; }
+  const float a = data[n - h] * win[n - h], b = data[3 * h - 1 - n] * win[3 * h - 1 - n];
+  return (double)a - (double)b;
+#endif
+}
+__attribute__((target("fma"))) void ve_dct_hw(const double (*dct)[VE_N / 2], const double *u, float *vec, int nout) {
+  for (int k = 0; k < nout; k++) { double a = 0; for (int n = 0; n < VE_N / 2; n++) a = __builtin_fma(dct[k][n], u[n], a); vec[k] = (float)a; }
+}
+void ve_dct_sw(const double (*dct)[VE_N / 2], const double *u, float *vec, int nout) {
+  for (int k = 0; k < nout; k++) { double a = 0; for (int n = 0; n < VE_N / 2; n++) a = fma(dct[k][n], u[n], a); vec[k] = (float)a; }
+}
 inline void ve_mdct(const Detector &D, const float *data, float *vec, int nout) {
-  float w[VE_N];
-  for (int i = 0; i < VE_N; i++) w[i] = data[i] * D.win[i];
-  for (int k = 0; k < nout; k++) { double a = 0; for (int t = 0; t < VE_N; t++) a += D.cs[k][t] * w[t]; vec[k] = (float)a; }
+  static const bool hw = __builtin_cpu_supports("fma");
+  double u[VE_N / 2];
+  for (int n = 0; n < VE_N / 2; n++) u[n] = ve_fold(data, D.win, n);
+  if (hw) ve_dct_hw(D.dct, u, vec, nout); else ve_dct_sw(D.dct, u, vec, nout);
 }
 __host__ __device__ inline float ve_neartemp(float v0, float v1, float v2) {
   return (float)((double)(v0 * v0) + .7 * (double)v1 * (double)v1 + .2 * (double)v2 * (double)v2);
@@ -398,8 +418,8 @@ extern "C" const float *vb200_segments_pcm(const vb200_segments *g, long *elems)
 namespace {
 
 struct EnvDev {            /* tables in HBM */
-  const double *cs;        /* [64][128] */
-  const double *cst;       /* [128][64] transposed */
+  const double *dct;       /* [64 k][64 n] */
+  const double *dctt;      /* [64 n][64 k] transposed */
   const float *win;        /* [128] */
   float bandwin[VE_BANDS][8], bandtotal[VE_BANDS];
   int bbegin[VE_BANDS], bend[VE_BANDS];
@@ -410,100 +430,118 @@ struct EnvStream { long long pcm_base; long long T; int nsteps; long long out_ba
 
 constexpr int EV_TILE = 32;      /* steps per CTA */
 constexpr int EV_HALO = 30;      /* the near-DC sum of a step depends on at most the 30 previous steps */
+constexpr int EV_M = VE_N / 2;   /* folded length = number of coefficients */
+constexpr int EV_US = EV_M + 1;  /* row stride of the folded steps in shared memory (doubles) */
 
-/* K0a: per (stream, channel, tile of steps): windowed 128-point MDCT -> near-DC decay -> spread/limit ->
-   12 band amplitudes.  Everything here is a pure function of the PCM, so tiles are independent. */
+/* K0a: per (stream, channel, tile of 32 steps): fold -> 64x64 DCT-IV in double -> near-DC decay ->
+   spread/limit -> 12 band amplitudes.  Everything here is a pure function of the PCM, so tiles are independent.
+   The matrix product is register-blocked 4 coefficients x 8 steps per thread: thread (kq, sg) owns coefficients
+   kq+16j of steps 8sg..8sg+7, so each pass over n costs 4 matrix loads + 8 broadcast reads for 32 DFMA. */
 __global__ void __launch_bounds__(64)
 k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams, int ch, const float *__restrict__ pcm,
             float *__restrict__ acc_out /*[stream][ch][step][12]*/, float *__restrict__ temp_out /*[stream][ch][step]*/) {
-  __shared__ float x[(EV_TILE + EV_HALO + 4) * VE_STEP + VE_STEP];
+  __shared__ double u[(EV_TILE + EV_HALO) * EV_US];
+  __shared__ float vec[EV_TILE][EV_M];
+  __shared__ float v2[EV_TILE][EV_M / 2 + 1];
   __shared__ float temps[EV_TILE + EV_HALO];
-  __shared__ float c3[(EV_TILE + EV_HALO) * 3];
   __shared__ float decay[EV_TILE];
-  __shared__ float vec4[4][VE_N / 2];
-  __shared__ float v2[VE_N / 4];
   const EnvStream S = streams[blockIdx.z];
   const int c = blockIdx.y, tid = threadIdx.x;
   const int j0 = blockIdx.x * EV_TILE;
   if (j0 >= S.nsteps) return;
   const int jn = min(EV_TILE, S.nsteps - j0);
-  const int h0 = max(0, j0 - EV_HALO);                      /* first step whose samples we stage */
+  const int h0 = max(0, j0 - EV_HALO);                      /* first step that is folded here */
+  const int nh = j0 + jn - h0, toff = j0 - h0;
   const float *src = pcm + S.pcm_base + (long long)c * S.T + (long long)h0 * VE_STEP;
-  const int nsamp = (j0 + jn - h0) * VE_STEP + VE_STEP;
-  for (int i = tid; i < nsamp; i += 64) x[i] = src[i];
-  for (int i = nsamp + tid; i < (EV_TILE + EV_HALO + 4) * VE_STEP + VE_STEP; i += 64) x[i] = 0.f;
+  const float *win = E->win;
+  for (int it = tid; it < nh * EV_M; it += 64) {
+    const int sidx = it >> 6, n = it & 63;
+    u[sidx * EV_US + n] = ve_fold(src + sidx * VE_STEP, win, n);
+  }
+  for (int it = nh * EV_M + tid; it < (EV_TILE + EV_HALO) * EV_M; it += 64) u[(it >> 6) * EV_US + (it & 63)] = 0.;
   __syncthreads();
   /* near-DC terms of the halo + tile steps: only coefficients 0..2 are needed */
-  const int nh = j0 + jn - h0;
-  for (int w = tid; w < nh * 3; w += 64) {
-    const int sidx = w / 3, k = w % 3;
-    const float *d = x + sidx * VE_STEP;
-    const double *row = E->cs + k * VE_N;
-    double a = 0;
-    for (int t = 0; t < VE_N; t++) a += row[t] * (double)__fmul_rn(d[t], E->win[t]);
-    c3[w] = (float)a;
+  for (int sidx = tid; sidx < nh; sidx += 64) {
+    const double *us = u + sidx * EV_US;
+    double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 4
+    for (int n = 0; n < EV_M; n++) {
+      const double x = us[n];
+      a0 = fma(E->dct[n], x, a0); a1 = fma(E->dct[EV_M + n], x, a1); a2 = fma(E->dct[2 * EV_M + n], x, a2);
+    }
+    temps[sidx] = ve_neartemp((float)a0, (float)a1, (float)a2);
   }
-  __syncthreads();
-  for (int sidx = tid; sidx < nh; sidx += 64) temps[sidx] = ve_neartemp(c3[sidx * 3], c3[sidx * 3 + 1], c3[sidx * 3 + 2]);
   __syncthreads();
   /* decay of every tile step: replay the refresh cycle it sits in (<= 44 float ops) */
   for (int q = tid; q < jn; q += 64) {
     const int j = j0 + q, ptr = j % VE_NEARDC, r = j - ptr;      /* r = last refresh step */
     auto T_ = [&](int step) { return step >= 0 ? temps[step - h0] : 0.f; };
     float partial = 0.f;
-    if (r >= VE_NEARDC) { partial = T_(r - VE_NEARDC); for (int u = r - VE_NEARDC + 1; u < r; u++) partial = __fadd_rn(partial, T_(u)); }
+    if (r >= VE_NEARDC) { partial = T_(r - VE_NEARDC); for (int w = r - VE_NEARDC + 1; w < r; w++) partial = __fadd_rn(partial, T_(w)); }
     float acc = __fadd_rn(partial, T_(r));
     float dec = acc;
     acc = __fsub_rn(acc, r >= VE_NEARDC ? T_(r - VE_NEARDC) : 0.f);
-    for (int u = r + 1; u <= j; u++) {
-      acc = __fadd_rn(acc, T_(u)); dec = acc;
-      acc = __fsub_rn(acc, u >= VE_NEARDC ? T_(u - VE_NEARDC) : 0.f);
+    for (int w = r + 1; w <= j; w++) {
+      acc = __fadd_rn(acc, T_(w)); dec = acc;
+      acc = __fsub_rn(acc, w >= VE_NEARDC ? T_(w - VE_NEARDC) : 0.f);
     }
     dec = (float)((double)dec * (1. / (VE_NEARDC + 1)));
     decay[q] = (float)((double)todB_hd(dec) * .5 - (double)15.f);
     temp_out[S.out_base * ch + (long long)c * S.nsteps + j] = T_(j);
   }
+  /* the full 64-coefficient transform of the 32 tile steps */
+  {
+    const int kq = tid & 15, sg = tid >> 4;
+    double a[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[j][i] = 0.;
+    const double *ub = u + (toff + sg * 8) * EV_US;
+    const double *mt = E->dctt + kq;
+#pragma unroll 2
+    for (int n = 0; n < EV_M; n++) {
+      double m[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) m[j] = mt[n * EV_M + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const double x = ub[i * EV_US + n];
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j][i] = fma(m[j], x, a[j][i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) vec[sg * 8 + i][kq + 16 * j] = (float)a[j][i];
+  }
   __syncthreads();
-  /* the full 64-coefficient transform, four steps per pass so that one load of the (transposed) matrix row
-     element feeds four dot products; thread k owns coefficient k */
-  for (int q0 = 0; q0 < jn; q0 += 4) {
-    const int nq = min(4, jn - q0);
-    {
-      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      const float *d0 = x + (j0 + q0 - h0) * VE_STEP;
-      const double *col = E->cst + tid;                  /* cst[t][k]: consecutive k -> coalesced */
-      for (int t = 0; t < VE_N; t++) {
-        const double c = col[t * (VE_N / 2)];
-        const float wv = E->win[t];
-        a0 += c * (double)__fmul_rn(d0[t], wv);
-        a1 += c * (double)__fmul_rn(d0[t + VE_STEP], wv);
-        a2 += c * (double)__fmul_rn(d0[t + 2 * VE_STEP], wv);
-        a3 += c * (double)__fmul_rn(d0[t + 3 * VE_STEP], wv);
-      }
-      vec4[0][tid] = (float)a0; vec4[1][tid] = (float)a1; vec4[2][tid] = (float)a2; vec4[3][tid] = (float)a3;
-    }
-    __syncthreads();
-    for (int qq = 0; qq < nq; qq++) {
-      const float *vec = vec4[qq];
-      const int q = q0 + qq;
-      if (tid < VE_N / 4) {
-        const int i = tid * 2;
-        float val = __fadd_rn(__fmul_rn(vec[i], vec[i]), __fmul_rn(vec[i + 1], vec[i + 1]));
+  /* spread / limit: thread (q, half) walks 16 of the 32 coefficient pairs of step q */
+  {
+    const int q = tid & 31, half = tid >> 5;
+    if (q < jn) {
+      float dec = decay[q];
+      for (int w = 0; w < half * 16; w++) dec = (float)((double)dec - 8.);
+      const float minV = E->minenergy;
+      for (int i = half * 16; i < half * 16 + 16; i++) {
+        const float x0 = vec[q][2 * i], x1 = vec[q][2 * i + 1];
+        float val = __fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1));
         val = __fmul_rn(todB_hd(val), .5f);
-        float dec = decay[q];
-        for (int u = 0; u < tid; u++) dec = (float)((double)dec - 8.);
         if (val < dec) val = dec;
-        if (val < E->minenergy) val = E->minenergy;
-        v2[tid] = val;
+        if (val < minV) val = minV;
+        v2[q][i] = val;
+        dec = (float)((double)dec - 8.);
       }
-      __syncthreads();
-      if (tid < VE_BANDS) {
-        float acc = 0.f;
-        for (int i = 0; i < E->bend[tid]; i++) acc = __fadd_rn(acc, __fmul_rn(v2[i + E->bbegin[tid]], E->bandwin[tid][i]));
-        acc_out[((S.out_base * ch + (long long)c * S.nsteps + (j0 + q)) * VE_BANDS) + tid] = __fmul_rn(acc, E->bandtotal[tid]);
-      }
-      __syncthreads();
     }
+  }
+  __syncthreads();
+  for (int it = tid; it < jn * VE_BANDS; it += 64) {
+    const int q = it / VE_BANDS, b = it - q * VE_BANDS;
+    float acc = 0.f;
+    const int bb = E->bbegin[b], be = E->bend[b];
+    for (int i = 0; i < be; i++) acc = __fadd_rn(acc, __fmul_rn(v2[q][i + bb], E->bandwin[b][i]));
+    acc_out[((S.out_base * ch + (long long)c * S.nsteps + j0) * VE_BANDS) + it] = __fmul_rn(acc, E->bandtotal[b]);
   }
 }
 
@@ -616,7 +654,7 @@ __global__ void k_env_tail(const EnvStream *__restrict__ streams, int ch, const 
 
 struct vb200_segmenter {
   vb200_setup *s; EnvParams env;
-  EnvDev *d_env; double *d_cs, *d_cst; float *d_win;
+  EnvDev *d_env; double *d_dct, *d_dctt; float *d_win;
   float *h_pcm, *d_pcm; size_t pcm_cap;          /* pinned host timeline + device timeline */
   float *d_acc, *d_temp; unsigned *d_flags; size_t step_cap;
   unsigned char *d_marks, *h_marks; size_t mark_cap;
@@ -636,16 +674,16 @@ extern "C" int vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out) {
   if (!env_params(s, &g->env)) { delete g; vb200_set_error("vb200_segmenter_create: setup blob lacks the envelope parameters"); return VB200_EINVAL; }
   const Detector &D = detector();
   EnvDev e;
-  CUDA_TRY(cudaMalloc(&g->d_cs, sizeof(D.cs))); CUDA_TRY(cudaMalloc(&g->d_win, sizeof(D.win))); CUDA_TRY(cudaMalloc(&g->d_env, sizeof(EnvDev)));
-  CUDA_TRY(cudaMemcpy(g->d_cs, D.cs, sizeof(D.cs), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&g->d_dct, sizeof(D.dct))); CUDA_TRY(cudaMalloc(&g->d_win, sizeof(D.win))); CUDA_TRY(cudaMalloc(&g->d_env, sizeof(EnvDev)));
+  CUDA_TRY(cudaMemcpy(g->d_dct, D.dct, sizeof(D.dct), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(g->d_win, D.win, sizeof(D.win), cudaMemcpyHostToDevice));
   {
-    std::vector<double> tr((size_t)VE_N * (VE_N / 2));
-    for (int k = 0; k < VE_N / 2; k++) for (int t = 0; t < VE_N; t++) tr[(size_t)t * (VE_N / 2) + k] = D.cs[k][t];
-    CUDA_TRY(cudaMalloc(&g->d_cst, tr.size() * sizeof(double)));
-    CUDA_TRY(cudaMemcpy(g->d_cst, tr.data(), tr.size() * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<double> tr((size_t)(VE_N / 2) * (VE_N / 2));
+    for (int k = 0; k < VE_N / 2; k++) for (int n = 0; n < VE_N / 2; n++) tr[(size_t)n * (VE_N / 2) + k] = D.dct[k][n];
+    CUDA_TRY(cudaMalloc(&g->d_dctt, tr.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(g->d_dctt, tr.data(), tr.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
-  e.cs = g->d_cs; e.cst = g->d_cst; e.win = g->d_win;
+  e.dct = g->d_dct; e.dctt = g->d_dctt; e.win = g->d_win;
   memcpy(e.bandwin, D.bandwin, sizeof(e.bandwin)); memcpy(e.bandtotal, D.bandtotal, sizeof(e.bandtotal));
   for (int i = 0; i < VE_BANDS; i++) { e.bbegin[i] = kBandBegin[i]; e.bend[i] = kBandEnd[i]; e.pre_th[i] = g->env.pre_th[i]; e.post_th[i] = g->env.post_th[i]; }
   e.minenergy = g->env.minenergy; e.stretch_penalty = g->env.stretch_penalty;
@@ -659,7 +697,7 @@ extern "C" void vb200_segmenter_destroy(vb200_segmenter *g) {
   if (!g) return;
   cudaSetDevice(g->s->device);
   cudaStreamDestroy(g->st);
-  cudaFree(g->d_cs); cudaFree(g->d_cst); cudaFree(g->d_win); cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
+  cudaFree(g->d_dct); cudaFree(g->d_dctt); cudaFree(g->d_win); cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
   cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_flags); cudaFree(g->d_marks); cudaFreeHost(g->h_marks);
   cudaFree(g->d_streams); cudaFreeHost(g->h_streams); cudaFree(g->d_mark_base); cudaFreeHost(g->h_mark_base);
   cudaFree(g->d_stretch); cudaFreeHost(g->h_stretch); cudaFree(g->d_acc_tail); cudaFreeHost(g->h_acc_tail);
