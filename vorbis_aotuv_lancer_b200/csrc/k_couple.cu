@@ -17,14 +17,25 @@
 
 namespace {
 
-constexpr int CH = VB200_MAX_CHANNELS;
 
+template <int CH>
 struct CoupleSmem {
   float raw[CH][32], quant[CH][32], floor[CH][32], res[CH][32];
   int flag[CH][32];
   int out[CH][32];
   int cand[32];
 };
+
+/* the next partition's inputs are fetched with asynchronous global->shared copies while the current one is
+   worked on: the partition loop is serial, so without this every partition starts with an exposed HBM round trip */
+template <int CH>
+struct CoupleStage { float md[2][CH][32], ep[2][CH][32]; int iw[2][CH][32]; };
+
+__device__ __forceinline__ void cp_async4(void *smem, const void *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int Pending> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(Pending) : "memory"); }
 
 __device__ __forceinline__ bool opposite(float a, float b) { return (a > 0.f && b < 0.f) || (b > 0.f && a < 0.f); }
 __device__ __forceinline__ bool big(float x) { return x < -0.5f || x >= 0.5f; }
@@ -46,7 +57,8 @@ __device__ __forceinline__ float dipole(float a, float b, float threv) {
 }
 
 /* noise_normalize (psy.c:4732-4854) for channel row k of the current partition; lane j = bin j */
-__device__ void normalize(CoupleSmem &sm, const DevPsy &P, int limit, int k, bool use_flags, float nepeak, int i, int jn, int lane) {
+template <int CH>
+__device__ void normalize(CoupleSmem<CH> &sm, const DevPsy &P, int limit, int k, bool use_flags, float nepeak, int i, int jn, int lane) {
   int start = P.normal_p ? P.normal_start - i : jn;
   if (start > jn || nepeak < -0.5f) start = jn;
   const int j = lane;
@@ -114,11 +126,13 @@ __device__ void normalize(CoupleSmem &sm, const DevPsy &P, int limit, int k, boo
   __syncwarp();
 }
 
+template <int CH>
 __global__ void __launch_bounds__(32)
 k_couple(const DevSetup *__restrict__ S, int W, const int *__restrict__ psyv, int blobno, int n, int ch, int map_index,
          const float *__restrict__ mdct, const float *__restrict__ epeak, float *__restrict__ npeak, int npeak_stride,
          int *__restrict__ iwork, int *__restrict__ nonzero) {
-  __shared__ CoupleSmem sm;
+  __shared__ CoupleSmem<CH> sm;
+  __shared__ CoupleStage<CH> stg;
   __shared__ float s_np[CH];
   const int blk = blockIdx.x, lane = threadIdx.x;
   const DevPsy &P = S->psy[psyv[blk]];
@@ -133,9 +147,10 @@ k_couple(const DevSetup *__restrict__ S, int W, const int *__restrict__ psyv, in
   if (lowpassr % P.normal_partition) lowpassr = (lowpassr / P.normal_partition + 1) * P.normal_partition;   /* mapping0.c:778-781 */
   if (pre_x < pre) pre_x = pre;
   if (post_x < pre) post_x = pre;
-  float resdef[VB200_MAX_COUPLING];
+  constexpr int NC = CH <= 2 ? 1 : VB200_MAX_COUPLING;     /* coupling steps a CH-channel mapping can hold */
+  float resdef[NC];
 #pragma unroll
-  for (int k = 0; k < VB200_MAX_COUPLING; k++) resdef[k] = -1.f;
+  for (int k = 0; k < NC; k++) resdef[k] = -1.f;
 
   const float *md = mdct + (size_t)blk * ch * n, *ep = epeak + (size_t)blk * ch * n;
   float *npk = npeak + (size_t)blk * ch * npeak_stride;
@@ -144,10 +159,24 @@ k_couple(const DevSetup *__restrict__ S, int W, const int *__restrict__ psyv, in
   unsigned nzmask0 = 0;
   for (int k = 0; k < ch; k++) if (nzg[k]) nzmask0 |= 1u << k;
 
+  auto prefetch = [&](int buf, int i) {
+    if (i < lowpassr && lane < n - i && lane < part)
+      for (int k = 0; k < ch; k++)
+        if (nzmask0 & (1u << k)) {
+          cp_async4(&stg.md[buf][k][lane], md + (size_t)k * n + i + lane);
+          cp_async4(&stg.ep[buf][k][lane], ep + (size_t)k * n + i + lane);
+          cp_async4(&stg.iw[buf][k][lane], iw + (size_t)k * n + i + lane);
+        }
+    cp_async_commit();
+  };
+  prefetch(0, 0);
   for (int i = 0, pi = 0; i < lowpassr; i += part, pi++) {
     const int jn = part > n - i ? n - i : part;
     const int j = lane;
+    const int buf = pi & 1;
     unsigned nz = nzmask0;
+    prefetch(buf ^ 1, i + part);
+    cp_async_wait<1>();
     if (lane < ch) s_np[lane] = npk[lane * npeak_stride + pi];
     __syncwarp();
     for (int k = 0; k < ch; k++) {
@@ -163,12 +192,12 @@ k_couple(const DevSetup *__restrict__ S, int W, const int *__restrict__ psyv, in
         } else { p1 = post; p2 = post_x; }
         if (ramp) for (int t = 0; t <= j && t < jn; t++) { p1 = __fadd_rn(p1, s1); p2 = __fadd_rn(p2, s2); }
         if (j < jn) {
-          const float m = __ldg(md + (size_t)k * n + i + j);
-          const float fl = S->fromdB[iw[(size_t)k * n + i + j]];
+          const float m = stg.md[buf][k][j];
+          const float fl = S->fromdB[stg.iw[buf][k][j]];
           const float res = __fdiv_rn(m, fl);
           sm.res[k][j] = res;
           const float r = fabsf(res);
-          float t = __fsub_rn(p1, __ldg(ep + (size_t)k * n + i + j));
+          float t = __fsub_rn(p1, stg.ep[buf][k][j]);
           if (t < pre) t = pre;
           sm.flag[k][j] = (r < t) ? ((r < p2) ? 0 : -1) : 1;
           float e = __fmul_rn(m, m);
@@ -282,7 +311,10 @@ int vb200_launch_couple(const vb200_setup *s, cudaStream_t st, int W, int blocks
   if (blocks <= 0) return VB200_OK;
   if (blobno < 0 || blobno >= VB200_PACKETBLOBS) { vb200_set_error("blob number out of range"); return VB200_EINVAL; }
   const int n = s->h.bs[W] / 2;
-  k_couple<<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
+  if (s->h.channels <= 2)
+    k_couple<2><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
+  else
+    k_couple<VB200_MAX_CHANNELS><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
   LAUNCH_CHECK();
   return VB200_OK;
 }

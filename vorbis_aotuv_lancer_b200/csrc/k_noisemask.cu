@@ -21,11 +21,13 @@ namespace {
 
 template <int N>
 struct NoiseSmem {
-  float sums[5][N + 1];   /* N, X, XX, Y, XY prefix sums; +1 keeps the five chain lanes on different banks */
+  float sums[5][N + 4];   /* N, X, XX, Y, XY prefix sums; +4 keeps the rows 16-byte aligned and the five chain
+                             lanes (one 128-bit access each) on different banks */
   float work[N];
   float noise[N];
-  float held[3];          /* A, B, D of the last fitted bin, reused above the last full window */
-  float tmp[256], inm[256];
+  float held[4];          /* A, B, D of the last fitted bin, reused above the last full window */
+  __device__ float *tmp() { return sums[1]; }      /* scratch of the M7 tone fix; the prefix sums are dead by then */
+  __device__ float *inm() { return sums[2]; }
 };
 
 /* one regression pass over all bins (the parallel part of bark_noise_hybridmp) */
@@ -88,17 +90,19 @@ __device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f
   if (tid == 0) { sm.held[0] = 0.f; sm.held[1] = 0.f; sm.held[2] = 1.f; }
   __syncthreads();
   if (tid < 5) {                       /* the five serial float32 chains */
-    float *r = sm.sums[tid];
+    float4 *r = reinterpret_cast<float4 *>(sm.sums[tid]);
     float acc = 0.f;
+    auto run4 = [&](float4 &v) {
+      acc = __fadd_rn(acc, v.x); v.x = acc; acc = __fadd_rn(acc, v.y); v.y = acc;
+      acc = __fadd_rn(acc, v.z); v.z = acc; acc = __fadd_rn(acc, v.w); v.w = acc;
+    };
+    float4 a0 = r[0], a1 = r[1];
 #pragma unroll 1
-    for (int i = 0; i < N; i += 8) {
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) v[k] = r[i + k];
-#pragma unroll
-      for (int k = 0; k < 8; k++) { acc = __fadd_rn(acc, v[k]); v[k] = acc; }
-#pragma unroll
-      for (int k = 0; k < 8; k++) r[i + k] = v[k];
+    for (int i = 0; i < N / 4; i += 4) {      /* two register sets: the next 8 values arrive while 8 are summed */
+      float4 b0 = r[i + 2], b1 = r[i + 3];
+      run4(a0); r[i] = a0; run4(a1); r[i + 1] = a1;
+      if (i + 4 < N / 4) { a0 = r[i + 4]; a1 = r[i + 5]; }
+      run4(b0); r[i + 2] = b0; run4(b1); r[i + 3] = b1;
     }
   }
   __syncthreads();
@@ -115,7 +119,9 @@ __device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restr
   const float *off1 = P.noiseoffset + N;
   const float limit = fabsf(__ldg(off1));
   float *noise = sm.work;
-  for (int i = 0; i < 256; i++) { sm.tmp[i] = 0.f; sm.inm[i] = 0.f; }
+  float *tmp_ = sm.tmp(), *inm_ = sm.inm();
+  constexpr int SCR = N < 256 ? N : 256;
+  for (int i = 0; i < SCR; i++) { tmp_[i] = 0.f; inm_[i] = 0.f; }
   if (block_mode <= 1) {
     const int up = 3, un = 4;
     int nxp = nx + un;
@@ -123,23 +129,23 @@ __device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restr
     if (nxp > N) { nx = N; nxp = N - un; }
     for (int i = 0; i < nxp; i++) {
       float s = spec[i];
-      sm.inm[i] = (s < -70.f) ? (float)(-70. + (double)__fadd_rn(s, 70.f) * .1) : s;
+      inm_[i] = (s < -70.f) ? (float)(-70. + (double)__fadd_rn(s, 70.f) * .1) : s;
     }
     for (int i = un; i < nx; i++) {
       if (!(spec[i] > spec[i - 1] && spec[i] > spec[i + 1])) continue;
       int ps = i - 1, pe = i + 1;
       for (int j = ps; j > i - up; j--) { if (spec[j + 1] < spec[j]) break; ps = j; }
       for (int j = pe; j < i + un; j++) { if (spec[j - 1] < spec[j]) break; pe = j; }
-      float ss = fmaxf(__fsub_rn(sm.inm[i], sm.inm[ps]), __fsub_rn(sm.inm[i], sm.inm[pe]));
+      float ss = fmaxf(__fsub_rn(inm_[i], inm_[ps]), __fsub_rn(inm_[i], inm_[pe]));
       if (ss > tol) {
         if (spec[i] > noise[i]) { ss = __fsub_rn(ss, tol); ss = __fmul_rn(ss, strength); }
-        for (int j = ps; j <= pe; j++) { float t = fmaxf(ss, sm.tmp[j]); if (t < 0.f) t = 0.f; sm.tmp[j] = t; }
+        for (int j = ps; j <= pe; j++) { float t = fmaxf(ss, tmp_[j]); if (t < 0.f) t = 0.f; tmp_[j] = t; }
       }
       i = pe;
     }
     for (int i = un - 1; i < nx; i++) {
       float cap = fminf(__ldg(P.ntfix + i), __fadd_rn(__ldg(off1 + i), limit));
-      float t = sm.tmp[i];
+      float t = tmp_[i];
       if (t > cap) t = cap;
       noise[i] = __fsub_rn(noise[i], t);
     }
@@ -148,15 +154,15 @@ __device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restr
     for (int i = 0; i < nx; i += 8, k++) {
       double a = 0;
       for (int j = 0; j < 8; j++) a += (double)noise[i + j];
-      sm.tmp[k] = (float)(a / 8);
+      tmp_[k] = (float)(a / 8);
     }
     const int groups = nx / 8;
     for (int i = 3; i < groups; i++) {
-      if (!(sm.tmp[i] > sm.tmp[i - 1] && sm.tmp[i] > sm.tmp[i + 1])) continue;
+      if (!(tmp_[i] > tmp_[i - 1] && tmp_[i] > tmp_[i + 1])) continue;
       float base; int a;
-      if (sm.tmp[i - 1] > sm.tmp[i - 2]) { base = sm.tmp[i - 2]; a = i - 3; } else { base = sm.tmp[i - 1]; a = i - 2; }
+      if (tmp_[i - 1] > tmp_[i - 2]) { base = tmp_[i - 2]; a = i - 3; } else { base = tmp_[i - 1]; a = i - 2; }
       const int b = i + 3;
-      float th = __fsub_rn(sm.tmp[i], base);
+      float th = __fsub_rn(tmp_[i], base);
       if (th > 2.f) {
         float cap = fminf(__ldg(P.ntfix + i * 8), __fadd_rn(__ldg(off1 + i * 8), limit));
         th = fminf(__fsub_rn(th, 2.f), cap);
@@ -167,7 +173,7 @@ __device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restr
 }
 
 template <int N, int T>
-__global__ void __launch_bounds__(T)
+__global__ void __launch_bounds__(T, (T == 256 ? 7 : 1))
 k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const int *__restrict__ block_mode,
             const float *__restrict__ lowcomp, const float *__restrict__ postev,
             const float *__restrict__ logmdct, LastRef last,

@@ -18,18 +18,23 @@ namespace {
 
 constexpr int PK_T = 128;
 constexpr int PK_WORDS = 4096;        /* 16 KB packet image: far above any block the setups produce */
-constexpr int PK_FSYM = 96;           /* floor symbols per channel: 2 + partitions*(1+cdim) <= 2+31*... clipped */
+constexpr int PK_ZERO0 = 512;         /* words cleared up front; more are cleared on demand as the packet grows */
+constexpr int PK_PARTS = 31;          /* floor1 partitions (5 bits in the header) */
+constexpr int PK_PSYM = 9;            /* symbols of one floor partition: class word + up to 8 values */
+constexpr int PK_PER = 4;             /* residue symbols per thread and pass */
 
+template <int CH>
 struct PackSmem {
   unsigned words[PK_WORDS];
-  unsigned fcode[VB200_MAX_CHANNELS][PK_FSYM];
-  unsigned char flen[VB200_MAX_CHANNELS][PK_FSYM];
-  int fn[VB200_MAX_CHANNELS], fbits[VB200_MAX_CHANNELS], fbase[VB200_MAX_CHANNELS];
-  int warp_tot[PK_T / 32];
+  unsigned pcode[CH][PK_PARTS][PK_PSYM];
+  unsigned char plen[CH][PK_PARTS][PK_PSYM + 3];
+  int pbits[CH][PK_PARTS], pbase[CH][PK_PARTS];
+  int warp_tot[2][PK_T / 32];
   int base, overflow;
 };
 
-__device__ __forceinline__ void put_bits(PackSmem &sm, int bitpos, unsigned value, int len) {
+template <int CH>
+__device__ __forceinline__ void put_bits(PackSmem<CH> &sm, int bitpos, unsigned value, int len) {
   if (len <= 0) return;
   if (bitpos + len > PK_WORDS * 32) { sm.overflow = 1; return; }
   if (len < 32) value &= (1u << len) - 1u;
@@ -40,55 +45,66 @@ __device__ __forceinline__ void put_bits(PackSmem &sm, int bitpos, unsigned valu
 
 __device__ __forceinline__ int ilog_(unsigned v) { return 32 - __clz(v); }
 
+template <int CH>
 __global__ void __launch_bounds__(PK_T)
 k_pack(const DevSetup *__restrict__ S, int W, int ch, const int *__restrict__ lWv, const int *__restrict__ nWv,
        const int *__restrict__ vals, const int *__restrict__ floor_nonzero,
        int submaps, const int *__restrict__ syms, const int *__restrict__ nsyms, int cap_blocks, int max_syms,
        unsigned char *__restrict__ pool, unsigned long long pool_cap, unsigned long long *__restrict__ pool_top,
        long long *__restrict__ pk_off, int *__restrict__ pk_bytes) {
-  __shared__ PackSmem sm;
+  __shared__ PackSmem<CH> sm;
   const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const DevBook *books = S->book;
-  for (int i = tid; i < PK_WORDS; i += PK_T) sm.words[i] = 0;
+  for (int i = tid; i < PK_ZERO0; i += PK_T) sm.words[i] = 0;
+  int zeroed = PK_ZERO0;               /* uniform: words [0, zeroed) are clear or already carry bits */
   if (tid == 0) sm.overflow = 0;
-  __syncthreads();
+  /* make sure the image is clear up to bit `endbit` before anything is OR-ed there; callers are uniform */
+  auto ensure = [&](int endbit) {
+    int need = (endbit >> 5) + 2;
+    if (need > PK_WORDS) need = PK_WORDS;
+    if (need > zeroed) {
+      const int upto = min(PK_WORDS, max(need, zeroed + PK_ZERO0));
+      for (int i = zeroed + tid; i < upto; i += PK_T) sm.words[i] = 0;
+      zeroed = upto;
+      __syncthreads();
+    }
+  };
 
-  /* floor symbols of channel c, generated by thread c in the order of floor1.c:850-942 */
-  if (tid < ch) {
-    const int c = tid, it = blk * ch + c;
+  /* floor symbols (floor1.c:850-942): one thread per (channel, partition) looks its <= 9 codewords up; the
+     bit offsets of the partitions follow from a short serial prefix */
+  for (int idx = tid; idx < ch * PK_PARTS; idx += PK_T) {
+    const int c = idx / PK_PARTS, i = idx - c * PK_PARTS, it = blk * ch + c;
     const DevFloor &F = S->flr[S->floor_of_ch[W][c]];
-    const int *v = vals + (size_t)it * VB200_MAX_POSTS;
-    int n = 0, bits = 0;
-    auto add = [&](unsigned code, int len) { if (n < PK_FSYM) { sm.fcode[c][n] = code; sm.flen[c][n] = (unsigned char)len; n++; bits += len; } else sm.overflow = 1; };
-    auto add_book = [&](int book, int entry) { const DevBook &B = books[book]; if (entry >= 0 && entry < B.entries) add(__ldg(B.code + entry), __ldg(B.len + entry)); };
-    if (!floor_nonzero[it]) add(0, 1);
-    else {
-      add(1, 1);
-      const int qb = ilog_((unsigned)(F.quant_q - 1));
-      add((unsigned)v[0], qb); add((unsigned)v[1], qb);
-      for (int i = 0, j = 2; i < F.partitions; i++) {
-        const int cls = F.partclass[i], cdim = F.class_dim[cls], csubbits = F.class_subs[cls], csub = 1 << csubbits;
-        int bookas[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cval = 0, cshift = 0;
-        if (csubbits) {
-          for (int k = 0; k < cdim; k++) {
-            for (int l = 0; l < csub; l++) {
-              const int bn = F.class_subbook[cls * 8 + l];
-              const int mv = bn < 0 ? 1 : books[bn].entries;
-              if (v[j + k] < mv) { bookas[k] = l; break; }
-            }
-            cval |= bookas[k] << cshift;
-            cshift += csubbits;
-          }
-          add_book(F.class_book[cls], cval);
-        }
+    int bits = 0, ns = 0;
+    if (i < F.partitions && floor_nonzero[it]) {
+      const int *v = vals + (size_t)it * VB200_MAX_POSTS;
+      int j = 2;
+      for (int q = 0; q < i; q++) j += F.class_dim[F.partclass[q]];
+      auto add_book = [&](int book, int entry) {
+        const DevBook &B = books[book];
+        if (entry >= 0 && entry < B.entries) { const int len = __ldg(B.len + entry); sm.pcode[c][i][ns] = __ldg(B.code + entry); sm.plen[c][i][ns] = (unsigned char)len; ns++; bits += len; }
+      };
+      const int cls = F.partclass[i], cdim = F.class_dim[cls], csubbits = F.class_subs[cls], csub = 1 << csubbits;
+      int bookas[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cval = 0, cshift = 0;
+      if (csubbits) {
         for (int k = 0; k < cdim; k++) {
-          const int book = F.class_subbook[cls * 8 + bookas[k]];
-          if (book >= 0 && v[j + k] < books[book].entries) add_book(book, v[j + k]);
+          for (int l = 0; l < csub; l++) {
+            const int bn = F.class_subbook[cls * 8 + l];
+            const int mv = bn < 0 ? 1 : books[bn].entries;
+            if (v[j + k] < mv) { bookas[k] = l; break; }
+          }
+          cval |= bookas[k] << cshift;
+          cshift += csubbits;
         }
-        j += cdim;
+        add_book(F.class_book[cls], cval);
+      }
+      for (int k = 0; k < cdim; k++) {
+        const int book = F.class_subbook[cls * 8 + bookas[k]];
+        if (book >= 0 && v[j + k] < books[book].entries) add_book(book, v[j + k]);
       }
     }
-    sm.fn[c] = n; sm.fbits[c] = bits;
+    for (int k = ns; k < PK_PSYM; k++) sm.plen[c][i][k] = 0;
+    sm.pbits[c][i] = bits;
   }
   __syncthreads();
   if (tid == 0) {
@@ -96,46 +112,72 @@ k_pack(const DevSetup *__restrict__ S, int W, int ch, const int *__restrict__ lW
     put_bits(sm, pos, 0, 1); pos += 1;                                  /* packet type: audio */
     put_bits(sm, pos, (unsigned)W, S->modebits); pos += S->modebits;     /* mode number */
     if (W) { put_bits(sm, pos, (unsigned)lWv[blk * ch], 1); pos++; put_bits(sm, pos, (unsigned)nWv[blk * ch], 1); pos++; }
-    for (int c = 0; c < ch; c++) { sm.fbase[c] = pos; pos += sm.fbits[c]; }
+    for (int c = 0; c < ch; c++) {
+      const int it = blk * ch + c;
+      const DevFloor &F = S->flr[S->floor_of_ch[W][c]];
+      if (!floor_nonzero[it]) { put_bits(sm, pos, 0, 1); pos++; }
+      else {
+        const int *v = vals + (size_t)it * VB200_MAX_POSTS;
+        const int qb = ilog_((unsigned)(F.quant_q - 1));
+        put_bits(sm, pos, 1, 1); pos++;
+        put_bits(sm, pos, (unsigned)v[0], qb); pos += qb;
+        put_bits(sm, pos, (unsigned)v[1], qb); pos += qb;
+      }
+      for (int i = 0; i < PK_PARTS; i++) { sm.pbase[c][i] = pos; pos += sm.pbits[c][i]; }
+    }
     sm.base = pos;
   }
   __syncthreads();
-  if (tid < ch) {
-    int pos = sm.fbase[tid];
-    for (int i = 0; i < sm.fn[tid]; i++) { put_bits(sm, pos, sm.fcode[tid][i], sm.flen[tid][i]); pos += sm.flen[tid][i]; }
+  int base = sm.base;
+  ensure(base);
+  for (int idx = tid; idx < ch * PK_PARTS; idx += PK_T) {
+    const int c = idx / PK_PARTS, i = idx - c * PK_PARTS;
+    int pos = sm.pbase[c][i];
+#pragma unroll
+    for (int k = 0; k < PK_PSYM; k++) { const int len = sm.plen[c][i][k]; put_bits(sm, pos, sm.pcode[c][i][k], len); pos += len; }
   }
-  __syncthreads();
 
-  /* residue symbols, submap by submap, in the emission order K7 produced */
+  /* residue symbols, submap by submap, in the emission order K7 produced; PK_PER consecutive symbols per
+     thread, one barrier per pass (the warp totals are double-buffered, the running base is uniform) */
+  int flip = 0;
   for (int smi = 0; smi < submaps; smi++) {
     const int n = nsyms[(size_t)smi * cap_blocks + blk];
-    const int *sy = syms + ((size_t)smi * cap_blocks + blk) * max_syms * 2;
-    for (int c0 = 0; c0 < n; c0 += PK_T) {
-      const int i = c0 + tid;
-      unsigned code = 0; int len = 0;
-      if (i < n) {
-        const int2 be = __ldg(reinterpret_cast<const int2 *>(sy) + i);
-        const DevBook &B = books[be.x];
-        if (be.y >= 0 && be.y < B.entries) { code = __ldg(B.code + be.y); len = __ldg(B.len + be.y); }
+    const int2 *sy = reinterpret_cast<const int2 *>(syms + ((size_t)smi * cap_blocks + blk) * max_syms * 2);
+    for (int c0 = 0; c0 < n; c0 += PK_T * PK_PER) {
+      const int i0 = c0 + tid * PK_PER;
+      unsigned code[PK_PER]; int len[PK_PER];
+      int mine = 0;
+#pragma unroll
+      for (int q = 0; q < PK_PER; q++) {
+        code[q] = 0; len[q] = 0;
+        if (i0 + q < n) {
+          const int2 be = __ldg(sy + i0 + q);
+          const DevBook &B = books[be.x];
+          if (be.y >= 0 && be.y < B.entries) { code[q] = __ldg(B.code + be.y); len[q] = __ldg(B.len + be.y); }
+        }
+        mine += len[q];
       }
-      int incl = len;
+      int incl = mine;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += y; }
-      if (lane == 31) sm.warp_tot[warp] = incl;
+      if (lane == 31) sm.warp_tot[flip][warp] = incl;
       __syncthreads();
       int wbase = 0, tot = 0;
 #pragma unroll
-      for (int w2 = 0; w2 < PK_T / 32; w2++) { const int t = sm.warp_tot[w2]; if (w2 < warp) wbase += t; tot += t; }
-      put_bits(sm, sm.base + wbase + incl - len, code, len);
-      __syncthreads();
-      if (tid == 0) sm.base += tot;
-      __syncthreads();
+      for (int w2 = 0; w2 < PK_T / 32; w2++) { const int t = sm.warp_tot[flip][w2]; if (w2 < warp) wbase += t; tot += t; }
+      flip ^= 1;
+      ensure(base + tot);
+      int pos = base + wbase + incl - mine;
+#pragma unroll
+      for (int q = 0; q < PK_PER; q++) { put_bits(sm, pos, code[q], len[q]); pos += len[q]; }
+      base += tot;
     }
   }
+  __syncthreads();
 
   /* publish */
   __shared__ unsigned long long s_off;
-  const int bits = sm.base, bytes = (bits + 7) >> 3, words = (bytes + 3) >> 2;
+  const int bits = base, bytes = (bits + 7) >> 3, words = (bytes + 3) >> 2;
   if (tid == 0) {
     unsigned long long off = atomicAdd(pool_top, (unsigned long long)words * 4ull);
     if (off + (unsigned long long)words * 4ull > pool_cap || sm.overflow) { off = ~0ull; }
@@ -157,8 +199,12 @@ int vb200_launch_pack(const vb200_setup *s, cudaStream_t st, int W, int blocks, 
                       int cap_blocks, int max_syms, unsigned char *pool, unsigned long long pool_cap,
                       unsigned long long *pool_top, long long *pk_off, int *pk_bytes) {
   if (blocks <= 0) return VB200_OK;
-  k_pack<<<blocks, PK_T, 0, st>>>(s->d, W, s->h.channels, lW, nW, vals, floor_nonzero, submaps, syms, nsyms, cap_blocks, max_syms,
-                                  pool, pool_cap, pool_top, pk_off, pk_bytes);
+  if (s->h.channels <= 2)
+    k_pack<2><<<blocks, PK_T, 0, st>>>(s->d, W, s->h.channels, lW, nW, vals, floor_nonzero, submaps, syms, nsyms, cap_blocks, max_syms,
+                                       pool, pool_cap, pool_top, pk_off, pk_bytes);
+  else
+    k_pack<VB200_MAX_CHANNELS><<<blocks, PK_T, 0, st>>>(s->d, W, s->h.channels, lW, nW, vals, floor_nonzero, submaps, syms, nsyms, cap_blocks, max_syms,
+                                                        pool, pool_cap, pool_top, pk_off, pk_bytes);
   LAUNCH_CHECK();
   return VB200_OK;
 }
