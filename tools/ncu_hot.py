@@ -33,6 +33,24 @@ for k, v in data.items():
         continue
     seen.add(base)
     h, body = v[0], v[1:]
+    # instruction / sample share of the code between barriers
+    ii_, si_, so_ = h.index("Instructions Executed"), h.index("# Samples"), h.index("Source")
+    ti_ = h.index("Thread Instructions Executed")
+    toti_ = sum(int(x[ii_]) for x in body) or 1
+    tots_ = sum(int(x[si_]) for x in body) or 1
+    acc = accs = acct = 0
+    start = 0
+    segs = []
+    for i, x in enumerate(body):
+        acc += int(x[ii_]); accs += int(x[si_]); acct += int(x[ti_])
+        if "BAR.SYNC" in x[so_] or i == len(body) - 1:
+            if acc * 100.0 / toti_ > 0.5 or accs * 100.0 / tots_ > 0.5:
+                segs.append("[%d-%d] inst %.1f%% smp %.1f%% lanes %.1f" % (start, i, acc * 100.0 / toti_, accs * 100.0 / tots_, acct / max(acc, 1)))
+            acc = accs = acct = 0
+            start = i + 1
+    print("\n## segments of", base)
+    for sg in segs:
+        print("     " + sg)
     si, ii, ti = h.index("# Samples"), h.index("Instructions Executed"), h.index("Avg. Threads Executed")
     stalls = [i for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
     tot = sum(int(x[si]) for x in body) or 1

@@ -20,9 +20,7 @@
 namespace {
 
 #define TM_NEGINF (-9999.f)
-constexpr int TM_ITEMS = 8;      /* ch-blocks per CTA: one warp each for the cooperative phases, 8 lanes for the chase */
-constexpr int TM_THREADS = 256;
-constexpr int TM_WARPS = TM_THREADS / 32;
+constexpr int TM_SVW = 33;       /* words of the survivor set of one ch-block (<= 1024 octave lines), odd stride */
 constexpr int TM_QCAP = 64;      /* per-warp queue of curves to splat */
 
 __device__ __forceinline__ void smem_atomic_max(float *addr, float v) {
@@ -32,13 +30,16 @@ __device__ __forceinline__ void smem_atomic_max(float *addr, float v) {
 
 struct SplatJob { float mx; int sp0; int curve; int k0, k1; };   /* amplitude, first seed position, curve offset in floats */
 
-template <int N>
-__global__ void __launch_bounds__(TM_THREADS)
+/* TM_ITEMS ch-blocks per CTA: one warp each for the cooperative phases, TM_ITEMS lanes for the chase */
+template <int N, int TM_ITEMS>
+__global__ void __launch_bounds__(TM_ITEMS * 32)
 k_tonemask(const DevSetup *__restrict__ S, int items, const int *__restrict__ psyv, const float *__restrict__ logfft,
            const float *__restrict__ global_ampmax, const float *__restrict__ local_ampmax, float *__restrict__ tone, int Lstride) {
+  constexpr int TM_THREADS = TM_ITEMS * 32, TM_WARPS = TM_ITEMS;
   extern __shared__ __align__(16) unsigned char dyn[];
   float *seed_all = reinterpret_cast<float *>(dyn);                                  /* [TM_ITEMS][Lstride] */
   unsigned short *pos_all = reinterpret_cast<unsigned short *>(seed_all + TM_ITEMS * Lstride);   /* [TM_ITEMS][Lstride] */
+  __shared__ unsigned surv_all[TM_ITEMS * TM_SVW];                                   /* surviving positions, one bit each */
   __shared__ SplatJob queue[TM_WARPS][TM_QCAP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int item0 = blockIdx.x * TM_ITEMS;
@@ -115,66 +116,131 @@ k_tonemask(const DevSetup *__restrict__ S, int items, const int *__restrict__ ps
   }
   __syncthreads();
 
-  /* ---- seed_chase: one lane per ch-block, amplitudes of the stack kept in place over the seeds ---- */
-  if (warp == 0 && lane < nloc) {
-    const int item = item0 + lane;
-    const DevPsy &P = S->psy[psyv[item]];
-    const int L = P.total_octave_lines, per = P.eighth;
-    float *seed = seed_all + lane * Lstride;           /* seed[i] for i >= top: input; seed[i] for i < top: stack amplitude */
-    unsigned short *pos = pos_all + lane * Lstride;
-    /* The two entries on top of the stack live in registers (a1,p1 / a2,p2); shared memory is only read
-       when a pop has to uncover a third one.  The seed two steps ahead is fetched early. */
-    int top = 0, p1 = 0, p2 = 0;
-    float a1 = 0.f, a2 = 0.f;
-    float s_next = seed[0];
-    for (int i = 0; i < L; i++) {
-      const float s = s_next;
-      s_next = (i + 1 < L) ? seed[i + 1] : 0.f;
-      if (top >= 2) {
-        while (!(s < a1)) {
-          if (i < p1 + per && a1 <= a2 && i < p2 + per) {
-            /* pop: the entry below becomes the top */
-            top--; a1 = a2; p1 = p2;
-            if (top >= 2) { a2 = seed[top - 2]; p2 = pos[top - 2]; }
-            if (top < 2) break;
-            continue;
-          }
-          break;
+  /* ---- seed_chase (psy.c:773-830).  Every position is pushed once and can only be popped while it is
+     "young" (less than `per` = 8 positions old), and a pop needs the entry below to be young too.  So the part
+     of the stack that can still change is a 7-bit set of the last 7 positions, an entry's amplitude is the
+     seed at its position, and every comparison a pop makes is between two seeds less than 8 apart.
+     (a) all those comparisons are evaluated up front, in parallel: per position a 7-bit word
+         GE[k] = !(seed[p] < seed[p-k]) and a 7-bit word LE[d] = seed[p] <= seed[p-d];
+     (b) the order-dependent walk then runs on bit masks in registers only -- one lane per ch-block, no
+         shared-memory access on its dependency chain -- and emits the set of surviving positions;
+     (c) spans and the fill are again data-parallel over the survivors. ---- */
+  for (int li = warp; li < nloc; li += TM_WARPS) {
+    const DevPsy &P = S->psy[psyv[item0 + li]];
+    const int L = P.total_octave_lines;
+    const float *seed = seed_all + li * Lstride;
+    unsigned short *cmp = pos_all + li * Lstride;
+    for (int p0 = 0; p0 < L; p0 += 32) {
+      const int p = p0 + lane;
+      if (p < L) {
+        const float s = seed[p];
+        unsigned ge = 0, le = 0;
+#pragma unroll
+        for (int k = 1; k < 8; k++) {
+          if (p - k >= 0) { const float o = seed[p - k]; if (!(s < o)) ge |= 1u << (k - 1); if (s <= o) le |= 1u << (k - 1); }
         }
+        cmp[p] = (unsigned short)(ge | (le << 8));
       }
-      pos[top] = (unsigned short)i; seed[top] = s;        /* top <= i: never clobbers unread input */
-      a2 = a1; p2 = p1; a1 = s; p1 = i; top++;
     }
-    /* turn (pos, amp) into the end of every entry's span: running maximum, clipped to L.  pos[i] becomes the
-       first position NOT covered by entries 0..i, which is all the fill needs. */
-    int run = 0;
-    for (int i = 0; i < top; i++) {
-      const int end = (i < top - 1 && seed[i + 1] > seed[i]) ? (int)pos[i + 1] : (int)pos[i] + per + 1;
-      /* pos[i+1] is still the raw position here: entry i+1 is rewritten only in the next iteration */
-      const int e2 = end > L ? L : end;
-      if (e2 > run) run = e2;
-      pos[i] = (unsigned short)run;
-    }
-    pos[L - 1 < Lstride - 1 ? Lstride - 1 : L - 1] = (unsigned short)top;   /* stash the stack height in the last slot */
+    if (lane < Lstride - L) cmp[L + lane] = 0;
   }
   __syncthreads();
 
-  /* ---- fill + max_seeds: warps take ch-blocks in turn ---- */
+  if (warp == 0 && lane < nloc) {
+    const DevPsy &P = S->psy[psyv[item0 + lane]];
+    const int L = P.total_octave_lines;
+    const unsigned short *cm = pos_all + lane * Lstride;
+    unsigned *sv = surv_all + lane * TM_SVW;
+    /* bit k-1 of M: position i-k is on the stack; same bit of Q: that entry's amplitude is <= the amplitude of
+       the entry it was pushed onto (which entry that is never changes while it stays on the stack).
+       One step, without a loop: the entries popped by seed[i] are the youngest ones up to the first entry that
+       is not poppable -- seed[i] below it (GE clear), amplitude above its predecessor (Q clear), or no young
+       predecessor left (the oldest young entry). */
+    unsigned M = 0, Q = 0, cur = 0;
+    unsigned c_next = cm[0];
+#pragma unroll 2
+    for (int i = 0; i < L; i++) {
+      const unsigned c = c_next;
+      c_next = cm[i + 1];
+      const unsigned ge = c & 0x7fu, le = c >> 8;
+      const unsigned oldest = M ? (0x80000000u >> __clz(M)) : 0u;
+      const unsigned stop = (M & ~(ge & Q)) | oldest;
+      const unsigned low = stop & (0u - stop);                     /* first entry that stays */
+      const unsigned m = M & ~(low - 1u);                          /* M == 0: low == 0, m == 0 */
+      const int p = i - 7;                                         /* this position's fate is now sealed */
+      if (p >= 0) { cur |= ((m >> 6) & 1u) << (p & 31); if ((p & 31) == 31) { sv[p >> 5] = cur; cur = 0; } }
+      const unsigned qbit = (le & low) ? 1u : 0u;                  /* new entry vs the entry it lands on, if young */
+      M = ((m << 1) | 1u) & 0x7fu;
+      Q = ((Q << 1) | qbit) & 0x7fu;
+    }
+    for (int k = 7; k >= 1; k--) {
+      const int p = L - k;
+      if (p >= 0) { cur |= ((M >> (k - 1)) & 1u) << (p & 31); if ((p & 31) == 31) { sv[p >> 5] = cur; cur = 0; } }
+    }
+    if (L & 31) sv[L >> 5] = cur;
+  }
+  __syncthreads();
+
+  /* ---- spans, fill + max_seeds: warps take ch-blocks in turn ---- */
   for (int li = warp; li < nloc; li += TM_WARPS) {
     const int item = item0 + li;
     const DevPsy &P = S->psy[psyv[item]];
-    const int L = P.total_octave_lines;
+    const int L = P.total_octave_lines, per = P.eighth;
     float *seed = seed_all + li * Lstride;
-    unsigned short *pos = pos_all + li * Lstride;
-    const int top = pos[Lstride - 1];
-    /* entry i covers [pos[i-1], pos[i]); amplitudes sit in seed[0..top).  Expand from the back so that an
-       amplitude is read before its slot is overwritten: positions written by entry i are >= pos[i-1] > i-1. */
-    for (int i0 = ((top - 1) / 32) * 32; i0 >= 0; i0 -= 32) {
-      const int i = i0 + lane;
+    unsigned short *run16 = pos_all + li * Lstride;          /* the comparison words are dead: reuse for the span ends */
+    const unsigned *sv = surv_all + li * TM_SVW;
+    const int nw = (L + 31) >> 5;
+    const unsigned myw = lane < nw ? sv[lane] : 0u;
+    /* first survivor after / last survivor before the word this lane holds */
+    const unsigned nzm = __ballot_sync(FULLMASK, myw != 0u);
+    int after = -1, before = -1;
+    {
+      const unsigned hi = lane < 31 ? (nzm & ~((2u << lane) - 1u)) : 0u;
+      const int w2 = hi ? __ffs(hi) - 1 : 0;
+      const unsigned ww = __shfl_sync(FULLMASK, myw, w2);
+      if (hi) after = w2 * 32 + __ffs(ww) - 1;
+      const unsigned lo = nzm & ((1u << lane) - 1u);
+      const int w0 = lo ? 31 - __clz(lo) : 0;
+      const unsigned wv = __shfl_sync(FULLMASK, myw, w0);
+      if (lo) before = w0 * 32 + 31 - __clz(wv);
+    }
+    /* end of every survivor's span, running maximum in position order (the fill pointer of the reference) */
+    int carry = 0;
+    for (int w = 0; w < nw; w++) {
+      const unsigned word = __shfl_sync(FULLMASK, myw, w);
+      const int aft = __shfl_sync(FULLMASK, after, w);
+      const int p = w * 32 + lane;
+      const bool sv_here = (word >> lane) & 1u;
+      int end = 0;
+      if (sv_here) {
+        const unsigned hb = lane < 31 ? (word & ~((2u << lane) - 1u)) : 0u;
+        const int nx = hb ? w * 32 + __ffs(hb) - 1 : aft;
+        end = (nx >= 0 && seed[nx] > seed[p]) ? nx : p + per + 1;
+        if (end > L) end = L;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, end, o); if (lane >= o && y > end) end = y; }
+      if (carry > end) end = carry;
+      if (sv_here) run16[p] = (unsigned short)end;
+      carry = __shfl_sync(FULLMASK, end, 31);
+    }
+    __syncwarp();
+    /* survivor p covers [end of the survivor before it, its own end); expand from the back so that a seed is
+       read before its slot is overwritten (everything written here lies above the previous survivor) */
+    for (int w = nw - 1; w >= 0; w--) {
+      const unsigned word = __shfl_sync(FULLMASK, myw, w);
+      const int bef = __shfl_sync(FULLMASK, before, w);
+      const int p = w * 32 + lane;
+      const bool sv_here = (word >> lane) & 1u;
       float a = 0.f; int lo = 0, hi = 0;
-      if (i < top) { a = seed[i]; hi = pos[i]; lo = i > 0 ? (int)pos[i - 1] : 0; }
+      if (sv_here) {
+        a = seed[p]; hi = run16[p];
+        const unsigned lb = word & ((1u << lane) - 1u);
+        const int pv = lb ? w * 32 + 31 - __clz(lb) : bef;
+        lo = pv >= 0 ? (int)run16[pv] : 0;
+      }
       __syncwarp();
-      if (i < top) for (int w = lo; w < hi; w++) seed[w] = a;
+      for (int x = lo; x < hi; x++) seed[x] = a;
       __syncwarp();
     }
     float att = __fadd_rn(local_ampmax[item], P.ath_adjatt);
@@ -197,21 +263,30 @@ k_tonemask(const DevSetup *__restrict__ S, int items, const int *__restrict__ ps
 
 }  // namespace
 
+template <int N, int TI>
+static int launch_tm(const vb200_setup *s, cudaStream_t st, int items, const int *psy, const float *logfft,
+                     const float *global_ampmax, const float *local_ampmax, float *tone, int Lstride) {
+  const size_t dyn = (size_t)TI * Lstride * (sizeof(float) + sizeof(unsigned short));
+  const int grid = (items + TI - 1) / TI;
+  CUDA_TRY(cudaFuncSetAttribute(k_tonemask<N, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  k_tonemask<N, TI><<<grid, TI * 32, dyn, st>>>(s->d, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+  LAUNCH_CHECK();
+  return VB200_OK;
+}
+
 int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
                           const float *logfft, const float *global_ampmax, const float *local_ampmax, float *tone) {
   if (items <= 0) return VB200_OK;
   int L = 0;
   for (int k = 0; k < s->h.psys; k++) if (s->h.psy[k].blockflag == W && s->h.psy[k].total_octave_lines > L) L = s->h.psy[k].total_octave_lines;
   const int Lstride = (L + 2) | 1;        /* odd: lanes walking equal positions hit different banks; +1 slot for the stack height */
-  const size_t dyn = (size_t)TM_ITEMS * Lstride * (sizeof(float) + sizeof(unsigned short));
-  const int grid = (items + TM_ITEMS - 1) / TM_ITEMS;
+  static const int ti = getenv("VB200_TM_ITEMS") ? atoi(getenv("VB200_TM_ITEMS")) : 8;
   if (W) {
-    CUDA_TRY(cudaFuncSetAttribute(k_tonemask<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    k_tonemask<1024><<<grid, TM_THREADS, dyn, st>>>(s->d, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
-  } else {
-    CUDA_TRY(cudaFuncSetAttribute(k_tonemask<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    k_tonemask<128><<<grid, TM_THREADS, dyn, st>>>(s->d, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+    if (ti == 2) return launch_tm<1024, 2>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+    if (ti == 4) return launch_tm<1024, 4>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+    return launch_tm<1024, 8>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
   }
-  LAUNCH_CHECK();
-  return VB200_OK;
+  if (ti == 2) return launch_tm<128, 2>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+  if (ti == 4) return launch_tm<128, 4>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+  return launch_tm<128, 8>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
 }

@@ -692,7 +692,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   const bool host_emit = b->host_emit != 0;
   struct HostRes { int *vals, *nonzero, *nsyms, *syms; } hr[2] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
   std::vector<long> &blob_sizes = b->blob_sizes;
-  blob_sizes.assign((size_t)nblocks * VB200_PACKETBLOBS, 0);
+  if (managed) blob_sizes.assign((size_t)nblocks * VB200_PACKETBLOBS, 0);
   if (host_emit) {
     for (int W = 0; W < 2; W++) {
       const size_t I = (size_t)nb[W] * ch;
@@ -833,17 +833,22 @@ static int batch_finish(vb200_batch *b) {
     if (top > b->pool_cap) { vb200_set_error("vb200_batch_collect: packet pool overflow (%llu > %llu bytes)", top, (unsigned long long)b->pool_cap); return VB200_EFAULT; }
     CUDA_TRY(cudaMemcpyAsync(b->h_pool, b->d_pool, top, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (!managed) {
+      b->pk_off.resize(nblocks); b->pk_bytes.resize(nblocks); b->pk_gp.resize(nblocks); b->pk_eos.resize(nblocks); b->pk_stream.resize(nblocks);
+    }
     for (int i = 0; i < nblocks; i++) {
       const HostBlock &h = b->hb[i];
+      if (!managed) {
+        const size_t o = (size_t)h.W * b->max_blocks + h.idx;
+        if (b->h_pk_off[o] < 0) { vb200_set_error("vb200_batch_collect: packet of block %d does not fit the packer's image", i); return VB200_EFAULT; }
+        b->pk_off[i] = (size_t)b->h_pk_off[o]; b->pk_bytes[i] = (size_t)b->h_pk_bytes[o];
+        b->pk_gp[i] = h.granulepos; b->pk_eos[i] = h.eof; b->pk_stream[i] = h.stream;
+        continue;
+      }
       for (int kk = 0; kk < nblobs; kk++) {
         const size_t o = ((size_t)kk * 2 + h.W) * b->max_blocks + h.idx;
         if (b->h_pk_off[o] < 0) { vb200_set_error("vb200_batch_collect: packet of block %d does not fit the packer's image", i); return VB200_EFAULT; }
         blob_sizes[(size_t)i * VB200_PACKETBLOBS + k_lo + kk] = b->h_pk_bytes[o];
-      }
-      if (!managed) {
-        const size_t o = (size_t)h.W * b->max_blocks + h.idx;
-        b->pk_off.push_back((size_t)b->h_pk_off[o]); b->pk_bytes.push_back((size_t)b->h_pk_bytes[o]);
-        b->pk_gp.push_back(h.granulepos); b->pk_eos.push_back(h.eof); b->pk_stream.push_back(h.stream);
       }
     }
     if (!managed) b->pk_base = b->h_pool;
