@@ -28,10 +28,7 @@ for x in rows:
         data[k].append(x)
 seen = set()
 for k, v in data.items():
-    base = k.split("#")[0]
-    if base in seen:
-        continue
-    seen.add(base)
+    base = k
     h, body = v[0], v[1:]
     # instruction / sample share of the code between barriers
     ii_, si_, so_ = h.index("Instructions Executed"), h.index("# Samples"), h.index("Source")

@@ -53,15 +53,14 @@ __device__ __forceinline__ int point_at(int x0, int x1, int y0, int y1, int x) {
   return dy < 0 ? y0 - off : y0 + off;
 }
 
-struct Seg { int x0, x1; int s[2][6]; };   /* s[class] = sum x, y, xx, yy, xy, count */
+struct Seg { int s[2][6]; };   /* s[class] = sum x, y, xx, yy, xy, count */
 
+/* ~5.5 KB for a long block, so that 32 one-warp CTAs (the per-SM CTA limit) are resident */
 template <int N>
 struct FitSmem {
-  unsigned short q[N];
-  unsigned char loud[N];
-  Seg seg[VB200_MAX_POSTS];
+  unsigned short q[N];            /* quantised mask, bit 15 = "loud" (mdct + twofitatten >= mask) */
   double T[VB200_MAX_POSTS][6];
-  int A[VB200_MAX_POSTS], B[VB200_MAX_POSTS], lo[VB200_MAX_POSTS], hi[VB200_MAX_POSTS], memo[VB200_MAX_POSTS];
+  short A[VB200_MAX_POSTS], B[VB200_MAX_POSTS], lo[VB200_MAX_POSTS], hi[VB200_MAX_POSTS], memo[VB200_MAX_POSTS];
 };
 
 /* fit_line, floor1.c:477-535, split in three so that the warp shares it:
@@ -110,7 +109,7 @@ __device__ __forceinline__ void fit_two(const double (*T)[6], int a0, int na, in
   for (int q = 0; q < 6; q++) { sa[q] = __shfl_sync(FULLMASK, acc, q); sb[q] = __shfl_sync(FULLMASK, acc, 6 + q); }
 }
 
-__device__ __forceinline__ int pick(const int *A, const int *B, int i) {
+__device__ __forceinline__ int pick(const short *A, const short *B, int i) {
   if (A[i] < 0) return B[i];
   if (B[i] < 0) return A[i];
   return (A[i] + B[i]) >> 1;
@@ -130,8 +129,7 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
 
   for (int i = lane; i < n; i += 32) {
     const float m = __ldg(mk + i);
-    sm.q[i] = (unsigned short)dbq(m);
-    sm.loud[i] = (__fadd_rn(__ldg(lm + i), F.twofitatten) >= m) ? 1 : 0;
+    sm.q[i] = (unsigned short)(dbq(m) | ((__fadd_rn(__ldg(lm + i), F.twofitatten) >= m) ? 0x8000 : 0));
   }
   __syncwarp();
   /* accumulate_fit: the warp walks the post intervals together; a lane takes every 32nd bin of the interval
@@ -142,8 +140,8 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     const int x0 = F.sorted[j], x1 = F.sorted[j + 1], xe = x1 >= n ? n - 1 : x1;
     int ax = 0, ay = 0, ax2 = 0, ay2 = 0, axy = 0, an = 0, bx = 0, by = 0, bx2 = 0, by2 = 0, bxy = 0, bnn = 0;
     for (int i = x0 + lane; i <= xe; i += 32) {
-      const int q = sm.q[i];
-      const int on = q != 0, la = on & (int)sm.loud[i], lb = on & (la ^ 1);
+      const int qv = sm.q[i], q = qv & 0x7fff;
+      const int on = q != 0, la = on & (qv >> 15), lb = on & (la ^ 1);
       const int ii = i * i, qq = q * q, iq = i * q;
       ax += la * i; ay += la * q; ax2 += la * ii; ay2 += la * qq; axy += la * iq; an += la;
       bx += lb * i; by += lb * q; bx2 += lb * ii; by2 += lb * qq; bxy += lb * iq; bnn += lb;
@@ -153,8 +151,7 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     bx = __reduce_add_sync(FULLMASK, bx); by = __reduce_add_sync(FULLMASK, by); bx2 = __reduce_add_sync(FULLMASK, bx2);
     by2 = __reduce_add_sync(FULLMASK, by2); bxy = __reduce_add_sync(FULLMASK, bxy); bnn = __reduce_add_sync(FULLMASK, bnn);
     if (lane == 0) {
-      Seg &g = sm.seg[j];
-      g.x0 = x0; g.x1 = x1;
+      Seg g;
       g.s[0][0] = ax; g.s[0][1] = ay; g.s[0][2] = ax2; g.s[0][3] = ay2; g.s[0][4] = axy; g.s[0][5] = an;
       g.s[1][0] = bx; g.s[1][1] = by; g.s[1][2] = bx2; g.s[1][3] = by2; g.s[1][4] = bxy; g.s[1][5] = bnn;
       fit_terms(g, F.twofitweight, sm.T[j]);
@@ -172,7 +169,7 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     fit_two(sm.T, 0, posts - 1, 0, 0, lane, sa, sb);
     if (lane == 0) {
       int y0 = -200, y1 = -200;
-      fit_solve(sa, sm.seg[0].x0, sm.seg[posts - 2].x1, &y0, &y1);
+      fit_solve(sa, F.sorted[0], F.sorted[posts - 1], &y0, &y1);
       sm.A[0] = sm.B[0] = y0; sm.A[1] = sm.B[1] = y1;
     }
   }
@@ -190,9 +187,10 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     int viol = 0, mse = 0;
     const LineK LK = line_setup(lx, hx, ly, hy);
     for (int x = lx + lane; x < hx; x += 32) {
-      const int y = line_eval(LK, x), v = sm.q[x];
+      const int qv = sm.q[x];
+      const int y = line_eval(LK, x), v = qv & 0x7fff;
       mse += (y - v) * (y - v);
-      if (sm.loud[x] && (x == lx || v)) {
+      if ((qv >> 15) && (x == lx || v)) {
         if (__fadd_rn((float)y, F.maxover) < (float)v) viol = 1;
         if (__fsub_rn((float)y, F.maxunder) > (float)v) viol = 1;
       }
@@ -214,8 +212,8 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     if (bad) {
       /* the two solves run side by side on lanes 0 and 6 */
       int ya = -200, yb = -200, rr = 0;
-      if (lane == 0) rr = fit_solve(sa, sm.seg[lsp].x0, sm.seg[sp - 1].x1, &ya, &yb);
-      else if (lane == 6) rr = fit_solve(sb, sm.seg[sp].x0, sm.seg[hsp - 1].x1, &ya, &yb);
+      if (lane == 0) rr = fit_solve(sa, F.sorted[lsp], F.sorted[sp], &ya, &yb);
+      else if (lane == 6) rr = fit_solve(sb, F.sorted[sp], F.sorted[hsp], &ya, &yb);
       r0 = __shfl_sync(FULLMASK, rr, 0); ly0 = __shfl_sync(FULLMASK, ya, 0); ly1 = __shfl_sync(FULLMASK, yb, 0);
       r1 = __shfl_sync(FULLMASK, rr, 6); hy0 = __shfl_sync(FULLMASK, ya, 6); hy1 = __shfl_sync(FULLMASK, yb, 6);
     }

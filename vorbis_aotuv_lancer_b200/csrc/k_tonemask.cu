@@ -280,7 +280,7 @@ int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int item
   int L = 0;
   for (int k = 0; k < s->h.psys; k++) if (s->h.psy[k].blockflag == W && s->h.psy[k].total_octave_lines > L) L = s->h.psy[k].total_octave_lines;
   const int Lstride = (L + 2) | 1;        /* odd: lanes walking equal positions hit different banks; +1 slot for the stack height */
-  static const int ti = getenv("VB200_TM_ITEMS") ? atoi(getenv("VB200_TM_ITEMS")) : 8;
+  static const int ti = getenv("VB200_TM_ITEMS") ? atoi(getenv("VB200_TM_ITEMS")) : 4;
   if (W) {
     if (ti == 2) return launch_tm<1024, 2>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
     if (ti == 4) return launch_tm<1024, 4>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
