@@ -357,7 +357,13 @@ static int f2(oggpack_buffer *o,struct vorbis_block *vb,vorbis_look_residue *vl,
 static vorbis_func_residue tapped1, tapped2;
 const vorbis_func_floor *const _floor_P[]={ &floor0_exportbundle, &floor1_exportbundle };
 const vorbis_func_residue *const _residue_P[]={ &residue0_exportbundle, &tapped1, &tapped2 };
+#ifdef REF_DROPIN
+/* drop-in flavour (ref_dropin.c): the reference's vorbis_analysis() reaches the B200 library through this entry */
+extern vorbis_func_mapping dropin_mapping_bundle;
+const vorbis_func_mapping *const _mapping_P[]={ &dropin_mapping_bundle };
+#else
 const vorbis_func_mapping *const _mapping_P[]={ &mapping0_exportbundle };
+#endif
 
 __attribute__((constructor)) static void tap_registry_init(void){
   tapped1=residue1_exportbundle; tapped1.class=c1; tapped1.forward=f1;

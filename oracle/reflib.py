@@ -40,6 +40,15 @@ def build(reference="/root/reference"):
     return True
 
 
+def build_dropin(reference="/root/reference"):
+    """Build the drop-in flavour (the reference bound to libvorbis_b200.so, ref_dropin.c); needs the product
+    library to exist already."""
+    if not os.path.isdir(reference):
+        return False
+    subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "REF=" + reference, "drop"], stdout=subprocess.DEVNULL)
+    return True
+
+
 def available(flavour="c"):
     return os.path.exists(os.path.join(REFDIR, "libvorbis_ref_%s.so" % flavour))
 
@@ -49,6 +58,10 @@ class RefLib:
         path = os.path.join(REFDIR, "libvorbis_ref_%s.so" % flavour)
         self.lib = L = C.CDLL(path)
         self.flavour = flavour
+        if flavour == "drop":
+            L.ref_dropin_constants.argtypes = [C.c_char_p, C.c_long]
+            L.ref_dropin_batch_blocks.argtypes = [C.c_int]
+            L.ref_dropin_error.restype = C.c_char_p
         L.ref_enc_open.restype = C.c_void_p
         L.ref_enc_open.argtypes = [C.c_int, C.c_long, C.c_float, C.c_long]
         L.ref_enc_close.argtypes = [C.c_void_p]
@@ -73,6 +86,15 @@ class RefLib:
         L.ref_tap_data.argtypes = [C.POINTER(C.c_long)]
 
     # ---------------------------------------------------------------- encode
+    def dropin_constants(self, raw_blob, batch_blocks=256):
+        """drop flavour only: hand over a shipped setup blob (for the configuration-independent constant tables)
+        and the number of blocks queued per vb200_batch_run."""
+        self.lib.ref_dropin_constants(raw_blob, len(raw_blob))
+        self.lib.ref_dropin_batch_blocks(int(batch_blocks))
+
+    def dropin_error(self):
+        return self.lib.ref_dropin_error().decode()
+
     def open(self, channels, rate, quality=0.4, managed_bitrate=0):
         h = self.lib.ref_enc_open(channels, rate, quality, managed_bitrate)
         if not h:

@@ -77,3 +77,50 @@ def test_stream_matches_reference(config, seconds):
     pk2 += bt.packets()
     assert [a[0] for a in pk2] == [a[0] for a in pk]
     st.close(); st2.close(); bt.close(); s.close()
+
+
+def test_device_bitrate_manager_equals_host_manager_over_many_streams():
+    """in managed mode the reservoirs are walked on the device, one thread per stream, and only
+    the chosen packets come back.  The host restatement of bitrate.c:73-227 (host-emission debug path) must give
+    the same packets, stream by stream, across two batches (the reservoirs carry over)."""
+    from vorbis_aotuv_lancer_b200 import blob as vblob, encoder, ops
+    from vorbis_aotuv_lancer_b200.lib import L
+    config = "abr128_44k_2ch"
+    ch, rate, _, _ = vblob.CATALOGUE[config]
+    s = ops.Setup(config)
+    assert s.managed
+    pcms = [refdata.synth(ch, rate, 2.0 + 0.5 * i, seed=31 + i) for i in range(5)]
+    enc = encoder.Encoder(s, 4096, threads=4, chunks=1)
+    blocks, timeline, counts = enc.segment(pcms)
+    view = np.frombuffer(blocks, dtype=encoder.BLOCK_DTYPE)
+    first = np.zeros(len(view), bool)                       # first half of every stream goes into batch one
+    pos = 0
+    for c in counts:
+        first[pos:pos + c // 2] = True
+        pos += c
+    parts = [np.ascontiguousarray(view[first]), np.ascontiguousarray(view[~first])]
+
+    def run(host_emit):
+        streams = [ops.Stream(s) for _ in pcms]
+        bt = ops.Batch(s, len(view))
+        L.vb200_batch_set_host_emit(bt.h, 1 if host_emit else 0)
+        out = []
+        for part in parts:
+            arr = (ops.Block * len(part)).from_buffer_copy(part.tobytes())
+            bt.run(streams, arr, timeline)
+            tab = encoder.table(bt)
+            out.append([encoder.packets_of(tab, i) for i in range(len(pcms))])
+        for st in streams:
+            st.close()
+        bt.close()
+        return out
+    dev, host = run(False), run(True)
+    for half in range(2):
+        for i in range(len(pcms)):
+            assert len(dev[half][i]) > 10
+            assert dev[half][i] == host[half][i], (half, i)
+    # nominal 128 kbit/s: the managed stream must sit near it (the reservoir keeps it there)
+    secs = sum(p.shape[1] for p in pcms) / rate
+    kbps = sum(len(p[0]) for h in dev for st in h for p in st) * 8 / secs / 1000
+    assert 100 < kbps < 150, kbps
+    enc.close(); s.close()

@@ -37,6 +37,11 @@ struct StatePool {
   unsigned char used[PIPE_MAX_STREAM_SLOTS];
 };
 
+/* the reservoirs of the bitrate manager (bitrate.h:26-38): plain data, so that the same code walks it on the
+   host (host-emission debug path) and on the device (k_bitrate) */
+struct BitrateState { long avg_reservoir, minmax_reservoir, avg_bitsper, min_bitsper, max_bitsper, short_per_long; double avgfloat; };
+struct BitrateParams { long reservoir_bits, rate; double bias, slew_damp; int bs[2]; };
+
 struct vb200_stream {
   vb200_setup *s;
   int slot;
@@ -45,8 +50,7 @@ struct vb200_stream {
   /* lastmdct source for the next block: in the state slot until a batch leaves a newer one there */
   /* bitrate manager (bitrate.h:26-38) */
   int managed;
-  long avg_reservoir, minmax_reservoir, avg_bitsper, min_bitsper, max_bitsper, short_per_long;
-  double avgfloat;
+  BitrateState br;
   int64_t sequence;
 };
 
@@ -220,6 +224,9 @@ struct vb200_batch {
   std::vector<BitWriter> bws; std::vector<std::vector<size_t>> boff;
   unsigned char *d_pool, *h_pool; size_t pool_cap; unsigned long long *d_pool_top, *h_pool_top;
   long long *d_pk_off, *h_pk_off; int *d_pk_bytes, *h_pk_bytes;
+  /* managed mode: the device bitrate manager's state, decisions and the pool of chosen packets */
+  BitrateState *d_br, *h_br; int *d_choice, *h_choice, *d_final, *h_final; long long *d_out_off, *h_out_off;
+  unsigned long long *d_out_top, *h_out_top; unsigned char *d_out_pool; size_t out_cap;
   std::vector<size_t> pk_off, pk_bytes; std::vector<int64_t> pk_gp; std::vector<int> pk_eos, pk_stream;
   /* timing */
   cudaEvent_t ev[16]; int nev; const char *evname[16]; float ev_ms[16]; float total_ms;
@@ -267,14 +274,14 @@ extern "C" int vb200_stream_create(vb200_setup *s, vb200_stream **out) {
   /* vorbis_bitrate_init, bitrate.c:28-61 */
   if (s->bi_i32[3] > 0) {
     const long rate = s->h.rate; const int half = s->h.bs[0] >> 1;
-    x->short_per_long = s->h.bs[1] / s->h.bs[0];
+    x->br.short_per_long = s->h.bs[1] / s->h.bs[0];
     x->managed = 1;
-    x->avg_bitsper = (long)rint(1. * s->bi_i32[0] * half / rate);
-    x->min_bitsper = (long)rint(1. * s->bi_i32[1] * half / rate);
-    x->max_bitsper = (long)rint(1. * s->bi_i32[2] * half / rate);
-    x->avgfloat = VB200_PACKETBLOBS / 2;
+    x->br.avg_bitsper = (long)rint(1. * s->bi_i32[0] * half / rate);
+    x->br.min_bitsper = (long)rint(1. * s->bi_i32[1] * half / rate);
+    x->br.max_bitsper = (long)rint(1. * s->bi_i32[2] * half / rate);
+    x->br.avgfloat = VB200_PACKETBLOBS / 2;
     const long fill = (long)(s->bi_i32[3] * s->bi_f64[0]);
-    x->minmax_reservoir = fill; x->avg_reservoir = fill;
+    x->br.minmax_reservoir = fill; x->br.avg_reservoir = fill;
   }
   *out = x;
   return VB200_OK;
@@ -366,6 +373,19 @@ extern "C" int vb200_batch_create(vb200_setup *s, int max_blocks, vb200_batch **
       cudaGetLastError(); vb200_set_error("vb200_batch_create: cannot allocate the packet pool"); return VB200_EFAULT;
     }
   }
+  b->d_br = nullptr; b->h_br = nullptr; b->d_choice = b->h_choice = b->d_final = b->h_final = nullptr; b->d_out_off = b->h_out_off = nullptr;
+  b->d_out_top = b->h_out_top = nullptr; b->d_out_pool = nullptr; b->out_cap = 0;
+  if (s->h.managed) {
+    const size_t n2 = 2 * (size_t)max_blocks;
+    b->out_cap = (size_t)max_blocks * 4096 + (1 << 16);
+    if (cudaMalloc(&b->d_br, sizeof(BitrateState) * PIPE_MAX_STREAM_SLOTS) != cudaSuccess || cudaMallocHost(&b->h_br, sizeof(BitrateState) * PIPE_MAX_STREAM_SLOTS) != cudaSuccess ||
+        cudaMalloc(&b->d_choice, sizeof(int) * n2) != cudaSuccess || cudaMallocHost(&b->h_choice, sizeof(int) * n2) != cudaSuccess ||
+        cudaMalloc(&b->d_final, sizeof(int) * n2) != cudaSuccess || cudaMallocHost(&b->h_final, sizeof(int) * n2) != cudaSuccess ||
+        cudaMalloc(&b->d_out_off, sizeof(long long) * n2) != cudaSuccess || cudaMallocHost(&b->h_out_off, sizeof(long long) * n2) != cudaSuccess ||
+        cudaMalloc(&b->d_out_top, 8) != cudaSuccess || cudaMallocHost(&b->h_out_top, 8) != cudaSuccess || cudaMalloc(&b->d_out_pool, b->out_cap) != cudaSuccess) {
+      cudaGetLastError(); vb200_set_error("vb200_batch_create: cannot allocate the bitrate manager's buffers"); return VB200_EFAULT;
+    }
+  }
   for (int i = 0; i < 16; i++) cudaEventCreate(&b->ev[i]);
   b->pending = false;
   if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess) { vb200_set_error("vb200_batch_create: cannot create a stream"); return VB200_EFAULT; }
@@ -383,21 +403,29 @@ extern "C" void vb200_batch_destroy(vb200_batch *b) {
   cudaFreeHost(b->pin.base);
   cudaFree(b->d_pool); cudaFree(b->d_pool_top); cudaFree(b->d_pk_off); cudaFree(b->d_pk_bytes);
   cudaFreeHost(b->h_pool); cudaFreeHost(b->h_pool_top); cudaFreeHost(b->h_pk_off); cudaFreeHost(b->h_pk_bytes);
+  cudaFree(b->d_br); cudaFreeHost(b->h_br); cudaFree(b->d_choice); cudaFreeHost(b->h_choice); cudaFree(b->d_final); cudaFreeHost(b->h_final);
+  cudaFree(b->d_out_off); cudaFreeHost(b->h_out_off); cudaFree(b->d_out_top); cudaFreeHost(b->h_out_top); cudaFree(b->d_out_pool);
   delete b;
 }
 
 /* ------------------------------------------------------------------ bitrate manager (host) */
 /* vorbis_bitrate_addblock, bitrate.c:73-227, restated over the 15 blob sizes of one block.
    Returns the chosen blob and the final byte size (after truncation / zero padding). */
-static int bitrate_choose(vb200_stream *x, const vb200_setup *s, int W, const long *blob_bytes, long *final_bytes) {
-  const long reservoir_bits = s->bi_i32[3]; const double bias = s->bi_f64[0], slew_damp = s->bi_f64[1];
+static BitrateParams bitrate_params(const vb200_setup *s) {
+  BitrateParams p;
+  p.reservoir_bits = s->bi_i32[3]; p.rate = s->h.rate; p.bias = s->bi_f64[0]; p.slew_damp = s->bi_f64[1]; p.bs[0] = s->h.bs[0]; p.bs[1] = s->h.bs[1];
+  return p;
+}
+
+__host__ __device__ static int bitrate_choose(BitrateState *x, const BitrateParams &P, int W, const long *blob_bytes, long *final_bytes) {
+  const long reservoir_bits = P.reservoir_bits; const double bias = P.bias, slew_damp = P.slew_damp;
   int choice = (int)rint(x->avgfloat);
   long this_bits = blob_bytes[choice] * 8;
   const long min_target = W ? x->min_bitsper * x->short_per_long : x->min_bitsper;
   const long max_target = W ? x->max_bitsper * x->short_per_long : x->max_bitsper;
-  const int samples = s->h.bs[W] >> 1;
+  const int samples = P.bs[W] >> 1;
   const long desired_fill = (long)(reservoir_bits * bias);
-  const long rate = s->h.rate;
+  const long rate = P.rate;
   if (x->avg_bitsper > 0) {
     double slew = 0.;
     const long avg_target = W ? x->avg_bitsper * x->short_per_long : x->avg_bitsper;
@@ -450,6 +478,60 @@ static int bitrate_choose(vb200_stream *x, const vb200_setup *s, int W, const lo
   *final_bytes = fb;
   return choice;
 }
+
+/* ------------------------------------------------------------------ bitrate manager (device) */
+namespace {
+
+/* vorbis_bitrate_addblock for every block of every stream: one thread per stream walks its blocks in order
+   (the reservoirs carry from block to block), streams run side by side.  Only the sizes of the 15 packet
+   blobs are read; the chosen blob's final size and a slot in the output pool come out. */
+__global__ void k_bitrate(BitrateParams P, int nstreams, const int *__restrict__ scan_start, const ScanBlock *__restrict__ scan, int ch,
+                          int max_blocks, const long long *__restrict__ pk_off, const int *__restrict__ pk_bytes,
+                          BitrateState *__restrict__ state, int *__restrict__ choice, int *__restrict__ final_bytes,
+                          long long *__restrict__ out_off, unsigned long long *__restrict__ out_top, unsigned long long out_cap) {
+  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= nstreams) return;
+  BitrateState x = state[sidx];
+  for (int pos = scan_start[sidx]; pos < scan_start[sidx + 1]; pos++) {
+    const int W = scan[pos].W, idx = scan[pos].first_item / ch;
+    long sz[VB200_PACKETBLOBS];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < VB200_PACKETBLOBS; k++) {
+      const size_t o = ((size_t)k * 2 + W) * max_blocks + idx;
+      sz[k] = pk_bytes[o];
+      if (pk_off[o] < 0) ok = false;              /* a blob did not fit the packer's image */
+    }
+    long fb = 0;
+    const int c = bitrate_choose(&x, P, W, sz, &fb);
+    const size_t o = (size_t)W * max_blocks + idx;
+    const unsigned long long need = ((unsigned long long)fb + 3ull) & ~3ull;
+    const unsigned long long off = atomicAdd(out_top, need);
+    if (off + need > out_cap) ok = false;
+    choice[o] = c;
+    final_bytes[o] = ok ? (int)fb : -1;
+    out_off[o] = (long long)off;
+  }
+  state[sidx] = x;
+}
+
+/* copy the chosen blob of every block into the output pool: truncated (oggpack_writetrunc) or zero-padded to
+   the size the manager decided (bitrate.c:178-215) */
+__global__ void __launch_bounds__(128)
+k_gather_choice(int W, int max_blocks, const int *__restrict__ choice, const int *__restrict__ final_bytes, const long long *__restrict__ out_off,
+                const long long *__restrict__ pk_off, const int *__restrict__ pk_bytes, const unsigned char *__restrict__ pool,
+                unsigned char *__restrict__ out_pool) {
+  const size_t o = (size_t)W * max_blocks + blockIdx.x;
+  const int fb = final_bytes[o];
+  if (fb < 0) return;
+  const size_t src_o = ((size_t)choice[o] * 2 + W) * max_blocks + blockIdx.x;
+  const unsigned char *src = pool + pk_off[src_o];
+  const int have = pk_bytes[src_o];
+  unsigned char *dst = out_pool + out_off[o];
+  for (int t = threadIdx.x; t < fb; t += 128) dst[t] = t < have ? src[t] : (unsigned char)0;
+}
+
+}  // namespace
 
 /* ------------------------------------------------------------------ the run */
 #define EV(name) do{ if (b->nev < 16) { b->evname[b->nev] = name; cudaEventRecord(b->ev[b->nev++], st); } }while(0)
@@ -798,7 +880,30 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     }
   }
   b->run_nb[0] = nb[0]; b->run_nb[1] = nb[1];
-  if (!host_emit) {
+  if (!host_emit && managed) {
+    /* the bitrate manager runs where the blobs are: only the chosen packets leave the device */
+    EV("bitrate manager");
+    for (int i = 0; i < nstreams; i++) b->h_br[i] = streams[i]->br;
+    CUDA_TRY(cudaMemcpyAsync(b->d_br, b->h_br, sizeof(BitrateState) * nstreams, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(b->d_out_top, 0, 8, st));
+    k_bitrate<<<(nstreams + 31) / 32, 32, 0, st>>>(bitrate_params(s), nstreams, b->d_scan_start, b->d_scan, ch, b->max_blocks, b->d_pk_off, b->d_pk_bytes,
+                                                   b->d_br, b->d_choice, b->d_final, b->d_out_off, b->d_out_top, (unsigned long long)b->out_cap);
+    LAUNCH_CHECK();
+    for (int W = 0; W < 2; W++) if (nb[W]) {
+      k_gather_choice<<<nb[W], 128, 0, st>>>(W, b->max_blocks, b->d_choice, b->d_final, b->d_out_off, b->d_pk_off, b->d_pk_bytes, b->d_pool, b->d_out_pool);
+      LAUNCH_CHECK();
+    }
+    EV("d2h packets");
+    CUDA_TRY(cudaMemcpyAsync(b->h_out_top, b->d_out_top, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(b->h_pool_top, b->d_pool_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(b->h_br, b->d_br, sizeof(BitrateState) * nstreams, cudaMemcpyDeviceToHost, st));
+    for (int W = 0; W < 2; W++) if (nb[W]) {
+      const size_t o = (size_t)W * b->max_blocks;
+      CUDA_TRY(cudaMemcpyAsync(b->h_choice + o, b->d_choice + o, sizeof(int) * nb[W], cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(b->h_final + o, b->d_final + o, sizeof(int) * nb[W], cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(b->h_out_off + o, b->d_out_off + o, sizeof(long long) * nb[W], cudaMemcpyDeviceToHost, st));
+    }
+  } else if (!host_emit) {
     /* first half of the only D2H of the path: packet offsets / sizes and the pool fill level */
     EV("d2h packets");
     CUDA_TRY(cudaMemcpyAsync(b->h_pool_top, b->d_pool_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -827,38 +932,46 @@ static int batch_finish(vb200_batch *b) {
   vb200_stream **streams = b->run_streams.data();
   b->pending = false;
   b->pk_base = nullptr;
-  if (!host_emit) {
+  if (!host_emit && managed) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (*b->h_pool_top > b->pool_cap) { vb200_set_error("vb200_batch_collect: packet pool overflow (%llu > %llu bytes)", *b->h_pool_top, (unsigned long long)b->pool_cap); return VB200_EFAULT; }
+    const unsigned long long top = *b->h_out_top;
+    if (top > b->out_cap) { vb200_set_error("vb200_batch_collect: chosen-packet pool overflow (%llu > %llu bytes)", top, (unsigned long long)b->out_cap); return VB200_EFAULT; }
+    CUDA_TRY(cudaMemcpyAsync(b->h_pool, b->d_out_pool, top, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->pk_off.resize(nblocks); b->pk_bytes.resize(nblocks); b->pk_gp.resize(nblocks); b->pk_eos.resize(nblocks); b->pk_stream.resize(nblocks);
+    for (int i = 0; i < nblocks; i++) {
+      const HostBlock &h = b->hb[i];
+      const size_t o = (size_t)h.W * b->max_blocks + h.idx;
+      if (b->h_final[o] < 0) { vb200_set_error("vb200_batch_collect: packet of block %d does not fit the packer's image or the pool", i); return VB200_EFAULT; }
+      b->pk_off[i] = (size_t)b->h_out_off[o]; b->pk_bytes[i] = (size_t)b->h_final[o];
+      b->pk_gp[i] = h.granulepos; b->pk_eos[i] = h.eof; b->pk_stream[i] = h.stream;
+    }
+    for (size_t i = 0; i < b->run_streams.size(); i++) streams[i]->br = b->h_br[i];
+    b->pk_base = b->h_pool;
+  } else if (!host_emit) {
     CUDA_TRY(cudaStreamSynchronize(st));
     const unsigned long long top = *b->h_pool_top;
     if (top > b->pool_cap) { vb200_set_error("vb200_batch_collect: packet pool overflow (%llu > %llu bytes)", top, (unsigned long long)b->pool_cap); return VB200_EFAULT; }
     CUDA_TRY(cudaMemcpyAsync(b->h_pool, b->d_pool, top, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (!managed) {
-      b->pk_off.resize(nblocks); b->pk_bytes.resize(nblocks); b->pk_gp.resize(nblocks); b->pk_eos.resize(nblocks); b->pk_stream.resize(nblocks);
-    }
+    b->pk_off.resize(nblocks); b->pk_bytes.resize(nblocks); b->pk_gp.resize(nblocks); b->pk_eos.resize(nblocks); b->pk_stream.resize(nblocks);
     for (int i = 0; i < nblocks; i++) {
       const HostBlock &h = b->hb[i];
-      if (!managed) {
-        const size_t o = (size_t)h.W * b->max_blocks + h.idx;
-        if (b->h_pk_off[o] < 0) { vb200_set_error("vb200_batch_collect: packet of block %d does not fit the packer's image", i); return VB200_EFAULT; }
-        b->pk_off[i] = (size_t)b->h_pk_off[o]; b->pk_bytes[i] = (size_t)b->h_pk_bytes[o];
-        b->pk_gp[i] = h.granulepos; b->pk_eos[i] = h.eof; b->pk_stream[i] = h.stream;
-        continue;
-      }
-      for (int kk = 0; kk < nblobs; kk++) {
-        const size_t o = ((size_t)kk * 2 + h.W) * b->max_blocks + h.idx;
-        if (b->h_pk_off[o] < 0) { vb200_set_error("vb200_batch_collect: packet of block %d does not fit the packer's image", i); return VB200_EFAULT; }
-        blob_sizes[(size_t)i * VB200_PACKETBLOBS + k_lo + kk] = b->h_pk_bytes[o];
-      }
+      const size_t o = (size_t)h.W * b->max_blocks + h.idx;
+      if (b->h_pk_off[o] < 0) { vb200_set_error("vb200_batch_collect: packet of block %d does not fit the packer's image", i); return VB200_EFAULT; }
+      b->pk_off[i] = (size_t)b->h_pk_off[o]; b->pk_bytes[i] = (size_t)b->h_pk_bytes[o];
+      b->pk_gp[i] = h.granulepos; b->pk_eos[i] = h.eof; b->pk_stream[i] = h.stream;
     }
-    if (!managed) b->pk_base = b->h_pool;
+    b->pk_base = b->h_pool;
   }
-  if (managed) {
+  if (managed && host_emit) {
     /* bitrate.c: choose one blob per block, in stream order (blocks arrive in stream order) */
+    const BitrateParams bparams = bitrate_params(s);
     for (int i = 0; i < nblocks; i++) {
       const HostBlock &h = b->hb[i];
       long fb = 0;
-      const int choice = bitrate_choose(streams[h.stream], s, h.W, &blob_sizes[(size_t)i * VB200_PACKETBLOBS], &fb);
+      const int choice = bitrate_choose(&streams[h.stream]->br, bparams, h.W, &blob_sizes[(size_t)i * VB200_PACKETBLOBS], &fb);
       const size_t start = b->bw.begin_packet();
       const unsigned char *src = host_emit ? bws[choice].buf + boff[choice][i]
                                            : b->h_pool + b->h_pk_off[((size_t)choice * 2 + h.W) * b->max_blocks + h.idx];
