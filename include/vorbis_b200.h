@@ -69,6 +69,20 @@ int  vb200_setup_posts(const vb200_setup *s, int W);        /* floor posts of th
 int  vb200_setup_partvals(const vb200_setup *s, int W, int submap);
 int  vb200_setup_header(const vb200_setup *s, int i, const unsigned char **data, long *bytes); /* the 3 stream headers */
 
+/* ---------------------------------------------------------------- Ogg framing
+   What the encoder's outer loop asks libogg for (examples/encoder_example.c:141-176,224-235:
+   ogg_stream_init/packetin/flush/pageout): pages with lacing, sequence numbers and CRC around the packets of one
+   logical stream.  Host-only.  The pages accumulate in the muxer; vb200_oggmux_data returns all of them. */
+typedef struct vb200_oggmux vb200_oggmux;
+int  vb200_oggmux_create(int32_t serialno, vb200_oggmux **out);                 /* ogg_stream_init */
+void vb200_oggmux_destroy(vb200_oggmux *m);                                     /* ogg_stream_clear */
+int  vb200_oggmux_packet(vb200_oggmux *m, const unsigned char *data, long bytes, int64_t granulepos, int eos);
+                                                                                /* ogg_stream_packetin + pageout loop */
+int  vb200_oggmux_flush(vb200_oggmux *m);                                       /* ogg_stream_flush loop (after the headers) */
+const unsigned char *vb200_oggmux_data(const vb200_oggmux *m, size_t *bytes);
+long vb200_oggmux_pages(const vb200_oggmux *m);
+uint32_t vb200_ogg_crc(const unsigned char *data, size_t bytes);                /* CRC-32 0x04c11db7, init 0, unreflected */
+
 /* ---------------------------------------------------------------- synthetic PCM (bench / tests) */
 uint64_t vb200_splitmix64(uint64_t x);
 /* planar out[c*stride + i]; seed 0 selects the survey's default seed */

@@ -1,0 +1,114 @@
+"""Ogg framing (csrc/oggframe.c).  libogg is not in this image and the reference pins nothing
+here, so the check is structural: an independent demultiplexer (written from RFC 3533, bitwise CRC) must get the
+same packets back, and the paging rules the module states must hold."""
+import struct
+
+import numpy as np
+
+
+def crc_bitwise(data):
+    r = 0
+    for b in data:
+        r ^= b << 24
+        for _ in range(8):
+            r = ((r << 1) ^ 0x04C11DB7) & 0xFFFFFFFF if r & 0x80000000 else (r << 1) & 0xFFFFFFFF
+    return r
+
+
+def demux(stream):
+    """-> pages [(flags, granulepos, serial, pageno, lacing, body)], packets [(bytes, page index where it ended)]"""
+    pages, packets, cur, pos = [], [], b"", 0
+    open_packet = False
+    while pos < len(stream):
+        assert stream[pos:pos + 4] == b"OggS" and stream[pos + 4] == 0
+        flags = stream[pos + 5]
+        gp, serial, pageno, crc, nseg = struct.unpack_from("<qIIIB", stream, pos + 6)
+        lacing = list(stream[pos + 27:pos + 27 + nseg])
+        blen = sum(lacing)
+        page = bytearray(stream[pos:pos + 27 + nseg + blen])
+        page[22:26] = b"\0\0\0\0"
+        assert crc_bitwise(page) == crc, "page %d CRC" % pageno
+        body = stream[pos + 27 + nseg:pos + 27 + nseg + blen]
+        assert bool(flags & 1) == open_packet, "continued flag of page %d" % pageno
+        o = 0
+        for v in lacing:
+            cur += body[o:o + v]
+            o += v
+            open_packet = v == 255
+            if v < 255:
+                packets.append((cur, len(pages)))
+                cur = b""
+        pages.append((flags, gp, serial, pageno, lacing, body))
+        pos += 27 + nseg + blen
+    assert not open_packet
+    return pages, packets
+
+
+def test_crc_known_answers():
+    from vorbis_aotuv_lancer_b200 import ogg
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 27, 255, 4096):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert ogg.crc(d) == crc_bitwise(d)
+    assert ogg.crc(b"\x00" * 8) == 0                       # initial value 0, no final xor
+    assert ogg.crc(b"\x01") == 0x04C11DB7                  # the polynomial itself
+
+
+def test_pages_round_trip_and_follow_the_paging_rules():
+    from vorbis_aotuv_lancer_b200 import ogg
+    rng = np.random.default_rng(7)
+    headers = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (30, 45, 3900)]
+    sizes = list(rng.integers(1, 700, 400)) + [0, 255, 510, 254, 256, 70000, 5, 65025, 1]
+    gp, packets = 0, []
+    for i, n in enumerate(sizes):
+        gp += 1024 if i % 3 else 576
+        packets.append((rng.integers(0, 256, int(n), dtype=np.uint8).tobytes(), gp, int(i == len(sizes) - 1)))
+    stream = ogg.mux(headers, packets, serial=0x1234)
+    pages, got = demux(stream)
+    assert [g[0] for g in got] == headers + [p[0] for p in packets]
+    assert [p[3] for p in pages] == list(range(len(pages)))            # page sequence numbers
+    assert all(p[2] == 0x1234 for p in pages)
+    # first page: BOS, the identification header alone, granule 0
+    assert pages[0][0] & 2 and pages[0][4] == [30] and pages[0][1] == 0
+    assert not any(p[0] & 2 for p in pages[1:])
+    # the other two headers are flushed before audio: audio packet 0 starts a page
+    first_audio_page = got[3][1] if len(packets[0][0]) < 255 * 255 else None
+    assert got[2][1] < got[3][1] or got[3][1] == first_audio_page
+    hdr_last = got[2][1]
+    assert all(idx > hdr_last for _, idx in got[3:])
+    # EOS on the last page only
+    assert pages[-1][0] & 4 and not any(p[0] & 4 for p in pages[:-1])
+    # granule position of a page = that of the last packet finished on it, -1 if none finished
+    ends = {}
+    for k, (_, idx) in enumerate(got):
+        ends[idx] = k
+    for idx, p in enumerate(pages):
+        if idx in ends and ends[idx] >= 3:
+            assert p[1] == packets[ends[idx] - 3][1]
+        elif idx not in ends:
+            assert p[1] == -1
+    # paging policy: an audio page that is not the last one is full (255 segments) or holds > 4096 bytes and >= 4
+    # finished packets
+    for idx, p in enumerate(pages[hdr_last + 1:-1], hdr_last + 1):
+        done = sum(1 for v in p[4] if v < 255)
+        assert len(p[4]) == 255 or (len(p[5]) > 4096 and done >= 4), (idx, len(p[4]), len(p[5]), done)
+    assert all(len(p[4]) <= 255 for p in pages)
+
+
+def test_reference_stream_muxes():
+    """real headers + packets from the reference encoder (oracle/_ref) -> .ogg; the demultiplexer gives them back and
+    the decoder input is unchanged"""
+    import pytest
+    from oracle import reflib
+    from tests import refdata
+    from vorbis_aotuv_lancer_b200 import ogg
+    if not reflib.available("c"):
+        pytest.skip("oracle/_ref not present")
+    cap = refdata.capture("q4_44k_2ch", 1.0)
+    headers, packets = [bytes(h) for h in cap["headers"]], [(bytes(p[0]), p[1], p[2]) for p in cap["packets"]]
+    assert headers[0][:7] == b"\x01vorbis" and headers[1][:7] == b"\x03vorbis" and headers[2][:7] == b"\x05vorbis"
+    stream = ogg.mux(headers, packets)
+    pages, got = demux(stream)
+    assert [x[0] for x in got] == headers + [p[0] for p in packets]
+    assert pages[-1][1] == packets[-1][1] and pages[-1][0] & 4
+    assert len(pages) >= 4
