@@ -131,6 +131,7 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
       const DevBook &B = books[bk];
       const int dim = B.dim, nvec = tab_nvec[cls * 8 + s], qv = B.quantvals, ze = qv >> 1;
       const int bdelta = B.delta, bmin = B.minval;
+      const unsigned brcp = B.delta_rcp;
       short *e_out = ent + (((size_t)s * partvals + p) * rows + row) * maxvec;
       for (int t0 = 0; t0 < nvec; t0 += 32) {
         const int t = t0 + lane;
@@ -142,7 +143,13 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
           bool on_lattice = true;          /* the input is exactly a lattice point inside the book's range */
           for (int i = 0, o = dim; i < dim; i++) {
             --o;
-            const int x = (bdelta != 1) ? (a[o] - bmin + (bdelta >> 1)) / bdelta : a[o] - bmin;
+            int x = a[o] - bmin;
+            if (bdelta != 1) {
+              /* C division (truncating) by the book's step: exact reciprocal multiply while the value is small */
+              const int num = x + (bdelta >> 1), an = abs(num);
+              if (brcp && an < (1 << 21)) { const int q = (int)__umulhi((unsigned)an, brcp); x = num < 0 ? -q : q; }
+              else x = num / bdelta;
+            }
             const int m = (x < ze) ? ((ze - x) << 1) - 1 : ((x - ze) << 1);
             index = index * qv + (m < 0 ? 0 : (m >= qv ? qv - 1 : m));
             pt[o] = x * bdelta + bmin;

@@ -322,6 +322,7 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
     if (!b.len || !b.code) break;
     DevBook &d = hb[k];
     d.dim = b.dim; d.entries = b.entries; d.quantvals = b.quantvals; d.minval = b.minval; d.delta = b.delta;
+    d.delta_rcp = (b.delta > 1 && b.delta < 1024) ? (unsigned)((0x100000000ull + (unsigned long long)b.delta - 1) / (unsigned long long)b.delta) : 0u;
     int used = 0;
     for (int i = 0; i < b.entries; i++) if (b.len[i] > 0) used++;
     d.used = used;

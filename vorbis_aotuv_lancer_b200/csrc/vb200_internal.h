@@ -59,6 +59,7 @@ struct DevResidue {
 
 struct DevBook {
   int dim, entries, quantvals, minval, delta;
+  unsigned delta_rcp;        /* ceil(2^32 / delta): |x| / delta == umulhi(|x|, delta_rcp) for |x| < 2^21, delta < 1024 */
   int used;                     /* number of entries with a codeword */
   const uint8_t  *len;          /* [entries] codeword lengths (0 = unused) */
   const uint32_t *code;         /* [entries] */
