@@ -235,6 +235,14 @@ def run_ours(args):
         achieved = algo / (kern[top] * 1e-3) / 1e9
         whole = sum((nlong * v[0] + nshort * v[1]) * ch for v in ALGO_BYTES.values())
         whole_gbs = whole / (sum(kern.values()) * 1e-3) / 1e9
+        # DRAM traffic of the dominant kernel: from the committed ncu capture of this very workload, else null
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tr["workload"]["streams_per_gpu"] == S and tr["workload"]["seconds_per_stream"] == T:
+                traffic = tr["bytes_per_launch"].get(top)
+        except Exception:
+            pass
         cores = os.cpu_count() or 1
         cpu = None
         if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
@@ -258,7 +266,7 @@ def run_ours(args):
                        "steps": e2e_steps, "includes": "host segmentation (LPC head/tail, window sequencing; detector kernels on the GPU), H2D PCM, all kernels, bit packing, D2H packets; %d pipelined stream groups" % args.chunks},
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "kernel_ms": kern[top],
+                            "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": int(algo), "kernel_ms": kern[top],
                             "all_kernels": {"algorithmic_GBps": whole_gbs, "frac": whole_gbs / peak, "ms": sum(kern.values())}},
                "stage_ms": stage_ms, "clocks": summarize_clocks(samples), "cpu_baseline": cpu,
                "packet_bytes_per_step": int(packet_bytes), "kbps": packet_bytes * 8 / audio / 1000.0}
