@@ -119,6 +119,18 @@ k_stream_scan(const DevSetup *__restrict__ S, int nstreams, const int *__restric
 #pragma unroll
     for (int c = 0; c < VB200_MAX_CHANNELS; c++) my_lv[c] = 0.f;
     const int cnt = min(32, b_end - b0);
+    /* loud-noise level: a block either carries the previous value, forces -1, or (rare: a long<->transition
+       change at q<=2) sets a new one.  Without a "new value" in these 32 blocks the carried level is known from two
+       ballots; only otherwise is it replayed block by block. */
+    bool slow = false;
+#pragma unroll
+    for (int c = 0; c < VB200_MAX_CHANNELS; c++) {
+      if (c >= ch) continue;
+      const unsigned m1 = __ballot_sync(FULLMASK, kind[c] == 1), m2 = __ballot_sync(FULLMASK, kind[c] == 2);
+      if (m2) { slow = true; continue; }
+      my_lv[c] = (m1 & (0xffffffffu >> (31 - lane))) ? -1.f : lv[c];
+      if (m1) lv[c] = -1.f;
+    }
     for (int t = 0; t < cnt; t++) {
       const float lm_t = __shfl_sync(FULLMASK, lmax, t), d_t = __shfl_sync(FULLMASK, decay, t);
       if (vbi > g) g = vbi;
@@ -128,12 +140,18 @@ k_stream_scan(const DevSetup *__restrict__ S, int nstreams, const int *__restric
       if (lm_t > gl) gl = lm_t;
       vbi = gl;
       if (lane == t) my_gl = gl;
+    }
+    if (slow) {                                /* uniform across the warp */
+      for (int t = 0; t < cnt; t++) {
 #pragma unroll
-      for (int c = 0; c < VB200_MAX_CHANNELS; c++) {
-        const int k_t = __shfl_sync(FULLMASK, kind[c], t);
-        const float n_t = __shfl_sync(FULLMASK, nv[c], t);
-        if (k_t == 1) lv[c] = -1.f; else if (k_t == 2) lv[c] = n_t;
-        if (lane == t) my_lv[c] = lv[c];
+        for (int c = 0; c < VB200_MAX_CHANNELS; c++) {
+          if (c >= ch) continue;
+          if (!__ballot_sync(FULLMASK, kind[c] == 2)) continue;
+          const int k_t = __shfl_sync(FULLMASK, kind[c], t);
+          const float n_t = __shfl_sync(FULLMASK, nv[c], t);
+          if (k_t == 1) lv[c] = -1.f; else if (k_t == 2) lv[c] = n_t;
+          if (lane == t) my_lv[c] = lv[c];
+        }
       }
     }
     if (have) {
