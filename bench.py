@@ -283,7 +283,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=60.0)
-    ap.add_argument("--chunks", type=int, default=4, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
+    ap.add_argument("--chunks", type=int, default=6, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # stdout carries the one JSON line and nothing else: libraries that write to fd 1 (NCCL's version banner)

@@ -204,6 +204,13 @@ int  vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out);
 void vb200_segmenter_destroy(vb200_segmenter *g);
 int  vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float *const *pcm, const long *nsamples,
                          const long *stride, int chunk, int threads);
+/* the same in two halves, for callers that overlap: _begin enqueues the uploads and the detector kernels and
+   returns at once; _finish waits for the marks, sequences the windows and uploads the extrapolated tails */
+int  vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const float *const *pcm, const long *nsamples,
+                           const long *stride, int chunk, int threads);
+int  vb200_segmenter_finish(vb200_segmenter *g);
+/* order g's uploads behind prev's (both begun before either is finished): the first group's PCM arrives first */
+int  vb200_segmenter_after(vb200_segmenter *g, const vb200_segmenter *prev);
 int  vb200_segmenter_count(const vb200_segmenter *g);
 const vb200_block *vb200_segmenter_blocks(const vb200_segmenter *g);
 const float *vb200_segmenter_device_pcm(const vb200_segmenter *g, size_t *elems);

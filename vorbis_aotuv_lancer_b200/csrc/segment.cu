@@ -632,6 +632,15 @@ __global__ void k_timeline_finish(const EnvStream *__restrict__ streams, int ch,
   }
 }
 
+/* the extrapolated tails (a few thousand samples per channel) are fetched by a kernel straight from the pinned host
+   timeline: a copy-engine transfer would queue behind the bulk uploads other segmenters have already issued */
+__global__ void k_tail_upload(const EnvStream *__restrict__ streams, int ch, const float *__restrict__ host_pcm, float *__restrict__ pcm) {
+  const EnvStream S = streams[blockIdx.x / ch];
+  const long long o = S.pcm_base + (long long)(blockIdx.x % ch) * S.T + S.eof;
+  const int n = (int)(S.T - S.eof);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) pcm[o + i] = host_pcm[o + i];
+}
+
 /* the last 17 band amplitudes and 45 near-DC terms of every (stream, channel): what the host needs to
    continue the detector over the extrapolated tail */
 __global__ void k_env_tail(const EnvStream *__restrict__ streams, int ch, const float *__restrict__ acc_in, const float *__restrict__ temp_in,
@@ -652,8 +661,13 @@ __global__ void k_env_tail(const EnvStream *__restrict__ streams, int ch, const 
 
 }  // namespace
 
+struct SegRun {            /* what a begun run keeps until it is finished */
+  std::vector<StreamSeg> seg; std::vector<long long> base, mark_base;
+  int nstreams, threads; size_t total, nmark; double t0, t1;
+};
+
 struct vb200_segmenter {
-  vb200_setup *s; EnvParams env;
+  vb200_setup *s; EnvParams env; SegRun *run;
   EnvDev *d_env; double *d_dct, *d_dctt; float *d_win;
   float *h_pcm, *d_pcm; size_t pcm_cap;          /* pinned host timeline + device timeline */
   float *d_acc, *d_temp; unsigned *d_flags; size_t step_cap;
@@ -661,6 +675,7 @@ struct vb200_segmenter {
   EnvStream *d_streams, *h_streams; long long *d_mark_base, *h_mark_base; int *d_stretch, *h_stretch;
   float *d_acc_tail, *h_acc_tail, *d_temp_tail, *h_temp_tail; int stream_cap;
   cudaStream_t st; int direct;
+  cudaEvent_t ev_h2d; const vb200_segmenter *after;   /* uploads are ordered behind another segmenter's (see _after) */
   std::vector<vb200_block> blocks; size_t pcm_elems;
 };
 
@@ -689,6 +704,7 @@ extern "C" int vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out) {
   e.minenergy = g->env.minenergy; e.stretch_penalty = g->env.stretch_penalty;
   CUDA_TRY(cudaMemcpy(g->d_env, &e, sizeof(e), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&g->ev_h2d, cudaEventDisableTiming));
   *out = g;
   return VB200_OK;
 }
@@ -697,6 +713,8 @@ extern "C" void vb200_segmenter_destroy(vb200_segmenter *g) {
   if (!g) return;
   cudaSetDevice(g->s->device);
   cudaStreamDestroy(g->st);
+  cudaEventDestroy(g->ev_h2d);
+  delete g->run;
   cudaFree(g->d_dct); cudaFree(g->d_dctt); cudaFree(g->d_win); cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
   cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_flags); cudaFree(g->d_marks); cudaFreeHost(g->h_marks);
   cudaFree(g->d_streams); cudaFreeHost(g->h_streams); cudaFree(g->d_mark_base); cudaFreeHost(g->h_mark_base);
@@ -718,16 +736,22 @@ template <typename F> static void parallel_for(int n, int threads, F f) {
 
 /* Segment `nstreams` streams at once.  pcm[i]: planar [channels][nsamples[i]] with stride[i].
    Afterwards the timeline of all streams sits in HBM (vb200_segmenter_device_pcm) and the blocks index it. */
-extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float *const *pcm, const long *nsamples,
-                                   const long *stride, int chunk, int threads) {
-  if (!g || nstreams < 1 || !pcm || !nsamples || !stride) { vb200_set_error("vb200_segmenter_run: bad arguments"); return VB200_EINVAL; }
+extern "C" int vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const float *const *pcm, const long *nsamples,
+                                     const long *stride, int chunk, int threads) {
+  if (!g || nstreams < 1 || !pcm || !nsamples || !stride) { vb200_set_error("vb200_segmenter_begin: bad arguments"); return VB200_EINVAL; }
   vb200_setup *s = g->s;
   CUDA_TRY(cudaSetDevice(s->device));
   cudaStream_t st = g->st;
   const int ch = s->h.channels;
   if (chunk <= 0) chunk = 1024;
-  std::vector<StreamSeg> seg(nstreams);
-  std::vector<long long> base(nstreams + 1, 0), step_base(nstreams + 1, 0), mark_base(nstreams + 1, 0);
+  if (g->run) { vb200_set_error("vb200_segmenter_begin: the previous run was not finished"); return VB200_EINVAL; }
+  SegRun *R = new SegRun();
+  g->run = R;
+  R->nstreams = nstreams; R->threads = threads;
+  R->seg.resize(nstreams); R->base.assign(nstreams + 1, 0); R->mark_base.assign(nstreams + 1, 0);
+  std::vector<StreamSeg> &seg = R->seg;
+  std::vector<long long> &base = R->base, &mark_base = R->mark_base;
+  std::vector<long long> step_base(nstreams + 1, 0);
   for (int i = 0; i < nstreams; i++) {
     const long T = StreamSeg::timeline_len(s, nsamples[i]);
     base[i + 1] = base[i] + (long long)T * ch;
@@ -736,6 +760,7 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
     mark_base[i + 1] = mark_base[i] + ((T / VE_STEP + VE_WIN + VE_POST + 4 + 15) & ~15LL);
   }
   const size_t total = (size_t)base[nstreams];
+  R->total = total;
   if (g->pcm_cap < total) {
     cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm); g->d_pcm = nullptr; g->h_pcm = nullptr; g->pcm_cap = 0;
     SEG_ALLOC(g->h_pcm, total * sizeof(float), true); SEG_ALLOC(g->d_pcm, total * sizeof(float), false);
@@ -767,7 +792,7 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
   }
   const bool trace = getenv("VB200_TRACE") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  double t0 = now(), t1, t2, t3, t4;
+  double t0 = now(), t1;
   /* inputs already in page-locked memory go up from where they are; otherwise they are staged through
      the segmenter's own pinned timeline */
   bool direct = getenv("VB200_SEG_STAGED") == nullptr;
@@ -787,6 +812,7 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
     g->h_mark_base[i] = mark_base[i];
     if (e.nsteps > max_steps) max_steps = e.nsteps;
   }
+  if (g->after) CUDA_TRY(cudaStreamWaitEvent(st, g->after->ev_h2d, 0));   /* the copy engine would otherwise share the link between both */
   CUDA_TRY(cudaMemcpyAsync(g->d_streams, g->h_streams, sizeof(EnvStream) * nstreams, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(g->d_mark_base, g->h_mark_base, sizeof(long long) * nstreams, cudaMemcpyHostToDevice, st));
   /* host: timelines (pre-amplified PCM + LPC head) into the pinned buffer; staged mode sends every finished
@@ -828,6 +854,7 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
     for (auto &x : th) x.join();
     CUDA_TRY(cerr);
   }
+  CUDA_TRY(cudaEventRecord(g->ev_h2d, st));
   t1 = now();
   /* the detector's heavy half on the device */
   CUDA_TRY(cudaMemsetAsync(g->d_marks, 0, nmark, st));
@@ -846,6 +873,26 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
   CUDA_TRY(cudaMemcpyAsync(g->h_stretch, g->d_stretch, sizeof(int) * nstreams, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(g->h_acc_tail, g->d_acc_tail, sizeof(float) * nstreams * ch * VE_AMP * VE_BANDS, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(g->h_temp_tail, g->d_temp_tail, sizeof(float) * nstreams * ch * 45, cudaMemcpyDeviceToHost, st));
+  R->t0 = t0; R->t1 = t1; R->nmark = nmark;
+  return VB200_OK;
+}
+
+/* second half: wait for the marks, sequence the windows, extrapolate and upload the tails */
+extern "C" int vb200_segmenter_finish(vb200_segmenter *g) {
+  if (!g || !g->run) { vb200_set_error("vb200_segmenter_finish: nothing was begun"); return VB200_EINVAL; }
+  vb200_setup *s = g->s;
+  CUDA_TRY(cudaSetDevice(s->device));
+  cudaStream_t st = g->st;
+  SegRun *R = g->run;
+  std::vector<StreamSeg> &seg = R->seg;
+  std::vector<long long> &base = R->base, &mark_base = R->mark_base;
+  const int nstreams = R->nstreams, threads = R->threads, ch = s->h.channels;
+  const size_t total = R->total;
+  const bool trace = getenv("VB200_TRACE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = R->t0, t1 = R->t1;
+  double t2, t3, t4;
+  const double tw = now();
   if (trace) { CUDA_TRY(cudaStreamSynchronize(st)); }
   t2 = now();
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -860,17 +907,31 @@ extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float
   });
   t3 = now();
   /* the extrapolated tails go up as well (small), then the blocks */
-  for (int i = 0; i < nstreams; i++)
-    for (int c = 0; c < ch; c++) {
-      const size_t o = (size_t)base[i] + (size_t)c * seg[i].T + seg[i].eof_abs;
-      CUDA_TRY(cudaMemcpyAsync(g->d_pcm + o, g->h_pcm + o, sizeof(float) * (seg[i].T - seg[i].eof_abs), cudaMemcpyHostToDevice, st));
-    }
+  k_tail_upload<<<nstreams * ch, 256, 0, st>>>(g->d_streams, ch, g->h_pcm, g->d_pcm);
+  LAUNCH_CHECK();
   g->blocks.clear();
   for (int i = 0; i < nstreams; i++) g->blocks.insert(g->blocks.end(), seg[i].blocks.begin(), seg[i].blocks.end());
   g->pcm_elems = total;
   CUDA_TRY(cudaStreamSynchronize(st));
   t4 = now();
-  if (trace) fprintf(stderr, "[vb200 segmenter] fill+head %.1f ms | h2d+detector+d2h %.1f ms | sequencing+tail %.1f ms | tail h2d+collect %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3);
+  if (trace) fprintf(stderr, "[vb200 segmenter] begin (fill+head, enqueue) %.1f ms | waited %.1f ms for h2d+detector+d2h (%.1f ms after begin) | sequencing+tail %.1f ms | tail h2d+collect %.1f ms\n", t1 - t0, t2 - tw, t2 - t1, t3 - t2, t4 - t3);
+  delete R;
+  g->run = nullptr;
+  return VB200_OK;
+}
+
+extern "C" int vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float *const *pcm, const long *nsamples,
+                                   const long *stride, int chunk, int threads) {
+  const int r = vb200_segmenter_begin(g, nstreams, pcm, nsamples, stride, chunk, threads);
+  if (r) { if (g && g->run) { delete g->run; g->run = nullptr; } return r; }
+  return vb200_segmenter_finish(g);
+}
+
+/* order this segmenter's uploads behind `prev`'s (NULL: no ordering).  Several segmenters begun back to back
+   would otherwise share the host link and all finish late; chained, the first one's data arrives first. */
+extern "C" int vb200_segmenter_after(vb200_segmenter *g, const vb200_segmenter *prev) {
+  if (!g || prev == g) { vb200_set_error("vb200_segmenter_after: bad arguments"); return VB200_EINVAL; }
+  g->after = prev;
   return VB200_OK;
 }
 

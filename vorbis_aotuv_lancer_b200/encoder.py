@@ -57,18 +57,28 @@ class Segmenter:
             L.vb200_segmenter_destroy(self.h)
             self.h = None
 
-    def run(self, pcms, chunk=1024, threads=8):
-        """pcms: list of float32 [channels, nsamples].  -> (Block array view, device address, elems)"""
-        pcms = [np.ascontiguousarray(p, np.float32) for p in pcms]
-        n = len(pcms)
-        ptrs = (C.c_void_p * n)(*[p.ctypes.data for p in pcms])
-        ns = (C.c_long * n)(*[p.shape[1] for p in pcms])
-        check(L.vb200_segmenter_run(self.h, n, ptrs, ns, ns, int(chunk), int(threads)), "vb200_segmenter_run")
+    def begin(self, pcms, chunk=1024, threads=8):
+        """Enqueue the uploads and the detector kernels of these streams; returns at once."""
+        self._pcms = [np.ascontiguousarray(p, np.float32) for p in pcms]       # kept alive until finish()
+        n = len(self._pcms)
+        ptrs = (C.c_void_p * n)(*[p.ctypes.data for p in self._pcms])
+        ns = (C.c_long * n)(*[p.shape[1] for p in self._pcms])
+        check(L.vb200_segmenter_begin(self.h, n, ptrs, ns, ns, int(chunk), int(threads)), "vb200_segmenter_begin")
+
+    def finish(self):
+        """-> (Block array view, device address, elems)"""
+        check(L.vb200_segmenter_finish(self.h), "vb200_segmenter_finish")
+        self._pcms = None
         nb = L.vb200_segmenter_count(self.h)
         blocks = C.cast(L.vb200_segmenter_blocks(self.h), C.POINTER(ops.Block * nb)).contents
         elems = C.c_size_t()
         dptr = L.vb200_segmenter_device_pcm(self.h, C.byref(elems))
         return blocks, dptr, elems.value
+
+    def run(self, pcms, chunk=1024, threads=8):
+        """pcms: list of float32 [channels, nsamples].  -> (Block array view, device address, elems)"""
+        self.begin(pcms, chunk, threads)
+        return self.finish()
 
     @property
     def direct(self):
@@ -88,13 +98,15 @@ class Encoder:
     its own segmenter and batch (own CUDA streams): while the kernels of group g run, the host segments group
     g+1 and its PCM goes up -- the host stage and the device stage overlap."""
 
-    def __init__(self, setup, max_blocks, threads=8, chunks=4):
+    def __init__(self, setup, max_blocks, threads=8, chunks=6):
         self.setup = setup
         self.threads = threads
         self.chunks = max(1, int(chunks))
-        per = (int(max_blocks) + self.chunks - 1) // self.chunks + 64
+        per = (int(max_blocks) + max(1, self.chunks - 1) - 1) // max(1, self.chunks - 1) + 64
         self.batches = [ops.Batch(setup, per) for _ in range(self.chunks)]
         self.segmenters = [Segmenter(setup) for _ in range(self.chunks)]
+        for a, b in zip(self.segmenters[:-1], self.segmenters[1:]):
+            check(L.vb200_segmenter_after(b.h, a.h), "vb200_segmenter_after")
         self.batch = self.batches[0]
         self.segmenter = self.segmenters[0]
         self.pool = ThreadPoolExecutor(max_workers=threads)
@@ -130,13 +142,21 @@ class Encoder:
         own = streams is None
         if own:
             streams = [ops.Stream(self.setup) for _ in pcms]
-        groups = [(g * n // self.chunks, (g + 1) * n // self.chunks) for g in range(self.chunks)]
-        groups = [(a, b) for a, b in groups if b > a]
+        # a small first group gets the device started early; the others share the rest evenly
+        k = min(self.chunks, n)
+        if k > 1:
+            first = max(1, n // (4 * k))
+            cuts = [0, first] + [first + (g + 1) * (n - first) // (k - 1) for g in range(k - 1)]
+        else:
+            cuts = [0, n]
+        groups = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
         trace = os.environ.get("VB200_TRACE")
         t0 = time.perf_counter()
         marks = []
-        for g, (a, b) in enumerate(groups):
-            blocks, dptr, elems = self.segmenters[g].run(pcms[a:b], threads=self.threads)
+        for g, (a, b) in enumerate(groups):            # all uploads and detector kernels are queued first ...
+            self.segmenters[g].begin(pcms[a:b], threads=self.threads)
+        for g, (a, b) in enumerate(groups):            # ... so the copy engine never waits for the host stage of a group
+            blocks, dptr, elems = self.segmenters[g].finish()
             t1 = time.perf_counter()
             self.batches[g].submit(streams[a:b], blocks, dptr, elems)
             marks.append((t1 - t0, time.perf_counter() - t0))
