@@ -102,7 +102,8 @@ class Encoder:
         self.setup = setup
         self.threads = threads
         self.chunks = max(1, int(chunks))
-        per = (int(max_blocks) + max(1, self.chunks - 1) - 1) // max(1, self.chunks - 1) + 64
+        # every group but the first holds about 1/(chunks-1) of the streams; 25 % slack for uneven stream lengths
+        per = int(1.25 * int(max_blocks) / max(1, self.chunks - 1)) + 64 if self.chunks > 1 else int(max_blocks)
         self.batches = [ops.Batch(setup, per) for _ in range(self.chunks)]
         self.segmenters = [Segmenter(setup) for _ in range(self.chunks)]
         for a, b in zip(self.segmenters[:-1], self.segmenters[1:]):
