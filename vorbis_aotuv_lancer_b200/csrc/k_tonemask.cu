@@ -8,11 +8,14 @@
  * a plain sliding maximum (a later, higher seed does not take over until the earlier entry's span
  * ends), so it is serial per ch-block.  Round-1 first version gave every ch-block one warp and let
  * lane 0 walk the chase: ncu showed 4 active lanes per instruction and an issue-bound SM
- * (profiles/r01_ncu_tonemask_full.md).  This version keeps 16 ch-blocks per CTA in shared memory:
- * the splat and the final min-over-span step run warp-cooperatively per ch-block, while the chase
- * runs lane-per-ch-block (16 independent stack walks advance together in one half-warp, their seed
- * vectors laid out with an odd stride so that equal positions fall into different banks).
- * HBM traffic: logfft in, tone out.
+ * (profiles/r01_ncu_tonemask_full.md).  Now the chase runs on bit masks (see tm_chase_step) and needs one
+ * lane per ch-block and ~36 instructions per position, so it wants 32 ch-blocks per warp, while splat and fill want
+ * a warp per ch-block.  Long blocks therefore take three kernels: k_tone_splat (warp per ch-block: splat + the
+ * 14 comparison bits per position) -> k_tone_chase (lane per ch-block, comparison words transposed through shared
+ * memory 32 positions at a time) -> k_tone_fill (warp per ch-block: spans, fill, min-over-span, output).  The seeds
+ * (3 KB), comparison words (1.5 KB) and survivor bits (100 B) of a ch-block travel through rows of two per-batch
+ * buffers that are dead at this point of the pipeline (logmask and iwork rows), +9.4 KB of HBM traffic per
+ * ch-block.  Short blocks (rows too small for that) keep the fused kernel k_tonemask.
  */
 #include "vb200_internal.h"
 #include "dev_util.cuh"
@@ -30,30 +33,14 @@ __device__ __forceinline__ void smem_atomic_max(float *addr, float v) {
 
 struct SplatJob { float mx; int sp0; int curve; int k0, k1; };   /* amplitude, first seed position, curve offset in floats */
 
-/* TM_ITEMS ch-blocks per CTA: one warp each for the cooperative phases, TM_ITEMS lanes for the chase */
-template <int N, int TM_ITEMS>
-__global__ void __launch_bounds__(TM_ITEMS * 32)
-k_tonemask(const DevSetup *__restrict__ S, int items, const int *__restrict__ psyv, const float *__restrict__ logfft,
-           const float *__restrict__ global_ampmax, const float *__restrict__ local_ampmax, float *__restrict__ tone, int Lstride) {
-  constexpr int TM_THREADS = TM_ITEMS * 32, TM_WARPS = TM_ITEMS;
-  extern __shared__ __align__(16) unsigned char dyn[];
-  float *seed_all = reinterpret_cast<float *>(dyn);                                  /* [TM_ITEMS][Lstride] */
-  unsigned short *pos_all = reinterpret_cast<unsigned short *>(seed_all + TM_ITEMS * Lstride);   /* [TM_ITEMS][Lstride] */
-  __shared__ unsigned surv_all[TM_ITEMS * TM_SVW];                                   /* surviving positions, one bit each */
-  __shared__ SplatJob queue[TM_WARPS][TM_QCAP];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int item0 = blockIdx.x * TM_ITEMS;
-  const int nloc = min(TM_ITEMS, items - item0);
-
-  for (int i = tid; i < TM_ITEMS * Lstride; i += TM_THREADS) seed_all[i] = TM_NEGINF;
-  __syncthreads();
-
-  /* ---- seed_loop: warps take ch-blocks in turn; lanes take the runs of bins that share an octave line ---- */
-  for (int li = warp; li < nloc; li += TM_WARPS) {
-    const int item = item0 + li;
+/* seed_loop (psy.c:719-771) of one ch-block by one warp: lanes take the runs of bins that share an octave line,
+   hits are queued, and when 32 wait every lane splats one whole curve (max-scatter: order does not matter) */
+template <int N>
+__device__ __forceinline__ void tm_splat(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const float *__restrict__ logfft,
+                                         const float *__restrict__ global_ampmax, const float *__restrict__ local_ampmax,
+                                         int item, float *seed, SplatJob (*queue)[TM_QCAP], int warp, int lane) {
     const DevPsy &P = S->psy[psyv[item]];
     const float *f = logfft + (size_t)item * N;
-    float *seed = seed_all + li * Lstride;
     const int L = P.total_octave_lines, per = P.eighth;
     float att = __fadd_rn(local_ampmax[item], P.ath_adjatt);
     if (att < P.ath_maxatt) att = P.ath_maxatt;
@@ -113,82 +100,46 @@ k_tonemask(const DevSetup *__restrict__ S, int items, const int *__restrict__ ps
         __syncwarp();
       }
     }
-  }
-  __syncthreads();
+}
 
-  /* ---- seed_chase (psy.c:773-830).  Every position is pushed once and can only be popped while it is
-     "young" (less than `per` = 8 positions old), and a pop needs the entry below to be young too.  So the part
-     of the stack that can still change is a 7-bit set of the last 7 positions, an entry's amplitude is the
-     seed at its position, and every comparison a pop makes is between two seeds less than 8 apart.
-     (a) all those comparisons are evaluated up front, in parallel: per position a 7-bit word
-         GE[k] = !(seed[p] < seed[p-k]) and a 7-bit word LE[d] = seed[p] <= seed[p-d];
-     (b) the order-dependent walk then runs on bit masks in registers only -- one lane per ch-block, no
-         shared-memory access on its dependency chain -- and emits the set of surviving positions;
-     (c) spans and the fill are again data-parallel over the survivors. ---- */
-  for (int li = warp; li < nloc; li += TM_WARPS) {
-    const DevPsy &P = S->psy[psyv[item0 + li]];
-    const int L = P.total_octave_lines;
-    const float *seed = seed_all + li * Lstride;
-    unsigned short *cmp = pos_all + li * Lstride;
-    for (int p0 = 0; p0 < L; p0 += 32) {
-      const int p = p0 + lane;
-      if (p < L) {
-        const float s = seed[p];
-        unsigned ge = 0, le = 0;
+/* the 7+7 comparison bits of every position: bit k-1 = !(seed[p] < seed[p-k]), bit 8+d-1 = seed[p] <= seed[p-d] */
+__device__ __forceinline__ unsigned tm_compare_word(const float *seed, int p) {
+  const float s = seed[p];
+  unsigned ge = 0, le = 0;
 #pragma unroll
-        for (int k = 1; k < 8; k++) {
-          if (p - k >= 0) { const float o = seed[p - k]; if (!(s < o)) ge |= 1u << (k - 1); if (s <= o) le |= 1u << (k - 1); }
-        }
-        cmp[p] = (unsigned short)(ge | (le << 8));
-      }
-    }
-    if (lane < Lstride - L) cmp[L + lane] = 0;
+  for (int k = 1; k < 8; k++) {
+    if (p - k >= 0) { const float o = seed[p - k]; if (!(s < o)) ge |= 1u << (k - 1); if (s <= o) le |= 1u << (k - 1); }
   }
-  __syncthreads();
+  return ge | (le << 8);
+}
 
-  if (warp == 0 && lane < nloc) {
-    const DevPsy &P = S->psy[psyv[item0 + lane]];
-    const int L = P.total_octave_lines;
-    const unsigned short *cm = pos_all + lane * Lstride;
-    unsigned *sv = surv_all + lane * TM_SVW;
-    /* bit k-1 of M: position i-k is on the stack; same bit of Q: that entry's amplitude is <= the amplitude of
-       the entry it was pushed onto (which entry that is never changes while it stays on the stack).
-       One step, without a loop: the entries popped by seed[i] are the youngest ones up to the first entry that
-       is not poppable -- seed[i] below it (GE clear), amplitude above its predecessor (Q clear), or no young
-       predecessor left (the oldest young entry). */
-    unsigned M = 0, Q = 0, cur = 0;
-    unsigned c_next = cm[0];
-#pragma unroll 2
-    for (int i = 0; i < L; i++) {
-      const unsigned c = c_next;
-      c_next = cm[i + 1];
+/* One step of seed_chase (psy.c:773-830) on bit masks.  Every position is pushed once and can only be popped
+   while it is "young" (less than 8 positions old), and a pop needs the entry below to be young too.  So the part of
+   the stack that can still change is a 7-bit set of the last 7 positions (bit k-1 of M: position i-k is on the
+   stack), an entry's amplitude is the seed at its position, and every comparison a pop makes is between two seeds
+   less than 8 apart -- all precomputed in c.  Q bit k-1: that entry's amplitude is <= the amplitude of the entry it
+   was pushed onto (which entry that is never changes while it stays on the stack).  The entries popped by seed[i]
+   are the youngest ones up to the first entry that is not poppable -- seed[i] below it (GE clear), amplitude above
+   its predecessor (Q clear), or no young predecessor left (the oldest young entry).  Returns the mask after the pops
+   (its bit 6 is the final fate of position i-7) and advances M, Q. */
+__device__ __forceinline__ unsigned tm_chase_step(unsigned c, unsigned &M, unsigned &Q) {
       const unsigned ge = c & 0x7fu, le = c >> 8;
       const unsigned oldest = M ? (0x80000000u >> __clz(M)) : 0u;
       const unsigned stop = (M & ~(ge & Q)) | oldest;
       const unsigned low = stop & (0u - stop);                     /* first entry that stays */
       const unsigned m = M & ~(low - 1u);                          /* M == 0: low == 0, m == 0 */
-      const int p = i - 7;                                         /* this position's fate is now sealed */
-      if (p >= 0) { cur |= ((m >> 6) & 1u) << (p & 31); if ((p & 31) == 31) { sv[p >> 5] = cur; cur = 0; } }
       const unsigned qbit = (le & low) ? 1u : 0u;                  /* new entry vs the entry it lands on, if young */
       M = ((m << 1) | 1u) & 0x7fu;
       Q = ((Q << 1) | qbit) & 0x7fu;
-    }
-    for (int k = 7; k >= 1; k--) {
-      const int p = L - k;
-      if (p >= 0) { cur |= ((M >> (k - 1)) & 1u) << (p & 31); if ((p & 31) == 31) { sv[p >> 5] = cur; cur = 0; } }
-    }
-    if (L & 31) sv[L >> 5] = cur;
-  }
-  __syncthreads();
+      return m;
+}
 
-  /* ---- spans, fill + max_seeds: warps take ch-blocks in turn ---- */
-  for (int li = warp; li < nloc; li += TM_WARPS) {
-    const int item = item0 + li;
-    const DevPsy &P = S->psy[psyv[item]];
+/* spans of the survivors (running maximum of their ends = the fill pointer of the reference), fill, max_seeds
+   (psy.c:936-992) and the ATH floor: one warp, one ch-block.  seed[] holds the raw seeds on entry. */
+template <int N>
+__device__ __forceinline__ void tm_fill(const DevSetup *__restrict__ S, const DevPsy &P, int item, float *seed, unsigned short *run16,
+                                        const unsigned *sv, const float *__restrict__ local_ampmax, float *__restrict__ tone, int lane) {
     const int L = P.total_octave_lines, per = P.eighth;
-    float *seed = seed_all + li * Lstride;
-    unsigned short *run16 = pos_all + li * Lstride;          /* the comparison words are dead: reuse for the span ends */
-    const unsigned *sv = surv_all + li * TM_SVW;
     const int nw = (L + 31) >> 5;
     const unsigned myw = lane < nw ? sv[lane] : 0u;
     /* first survivor after / last survivor before the word this lane holds */
@@ -258,7 +209,145 @@ k_tonemask(const DevSetup *__restrict__ S, int items, const int *__restrict__ ps
       const float mv = seed[L - 1];
       for (int i = P.tone_tail + lane; i < N; i += 32) { const float fl = __fadd_rn(__ldg(P.ath + i), att); out[i] = fl < mv ? mv : fl; }
     }
+}
+
+/* ---------------------------------------------------------------- fused kernel (short blocks) */
+/* TM_ITEMS ch-blocks per CTA: one warp each for the cooperative phases, TM_ITEMS lanes for the chase */
+template <int N, int TM_ITEMS>
+__global__ void __launch_bounds__(TM_ITEMS * 32)
+k_tonemask(const DevSetup *__restrict__ S, int items, const int *__restrict__ psyv, const float *__restrict__ logfft,
+           const float *__restrict__ global_ampmax, const float *__restrict__ local_ampmax, float *__restrict__ tone, int Lstride) {
+  constexpr int TM_THREADS = TM_ITEMS * 32, TM_WARPS = TM_ITEMS;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  float *seed_all = reinterpret_cast<float *>(dyn);                                  /* [TM_ITEMS][Lstride] */
+  unsigned short *pos_all = reinterpret_cast<unsigned short *>(seed_all + TM_ITEMS * Lstride);   /* [TM_ITEMS][Lstride] */
+  __shared__ unsigned surv_all[TM_ITEMS * TM_SVW];                                   /* surviving positions, one bit each */
+  __shared__ SplatJob queue[TM_WARPS][TM_QCAP];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int item0 = blockIdx.x * TM_ITEMS;
+  const int nloc = min(TM_ITEMS, items - item0);
+
+  for (int i = tid; i < TM_ITEMS * Lstride; i += TM_THREADS) seed_all[i] = TM_NEGINF;
+  __syncthreads();
+  for (int li = warp; li < nloc; li += TM_WARPS) {
+    float *seed = seed_all + li * Lstride;
+    tm_splat<N>(S, psyv, logfft, global_ampmax, local_ampmax, item0 + li, seed, queue, warp, lane);
+    __syncwarp();
+    const int L = S->psy[psyv[item0 + li]].total_octave_lines;
+    unsigned short *cmp = pos_all + li * Lstride;
+    for (int p = lane; p < L; p += 32) cmp[p] = (unsigned short)tm_compare_word(seed, p);
+    if (lane < Lstride - L) cmp[L + lane] = 0;
   }
+  __syncthreads();
+  if (warp == 0 && lane < nloc) {
+    const int L = S->psy[psyv[item0 + lane]].total_octave_lines;
+    const unsigned short *cm = pos_all + lane * Lstride;
+    unsigned *sv = surv_all + lane * TM_SVW;
+    unsigned M = 0, Q = 0, cur = 0;
+    unsigned c_next = cm[0];
+#pragma unroll 2
+    for (int i = 0; i < L; i++) {
+      const unsigned c = c_next;
+      c_next = cm[i + 1];
+      const unsigned m = tm_chase_step(c, M, Q);
+      const int p = i - 7;                                         /* this position's fate is now sealed */
+      if (p >= 0) { cur |= ((m >> 6) & 1u) << (p & 31); if ((p & 31) == 31) { sv[p >> 5] = cur; cur = 0; } }
+    }
+    for (int k = 7; k >= 1; k--) {
+      const int p = L - k;
+      if (p >= 0) { cur |= ((M >> (k - 1)) & 1u) << (p & 31); if ((p & 31) == 31) { sv[p >> 5] = cur; cur = 0; } }
+    }
+    if (L & 31) sv[L >> 5] = cur;
+  }
+  __syncthreads();
+  for (int li = warp; li < nloc; li += TM_WARPS)
+    tm_fill<N>(S, S->psy[psyv[item0 + li]], item0 + li, seed_all + li * Lstride, pos_all + li * Lstride, surv_all + li * TM_SVW, local_ampmax, tone, lane);
+}
+
+/* ---------------------------------------------------------------- three kernels (long blocks) */
+constexpr int TS_WARPS = 4;
+/* rows of the two scratch buffers: seeds in row `item` of rowA (N floats); comparison words at the start of row
+   `item` of rowB (N ints = 2N u16), survivor words in its last TM_SVW ints */
+template <int N>
+__global__ void __launch_bounds__(TS_WARPS * 32)
+k_tone_splat(const DevSetup *__restrict__ S, int items, const int *__restrict__ psyv, const float *__restrict__ logfft,
+             const float *__restrict__ global_ampmax, const float *__restrict__ local_ampmax, float *__restrict__ rowA, int *__restrict__ rowB, int Lstride) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  float *seed_all = reinterpret_cast<float *>(dyn);
+  __shared__ SplatJob queue[TS_WARPS][TM_QCAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * TS_WARPS + warp;
+  if (item >= items) return;
+  float *seed = seed_all + warp * Lstride;
+  for (int i = lane; i < Lstride; i += 32) seed[i] = TM_NEGINF;
+  __syncwarp();
+  tm_splat<N>(S, psyv, logfft, global_ampmax, local_ampmax, item, seed, queue, warp, lane);
+  __syncwarp();
+  const int L = S->psy[psyv[item]].total_octave_lines;
+  float *sg = rowA + (size_t)item * N;
+  unsigned short *cg = reinterpret_cast<unsigned short *>(rowB + (size_t)item * N);
+  for (int p = lane; p < L; p += 32) { sg[p] = seed[p]; cg[p] = (unsigned short)tm_compare_word(seed, p); }
+}
+
+__global__ void __launch_bounds__(TS_WARPS * 32)
+k_tone_chase(int items, int L, int N, int *__restrict__ rowB) {
+  __shared__ unsigned short tile[TS_WARPS][32][34];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item0 = (blockIdx.x * TS_WARPS + warp) * 32;
+  if (item0 >= items) return;
+  const int nloc = min(32, items - item0);
+  const bool mine = lane < nloc;
+  unsigned *sv = reinterpret_cast<unsigned *>(rowB + (size_t)(item0 + (mine ? lane : 0)) * N + (N - TM_SVW));
+  unsigned M = 0, Q = 0, cur = 0;
+  for (int p0 = 0; p0 < L; p0 += 32) {
+    /* 32 positions of 32 ch-blocks: row r is read with one 64-byte access, then every lane walks its own row */
+    for (int r = 0; r < nloc; r++) {
+      const unsigned short *cg = reinterpret_cast<const unsigned short *>(rowB + (size_t)(item0 + r) * N);
+      tile[warp][r][lane] = (p0 + lane < L) ? cg[p0 + lane] : (unsigned short)0;
+    }
+    __syncwarp();
+    const int n = min(32, L - p0);
+    if (mine) {
+#pragma unroll 4
+      for (int k = 0; k < n; k++) {
+        const unsigned m = tm_chase_step(tile[warp][lane][k], M, Q);
+        const int p = p0 + k - 7;
+        if (p >= 0) { cur |= ((m >> 6) & 1u) << (p & 31); if ((p & 31) == 31) { sv[p >> 5] = cur; cur = 0; } }
+      }
+    }
+    __syncwarp();
+  }
+  if (mine) {
+    for (int k = 7; k >= 1; k--) {
+      const int p = L - k;
+      if (p >= 0) { cur |= ((M >> (k - 1)) & 1u) << (p & 31); if ((p & 31) == 31) { sv[p >> 5] = cur; cur = 0; } }
+    }
+    if (L & 31) sv[L >> 5] = cur;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(TS_WARPS * 32)
+k_tone_fill(const DevSetup *__restrict__ S, int items, const int *__restrict__ psyv, const float *__restrict__ local_ampmax,
+            const float *__restrict__ rowA, const int *__restrict__ rowB, float *__restrict__ tone, int Lstride) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  float *seed_all = reinterpret_cast<float *>(dyn);
+  unsigned short *run_all = reinterpret_cast<unsigned short *>(seed_all + TS_WARPS * Lstride);
+  __shared__ unsigned surv_all[TS_WARPS * TM_SVW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * TS_WARPS + warp;
+  if (item >= items) return;
+  const DevPsy &P = S->psy[psyv[item]];
+  const int L = P.total_octave_lines;
+  float *seed = seed_all + warp * Lstride;
+  const float *sg = rowA + (size_t)item * N;
+  for (int p = lane; p < L; p += 32) seed[p] = sg[p];
+  if (lane < Lstride - L) seed[L + lane] = TM_NEGINF;
+  const unsigned *svg = reinterpret_cast<const unsigned *>(rowB + (size_t)item * N + (N - TM_SVW));
+  unsigned *sv = surv_all + warp * TM_SVW;
+  if (lane < ((L + 31) >> 5)) sv[lane] = svg[lane];
+  __syncwarp();
+  tm_fill<N>(S, P, item, seed, run_all + warp * Lstride, sv, local_ampmax, tone, lane);
 }
 
 }  // namespace
@@ -274,19 +363,32 @@ static int launch_tm(const vb200_setup *s, cudaStream_t st, int items, const int
   return VB200_OK;
 }
 
+/* rowA / rowB: two scratch buffers of `items` rows of N2 floats / ints that are dead while K3 runs (the pipeline
+   lends the logmask and iwork rows); NULL selects the fused kernel */
 int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
-                          const float *logfft, const float *global_ampmax, const float *local_ampmax, float *tone) {
+                          const float *logfft, const float *global_ampmax, const float *local_ampmax, float *tone,
+                          float *rowA, int *rowB) {
   if (items <= 0) return VB200_OK;
-  int L = 0;
-  for (int k = 0; k < s->h.psys; k++) if (s->h.psy[k].blockflag == W && s->h.psy[k].total_octave_lines > L) L = s->h.psy[k].total_octave_lines;
-  const int Lstride = (L + 2) | 1;        /* odd: lanes walking equal positions hit different banks; +1 slot for the stack height */
-  static const int ti = getenv("VB200_TM_ITEMS") ? atoi(getenv("VB200_TM_ITEMS")) : 4;
-  if (W) {
-    if (ti == 2) return launch_tm<1024, 2>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
-    if (ti == 4) return launch_tm<1024, 4>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
-    return launch_tm<1024, 8>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+  int L = 0, Lmin = 1 << 30;
+  for (int k = 0; k < s->h.psys; k++) if (s->h.psy[k].blockflag == W) {
+    if (s->h.psy[k].total_octave_lines > L) L = s->h.psy[k].total_octave_lines;
+    if (s->h.psy[k].total_octave_lines < Lmin) Lmin = s->h.psy[k].total_octave_lines;
   }
-  if (ti == 2) return launch_tm<128, 2>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
-  if (ti == 4) return launch_tm<128, 4>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
-  return launch_tm<128, 8>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+  const int Lstride = (L + 2) | 1;        /* odd: lanes walking equal positions hit different banks */
+  const int N = s->h.bs[W] / 2;
+  static const bool no_split = getenv("VB200_TM_FUSED") != nullptr;
+  if (W && rowA && rowB && !no_split && L == Lmin && N == 1024 && L <= N && 2 * L <= 4 * (N - TM_SVW)) {
+    const int grid = (items + TS_WARPS - 1) / TS_WARPS;
+    const size_t dynA = (size_t)TS_WARPS * Lstride * sizeof(float);
+    const size_t dynC = (size_t)TS_WARPS * Lstride * (sizeof(float) + sizeof(unsigned short));
+    k_tone_splat<1024><<<grid, TS_WARPS * 32, dynA, st>>>(s->d, items, psy, logfft, global_ampmax, local_ampmax, rowA, rowB, Lstride);
+    LAUNCH_CHECK();
+    k_tone_chase<<<(items + TS_WARPS * 32 - 1) / (TS_WARPS * 32), TS_WARPS * 32, 0, st>>>(items, L, N, rowB);
+    LAUNCH_CHECK();
+    k_tone_fill<1024><<<grid, TS_WARPS * 32, dynC, st>>>(s->d, items, psy, local_ampmax, rowA, rowB, tone, Lstride);
+    LAUNCH_CHECK();
+    return VB200_OK;
+  }
+  if (W) return launch_tm<1024, 4>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+  return launch_tm<128, 4>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
 }

@@ -737,7 +737,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   EV("K3 tonemask");
   for (int W = 0; W < 2; W++) {
     ClassBufs &c = b->c[W];
-    RUN(vb200_launch_tonemask(s, st, W, nb[W] * ch, c.psy_item, c.logfft, c.global_ampmax, c.local_ampmax, c.tone));
+    RUN(vb200_launch_tonemask(s, st, W, nb[W] * ch, c.psy_item, c.logfft, c.global_ampmax, c.local_ampmax, c.tone, c.logmask, c.iwork));   /* logmask / iwork rows are dead until K4 / K5b */
   }
   /* ---- K4 ---- */
   EV("K4 offset_and_mix");
