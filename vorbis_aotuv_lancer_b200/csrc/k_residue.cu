@@ -70,8 +70,11 @@ k_residue_class(const DevSetup *__restrict__ S, int resnum, int n, int ch, const
 constexpr int RF_WARPS = 4;
 constexpr int RF_MAXG = 64;     /* largest partition size handled (grouping) */
 
+constexpr int RF_SLOTS = 4;     /* partitions a warp works on at once */
+constexpr int RF_LP = 32 / RF_SLOTS;
+
 struct RfShared {
-  int vec[RF_WARPS][RF_MAXG];
+  int vec[RF_WARPS][RF_SLOTS][RF_MAXG];
   int red_d[RF_WARPS], red_i[RF_WARPS];
 };
 
@@ -109,32 +112,36 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
   const int pd_mask = (R.phrase_dim & (R.phrase_dim - 1)) == 0 ? R.phrase_dim - 1 : -1;
   __syncthreads();
 
-  /* ---- pass 1: cascade VQ per (partition,row), warps stride over them ---- */
-  for (int pr = warp; pr < partvals * rows; pr += RF_WARPS) {
-    const int p = rows == 1 ? pr : pr / rows, row = rows == 1 ? 0 : pr % rows;
-    const int cls = pw[row * partvals + p];
-    int *v = sh.vec[warp];
+  /* ---- pass 1: cascade VQ per (partition,row).  A partition holds G/dim <= 16 vectors (often 4 or 8), so a warp
+     works on RF_SLOTS partitions at once, RF_LP lanes each; the stage loop is shared, the books differ per slot ---- */
+  const int slot = lane / RF_LP, l = lane % RF_LP;
+  for (int pr0 = warp * RF_SLOTS; pr0 < partvals * rows; pr0 += RF_WARPS * RF_SLOTS) {
+    const int pr = pr0 + slot;
+    const bool valid = pr < partvals * rows;
+    const int p = valid ? (rows == 1 ? pr : pr / rows) : 0, row = valid ? (rows == 1 ? 0 : pr % rows) : 0;
+    const int cls = valid ? pw[row * partvals + p] : 0;
+    int *v = sh.vec[warp][slot];
     const int off = p * G + R.begin;
     /* stage the partition: res2 reads the channel-interleaved vector work[j*ch+c]=in[c][j] (res0.c:782-787) */
-    for (int t = lane; t < G; t += 32) {
-      if (R.type == 2) {
-        const int w = off + t;
-        const int wc = ch_shift >= 0 ? (w & (ch - 1)) : w % ch, wj = ch_shift >= 0 ? (w >> ch_shift) : w / ch;
-        v[t] = base[(size_t)chlist[wc] * n + wj];
+    if (valid)
+      for (int t = l; t < G; t += RF_LP) {
+        if (R.type == 2) {
+          const int w = off + t;
+          const int wc = ch_shift >= 0 ? (w & (ch - 1)) : w % ch, wj = ch_shift >= 0 ? (w >> ch_shift) : w / ch;
+          v[t] = base[(size_t)chlist[wc] * n + wj];
+        }
+        else v[t] = base[(size_t)rowch[row] * n + off + t];
       }
-      else v[t] = base[(size_t)rowch[row] * n + off + t];
-    }
     __syncwarp();
     for (int s = 0; s < stages; s++) {
-      const int bk = tab_bk[cls * 8 + s];
-      if (bk < 0) continue;
-      const DevBook &B = books[bk];
-      const int dim = B.dim, nvec = tab_nvec[cls * 8 + s], qv = B.quantvals, ze = qv >> 1;
+      const int bk = valid ? tab_bk[cls * 8 + s] : -1;
+      if (!__any_sync(FULLMASK, bk >= 0)) continue;
+      const DevBook &B = books[bk >= 0 ? bk : 0];
+      const int dim = B.dim, nvec = bk >= 0 ? tab_nvec[cls * 8 + s] : 0, qv = B.quantvals, ze = qv >> 1;
       const int bdelta = B.delta, bmin = B.minval;
       const unsigned brcp = B.delta_rcp;
       short *e_out = ent + (((size_t)s * partvals + p) * rows + row) * maxvec;
-      for (int t0 = 0; t0 < nvec; t0 += 32) {
-        const int t = t0 + lane;
+      for (int t = l; __any_sync(FULLMASK, t < nvec); t += RF_LP) {
         bool fb = false;
         int index = 0;
         if (t < nvec) {
@@ -165,17 +172,19 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
             } else fb = true;
           } else { for (int i = 0; i < dim; i++) a[i] -= pt[i]; e_out[t] = (short)index; }
         }
-        /* entries without a codeword: warp-wide exhaustive search over the used entries */
+        /* entries without a codeword: warp-wide exhaustive search over the used entries, one vector at a time */
         unsigned fm = __ballot_sync(FULLMASK, fb);
         while (fm) {
           const int src = __ffs(fm) - 1; fm &= fm - 1;
-          const int tv = t0 + src;
-          int *a = v + tv * dim;
+          const int tv = __shfl_sync(FULLMASK, t, src), sbk = __shfl_sync(FULLMASK, bk, src);
+          const DevBook &SB = books[sbk];
+          const int sdim = SB.dim;
+          int *a = sh.vec[warp][src / RF_LP] + tv * sdim;
           int bestd = 0x7fffffff, besti = 0x7fffffff;
-          for (int u = lane; u < B.used; u += 32) {
-            const int *ev = B.used_vals + (size_t)u * 8;
+          for (int u = lane; u < SB.used; u += 32) {
+            const int *ev = SB.used_vals + (size_t)u * 8;
             int d = 0;
-            for (int j = 0; j < dim; j++) { const int df = __ldg(ev + j) - a[j]; d += df * df; }
+            for (int j = 0; j < sdim; j++) { const int df = __ldg(ev + j) - a[j]; d += df * df; }
             if (d < bestd) { bestd = d; besti = u; }      /* u ascending per lane: first minimum kept */
           }
 #pragma unroll
@@ -184,17 +193,19 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
             if (od < bestd || (od == bestd && oi < besti)) { bestd = od; besti = oi; }
           }
           __syncwarp();
+          const int ps = __shfl_sync(FULLMASK, p, src), rs2 = __shfl_sync(FULLMASK, row, src);
+          short *eo = ent + (((size_t)s * partvals + ps) * rows + rs2) * maxvec;
           if (besti != 0x7fffffff) {
-            if (lane < dim) a[lane] -= __ldg(B.used_vals + (size_t)besti * 8 + lane);
-            if (lane == 0) e_out[tv] = (short)__ldg(B.used_list + besti);
-          } else if (lane == 0) e_out[tv] = -1;
+            if (lane < sdim) a[lane] -= __ldg(SB.used_vals + (size_t)besti * 8 + lane);
+            if (lane == 0) eo[tv] = (short)__ldg(SB.used_list + besti);
+          } else if (lane == 0) eo[tv] = -1;
           __syncwarp();
         }
       }
       __syncwarp();
     }
     /* res1 leaves the cascade residual in place (res2 worked on a private interleaved copy) */
-    if (R.type != 2) for (int t = lane; t < G; t += 32) base[(size_t)rowch[row] * n + off + t] = v[t];
+    if (R.type != 2 && valid) for (int t = l; t < G; t += RF_LP) base[(size_t)rowch[row] * n + off + t] = v[t];
     __syncwarp();
   }
   __syncthreads();
