@@ -321,7 +321,8 @@ k_floor_encode(const DevSetup *__restrict__ S, int floor_index, int W, int ch, i
   for (int s = 0; s + 1 < ns; s++) {
     const int lx = segx[s], hx = segx[s + 1], ly = segy[s], hy = segy[s + 1];
     const int lim = N < hx ? N : hx;
-    for (int x = lx + lane; x < lim; x += 32) ilog[x] = line_at(lx, hx, ly, hy, x);
+    const LineK LK = line_setup(lx, hx, ly, hy);         /* warp-uniform per segment; one exact reciprocal division per bin */
+    for (int x = lx + lane; x < lim; x += 32) ilog[x] = line_eval(LK, x);
   }
   { const int hx = ns > 1 ? segx[ns - 1] : 0, ly = segy[ns - 1]; for (int x = hx + lane; x < N; x += 32) ilog[x] = ly; }
 }

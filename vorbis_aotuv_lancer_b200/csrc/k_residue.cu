@@ -242,24 +242,26 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
     if (lane == 0) { offs[nslots] = carry; nsyms[blk] = carry < max_syms ? carry : max_syms; }
   }
   __syncthreads();
+  /* scatter: one thread per (stage, partition, row) slot -- most slots hold nothing (the class has no book at that
+     stage) and the others 4..16 symbols, too few to give a warp */
   int *out = syms + (size_t)blk * max_syms * 2;
-  for (int s = 0; s < stages; s++)
-    for (int pr = warp; pr < prow; pr += RF_WARPS) {
-      const int p = rows == 1 ? pr : pr / rows, row = rows == 1 ? 0 : pr % rows;
-      int o = offs[s * prow + pr];
-      if (s == 0 && row == 0 && (pd_mask >= 0 ? (p & pd_mask) == 0 : (p % pd) == 0)) {
-        for (int r2 = 0; r2 < rows; r2++) {
-          const int val = phrase_val(r2, p);
-          if (val < phrase_entries) { if (lane == 0 && o < max_syms) { out[o * 2] = R.groupbook; out[o * 2 + 1] = val; } o++; }
-        }
+  for (int sl = tid; sl < nslots; sl += RF_WARPS * 32) {
+    const int s = sl / prow, pr = sl - s * prow;
+    const int p = rows == 1 ? pr : pr / rows, row = rows == 1 ? 0 : pr % rows;
+    int o = offs[sl];
+    if (s == 0 && row == 0 && (pd_mask >= 0 ? (p & pd_mask) == 0 : (p % pd) == 0)) {
+      for (int r2 = 0; r2 < rows; r2++) {
+        const int val = phrase_val(r2, p);
+        if (val < phrase_entries) { if (o < max_syms) { out[o * 2] = R.groupbook; out[o * 2 + 1] = val; } o++; }
       }
-      const int cls = pw[row * partvals + p];
-      const int bk = tab_bk[cls * 8 + s];
-      if (bk < 0) continue;
-      const int nvec = tab_nvec[cls * 8 + s];
-      const short *e_in = ent + (((size_t)s * partvals + p) * rows + row) * maxvec;
-      for (int t = lane; t < nvec; t += 32) if (o + t < max_syms) { out[(o + t) * 2] = bk; out[(o + t) * 2 + 1] = e_in[t]; }
     }
+    const int cls = pw[row * partvals + p];
+    const int bk = tab_bk[cls * 8 + s];
+    if (bk < 0) continue;
+    const int nvec = tab_nvec[cls * 8 + s];
+    const short *e_in = ent + (((size_t)s * partvals + p) * rows + row) * maxvec;
+    for (int t = 0; t < nvec; t++) if (o + t < max_syms) *reinterpret_cast<int2 *>(out + (size_t)(o + t) * 2) = make_int2(bk, e_in[t]);
+  }
 }
 
 }  // namespace
