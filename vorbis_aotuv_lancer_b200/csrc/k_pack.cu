@@ -107,25 +107,38 @@ k_pack(const DevSetup *__restrict__ S, int W, int ch, const int *__restrict__ lW
     sm.pbits[c][i] = bits;
   }
   __syncthreads();
-  if (tid == 0) {
-    int pos = 0;
-    put_bits(sm, pos, 0, 1); pos += 1;                                  /* packet type: audio */
-    put_bits(sm, pos, (unsigned)W, S->modebits); pos += S->modebits;     /* mode number */
-    if (W) { put_bits(sm, pos, (unsigned)lWv[blk * ch], 1); pos++; put_bits(sm, pos, (unsigned)nWv[blk * ch], 1); pos++; }
+  if (warp == 0) {
+    /* bit offsets: header, then per channel [nonzero flag, two first posts, the partitions].  Lane i owns partition i
+       (PK_PARTS = 31 <= 32): a warp scan replaces the serial walk over channels x partitions. */
+    int pos = 1 + S->modebits + (W ? 2 : 0);
     for (int c = 0; c < ch; c++) {
       const int it = blk * ch + c;
       const DevFloor &F = S->flr[S->floor_of_ch[W][c]];
-      if (!floor_nonzero[it]) { put_bits(sm, pos, 0, 1); pos++; }
-      else {
-        const int *v = vals + (size_t)it * VB200_MAX_POSTS;
-        const int qb = ilog_((unsigned)(F.quant_q - 1));
-        put_bits(sm, pos, 1, 1); pos++;
-        put_bits(sm, pos, (unsigned)v[0], qb); pos += qb;
-        put_bits(sm, pos, (unsigned)v[1], qb); pos += qb;
+      const int nzf = floor_nonzero[it];
+      const int qb = ilog_((unsigned)(F.quant_q - 1));
+      const int hdr = nzf ? 1 + 2 * qb : 1;
+      const int mine = lane < PK_PARTS ? sm.pbits[c][lane] : 0;
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += y; }
+      if (lane < PK_PARTS) sm.pbase[c][lane] = pos + hdr + incl - mine;
+      if (lane == 0) {
+        if (c == 0) {
+          put_bits(sm, 0, 0, 1);                                          /* packet type: audio */
+          put_bits(sm, 1, (unsigned)W, S->modebits);                      /* mode number */
+          if (W) { put_bits(sm, 1 + S->modebits, (unsigned)lWv[blk * ch], 1); put_bits(sm, 2 + S->modebits, (unsigned)nWv[blk * ch], 1); }
+        }
+        if (!nzf) put_bits(sm, pos, 0, 1);
+        else {
+          const int *v = vals + (size_t)it * VB200_MAX_POSTS;
+          put_bits(sm, pos, 1, 1);
+          put_bits(sm, pos + 1, (unsigned)v[0], qb);
+          put_bits(sm, pos + 1 + qb, (unsigned)v[1], qb);
+        }
       }
-      for (int i = 0; i < PK_PARTS; i++) { sm.pbase[c][i] = pos; pos += sm.pbits[c][i]; }
+      pos += hdr + __shfl_sync(FULLMASK, incl, 31);
     }
-    sm.base = pos;
+    if (lane == 0) sm.base = pos;
   }
   __syncthreads();
   int base = sm.base;
