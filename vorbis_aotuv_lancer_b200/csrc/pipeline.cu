@@ -21,6 +21,10 @@
 #include <string.h>
 #include <math.h>
 #include <vector>
+#include <chrono>
+#include <algorithm>
+#include <atomic>
+#include <thread>
 #include "vb200_internal.h"
 #include "dev_util.cuh"
 #include "emit.h"
@@ -577,9 +581,9 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   if (nblocks == 0) return VB200_OK;
 
   /* ---- host pre-pass over the block descriptors ---- */
+  const double t_prep0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   b->hb.resize(nblocks);
   int nb[2] = {0, 0};
-  std::vector<int> last_of_stream(nstreams, -1);
   b->pin.top = 0;
   struct HostClass { int *psy_item, *psy_blk, *block_mode, *lW_block_mode, *lW, *nW, *params; long long *pcm_off, *last_addr; int *last_rule;
                      int *chain_start, *chain_len, *chain_items; long long *temp_off; int nchains, nchain_items; } hc[2];
@@ -594,94 +598,122 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   }
   ScanBlock *h_scan = b->pin.take<ScanBlock>(nblocks);
   int *h_scan_start = b->pin.take<int>(nstreams + 1), *h_slot = b->pin.take<int>(nstreams);
-  /* stream-major ordering for the scan kernel */
-  std::vector<std::vector<int>> per_stream(nstreams);
+  /* (1) serial and light: validate, give every block its index inside its size class, bucket the blocks by stream
+     (counting sort: blocks of one stream stay in submission order) */
+  std::vector<int> sstart(nstreams + 1, 0), order(nblocks);
   for (int i = 0; i < nblocks; i++) {
     const vb200_block &q = blocks[i];
     if (q.stream < 0 || q.stream >= nstreams || (q.W != 0 && q.W != 1)) { vb200_set_error("vb200_batch_run: block %d malformed", i); return VB200_EINVAL; }
-    per_stream[q.stream].push_back(i);
+    sstart[q.stream + 1]++;
+    b->hb[i].idx = nb[q.W]++;
   }
+  for (int k = 0; k < nstreams; k++) sstart[k + 1] += sstart[k];
+  {
+    std::vector<int> fill(sstart.begin(), sstart.end() - 1);
+    for (int i = 0; i < nblocks; i++) order[fill[blocks[i].stream]++] = i;
+  }
+  const double t_prep1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   const int flr_of_end[2] = { s->h.flr[s->h.floor_of_ch[0][0]].info_n, s->h.flr[s->h.floor_of_ch[1][0]].info_n };
   const bool hs = s->h.rate >= 26000;
-  for (int i = 0; i < nblocks; i++) {
-    const vb200_block &q = blocks[i];
-    vb200_stream *x = streams[q.stream];
-    HostBlock &h = b->hb[i];
-    const int W = q.W;
-    h.stream = q.stream; h.W = W; h.lW = (int)q.lW; h.nW = (int)q.nW; h.blocktype = q.blocktype;
-    h.block_mode = q.blocktype | (W << 1); h.psy = q.blocktype + (W ? 2 : 0);
-    h.granulepos = q.granulepos; h.eof = q.eofflag;
-    h.idx = nb[W]++;
-    h.hist[0] = x->lW_block_mode; h.hist[1] = x->lW_no; h.hist[2] = x->impadnum;
-    HostClass &c = hc[W];
-    ClassBufs &dc = b->c[W];
-    c.psy_blk[h.idx] = h.psy;
-    /* where this block finds lastmdct */
-    const int prev = last_of_stream[q.stream];
-    for (int k = 0; k < ch; k++) {
-      const int it = h.idx * ch + k;
-      c.psy_item[it] = h.psy; c.block_mode[it] = h.block_mode; c.lW_block_mode[it] = x->lW_block_mode;
-      c.lW[it] = h.lW; c.nW[it] = h.nW;
-      int *pr = c.params + (size_t)it * 8;
-      pr[0] = 1; pr[1] = managed; pr[2] = flr_of_end[W]; pr[3] = h.block_mode; pr[4] = h.nW; pr[5] = x->lW_block_mode; pr[6] = x->lW_no; pr[7] = x->impadnum;
-      c.pcm_off[it] = q.pcm_offset + (long long)k * q.pcm_stride;
-      if (!hs) { c.last_addr[it] = (long long)(uintptr_t)(pool->last + ((size_t)x->slot * ch + k) * 2048); c.last_rule[it] = LAST_ZERO; }
-      else if (prev < 0) { c.last_addr[it] = (long long)(uintptr_t)(pool->last + ((size_t)x->slot * ch + k) * 2048); c.last_rule[it] = LAST_COPY; }
-      else {
-        const HostBlock &p = b->hb[prev];
-        const ClassBufs &pc = b->c[p.W];
-        c.last_addr[it] = (long long)(uintptr_t)(pc.logmdct + ((size_t)p.idx * ch + k) * pc.N2);
-        c.last_rule[it] = (p.block_mode <= 1) ? (W ? LAST_EXPAND8 : LAST_COPY) : ((p.block_mode == 2 && !W) ? LAST_MINPOOL8 : LAST_COPY);
+  /* (2) per stream, independent of the other streams (history, lastmdct links, K4 chains, scan list): host threads */
+  struct StreamChains { std::vector<int> start[2], len[2], items[2]; };
+  std::vector<StreamChains> sc(nstreams);
+  auto do_stream = [&](int sidx) {
+    vb200_stream *x = streams[sidx];
+    const int *lst = order.data() + sstart[sidx];
+    const int cnt = sstart[sidx + 1] - sstart[sidx];
+    int prev = -1;
+    for (int j = 0; j < cnt; j++) {
+      const int i = lst[j];
+      const vb200_block &q = blocks[i];
+      HostBlock &h = b->hb[i];
+      const int W = q.W;
+      h.stream = q.stream; h.W = W; h.lW = (int)q.lW; h.nW = (int)q.nW; h.blocktype = q.blocktype;
+      h.block_mode = q.blocktype | (W << 1); h.psy = q.blocktype + (W ? 2 : 0);
+      h.granulepos = q.granulepos; h.eof = q.eofflag;
+      h.hist[0] = x->lW_block_mode; h.hist[1] = x->lW_no; h.hist[2] = x->impadnum;
+      HostClass &c = hc[W];
+      c.psy_blk[h.idx] = h.psy;
+      for (int k = 0; k < ch; k++) {
+        const int it = h.idx * ch + k;
+        c.psy_item[it] = h.psy; c.block_mode[it] = h.block_mode; c.lW_block_mode[it] = x->lW_block_mode;
+        c.lW[it] = h.lW; c.nW[it] = h.nW;
+        int *pr = c.params + (size_t)it * 8;
+        pr[0] = 1; pr[1] = managed; pr[2] = flr_of_end[W]; pr[3] = h.block_mode; pr[4] = h.nW; pr[5] = x->lW_block_mode; pr[6] = x->lW_no; pr[7] = x->impadnum;
+        c.pcm_off[it] = q.pcm_offset + (long long)k * q.pcm_stride;
+        /* where this block finds lastmdct */
+        if (!hs) { c.last_addr[it] = (long long)(uintptr_t)(pool->last + ((size_t)x->slot * ch + k) * 2048); c.last_rule[it] = LAST_ZERO; }
+        else if (prev < 0) { c.last_addr[it] = (long long)(uintptr_t)(pool->last + ((size_t)x->slot * ch + k) * 2048); c.last_rule[it] = LAST_COPY; }
+        else {
+          const HostBlock &p = b->hb[prev];
+          const ClassBufs &pc = b->c[p.W];
+          c.last_addr[it] = (long long)(uintptr_t)(pc.logmdct + ((size_t)p.idx * ch + k) * pc.N2);
+          c.last_rule[it] = (p.block_mode <= 1) ? (W ? LAST_EXPAND8 : LAST_COPY) : ((p.block_mode == 2 && !W) ? LAST_MINPOOL8 : LAST_COPY);
+        }
+        c.temp_off[it] = ((long long)x->slot * ch + k) * 256;
       }
-      c.temp_off[it] = ((long long)x->slot * ch + k) * 256;
+      prev = i;
+      /* aoTuV history, mapping0.c:1297-1305 -- once per packet blob */
+      for (int rep = 0; rep < (managed ? VB200_PACKETBLOBS : 1); rep++) {
+        if (h.block_mode >= 2) x->impadnum = 0;
+        if (!x->lW_block_mode && h.block_mode == 1) x->impadnum = 1;
+        else if (x->impadnum && x->impadnum < 8) x->impadnum++;
+        if (x->lW_block_mode == h.block_mode) x->lW_no++; else x->lW_no = 1;
+        x->lW_block_mode = h.block_mode;
+      }
+      ScanBlock &sb = h_scan[sstart[sidx] + j];
+      sb.W = W; sb.first_item = h.idx * ch; sb.block_mode = h.block_mode; sb.lW_block_mode = h.hist[0]; sb.psy = h.psy;
     }
-    last_of_stream[q.stream] = i;
-    /* aoTuV history, mapping0.c:1297-1305 -- once per packet blob */
-    for (int rep = 0; rep < (managed ? VB200_PACKETBLOBS : 1); rep++) {
-      if (h.block_mode >= 2) x->impadnum = 0;
-      if (!x->lW_block_mode && h.block_mode == 1) x->impadnum = 1;
-      else if (x->impadnum && x->impadnum < 8) x->impadnum++;
-      if (x->lW_block_mode == h.block_mode) x->lW_no++; else x->lW_no = 1;
-      x->lW_block_mode = h.block_mode;
-    }
-    (void)dc;
-  }
-  /* chains for K4: runs of consecutive impulse blocks of one stream, per channel; everything else is its own chain */
-  for (int sidx = 0; sidx < nstreams; sidx++) {
-    const std::vector<int> &lst = per_stream[sidx];
+    /* chains for K4: runs of consecutive impulse blocks of one stream, per channel; everything else is its own
+       chain.  Offsets are local to the stream here and rebased when the streams are concatenated. */
+    StreamChains &C = sc[sidx];
     for (int k = 0; k < ch; k++) {
-      size_t j = 0;
-      while (j < lst.size()) {
+      int j = 0;
+      while (j < cnt) {
         const HostBlock &h = b->hb[lst[j]];
-        HostClass &c = hc[h.W];
-        const int start = c.nchain_items;
-        c.chain_items[c.nchain_items++] = h.idx * ch + k;
-        size_t e = j + 1;
-        if (h.W == 0 && h.block_mode == 0)
-          while (e < lst.size() && b->hb[lst[e]].W == 0 && b->hb[lst[e]].block_mode == 0) { c.chain_items[c.nchain_items++] = b->hb[lst[e]].idx * ch + k; e++; }
+        const int W = h.W;
+        const int start = (int)C.items[W].size();
+        C.items[W].push_back(h.idx * ch + k);
+        int e = j + 1;
+        if (W == 0 && h.block_mode == 0)
+          while (e < cnt && b->hb[lst[e]].W == 0 && b->hb[lst[e]].block_mode == 0) { C.items[W].push_back(b->hb[lst[e]].idx * ch + k); e++; }
         /* only the chain holding the stream's first block may read tempmdct from the state slot, and only
            the one holding its last block leaves it there */
-        c.chain_start[c.nchains] = start;
-        c.chain_len[c.nchains] = (c.nchain_items - start) | (j == 0 ? 0 : (1 << 30)) | (e == lst.size() ? 0 : (1 << 29));
-        c.nchains++;
+        C.start[W].push_back(start);
+        C.len[W].push_back(((int)C.items[W].size() - start) | (j == 0 ? 0 : (1 << 30)) | (e == cnt ? 0 : (1 << 29)));
         j = e;
       }
     }
-  }
+  };
   {
-    int pos = 0;
-    for (int sidx = 0; sidx < nstreams; sidx++) {
-      h_scan_start[sidx] = pos; h_slot[sidx] = streams[sidx]->slot;
-      for (int bi : per_stream[sidx]) {
-        const HostBlock &h = b->hb[bi];
-        h_scan[pos].W = h.W; h_scan[pos].first_item = h.idx * ch; h_scan[pos].block_mode = h.block_mode; h_scan[pos].lW_block_mode = h.hist[0]; h_scan[pos].psy = h.psy;
-        pos++;
-      }
+    int nthr = nblocks >= 8192 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (nthr > nstreams) nthr = nstreams;
+    if (nthr <= 1) { for (int sidx = 0; sidx < nstreams; sidx++) do_stream(sidx); }
+    else {
+      std::vector<std::thread> th;
+      std::atomic<int> next(0);
+      for (int t = 0; t < nthr; t++) th.emplace_back([&]() { for (int k; (k = next.fetch_add(1)) < nstreams;) do_stream(k); });
+      for (auto &t : th) t.join();
     }
-    h_scan_start[nstreams] = pos;
   }
+  const double t_prep2 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  /* (3) concatenate the chains */
+  for (int sidx = 0; sidx < nstreams; sidx++)
+    for (int W = 0; W < 2; W++) {
+      HostClass &c = hc[W];
+      const StreamChains &C = sc[sidx];
+      const int base = c.nchain_items;
+      memcpy(c.chain_items + base, C.items[W].data(), sizeof(int) * C.items[W].size());
+      for (size_t q = 0; q < C.start[W].size(); q++) { c.chain_start[c.nchains] = base + C.start[W][q]; c.chain_len[c.nchains] = C.len[W][q]; c.nchains++; }
+      c.nchain_items += (int)C.items[W].size();
+    }
+  for (int sidx = 0; sidx < nstreams; sidx++) { h_scan_start[sidx] = sstart[sidx]; h_slot[sidx] = streams[sidx]->slot; }
+  h_scan_start[nstreams] = nblocks;
+  std::vector<int> last_of_stream(nstreams, -1);          /* the last block every stream has in this batch */
+  for (int sidx = 0; sidx < nstreams; sidx++) if (sstart[sidx + 1] > sstart[sidx]) last_of_stream[sidx] = order[sstart[sidx + 1] - 1];
   b->n_blocks[0] = nb[0]; b->n_blocks[1] = nb[1]; b->n_items[0] = nb[0] * ch; b->n_items[1] = nb[1] * ch;
 
+  if (getenv("VB200_TRACE")) fprintf(stderr, "[vb200 batch] host pre-pass %.2f ms for %d blocks (index %.2f, per-stream %.2f)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_prep0, nblocks, t_prep1 - t_prep0, t_prep2 - t_prep1);
   /* ---- uploads ---- */
   EV("h2d");
   const float *d_pcm = pcm;
