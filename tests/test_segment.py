@@ -32,3 +32,51 @@ def test_blocks_match_reference(config, seconds):
                 nbad_pcm += 1
     print("%s: %d blocks, %d ch-blocks with rounding-level PCM differences" % (config, len(blocks), nbad_pcm))
     s.close()
+
+
+def _ref_blocklist(config, pcm):
+    from oracle import reflib
+    from vorbis_aotuv_lancer_b200 import blob as vblob
+    ch, rate, q, abr = vblob.CATALOGUE[config]
+    R = reflib.RefLib("c")
+    h = R.open(ch, rate, q, abr)
+    R.write(h, pcm)
+    bl, pk = R.blocks(h), R.packets(h)
+    R.close(h)
+    return bl, pk
+
+
+@pytest.mark.parametrize("nsamples", [1, 63, 64, 1000, 2047, 2048, 2049, 5000, 9999])
+def test_short_and_odd_lengths(nsamples):
+    """ragged ends: streams shorter than one block, not a multiple of anything, exactly on block boundaries"""
+    config = "q4_44k_2ch"
+    pcm = refdata.synth(2, 44100, 1.0, seed=3)[:, :nsamples].copy()
+    ref, pk = _ref_blocklist(config, pcm)
+    s = ops.Setup(config, device=-1)
+    blocks, _ = segment.segment_stream(s, pcm)
+    assert len(blocks) == len(ref) == len(pk)
+    for b, r, p in zip(blocks, ref, pk):
+        assert (b.W, b.lW, b.nW, b.blocktype) == tuple(int(v) for v in r[:4])
+        assert b.granulepos == p[1]
+    assert blocks[-1].eofflag == 1 and blocks[-1].granulepos == nsamples
+    s.close()
+
+
+@pytest.mark.parametrize("kind", ["silence", "fullscale", "impulses"])
+def test_degenerate_signals(kind):
+    """digital silence (no transient ever), a clipped square wave, a click train (a transient in every block)"""
+    config = "q4_44k_2ch"
+    n = 44100
+    if kind == "silence":
+        pcm = np.zeros((2, n), np.float32)
+    elif kind == "fullscale":
+        pcm = np.where((np.arange(n) // 50) % 2 == 0, 0.99, -0.99).astype(np.float32)[None, :].repeat(2, 0).copy()
+    else:
+        pcm = np.zeros((2, n), np.float32)
+        pcm[:, ::700] = 0.9
+    ref, pk = _ref_blocklist(config, pcm)
+    s = ops.Setup(config, device=-1)
+    blocks, _ = segment.segment_stream(s, pcm)
+    assert [(b.W, b.lW, b.nW, b.blocktype) for b in blocks] == [tuple(int(v) for v in r[:4]) for r in ref]
+    assert [b.granulepos for b in blocks] == [p[1] for p in pk]
+    s.close()
