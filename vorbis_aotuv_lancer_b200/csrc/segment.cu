@@ -429,6 +429,7 @@ struct EnvDev {            /* tables in HBM */
 struct EnvStream { long long pcm_base; long long T; int nsteps; long long out_base; /* step-major output offset */ long long eof; };
 
 constexpr int EV_TILE = 32;      /* steps per CTA */
+constexpr int EV_THREADS = 128;
 constexpr int EV_HALO = 30;      /* the near-DC sum of a step depends on at most the 30 previous steps */
 constexpr int EV_M = VE_N / 2;   /* folded length = number of coefficients */
 constexpr int EV_US = EV_M + 1;  /* row stride of the folded steps in shared memory (doubles) */
@@ -437,12 +438,11 @@ constexpr int EV_US = EV_M + 1;  /* row stride of the folded steps in shared mem
    spread/limit -> 12 band amplitudes.  Everything here is a pure function of the PCM, so tiles are independent.
    The matrix product is register-blocked 4 coefficients x 8 steps per thread: thread (kq, sg) owns coefficients
    kq+16j of steps 8sg..8sg+7, so each pass over n costs 4 matrix loads + 8 broadcast reads for 32 DFMA. */
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(EV_THREADS, 6)
 k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams, int ch, const float *__restrict__ pcm,
             float *__restrict__ acc_out /*[stream][ch][step][12]*/, float *__restrict__ temp_out /*[stream][ch][step]*/) {
   __shared__ double u[(EV_TILE + EV_HALO) * EV_US];
-  __shared__ float vec[EV_TILE][EV_M];
-  __shared__ float v2[EV_TILE][EV_M / 2 + 1];
+  __shared__ float wins[VE_N];
   __shared__ float temps[EV_TILE + EV_HALO];
   __shared__ float decay[EV_TILE];
   const EnvStream S = streams[blockIdx.z];
@@ -453,15 +453,26 @@ k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams,
   const int h0 = max(0, j0 - EV_HALO);                      /* first step that is folded here */
   const int nh = j0 + jn - h0, toff = j0 - h0;
   const float *src = pcm + S.pcm_base + (long long)c * S.T + (long long)h0 * VE_STEP;
-  const float *win = E->win;
-  for (int it = tid; it < nh * EV_M; it += 64) {
-    const int sidx = it >> 6, n = it & 63;
-    u[sidx * EV_US + n] = ve_fold(src + sidx * VE_STEP, win, n);
+  for (int i = tid; i < VE_N; i += EV_THREADS) wins[i] = E->win[i];
+  __syncthreads();
+  const float *win = wins;
+  {
+    /* ve_fold with everything that depends only on n hoisted: EV_THREADS is a multiple of 64, so a thread keeps its n */
+    constexpr int h = VE_N / 4;
+    const int n = tid & 63;
+    const int ia = n < h ? 3 * h - 1 - n : n - h, ib = n < h ? 3 * h + n : 3 * h - 1 - n;
+    const float wa = win[ia], wb = win[ib];
+    const bool neg = n < h;
+    for (int sidx = tid >> 6; sidx < nh; sidx += EV_THREADS / 64) {
+      const float *d = src + sidx * VE_STEP;
+      const double pa = (double)__fmul_rn(d[ia], wa), pb = (double)__fmul_rn(d[ib], wb);
+      u[sidx * EV_US + n] = (neg ? -pa : pa) - pb;
+    }
   }
-  for (int it = nh * EV_M + tid; it < (EV_TILE + EV_HALO) * EV_M; it += 64) u[(it >> 6) * EV_US + (it & 63)] = 0.;
+  for (int it = nh * EV_M + tid; it < (EV_TILE + EV_HALO) * EV_M; it += EV_THREADS) u[(it >> 6) * EV_US + (it & 63)] = 0.;
   __syncthreads();
   /* near-DC terms of the halo + tile steps: only coefficients 0..2 are needed */
-  for (int sidx = tid; sidx < nh; sidx += 64) {
+  for (int sidx = tid; sidx < nh; sidx += EV_THREADS) {
     const double *us = u + sidx * EV_US;
     double a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll 4
@@ -473,7 +484,7 @@ k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams,
   }
   __syncthreads();
   /* decay of every tile step: replay the refresh cycle it sits in (<= 44 float ops) */
-  for (int q = tid; q < jn; q += 64) {
+  for (int q = tid; q < jn; q += EV_THREADS) {
     const int j = j0 + q, ptr = j % VE_NEARDC, r = j - ptr;      /* r = last refresh step */
     auto T_ = [&](int step) { return step >= 0 ? temps[step - h0] : 0.f; };
     float partial = 0.f;
@@ -489,42 +500,48 @@ k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams,
     decay[q] = (float)((double)todB_hd(dec) * .5 - (double)15.f);
     temp_out[S.out_base * ch + (long long)c * S.nsteps + j] = T_(j);
   }
-  /* the full 64-coefficient transform of the 32 tile steps */
+  /* results go where the folded steps were: u is dead once every thread has finished its products */
+  float (*vec)[EV_M] = reinterpret_cast<float (*)[EV_M]>(u);
+  float (*v2)[EV_M / 2 + 1] = reinterpret_cast<float (*)[EV_M / 2 + 1]>(reinterpret_cast<float *>(u) + EV_TILE * EV_M);
+  /* the full 64-coefficient transform of the 32 tile steps: thread (kq, sg) owns coefficients kq+16j of the four
+     steps 4sg..4sg+3 */
   {
     const int kq = tid & 15, sg = tid >> 4;
-    double a[4][8];
+    double a[4][4];
 #pragma unroll
     for (int j = 0; j < 4; j++)
 #pragma unroll
-      for (int i = 0; i < 8; i++) a[j][i] = 0.;
-    const double *ub = u + (toff + sg * 8) * EV_US;
+      for (int i = 0; i < 4; i++) a[j][i] = 0.;
+    const double *ub = u + (toff + sg * 4) * EV_US;
     const double *mt = E->dctt + kq;
-#pragma unroll 2
+#pragma unroll 4
     for (int n = 0; n < EV_M; n++) {
       double m[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) m[j] = mt[n * EV_M + 16 * j];
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
+      for (int i = 0; i < 4; i++) {
         const double x = ub[i * EV_US + n];
 #pragma unroll
         for (int j = 0; j < 4; j++) a[j][i] = fma(m[j], x, a[j][i]);
       }
     }
+    __syncthreads();                        /* everybody is done reading u */
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) vec[sg * 8 + i][kq + 16 * j] = (float)a[j][i];
+      for (int j = 0; j < 4; j++) vec[sg * 4 + i][kq + 16 * j] = (float)a[j][i];
   }
   __syncthreads();
-  /* spread / limit: thread (q, half) walks 16 of the 32 coefficient pairs of step q */
+  /* spread / limit: thread (q, part) walks its share of the 32 coefficient pairs of step q */
   {
-    const int q = tid & 31, half = tid >> 5;
+    constexpr int PER = (EV_M / 2) / (EV_THREADS / 32);       /* coefficient pairs per thread */
+    const int q = tid & 31, part = tid >> 5;
     if (q < jn) {
       float dec = decay[q];
-      for (int w = 0; w < half * 16; w++) dec = (float)((double)dec - 8.);
+      for (int w = 0; w < part * PER; w++) dec = (float)((double)dec - 8.);
       const float minV = E->minenergy;
-      for (int i = half * 16; i < half * 16 + 16; i++) {
+      for (int i = part * PER; i < part * PER + PER; i++) {
         const float x0 = vec[q][2 * i], x1 = vec[q][2 * i + 1];
         float val = __fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1));
         val = __fmul_rn(todB_hd(val), .5f);
@@ -536,7 +553,7 @@ k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams,
     }
   }
   __syncthreads();
-  for (int it = tid; it < jn * VE_BANDS; it += 64) {
+  for (int it = tid; it < jn * VE_BANDS; it += EV_THREADS) {
     const int q = it / VE_BANDS, b = it - q * VE_BANDS;
     float acc = 0.f;
     const int bb = E->bbegin[b], be = E->bend[b];
@@ -860,7 +877,7 @@ extern "C" int vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const flo
   CUDA_TRY(cudaMemsetAsync(g->d_marks, 0, nmark, st));
   if (max_steps > 0) {
     dim3 grid((max_steps + EV_TILE - 1) / EV_TILE, ch, nstreams);
-    k_env_bands<<<grid, 64, 0, st>>>(g->d_env, g->d_streams, ch, g->d_pcm, g->d_acc, g->d_temp);
+    k_env_bands<<<grid, EV_THREADS, 0, st>>>(g->d_env, g->d_streams, ch, g->d_pcm, g->d_acc, g->d_temp);
     LAUNCH_CHECK();
     k_env_flags<<<dim3((max_steps + 127) / 128, nstreams), 128, 0, st>>>(g->d_env, g->d_streams, ch, g->d_acc, g->d_flags);
     LAUNCH_CHECK();
