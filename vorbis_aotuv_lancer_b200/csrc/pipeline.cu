@@ -598,15 +598,17 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   }
   ScanBlock *h_scan = b->pin.take<ScanBlock>(nblocks);
   int *h_scan_start = b->pin.take<int>(nstreams + 1), *h_slot = b->pin.take<int>(nstreams);
+  const double t_prepA = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   /* (1) serial and light: validate, give every block its index inside its size class, bucket the blocks by stream
      (counting sort: blocks of one stream stay in submission order) */
-  std::vector<int> sstart(nstreams + 1, 0), order(nblocks);
+  std::vector<int> sstart(nstreams + 1, 0), order(nblocks), idx_of(nblocks);      /* compact: this pass is memory-bound */
   for (int i = 0; i < nblocks; i++) {
     const vb200_block &q = blocks[i];
     if (q.stream < 0 || q.stream >= nstreams || (q.W != 0 && q.W != 1)) { vb200_set_error("vb200_batch_run: block %d malformed", i); return VB200_EINVAL; }
     sstart[q.stream + 1]++;
-    b->hb[i].idx = nb[q.W]++;
+    idx_of[i] = nb[q.W]++;
   }
+  const double t_prepB = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   for (int k = 0; k < nstreams; k++) sstart[k + 1] += sstart[k];
   {
     std::vector<int> fill(sstart.begin(), sstart.end() - 1);
@@ -630,7 +632,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       const int W = q.W;
       h.stream = q.stream; h.W = W; h.lW = (int)q.lW; h.nW = (int)q.nW; h.blocktype = q.blocktype;
       h.block_mode = q.blocktype | (W << 1); h.psy = q.blocktype + (W ? 2 : 0);
-      h.granulepos = q.granulepos; h.eof = q.eofflag;
+      h.granulepos = q.granulepos; h.eof = q.eofflag; h.idx = idx_of[i];
       h.hist[0] = x->lW_block_mode; h.hist[1] = x->lW_no; h.hist[2] = x->impadnum;
       HostClass &c = hc[W];
       c.psy_blk[h.idx] = h.psy;
@@ -667,6 +669,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     /* chains for K4: runs of consecutive impulse blocks of one stream, per channel; everything else is its own
        chain.  Offsets are local to the stream here and rebased when the streams are concatenated. */
     StreamChains &C = sc[sidx];
+    for (int W = 0; W < 2; W++) { C.items[W].reserve((size_t)cnt * ch); C.start[W].reserve((size_t)cnt * ch); C.len[W].reserve((size_t)cnt * ch); }
     for (int k = 0; k < ch; k++) {
       int j = 0;
       while (j < cnt) {
@@ -686,7 +689,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     }
   };
   {
-    int nthr = nblocks >= 8192 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    int nthr = nblocks >= 8192 ? (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
     if (nthr > nstreams) nthr = nstreams;
     if (nthr <= 1) { for (int sidx = 0; sidx < nstreams; sidx++) do_stream(sidx); }
     else {
@@ -713,7 +716,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   for (int sidx = 0; sidx < nstreams; sidx++) if (sstart[sidx + 1] > sstart[sidx]) last_of_stream[sidx] = order[sstart[sidx + 1] - 1];
   b->n_blocks[0] = nb[0]; b->n_blocks[1] = nb[1]; b->n_items[0] = nb[0] * ch; b->n_items[1] = nb[1] * ch;
 
-  if (getenv("VB200_TRACE")) fprintf(stderr, "[vb200 batch] host pre-pass %.2f ms for %d blocks (index %.2f, per-stream %.2f)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_prep0, nblocks, t_prep1 - t_prep0, t_prep2 - t_prep1);
+  if (getenv("VB200_TRACE")) fprintf(stderr, "[vb200 batch] host pre-pass %.2f ms for %d blocks (setup %.2f, count %.2f, order %.2f, per-stream %.2f)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_prep0, nblocks, t_prepA - t_prep0, t_prepB - t_prepA, t_prep1 - t_prepB, t_prep2 - t_prep1);
   /* ---- uploads ---- */
   EV("h2d");
   const float *d_pcm = pcm;
