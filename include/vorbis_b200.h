@@ -248,6 +248,9 @@ int  vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int nstreams,
                         const vb200_block *blocks, int nblocks,
                         const float *pcm, size_t pcm_elems, int pcm_on_device);
 int  vb200_batch_collect(vb200_batch *b);
+/* order b's kernels behind prev's (both may be submitted back to back): the host half of one job overlaps the device
+   half of the previous one without the two sharing the SMs */
+int  vb200_batch_after(vb200_batch *b, vb200_batch *prev);
 /* Debug/verification switch: 1 = emit codewords on the host from the device's symbol lists (the
  * reference-order implementation in emit.cu), 0 (default) = pack bits on the device (K8). */
 int  vb200_batch_set_host_emit(vb200_batch *b, int on);

@@ -241,6 +241,7 @@ struct vb200_batch {
   const unsigned char *pk_base;
   int host_emit, host_emit_ready;
   cudaStream_t st;                 /* this batch's own stream: batches and segmenters overlap */
+  cudaEvent_t ev_done; bool ev_done_set; vb200_batch *after;   /* device work ordered behind another batch's (vb200_batch_after) */
   bool pending; int run_nblocks, run_nb[2];
   std::vector<vb200_stream *> run_streams; std::vector<long> blob_sizes;
   std::vector<BitWriter> bws; std::vector<std::vector<size_t>> boff;
@@ -409,6 +410,7 @@ extern "C" int vb200_batch_create(vb200_setup *s, int max_blocks, vb200_batch **
     }
   }
   for (int i = 0; i < 16; i++) cudaEventCreate(&b->ev[i]);
+  cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming); b->ev_done_set = false; b->after = nullptr;
   b->pending = false;
   if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess) { vb200_set_error("vb200_batch_create: cannot create a stream"); return VB200_EFAULT; }
   *out = b;
@@ -419,6 +421,7 @@ extern "C" void vb200_batch_destroy(vb200_batch *b) {
   if (!b) return;
   cudaSetDevice(b->s->device);
   for (int i = 0; i < 16; i++) cudaEventDestroy(b->ev[i]);
+  cudaEventDestroy(b->ev_done);
   cudaStreamDestroy(b->st);
   if (b->d_pcm) cudaFree(b->d_pcm);
   cudaFree(b->dev.base);
@@ -718,6 +721,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
 
   if (getenv("VB200_TRACE")) fprintf(stderr, "[vb200 batch] host pre-pass %.2f ms for %d blocks (setup %.2f, count %.2f, order %.2f, per-stream %.2f)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_prep0, nblocks, t_prepA - t_prep0, t_prepB - t_prepA, t_prep1 - t_prepB, t_prep2 - t_prep1);
   /* ---- uploads ---- */
+  if (b->after && b->after->ev_done_set) CUDA_TRY(cudaStreamWaitEvent(st, b->after->ev_done, 0));   /* its kernels first */
   EV("h2d");
   const float *d_pcm = pcm;
   if (!pcm_on_device) {
@@ -966,6 +970,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       CUDA_TRY(cudaMemcpyAsync(b->h_pk_bytes + o, b->d_pk_bytes + o, sizeof(int) * nb[W], cudaMemcpyDeviceToHost, st));
     }
   }
+  CUDA_TRY(cudaEventRecord(b->ev_done, st)); b->ev_done_set = true;
   b->pending = true;
   if (host_emit) return batch_finish(b);
   return VB200_OK;
@@ -1040,6 +1045,14 @@ static int batch_finish(vb200_batch *b) {
   b->total_ms = 0;
   for (int i = 0; i + 1 < b->nev; i++) { cudaEventElapsedTime(&b->ev_ms[i], b->ev[i], b->ev[i + 1]); }
   if (b->nev > 1) cudaEventElapsedTime(&b->total_ms, b->ev[0], b->ev[b->nev - 1]);
+  return VB200_OK;
+}
+
+/* Order b's device work behind prev's: b can be submitted (host pre-pass, launches) while prev still runs, and its
+   kernels start when prev's have finished -- successive jobs overlap host and device halves without sharing the SMs. */
+extern "C" int vb200_batch_after(vb200_batch *b, vb200_batch *prev) {
+  if (!b || prev == b) { vb200_set_error("vb200_batch_after: bad arguments"); return VB200_EINVAL; }
+  b->after = prev;
   return VB200_OK;
 }
 
