@@ -126,3 +126,56 @@ def test_ragged_batch_of_degenerate_streams():
         elif len(ref) > 20:
             assert same > 0.8, (i, same)
     enc.close(); s.close()
+
+
+def test_full_length_streams_properties():
+    """BASELINE-size streams (60 s, q4 44.1 kHz stereo, the bench's synthetic signal): the result must not depend on
+    how the streams are grouped into batches (one group vs three), a second run must reproduce it bit for bit, and
+    the streams must sit where the reference puts them: packet count, granule positions, size within 0.5 %, decodable,
+    > 30 dB SNR against the reference-encoded stream."""
+    import ctypes as C
+    from oracle import reflib
+    from vorbis_aotuv_lancer_b200 import blob as vblob, encoder, ops
+    from vorbis_aotuv_lancer_b200.lib import L
+    if not reflib.available("c"):
+        pytest.skip("oracle/_ref not present")
+    config = "q4_44k_2ch"
+    ch, rate, q, abr = vblob.CATALOGUE[config]
+    n, S = 60 * rate, 6
+    pcms = []
+    for i in range(S):
+        a = np.empty((ch, n), np.float32)
+        seed = L.vb200_splitmix64(C.c_uint64(88172645463325252 + i))
+        L.vb200_synth_pcm(C.c_uint64(seed), ch, C.c_long(rate), C.c_long(n), a.ctypes.data_as(C.c_void_p), C.c_long(n))
+        pcms.append(a)
+    s = ops.Setup(config)
+
+    def run(chunks):
+        enc = encoder.Encoder(s, S * 4000, threads=4, chunks=chunks)
+        tabs = enc.encode(pcms)
+        out = [encoder.packets_of(tabs, i) for i in range(S)]
+        enc.close()
+        return out
+    one, three, again = run(1), run(3), run(3)
+    assert one == three, "grouping into batches changed the stream"
+    assert three == again, "not reproducible"
+    R = reflib.RefLib("c")
+    for i in (0, S - 1):
+        h = R.open(ch, rate, q, abr)
+        R.write(h, pcms[i])
+        ref, hdr = R.packets(h), R.headers(h)
+        R.close(h)
+        pk = one[i]
+        assert len(pk) == len(ref) and [p[1] for p in pk] == [r[1] for r in ref]
+        gb, rb = sum(len(p[0]) for p in pk), sum(len(r[0]) for r in ref)
+        same = sum(1 for a, r in zip(pk, ref) if a[0] == r[0]) / len(ref)
+        assert abs(gb - rb) / rb < 0.005 and same > 0.8, (i, gb, rb, same)
+        dec, _ = R.decode(hdr, pk, n + 8192)
+        decr, _ = R.decode(hdr, ref, n + 8192)
+        m = min(dec.shape[1], decr.shape[1])
+        assert m > n - 4096
+        err = (dec[:, :m] - decr[:, :m]).astype(np.float64)
+        snr = 10 * np.log10((decr[:, :m].astype(np.float64) ** 2).sum() / (err ** 2).sum())
+        print("stream %d: %d packets, identical %.1f%%, bytes %d vs %d, SNR vs reference-encoded %.1f dB" % (i, len(ref), 100 * same, gb, rb, snr))
+        assert snr > 30.0
+    s.close()
