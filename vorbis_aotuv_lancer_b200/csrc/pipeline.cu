@@ -252,7 +252,7 @@ struct vb200_batch {
   unsigned long long *d_out_top, *h_out_top; unsigned char *d_out_pool; size_t out_cap;
   std::vector<size_t> pk_off, pk_bytes; std::vector<int64_t> pk_gp; std::vector<int> pk_eos, pk_stream;
   /* timing */
-  cudaEvent_t ev[16]; int nev; const char *evname[16]; float ev_ms[16]; float total_ms;
+  cudaEvent_t ev[24]; int nev; const char *evname[24]; float ev_ms[24]; float total_ms;
   /* host copies for vb200_batch_get */
   int n_items[2], n_blocks[2];
 };
@@ -409,7 +409,7 @@ extern "C" int vb200_batch_create(vb200_setup *s, int max_blocks, vb200_batch **
       cudaGetLastError(); vb200_set_error("vb200_batch_create: cannot allocate the bitrate manager's buffers"); return VB200_EFAULT;
     }
   }
-  for (int i = 0; i < 16; i++) cudaEventCreate(&b->ev[i]);
+  for (int i = 0; i < 24; i++) cudaEventCreate(&b->ev[i]);
   cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming); b->ev_done_set = false; b->after = nullptr;
   b->pending = false;
   if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess) { vb200_set_error("vb200_batch_create: cannot create a stream"); return VB200_EFAULT; }
@@ -420,7 +420,7 @@ extern "C" int vb200_batch_create(vb200_setup *s, int max_blocks, vb200_batch **
 extern "C" void vb200_batch_destroy(vb200_batch *b) {
   if (!b) return;
   cudaSetDevice(b->s->device);
-  for (int i = 0; i < 16; i++) cudaEventDestroy(b->ev[i]);
+  for (int i = 0; i < 24; i++) cudaEventDestroy(b->ev[i]);
   cudaEventDestroy(b->ev_done);
   cudaStreamDestroy(b->st);
   if (b->d_pcm) cudaFree(b->d_pcm);
@@ -559,7 +559,7 @@ k_gather_choice(int W, int max_blocks, const int *__restrict__ choice, const int
 }  // namespace
 
 /* ------------------------------------------------------------------ the run */
-#define EV(name) do{ if (b->nev < 16) { b->evname[b->nev] = name; cudaEventRecord(b->ev[b->nev++], st); } }while(0)
+#define EV(name) do{ if (b->nev < 24) { b->evname[b->nev] = name; cudaEventRecord(b->ev[b->nev++], st); } }while(0)
 #define RUN(x) do{ int r_ = (x); if (r_) return r_; }while(0)
 
 static int batch_finish(vb200_batch *b);
@@ -865,11 +865,12 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   bws.clear(); boff.clear();
   if (managed && host_emit) { bws.resize(VB200_PACKETBLOBS); boff.resize(VB200_PACKETBLOBS); }
   for (int k = k_lo; k <= k_hi; k++) {
-    EV(k == k_lo ? "K5b floor encode" : "blob");
+    if (k != k_lo) EV("blob");
     for (int W = 0; W < 2; W++) {
       ClassBufs &c = b->c[W];
       const int I = nb[W] * ch;
       if (!I) continue;
+      if (k == k_lo) EV("K5b floor encode");
       const DevMap &M = s->h.map[s->h.mode_mapping[W]];
       /* posts of blob k (mapping0.c:1090-1181) into posts_k (floor1_encode mutates them) */
       const int H = VB200_PACKETBLOBS / 2;

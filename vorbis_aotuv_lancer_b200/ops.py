@@ -272,9 +272,9 @@ class Batch:
         return float(L.vb200_batch_kernel_ms(self.h))
 
     def kernel_times(self):
-        names = (C.c_char_p * 16)()
-        ms = (C.c_float * 16)()
-        n = L.vb200_batch_kernel_times(self.h, names, ms, 16)
+        names = (C.c_char_p * 24)()
+        ms = (C.c_float * 24)()
+        n = L.vb200_batch_kernel_times(self.h, names, ms, 24)
         return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
     def get(self, what, block, ch, count, dtype=np.float32):
