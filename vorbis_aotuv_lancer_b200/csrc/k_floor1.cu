@@ -23,6 +23,13 @@ __device__ __forceinline__ int dbq(float x) {      /* vorbis_dBquant, floor1.c:2
   return i > 1023 ? 1023 : (i < 0 ? 0 : i);
 }
 
+/* num / den for 0 <= num < 2^21, den > 0: reciprocal multiply (num is exact in float) + correction */
+__device__ __forceinline__ int div_small(int num, int den) {
+  int q = (int)__fmul_rn((float)num, __frcp_rn((float)den));
+  if (q * den > num) q--;
+  if ((q + 1) * den <= num) q++;
+  return q;
+}
 /* integer line (x0,y0)-(x1,y1) at x, as render_line0 / inspect_error step it (floor1.c:397-425) */
 __device__ __forceinline__ int line_at(int x0, int x1, int y0, int y1, int x) {
   const int dy = y1 - y0, adx = x1 - x0, base = dy / adx;
@@ -34,8 +41,10 @@ __device__ __forceinline__ int line_at(int x0, int x1, int y0, int y1, int x) {
    per-bin division done as an exact reciprocal-multiply + correction: rem*k < 2^21 is exact in float */
 struct LineK { int x0, y0, base, rem, adx, neg; float radx; };
 __device__ __forceinline__ LineK line_setup(int x0, int x1, int y0, int y1) {
-  LineK L; const int dy = y1 - y0; L.x0 = x0; L.y0 = y0; L.adx = x1 - x0; L.base = dy / L.adx;
-  L.rem = abs(dy) - abs(L.base * L.adx); L.neg = dy < 0; L.radx = 1.0f / (float)L.adx;
+  LineK L; const int dy = y1 - y0; L.x0 = x0; L.y0 = y0; L.adx = x1 - x0;
+  const int ab = div_small(abs(dy), L.adx);       /* |dy| < 2^11; C division truncates toward zero */
+  L.base = dy < 0 ? -ab : ab;
+  L.rem = abs(dy) - ab * L.adx; L.neg = dy < 0; L.radx = __frcp_rn((float)L.adx);
   return L;
 }
 __device__ __forceinline__ int line_eval(const LineK &L, int x) {
@@ -49,18 +58,27 @@ __device__ __forceinline__ int line_eval(const LineK &L, int x) {
 __device__ __forceinline__ int point_at(int x0, int x1, int y0, int y1, int x) {
   y0 &= 0x7fff; y1 &= 0x7fff;
   const int dy = y1 - y0, adx = x1 - x0;
-  const int off = (abs(dy) * (x - x0)) / adx;
+  const int off = div_small(abs(dy) * (x - x0), adx);     /* < 2^10 * 2^10 */
   return dy < 0 ? y0 - off : y0 + off;
 }
 
 struct Seg { int s[2][6]; };   /* s[class] = sum x, y, xx, yy, xy, count */
 
-/* ~5.5 KB for a long block, so that 32 one-warp CTAs (the per-SM CTA limit) are resident */
+/* Per-warp shared memory, carved from the CTA's dynamic allocation with the post capacity of this setup's floors
+   (q: 2 KB for a long block, T: 48 B per post interval, 10 B of bookkeeping per post => ~3.7 KB at 29 posts), so that
+   ~60 warps are resident per SM; FIT_WARPS ch-blocks share a CTA (the per-SM CTA limit is 32). */
+constexpr int FIT_WARPS = 4;
 template <int N>
 struct FitSmem {
-  unsigned short q[N];            /* quantised mask, bit 15 = "loud" (mdct + twofitatten >= mask) */
-  double T[VB200_MAX_POSTS][6];
-  short A[VB200_MAX_POSTS], B[VB200_MAX_POSTS], lo[VB200_MAX_POSTS], hi[VB200_MAX_POSTS], memo[VB200_MAX_POSTS];
+  double (*T)[6];                 /* [pcap] weighted sums of a post interval */
+  short *A, *B, *lo, *hi, *memo;  /* [pcap] each */
+  unsigned short *q;              /* [N] quantised mask, bit 15 = "loud" (mdct + twofitatten >= mask) */
+  static __host__ __device__ size_t bytes(int pcap) { return ((size_t)pcap * 48 + (size_t)pcap * 10 + (size_t)N * 2 + 15) & ~(size_t)15; }
+  __device__ FitSmem(unsigned char *base, int pcap) {
+    T = reinterpret_cast<double (*)[6]>(base);
+    q = reinterpret_cast<unsigned short *>(base + (size_t)pcap * 48);
+    A = reinterpret_cast<short *>(q + N); B = A + pcap; lo = B + pcap; hi = lo + pcap; memo = hi + pcap;
+  }
 };
 
 /* fit_line, floor1.c:477-535, split in three so that the warp shares it:
@@ -96,9 +114,10 @@ __device__ __forceinline__ int fit_solve(const double *sum, int x0, int x1, int 
   return 1;
 }
 
-/* lanes 0-5 sum run A = segments [a0,a0+na), lanes 6-11 run B = [b0,b0+nb); every lane returns with both
-   sets of six sums (broadcast), so lane 0 can solve both */
-__device__ __forceinline__ void fit_two(const double (*T)[6], int a0, int na, int b0, int nb, int lane, double *sa, double *sb) {
+/* lanes 0-5 sum run A = segments [a0,a0+na), lanes 6-11 run B = [b0,b0+nb), each in segment order; lane 0 then holds
+   the six sums of run A and lane 6 those of run B (the other lanes' copies are meaningless), so that the two solves
+   of a split run as ONE pass of fit_solve on lanes 0 and 6 */
+__device__ __forceinline__ void fit_two(const double (*T)[6], int a0, int na, int b0, int nb, int lane, double *s) {
   double acc = 0.;
   const int k = lane < 6 ? lane : lane - 6;
   if (lane < 12) {
@@ -106,7 +125,7 @@ __device__ __forceinline__ void fit_two(const double (*T)[6], int a0, int na, in
     for (int i = 0; i < n; i++) acc += T[s0 + i][k];
   }
 #pragma unroll
-  for (int q = 0; q < 6; q++) { sa[q] = __shfl_sync(FULLMASK, acc, q); sb[q] = __shfl_sync(FULLMASK, acc, 6 + q); }
+  for (int q = 0; q < 6; q++) s[q] = __shfl_down_sync(FULLMASK, acc, q);
 }
 
 __device__ __forceinline__ int pick(const short *A, const short *B, int i) {
@@ -115,12 +134,15 @@ __device__ __forceinline__ int pick(const short *A, const short *B, int i) {
   return (A[i] + B[i]) >> 1;
 }
 
-template <int N>
-__global__ void __launch_bounds__(32)
+template <int N, int MINB>
+__global__ void __launch_bounds__(FIT_WARPS * 32, MINB)
 k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, const float *__restrict__ logmdct, const float *__restrict__ logmask,
-            int mdct_stride, int mask_stride, const int *__restrict__ gate, int *__restrict__ posts_out, int *__restrict__ fitted) {
-  __shared__ FitSmem<N> sm;
-  const int item = blockIdx.x, lane = threadIdx.x;
+            int mdct_stride, int mask_stride, const int *__restrict__ gate, int *__restrict__ posts_out, int *__restrict__ fitted, int items, int pcap) {
+  extern __shared__ __align__(16) unsigned char fit_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * FIT_WARPS + warp;
+  if (item >= items) return;                      /* warps are independent: only __syncwarp below */
+  FitSmem<N> sm(fit_dyn + (size_t)warp * FitSmem<N>::bytes(pcap), pcap);
   const DevFloor &F = S->flr[floor_index >= 0 ? floor_index : S->floor_of_ch[W][item % ch]];
   const int n = F.n, posts = F.posts;
   int *out = posts_out + (size_t)item * VB200_MAX_POSTS;
@@ -136,6 +158,9 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
      and the twelve integer sums are closed with the hardware warp reduction (integer sums are exact in any
      order).  Branch-free: class a = loud bins, class b = the rest, both only where the quantised mask != 0. */
   int mine = 0;
+  Seg keep;                                         /* lane j & 31 keeps the sums of interval j; fit_terms runs once per 32 */
+#pragma unroll
+  for (int k = 0; k < 6; k++) { keep.s[0][k] = 0; keep.s[1][k] = 0; }
   for (int j = 0; j < posts - 1; j++) {
     const int x0 = F.sorted[j], x1 = F.sorted[j + 1], xe = x1 >= n ? n - 1 : x1;
     int ax = 0, ay = 0, ax2 = 0, ay2 = 0, axy = 0, an = 0, bx = 0, by = 0, bx2 = 0, by2 = 0, bxy = 0, bnn = 0;
@@ -150,11 +175,12 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     ay2 = __reduce_add_sync(FULLMASK, ay2); axy = __reduce_add_sync(FULLMASK, axy); an = __reduce_add_sync(FULLMASK, an);
     bx = __reduce_add_sync(FULLMASK, bx); by = __reduce_add_sync(FULLMASK, by); bx2 = __reduce_add_sync(FULLMASK, bx2);
     by2 = __reduce_add_sync(FULLMASK, by2); bxy = __reduce_add_sync(FULLMASK, bxy); bnn = __reduce_add_sync(FULLMASK, bnn);
-    if (lane == 0) {
-      Seg g;
-      g.s[0][0] = ax; g.s[0][1] = ay; g.s[0][2] = ax2; g.s[0][3] = ay2; g.s[0][4] = axy; g.s[0][5] = an;
-      g.s[1][0] = bx; g.s[1][1] = by; g.s[1][2] = bx2; g.s[1][3] = by2; g.s[1][4] = bxy; g.s[1][5] = bnn;
-      fit_terms(g, F.twofitweight, sm.T[j]);
+    if (lane == (j & 31)) {
+      keep.s[0][0] = ax; keep.s[0][1] = ay; keep.s[0][2] = ax2; keep.s[0][3] = ay2; keep.s[0][4] = axy; keep.s[0][5] = an;
+      keep.s[1][0] = bx; keep.s[1][1] = by; keep.s[1][2] = bx2; keep.s[1][3] = by2; keep.s[1][4] = bxy; keep.s[1][5] = bnn;
+    }
+    if ((j & 31) == 31 || j == posts - 2) {
+      if (lane <= (j & 31)) fit_terms(keep, F.twofitweight, sm.T[(j & ~31) + lane]);
     }
     mine += an;
   }
@@ -165,8 +191,8 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
   for (int i = lane; i < posts; i += 32) { sm.A[i] = -200; sm.B[i] = -200; sm.lo[i] = 0; sm.hi[i] = 1; sm.memo[i] = -1; }
   __syncwarp();
   {
-    double sa[6], sb[6];
-    fit_two(sm.T, 0, posts - 1, 0, 0, lane, sa, sb);
+    double sa[6];
+    fit_two(sm.T, 0, posts - 1, 0, 0, lane, sa);
     if (lane == 0) {
       int y0 = -200, y1 = -200;
       fit_solve(sa, F.sorted[0], F.sorted[posts - 1], &y0, &y1);
@@ -206,14 +232,13 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
       else bad = ((float)(mse / cnt) > F.maxerr) ? 1 : 0;
     }
     __syncwarp();
-    double sa[6], sb[6];
-    if (bad) fit_two(sm.T, lsp, sp - lsp, sp, hsp - sp, lane, sa, sb);      /* `bad` is warp-uniform */
     int r0 = 0, r1 = 0, ly0 = -200, ly1 = -200, hy0 = -200, hy1 = -200;
-    if (bad) {
-      /* the two solves run side by side on lanes 0 and 6 */
+    if (bad) {                                             /* `bad` is warp-uniform */
+      double ss[6];
+      fit_two(sm.T, lsp, sp - lsp, sp, hsp - sp, lane, ss);
+      /* the two solves run side by side on lanes 0 and 6, one pass through the code */
       int ya = -200, yb = -200, rr = 0;
-      if (lane == 0) rr = fit_solve(sa, F.sorted[lsp], F.sorted[sp], &ya, &yb);
-      else if (lane == 6) rr = fit_solve(sb, F.sorted[sp], F.sorted[hsp], &ya, &yb);
+      if (lane == 0 || lane == 6) rr = fit_solve(ss, F.sorted[lane ? sp : lsp], F.sorted[lane ? hsp : sp], &ya, &yb);
       r0 = __shfl_sync(FULLMASK, rr, 0); ly0 = __shfl_sync(FULLMASK, ya, 0); ly1 = __shfl_sync(FULLMASK, yb, 0);
       r1 = __shfl_sync(FULLMASK, rr, 6); hy0 = __shfl_sync(FULLMASK, ya, 6); hy1 = __shfl_sync(FULLMASK, yb, 6);
     }
@@ -335,8 +360,19 @@ int vb200_launch_floor_fit(const vb200_setup *s, cudaStream_t st, int W, int ite
   if (items <= 0) return VB200_OK;
   /* look->n = postlist[1] may be smaller than N2 (the 5.1 LFE floor covers 10 bins) */
   if (floor_index >= 0 && (s->h.flr[floor_index].type != 1 || s->h.flr[floor_index].n > s->h.bs[W] / 2 || s->h.flr[floor_index].posts < 2)) { vb200_set_error("floor %d is not a floor-1 of this block size", floor_index); return VB200_EINVAL; }
-  if (W) k_floor_fit<1024><<<items, 32, 0, st>>>(s->d, floor_index, W, s->h.channels, logmdct, logmask, mdct_stride, mask_stride, gate, posts, fitted);
-  else   k_floor_fit<128><<<items, 32, 0, st>>>(s->d, floor_index, W, s->h.channels, logmdct, logmask, mdct_stride, mask_stride, gate, posts, fitted);
+  int pcap = 2;
+  for (int k = 0; k < s->h.floors; k++) if (s->h.flr[k].type == 1 && s->h.flr[k].posts > pcap) pcap = s->h.flr[k].posts;
+  pcap = (pcap + 3) & ~3;
+  const int grid = (items + FIT_WARPS - 1) / FIT_WARPS;
+  static const int occ = getenv("VB200_FIT_OCC") ? atoi(getenv("VB200_FIT_OCC")) : 8;    /* resident CTAs per SM the register budget aims at */
+#define FIT_ARGS s->d, floor_index, W, s->h.channels, logmdct, logmask, mdct_stride, mask_stride, gate, posts, fitted, items, pcap
+  if (W) {
+    const size_t sh = FIT_WARPS * FitSmem<1024>::bytes(pcap);
+    if (occ <= 8) k_floor_fit<1024, 8><<<grid, FIT_WARPS * 32, sh, st>>>(FIT_ARGS);
+    else if (occ <= 10) k_floor_fit<1024, 10><<<grid, FIT_WARPS * 32, sh, st>>>(FIT_ARGS);
+    else k_floor_fit<1024, 12><<<grid, FIT_WARPS * 32, sh, st>>>(FIT_ARGS);
+  } else k_floor_fit<128, 8><<<grid, FIT_WARPS * 32, FIT_WARPS * FitSmem<128>::bytes(pcap), st>>>(FIT_ARGS);
+#undef FIT_ARGS
   LAUNCH_CHECK();
   return VB200_OK;
 }

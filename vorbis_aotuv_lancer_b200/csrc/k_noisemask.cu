@@ -173,7 +173,7 @@ __device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restr
 }
 
 template <int N, int T>
-__global__ void __launch_bounds__(T, (T == 256 ? 7 : 1))
+__global__ void __launch_bounds__(T, (T >= 128 ? 7 : 1))
 k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const int *__restrict__ block_mode,
             const float *__restrict__ lowcomp, const float *__restrict__ postev,
             const float *__restrict__ logmdct, LastRef last,
@@ -259,7 +259,13 @@ int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int ite
                            const int *block_mode, const float *lowcomp, const float *poste,
                            const float *logmdct, LastRef last, float *noise, float *epeak, float *npeak, int npeak_stride) {
   if (items <= 0) return VB200_OK;
-  if (W) {
+  static const int nmt = getenv("VB200_NM_T") ? atoi(getenv("VB200_NM_T")) : 256;
+  if (W && nmt == 128) {
+    constexpr int N = 1024, T = 128;
+    static bool attr = false;
+    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(k_noisemask<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NoiseSmem<N>))); attr = true; }
+    k_noisemask<N, T><<<items, T, sizeof(NoiseSmem<N>), st>>>(s->d, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
+  } else if (W) {
     constexpr int N = 1024, T = 256;
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(k_noisemask<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NoiseSmem<N>))); attr = true; }
