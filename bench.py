@@ -24,6 +24,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # before any CUDA context exists (see vorbis_aotuv_lancer_b200/lib.py)
 
 import numpy as np  # noqa: E402
 
@@ -303,7 +304,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=60.0)
-    ap.add_argument("--chunks", type=int, default=6, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
+    ap.add_argument("--chunks", type=int, default=8, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
     ap.add_argument("--depth", type=int, default=2, help="resident arm: batches in flight (2: host half of step i+1 overlaps device half of step i)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -251,6 +251,10 @@ int  vb200_batch_collect(vb200_batch *b);
 /* order b's kernels behind prev's (both may be submitted back to back): the host half of one job overlaps the device
    half of the previous one without the two sharing the SMs */
 int  vb200_batch_after(vb200_batch *b, vb200_batch *prev);
+/* Scheduling rank of this batch's CUDA stream among batches that are in flight together: 0 = served first.  Segmenter
+   streams always rank above every batch (their detector kernels gate the host's block-size decision).  Call while the
+   batch is idle. */
+int  vb200_batch_set_rank(vb200_batch *b, int rank);
 /* Debug/verification switch: 1 = emit codewords on the host from the device's symbol lists (the
  * reference-order implementation in emit.cu), 0 (default) = pack bits on the device (K8). */
 int  vb200_batch_set_host_emit(vb200_batch *b, int on);

@@ -195,6 +195,20 @@ __global__ void k_save_last(int n, const float *const *__restrict__ src, const i
 __global__ void k_copy_i32(const int *__restrict__ src, int *__restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
+/* Descriptor upload without the copy engine: the arrays of a batch's host pre-pass lie in page-locked (device-visible)
+   memory, and a kernel fetches them all in one launch.  A cudaMemcpyAsync would queue behind the PCM uploads of the
+   stream groups that follow (the H2D engine is FIFO), holding back this batch's first kernel by milliseconds. */
+constexpr int FETCH_MAX = 48;
+struct FetchTable { void *dst[FETCH_MAX]; const void *src[FETCH_MAX]; unsigned bytes[FETCH_MAX]; int n; };
+__global__ void __launch_bounds__(256) k_fetch(const FetchTable t) {
+  const int e = blockIdx.y;
+  const unsigned bytes = t.bytes[e];
+  const unsigned n16 = bytes >> 4;
+  const int4 *s16 = reinterpret_cast<const int4 *>(t.src[e]); int4 *d16 = reinterpret_cast<int4 *>(t.dst[e]);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) d16[i] = s16[i];
+  const int *s4 = reinterpret_cast<const int *>(t.src[e]); int *d4 = reinterpret_cast<int *>(t.dst[e]);
+  if (blockIdx.x == 0) for (unsigned i = (n16 << 2) + threadIdx.x; i < (bytes >> 2); i += blockDim.x) d4[i] = s4[i];
+}
 __global__ void k_copy_f32(const float *__restrict__ src, float *__restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
@@ -734,7 +748,23 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     CUDA_TRY(cudaMemcpyAsync(b->d_pcm, pcm, pcm_elems * sizeof(float), cudaMemcpyHostToDevice, st));
     d_pcm = b->d_pcm;
   }
-#define UP(dst, src, n) CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(*(src)) * (size_t)(n), cudaMemcpyHostToDevice, st))
+  /* every source below is 256-byte aligned pinned staging (b->pin), every destination a 256-byte aligned arena slice,
+     every size a multiple of 4 bytes */
+  FetchTable ft; ft.n = 0;
+  auto fetch_flush = [&]() -> int {
+    if (!ft.n) return VB200_OK;
+    k_fetch<<<dim3(32, ft.n), 256, 0, st>>>(ft);
+    ft.n = 0;
+    LAUNCH_CHECK();
+    return VB200_OK;
+  };
+  auto fetch_add = [&](void *dst, const void *src, size_t bytes) -> int {
+    if (!bytes) return VB200_OK;
+    if (bytes >> 32) { vb200_set_error("vb200_batch_submit: descriptor array too large"); return VB200_EINVAL; }
+    ft.dst[ft.n] = dst; ft.src[ft.n] = src; ft.bytes[ft.n] = (unsigned)bytes; ft.n++;
+    return ft.n == FETCH_MAX ? fetch_flush() : VB200_OK;
+  };
+#define UP(dst, src, n) RUN(fetch_add(dst, src, sizeof(*(src)) * (size_t)(n)))
   for (int W = 0; W < 2; W++) {
     const int I = nb[W] * ch;
     if (!I) continue;
@@ -754,6 +784,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     UP(d_ptrs, h_ptrs, 8);
   }
 
+  RUN(fetch_flush());
   /* ---- K1: window + MDCT + FFT/dB ---- */
   EV("K1 transform");
   for (int W = 0; W < 2; W++) {
@@ -820,6 +851,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     if (n) {
       const float **d_src = b->d_save_src; float **d_dst = b->d_save_dst; int *d_rule = b->d_save_rule, *d_N = b->d_save_N;
       UP(d_src, h_src, n); UP(d_dst, h_dst, n); UP(d_rule, h_rule, n); UP(d_N, h_N, n);
+      RUN(fetch_flush());
       k_save_last<<<n, 128, 0, st>>>(n, d_src, d_rule, d_N, d_dst);
       LAUNCH_CHECK();
     }
@@ -859,6 +891,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       }
     }
     UP(d_cl, h_cl, 2 * VB200_MAX_SUBMAPS * VB200_MAX_CHANNELS);
+    RUN(fetch_flush());
   }
 
   std::vector<BitWriter> &bws = b->bws; std::vector<std::vector<size_t>> &boff = b->boff;
@@ -1046,11 +1079,35 @@ static int batch_finish(vb200_batch *b) {
   b->total_ms = 0;
   for (int i = 0; i + 1 < b->nev; i++) { cudaEventElapsedTime(&b->ev_ms[i], b->ev[i], b->ev[i + 1]); }
   if (b->nev > 1) cudaEventElapsedTime(&b->total_ms, b->ev[0], b->ev[b->nev - 1]);
+  if (getenv("VB200_TRACE") && b->nev > 1) {
+    /* device-side timeline of this batch against a process-wide reference event (recorded at the first traced collect) */
+    static cudaEvent_t ref = nullptr;
+    if (!ref) { cudaEventCreate(&ref); cudaEventRecord(ref, st); cudaEventSynchronize(ref); }
+    fprintf(stderr, "[vb200 batch] device timeline (ms, vs ref):");
+    for (int i = 0; i < b->nev; i++) { float t = 0; cudaEventElapsedTime(&t, ref, b->ev[i]); fprintf(stderr, " %s@%.1f", b->evname[i], t); }
+    fprintf(stderr, "\n");
+  }
   return VB200_OK;
 }
 
 /* Order b's device work behind prev's: b can be submitted (host pre-pass, launches) while prev still runs, and its
    kernels start when prev's have finished -- successive jobs overlap host and device halves without sharing the SMs. */
+extern "C" int vb200_batch_set_rank(vb200_batch *b, int rank) {
+  if (!b || rank < 0) { vb200_set_error("vb200_batch_set_rank: bad arguments"); return VB200_EINVAL; }
+  if (b->pending) { vb200_set_error("vb200_batch_set_rank: the batch is running"); return VB200_EINVAL; }
+  CUDA_TRY(cudaSetDevice(b->s->device));
+  int least = 0, greatest = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));      /* numerically lower = served first */
+  int prio = greatest + 1 + rank;
+  if (prio > least) prio = least;
+  cudaStream_t st;
+  CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio));
+  CUDA_TRY(cudaStreamSynchronize(b->st));
+  cudaStreamDestroy(b->st);
+  b->st = st;
+  return VB200_OK;
+}
+
 extern "C" int vb200_batch_after(vb200_batch *b, vb200_batch *prev) {
   if (!b || prev == b) { vb200_set_error("vb200_batch_after: bad arguments"); return VB200_EINVAL; }
   b->after = prev;

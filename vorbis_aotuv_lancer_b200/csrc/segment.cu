@@ -720,7 +720,13 @@ extern "C" int vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out) {
   for (int i = 0; i < VE_BANDS; i++) { e.bbegin[i] = kBandBegin[i]; e.bend[i] = kBandEnd[i]; e.pre_th[i] = g->env.pre_th[i]; e.post_th[i] = g->env.post_th[i]; }
   e.minenergy = g->env.minenergy; e.stretch_penalty = g->env.stretch_penalty;
   CUDA_TRY(cudaMemcpy(g->d_env, &e, sizeof(e), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
+  {
+    /* served before any batch stream: the detector kernels gate the host's block-size decision, the batch kernels of
+       earlier groups would otherwise keep them waiting for SM slots */
+    int least = 0, greatest = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CUDA_TRY(cudaStreamCreateWithPriority(&g->st, cudaStreamNonBlocking, greatest));
+  }
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_h2d, cudaEventDisableTiming));
   *out = g;
   return VB200_OK;

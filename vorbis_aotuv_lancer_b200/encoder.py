@@ -102,9 +102,15 @@ class Encoder:
         self.setup = setup
         self.threads = threads
         self.chunks = max(1, int(chunks))
-        # every group but the first holds about 1/(chunks-1) of the streams; 25 % slack for uneven stream lengths
-        per = int(1.25 * int(max_blocks) / max(1, self.chunks - 1)) + 64 if self.chunks > 1 else int(max_blocks)
+        # group sizes ramp up (1, 2, 4, 8, then equal shares): the device gets its first work after one stream's upload
+        # and never starves while the rest arrives; 25 % slack for uneven stream lengths
+        env = os.environ.get("VB200_GROUP_WEIGHTS")
+        self.weights = [float(x) for x in env.split(",")] if env else [min(2.0 ** g, 12.0) for g in range(self.chunks)]
+        self.chunks = len(self.weights)
+        per = int(1.25 * int(max_blocks) * max(self.weights) / sum(self.weights)) + 64 if self.chunks > 1 else int(max_blocks)
         self.batches = [ops.Batch(setup, per) for _ in range(self.chunks)]
+        for rank, b in enumerate(self.batches):      # earlier groups are served first, so their packets are out first
+            check(L.vb200_batch_set_rank(b.h, rank), "vb200_batch_set_rank")
         self.segmenters = [Segmenter(setup) for _ in range(self.chunks)]
         for a, b in zip(self.segmenters[:-1], self.segmenters[1:]):
             check(L.vb200_segmenter_after(b.h, a.h), "vb200_segmenter_after")
@@ -143,13 +149,13 @@ class Encoder:
         own = streams is None
         if own:
             streams = [ops.Stream(self.setup) for _ in pcms]
-        # a small first group gets the device started early; the others share the rest evenly
         k = min(self.chunks, n)
-        if k > 1:
-            first = max(1, n // (4 * k))
-            cuts = [0, first] + [first + (g + 1) * (n - first) // (k - 1) for g in range(k - 1)]
-        else:
-            cuts = [0, n]
+        w = self.weights[:k]
+        acc, cuts = 0.0, [0]
+        for g in range(k):
+            acc += w[g]
+            cuts.append(max(cuts[-1] + 1, min(n - (k - 1 - g), int(round(n * acc / sum(w))))))
+        cuts[-1] = n
         groups = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
         trace = os.environ.get("VB200_TRACE")
         t0 = time.perf_counter()

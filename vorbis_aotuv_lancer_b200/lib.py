@@ -8,6 +8,10 @@ import os
 import re
 import subprocess
 
+# The encoder keeps a dozen CUDA streams busy (one per segmenter and per batch of every stream group); with the default 8
+# hardware queues they would alias and serialise each other.  Read by the CUDA driver when the context is created.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.path.join(HERE, "libvorbis_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "vorbis_b200.h")
