@@ -74,8 +74,10 @@ __device__ __forceinline__ void fit_pass(NoiseSmem<N> &sm, const int *__restrict
 template <int N, int T, typename F>
 __device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f, float offset, int fixed) {
   const int tid = threadIdx.x;
-  for (int i = tid; i < N; i += T) {
-    float y = __fadd_rn(f(i), offset);
+#pragma unroll
+  for (int q = 0; q < N / T; q++) {
+    const int i = tid + q * T;
+    float y = __fadd_rn(f(q, i), offset);
     if (y < 1.f) y = 1.f;
     float w = __fmul_rn(y, y);
     if (i == 0) {
@@ -187,20 +189,35 @@ k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const 
   const float level = lowcomp[item], poste = postev[item];
   const int part = P.partition;
 
-  noise_fit<N, T>(sm, P, [&](int i) { return __ldg(lm + i); }, 140.f, -1);
-  for (int i = tid; i < N; i += T) sm.work[i] = __fsub_rn(__ldg(lm + i), sm.noise[i]);
+  /* this thread's bins tid + q*T: logmdct (and, for M9, lastmdct) are read once and stay in registers */
+  float lmr[N / T], lastr[N / T];
+#pragma unroll
+  for (int q = 0; q < N / T; q++) lmr[q] = __ldg(lm + tid + q * T);
+  const bool m9 = mode > 1;
+#pragma unroll
+  for (int q = 0; q < N / T; q++) lastr[q] = (m9 && tid + q * T < P.tonecomp_endp) ? last.at(item, tid + q * T) : 0.f;
+
+  noise_fit<N, T>(sm, P, [&](int q, int) { return lmr[q]; }, 140.f, -1);
+#pragma unroll
+  for (int q = 0; q < N / T; q++) { const int i = tid + q * T; sm.work[i] = __fsub_rn(lmr[q], sm.noise[i]); }
   __syncthreads();
-  noise_fit<N, T>(sm, P, [&](int i) { return sm.work[i]; }, 0.f, P.noisewindowfixed);
-  for (int i = tid; i < N; i += T) sm.work[i] = __fsub_rn(__ldg(lm + i), sm.work[i]);
+  noise_fit<N, T>(sm, P, [&](int, int i) { return sm.work[i]; }, 0.f, P.noisewindowfixed);
+#pragma unroll
+  for (int q = 0; q < N / T; q++) { const int i = tid + q * T; sm.work[i] = __fsub_rn(lmr[q], sm.work[i]); }
   __syncthreads();
   if (mode <= 2 && P.tonefix_end) {
     if (tid == 0) tone_fix<N>(sm, P, lm, mode);
     __syncthreads();
   }
 
-  /* compander (psy.c:3878-4012); epeak staged in sums[0] for M9 */
+  /* compander (psy.c:3878-4012); epeak staged in sums[0] for M9.  The companded noise and logmdct also go to two
+     padded copies (index + index/32: a partition's bins then lie in different banks for every partition), which the
+     per-partition pass below walks one thread per partition without bank conflicts */
   float *ep = sm.sums[0];
-  for (int i = tid; i < N; i += T) {
+  float *npad = sm.sums[1], *lpad = sm.sums[3];          /* N + N/32 floats each: they run over into rows 2 and 4 */
+#pragma unroll
+  for (int q = 0; q < N / T; q++) {
+    const int i = tid + q * T;
     int dB = (int)((double)sm.noise[i] + .5);
     if (dB >= VB200_COMPAND_LEVELS) dB = VB200_COMPAND_LEVELS - 1;
     if (dB < 0) dB = 0;
@@ -209,6 +226,7 @@ k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const 
     float v = __fadd_rn(w, c);
     if (level > 0.f && i < P.n33p) v = __fsub_rn(v, __fmul_rn(__fsub_rn(c, P.compand_hi[dB]), level));
     sm.noise[i] = v;
+    npad[i + (i >> 5)] = v; lpad[i + (i >> 5)] = lmr[q];
   }
   __syncthreads();
 
@@ -221,15 +239,20 @@ k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const 
     if (i < P.min_nn_lp) {
       if (poste > 0.f) {
         float t = fminf(fminf(poste, 30.f), __fadd_rn(__ldg(off1 + i), 30.f));
-        if (t > 0.f) { np = -1.f; for (int j = 0; j < part; j++) sm.noise[i + j] = __fsub_rn(sm.noise[i + j], t); }
+        if (t > 0.f) {
+          np = -1.f;
+          for (int j = 0; j < part; j++) { const float v = __fsub_rn(sm.noise[i + j], t); sm.noise[i + j] = v; npad[i + j + ((i + j) >> 5)] = v; }
+        }
       }
       const float nt = 4.f;
       const float o = __fadd_rn(__ldg(off1 + i + part - 1), 6.f);
       if (o > 0.f && !(np < -0.5f)) {
         float me = 0.f, av = 0.f;
+#pragma unroll 8
         for (int j = 0; j < part; j++) {
-          const float l = __ldg(lm + i + j);
-          const float t = __fsub_rn(l, sm.noise[i + j]);
+          const int pi = i + j + ((i + j) >> 5);
+          const float l = lpad[pi];
+          const float t = __fsub_rn(l, npad[pi]);
           if (me < t) me = t;
           av = __fadd_rn(av, l);
         }
@@ -242,11 +265,13 @@ k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const 
 
   /* M9 (psy.c:4065-4073) + stores */
   float *no = noise_out + (size_t)item * N, *eo = epeak_out + (size_t)item * N;
-  for (int i = tid; i < N; i += T) {
+#pragma unroll
+  for (int q = 0; q < N / T; q++) {
+    const int i = tid + q * T;
     float e = 0.f;
-    if (mode > 1 && i < P.tonecomp_endp) {
-      const float l = __ldg(lm + i);
-      if (__fsub_rn(l, ep[i]) >= 12.f) { const float mi = __fsub_rn(l, last.at(item, i)); if (mi >= 1.f) e = mi; }
+    if (m9 && i < P.tonecomp_endp) {
+      const float l = lmr[q];
+      if (__fsub_rn(l, ep[i]) >= 12.f) { const float mi = __fsub_rn(l, lastr[q]); if (mi >= 1.f) e = mi; }
     }
     eo[i] = e;
     no[i] = sm.noise[i];
