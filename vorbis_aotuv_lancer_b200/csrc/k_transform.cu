@@ -20,48 +20,64 @@
 
 namespace {
 
-/* M-point complex FFT, forward (exp(-i...)), data in `a`, scratch `b`.  Stockham autosort, radix-4 passes (plus one
-   radix-2 pass when log2 M is odd): a pass reads a[j + r*M/4], multiplies by w^r, w = exp(-2*pi*i*k/(4*Ns)),
-   k = j mod Ns, and writes the 4-point DFT to b[4(j-k) + k + q*Ns].  `root` (shared memory) holds
-   exp(-2*pi*i*t/rootM) for t < rootM/2; the other half is its negative.  Returns the buffer holding the result. */
 __device__ __forceinline__ float2 cmulf(float2 v, float2 w) {
   return make_float2(__fsub_rn(__fmul_rn(v.x, w.x), __fmul_rn(v.y, w.y)), __fadd_rn(__fmul_rn(v.x, w.y), __fmul_rn(v.y, w.x)));
 }
-template <int M, int THREADS>
-__device__ __forceinline__ float2 *cta_fft(float2 *a, float2 *b, const float2 *root, int rootM) {
-  const int tid = threadIdx.x;
-  const int rs = rootM / M;                 /* root index of exp(-2*pi*i/M) */
-  const int half = rootM / 2;
-  int Ns = 1;
-#pragma unroll 1
-  for (; Ns * 4 <= M; Ns <<= 2) {
-    for (int j = tid; j < M / 4; j += THREADS) {
-      const int k = j & (Ns - 1);
-      float2 v0 = a[j], v1 = a[j + M / 4], v2 = a[j + M / 2], v3 = a[j + 3 * (M / 4)];
-      if (Ns > 1) {
-        const int t = k * (M / (4 * Ns)) * rs;          /* t < rootM/4 */
-        const float2 w1 = root[t], w2 = root[2 * t];
-        float2 w3;
-        if (3 * t < half) w3 = root[3 * t]; else { const float2 q = root[3 * t - half]; w3 = make_float2(-q.x, -q.y); }
-        v1 = cmulf(v1, w1); v2 = cmulf(v2, w2); v3 = cmulf(v3, w3);
-      }
-      const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
-      const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
-      const int o = ((j - k) << 2) + k;
-      b[o] = make_float2(s02.x + s13.x, s02.y + s13.y);
-      b[o + Ns] = make_float2(d02.x + d13.y, d02.y - d13.x);          /* d02 - i*d13 */
-      b[o + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
-      b[o + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);      /* d02 + i*d13 */
+/* Index swizzles of the first two passes.  A radix-4 pass writes b[4(j-k) + k + q*Ns]: for Ns = 1 and Ns = 4 the 16
+   lanes of a half-warp would hit only 4 of the 16 eight-byte bank pairs (4-way conflicts).  XOR-ing two index bits with
+   bits of i >> 4 makes the 16 slots distinct, and the following pass, which reads 16 consecutive aligned elements per
+   half-warp, sees a permutation inside the aligned 16 -- conflict-free both ways, no padding. */
+template <int MODE> __device__ __forceinline__ int swz(int i) {
+  if (MODE == 1) return i ^ ((i >> 4) & 3);
+  if (MODE == 2) return i ^ (((i >> 4) & 3) << 2);
+  return i;
+}
+template <int M, int THREADS, int Ns, int RD, int WR>
+__device__ __forceinline__ void fft_pass4(const float2 *a, float2 *b, const float2 *__restrict__ ptw) {
+  for (int j = threadIdx.x; j < M / 4; j += THREADS) {
+    const int k = j & (Ns - 1);
+    float2 v0 = a[swz<RD>(j)], v1 = a[swz<RD>(j + M / 4)], v2 = a[swz<RD>(j + M / 2)], v3 = a[swz<RD>(j + 3 * (M / 4))];
+    if (Ns > 1) {
+      /* this pass's twiddles w^1, w^2, w^3 (w = exp(-2*pi*i*k/(4*Ns))) at unit stride: a table of 8 KB for all
+         passes that stays in L1 (setup.cu: fft_pass_tw) */
+      const float2 *tp = ptw + (Ns - 4) + k;
+      const float2 w1 = __ldg(tp), w2 = __ldg(tp + Ns), w3 = __ldg(tp + 2 * Ns);
+      v1 = cmulf(v1, w1); v2 = cmulf(v2, w2); v3 = cmulf(v3, w3);
     }
-    __syncthreads();
-    float2 *tmp = a; a = b; b = tmp;
+    const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+    const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+    const int o = ((j - k) << 2) + k;
+    b[swz<WR>(o)] = make_float2(s02.x + s13.x, s02.y + s13.y);
+    b[swz<WR>(o + Ns)] = make_float2(d02.x + d13.y, d02.y - d13.x);          /* d02 - i*d13 */
+    b[swz<WR>(o + 2 * Ns)] = make_float2(s02.x - s13.x, s02.y - s13.y);
+    b[swz<WR>(o + 3 * Ns)] = make_float2(d02.x - d13.y, d02.y + d13.x);      /* d02 + i*d13 */
+  }
+  __syncthreads();
+}
+/* M-point complex FFT, forward (exp(-i...)), data in `a`, scratch `b`.  Stockham autosort, radix-4 passes (plus one
+   radix-2 pass when log2 M is odd): a pass reads a[j + r*M/4], multiplies by w^r, w = exp(-2*pi*i*k/(4*Ns)),
+   k = j mod Ns, and writes the 4-point DFT to b[4(j-k) + k + q*Ns].  Returns the buffer holding the result. */
+template <int M, int THREADS>
+__device__ __forceinline__ float2 *cta_fft(float2 *a, float2 *b, const float2 *__restrict__ ptw, int r2off) {
+  static_assert(M >= 32 && M <= 1024, "sizes of the 256/2048 block pair");
+  fft_pass4<M, THREADS, 1, 0, 1>(a, b, ptw);
+  fft_pass4<M, THREADS, 4, 1, 2>(b, a, ptw);
+  int Ns = 16;
+  if (M >= 64) {
+    fft_pass4<M, THREADS, 16, 2, 0>(a, b, ptw);
+    { float2 *tmp = a; a = b; b = tmp; }
+    Ns = 64;
+    if (M >= 256) { fft_pass4<M, THREADS, 64, 0, 0>(a, b, ptw); float2 *tmp = a; a = b; b = tmp; Ns = 256; }
+    if (M >= 1024) { fft_pass4<M, THREADS, 256, 0, 0>(a, b, ptw); float2 *tmp = a; a = b; b = tmp; Ns = 1024; }
   }
   if (Ns < M) {                              /* one radix-2 pass left: Ns == M/2 */
-    for (int j = tid; j < M / 2; j += THREADS) {
-      const float2 w = root[j * rs];          /* k == j, M/(2*Ns) == 1 */
-      const float2 u = a[j], t = cmulf(a[j + M / 2], w);
+    for (int j = threadIdx.x; j < M / 2; j += THREADS) {
+      const float2 w = __ldg(ptw + r2off + j);      /* exp(-2*pi*i*j/M) */
+      float2 u, t;
+      if (M == 32) { u = a[swz<2>(j)]; t = cmulf(a[swz<2>(j + M / 2)], w); }       /* straight after the Ns = 4 pass */
+      else { u = a[j]; t = cmulf(a[j + M / 2], w); }
       b[j] = make_float2(u.x + t.x, u.y + t.y);
-      b[j + Ns] = make_float2(u.x - t.x, u.y - t.y);
+      b[j + M / 2] = make_float2(u.x - t.x, u.y - t.y);
     }
     __syncthreads();
     float2 *tmp = a; a = b; b = tmp;
@@ -80,14 +96,13 @@ k_transform(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm
   __shared__ __align__(16) float x[N];
   __shared__ __align__(16) float2 bufA[N2];
   __shared__ __align__(16) float2 bufB[N2];
-  __shared__ __align__(16) float2 roots[N4];          /* exp(-2*pi*i*t/N2), t < N2/2 */
   __shared__ double red[2][THREADS / 32];
   __shared__ float redf[THREADS / 32];
 
   const int item = blockIdx.x, tid = threadIdx.x;
   const float *src = pcm + (pcm_off ? pcm_off[item] : (long long)item * N);
 
-  for (int i = tid; i < N4; i += THREADS) roots[i] = __ldg(&S->fft_root[W][i]);
+  const float2 *ptw = S->fft_pass_tw[W]; const int r2off = S->fft_r2_off[W];
   /* ---- stage the block ---- */
   if ((((uintptr_t)src) & 15) == 0) {
     for (int i = tid; i < N / 4; i += THREADS) reinterpret_cast<float4 *>(x)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
@@ -153,7 +168,7 @@ k_transform(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm
       bufA[m] = make_float2(u0 * t.x - u1 * t.y, u0 * t.y + u1 * t.x);
     }
     __syncthreads();
-    float2 *Z = cta_fft<N4, THREADS>(bufA, bufB, roots, N2);
+    float2 *Z = cta_fft<N4, THREADS>(bufA, bufB, ptw, r2off);
     const float scale = 4.f / N;
     float *gm = gmdct + (size_t)item * N2, *lm = logmdct + (size_t)item * N2;
     float2 *Y = (Z == bufA) ? bufB : bufA;   /* stage the interleaved result for coalesced stores */
@@ -177,7 +192,7 @@ k_transform(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm
   {
     for (int m = tid; m < N2; m += THREADS) bufA[m] = make_float2(x[2 * m], x[2 * m + 1]);
     __syncthreads();
-    float2 *Z = cta_fft<N2, THREADS>(bufA, bufB, roots, N2);
+    float2 *Z = cta_fft<N2, THREADS>(bufA, bufB, ptw, r2off);
     const float2 *rt = S->rfft_tw[W];
     const float scale = 4.f / N;
     const float scale_dB = todB_p345(scale);

@@ -9,6 +9,7 @@
 #include <stdarg.h>
 #include <math.h>
 #include "vb200_internal.h"
+#include <vector>
 
 static thread_local char g_err[512] = "";
 static long g_launches = 0;
@@ -138,6 +139,29 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
     h.mdct_tw[w] = (const float2 *)L.up(t, sizeof(float2) * q);
     for (int k = 0; k < q; k++) { double a = -2.0 * M_PI * k / (double)N2; t[k].x = (float)cos(a); t[k].y = (float)sin(a); }
     h.fft_root[w] = (const float2 *)L.up(t, sizeof(float2) * q);
+    {
+      /* the same roots laid out per radix-4 pass: level Ns (4, 16, ... <= N2/4) holds w^1[Ns], w^2[Ns], w^3[Ns] with
+         w = root[k * N2 / (4 Ns)], at float2 offset Ns - 4; then the twiddles of the one radix-2 pass.  A pass reads its twiddles at unit stride (the strided reads of the root table cost
+         up to 16-way shared-memory bank conflicts).  Values are taken from the root table, so results do not change. */
+      const int half = N2 / 2;
+      std::vector<float2> pt;
+      for (int Ns = 4; Ns * 4 <= N2; Ns <<= 2) {
+        pt.resize((size_t)(Ns - 4) + 3 * Ns);
+        for (int k = 0; k < Ns; k++) {
+          const int tt = k * (N2 / (4 * Ns));
+          pt[(Ns - 4) + k] = t[tt];
+          pt[(Ns - 4) + Ns + k] = t[2 * tt];
+          float2 w3; if (3 * tt < half) w3 = t[3 * tt]; else { w3.x = -t[3 * tt - half].x; w3.y = -t[3 * tt - half].y; }
+          pt[(Ns - 4) + 2 * Ns + k] = w3;
+        }
+      }
+      h.fft_r2_off[w] = (int)pt.size();
+      /* only one of the two transform sizes (N2 and N2/2 points) has an odd log2, i.e. a radix-2 pass */
+      int lg = 0; while ((1 << lg) < N2) lg++;
+      if (lg & 1) for (int j = 0; j < N2 / 2; j++) pt.push_back(t[j]);         /* N2 points: exp(-2*pi*i*j/N2) */
+      else for (int j = 0; j < N2 / 4; j++) pt.push_back(t[2 * j]);            /* N2/2 points */
+      h.fft_pass_tw[w] = (const float2 *)L.up(pt.data(), sizeof(float2) * pt.size());
+    }
     for (int k = 0; k < N2; k++) { double a = -2.0 * M_PI * k / (double)n; t[k].x = (float)cos(a); t[k].y = (float)sin(a); }
     h.rfft_tw[w] = (const float2 *)L.up(t, sizeof(float2) * N2);
     free(t);

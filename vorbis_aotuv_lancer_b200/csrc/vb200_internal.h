@@ -99,6 +99,8 @@ struct DevSetup {
   const float2 *mdct_tw[2];     /* [n/4]  exp(-i*pi*(8m+1)/(8*N2)) */
   const float2 *fft_root[2];    /* [n/4]  exp(-2*pi*i*k/(n/2)), k<n/4 : roots for the n/2-point FFT */
   const float2 *rfft_tw[2];     /* [n/2]  exp(-2*pi*i*k/n) */
+  const float2 *fft_pass_tw[2]; /* fft_root regrouped per radix-4 pass (setup.cu), unit-stride reads */
+  int fft_r2_off[2];            /* float2 offset of the radix-2 pass's twiddles in fft_pass_tw */
 };
 
 /* ---- host-side object behind vb200_setup ---- */
