@@ -142,20 +142,22 @@ __device__ __forceinline__ void tm_fill(const DevSetup *__restrict__ S, const De
     const int L = P.total_octave_lines, per = P.eighth;
     const int nw = (L + 31) >> 5;
     const unsigned myw = lane < nw ? sv[lane] : 0u;
-    /* first survivor after / last survivor before the word this lane holds */
+    /* first survivor after the word this lane holds */
     const unsigned nzm = __ballot_sync(FULLMASK, myw != 0u);
-    int after = -1, before = -1;
+    int after = -1;
     {
       const unsigned hi = lane < 31 ? (nzm & ~((2u << lane) - 1u)) : 0u;
       const int w2 = hi ? __ffs(hi) - 1 : 0;
       const unsigned ww = __shfl_sync(FULLMASK, myw, w2);
       if (hi) after = w2 * 32 + __ffs(ww) - 1;
-      const unsigned lo = nzm & ((1u << lane) - 1u);
-      const int w0 = lo ? 31 - __clz(lo) : 0;
-      const unsigned wv = __shfl_sync(FULLMASK, myw, w0);
-      if (lo) before = w0 * 32 + 31 - __clz(wv);
     }
-    /* end of every survivor's span, running maximum in position order (the fill pointer of the reference) */
+    /* End of every survivor's span, running maximum in position order (the fill pointer of the reference).  Survivor p
+       covers [end of the survivor before it, its own end); the spans tile [0, L).  Instead of filling the seed vector
+       span by span (a serial loop per survivor), every survivor with a non-empty span leaves its position at the
+       span's first slot, and a second sweep gives every position the last mark at or before it: run16[x] = the survivor
+       whose amplitude the reference would have filled in at x.  The seeds themselves are never overwritten. */
+    for (int x = lane; x < L; x += 32) run16[x] = 0xffff;
+    __syncwarp();
     int carry = 0;
     for (int w = 0; w < nw; w++) {
       const unsigned word = __shfl_sync(FULLMASK, myw, w);
@@ -172,41 +174,40 @@ __device__ __forceinline__ void tm_fill(const DevSetup *__restrict__ S, const De
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, end, o); if (lane >= o && y > end) end = y; }
       if (carry > end) end = carry;
-      if (sv_here) run16[p] = (unsigned short)end;
+      int lo = __shfl_up_sync(FULLMASK, end, 1);            /* running maximum before this position */
+      if (lane == 0) lo = carry;
+      if (sv_here && end > lo) run16[lo] = (unsigned short)p;       /* spans are disjoint: one writer per slot */
       carry = __shfl_sync(FULLMASK, end, 31);
     }
     __syncwarp();
-    /* survivor p covers [end of the survivor before it, its own end); expand from the back so that a seed is
-       read before its slot is overwritten (everything written here lies above the previous survivor) */
-    for (int w = nw - 1; w >= 0; w--) {
-      const unsigned word = __shfl_sync(FULLMASK, myw, w);
-      const int bef = __shfl_sync(FULLMASK, before, w);
-      const int p = w * 32 + lane;
-      const bool sv_here = (word >> lane) & 1u;
-      float a = 0.f; int lo = 0, hi = 0;
-      if (sv_here) {
-        a = seed[p]; hi = run16[p];
-        const unsigned lb = word & ((1u << lane) - 1u);
-        const int pv = lb ? w * 32 + 31 - __clz(lb) : bef;
-        lo = pv >= 0 ? (int)run16[pv] : 0;
+    {
+      int last = 0xffff;                                     /* slot 0 is always marked (the first survivor's span starts at 0) */
+      for (int x0 = 0; x0 < L; x0 += 32) {
+        const int x = x0 + lane;
+        const int m = x < L ? (int)run16[x] : 0xffff;
+        const unsigned has = __ballot_sync(FULLMASK, m != 0xffff);
+        const unsigned below = has & ((2u << lane) - 1u);    /* lane 31: 2u << 31 == 0, mask == all ones */
+        const int src = below ? 31 - __clz(below) : 0;
+        const int got = __shfl_sync(FULLMASK, m, src);
+        const int v = below ? got : last;
+        if (x < L) run16[x] = (unsigned short)v;
+        last = __shfl_sync(FULLMASK, v, 31);
       }
-      __syncwarp();
-      for (int x = lo; x < hi; x++) seed[x] = a;
-      __syncwarp();
     }
+    __syncwarp();
     float att = __fadd_rn(local_ampmax[item], P.ath_adjatt);
     if (att < P.ath_maxatt) att = P.ath_maxatt;
     float *out = tone + (size_t)item * N;
     const float lim = P.tone_abs_limit;
     for (int g = lane; g < P.n_tone_groups; g += 32) {
       const int4 q = __ldg(P.tone_groups + g);
-      float mv = seed[q.x];
+      float mv = seed[run16[q.x]];
       if (mv > lim) mv = lim;
-      for (int p = q.x + 1; p <= q.y; p++) { const float v = seed[p]; if ((v > TM_NEGINF && v < mv) || mv == TM_NEGINF) mv = v; }
+      for (int p = q.x + 1; p <= q.y; p++) { const float v = seed[run16[p]]; if ((v > TM_NEGINF && v < mv) || mv == TM_NEGINF) mv = v; }
       for (int i = q.z; i < q.w; i++) { const float fl = __fadd_rn(__ldg(P.ath + i), att); out[i] = fl < mv ? mv : fl; }
     }
     {
-      const float mv = seed[L - 1];
+      const float mv = seed[run16[L - 1]];
       for (int i = P.tone_tail + lane; i < N; i += 32) { const float fl = __fadd_rn(__ldg(P.ath + i), att); out[i] = fl < mv ? mv : fl; }
     }
 }
