@@ -201,6 +201,9 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
   }
   __syncwarp();
 
+  const int imaxover = (int)F.maxover, imaxunder = (int)F.maxunder;
+  const bool int_limits = (float)imaxover == F.maxover && (float)imaxunder == F.maxunder && imaxover >= 0 && imaxunder >= 0 &&
+                          imaxover < 4096 && imaxunder < 4096;
   for (int i = 2; i < posts; i++) {
     const int sp = F.reverse[i], ln = sm.lo[sp], hn = sm.hi[sp];
     if (sm.memo[ln] == hn) continue;            /* uniform across the warp */
@@ -212,13 +215,23 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     /* inspect_error across the warp */
     int viol = 0, mse = 0;
     const LineK LK = line_setup(lx, hx, ly, hy);
-    for (int x = lx + lane; x < hx; x += 32) {
-      const int qv = sm.q[x];
-      const int y = line_eval(LK, x), v = qv & 0x7fff;
-      mse += (y - v) * (y - v);
-      if ((qv >> 15) && (x == lx || v)) {
-        if (__fadd_rn((float)y, F.maxover) < (float)v) viol = 1;
-        if (__fsub_rn((float)y, F.maxunder) > (float)v) viol = 1;
+    if (int_limits) {
+      /* y, v < 2^10 and the limits are whole numbers: the reference's float comparisons are exact integer ones */
+      for (int x = lx + lane; x < hx; x += 32) {
+        const int qv = sm.q[x];
+        const int y = line_eval(LK, x), v = qv & 0x7fff, d = y - v;
+        mse += d * d;
+        if ((qv >> 15) && (x == lx || v) && (d + imaxover < 0 || d - imaxunder > 0)) viol = 1;
+      }
+    } else {
+      for (int x = lx + lane; x < hx; x += 32) {
+        const int qv = sm.q[x];
+        const int y = line_eval(LK, x), v = qv & 0x7fff;
+        mse += (y - v) * (y - v);
+        if ((qv >> 15) && (x == lx || v)) {
+          if (__fadd_rn((float)y, F.maxover) < (float)v) viol = 1;
+          if (__fsub_rn((float)y, F.maxunder) > (float)v) viol = 1;
+        }
       }
     }
     viol = __any_sync(FULLMASK, viol);

@@ -83,12 +83,13 @@ __device__ __forceinline__ void tm_splat(const DevSetup *__restrict__ S, const i
         if (lane < take) {
           const SplatJob jb = queue[warp][lane];
           const float *curve = P.tonecurves + jb.curve + 2;
-          int sp = jb.sp0;
-          for (int k = jb.k0; k < jb.k1; k++) {
-            if (sp >= L) break;
-            if (sp > 0) smem_atomic_max(&seed[sp], __fadd_rn(jb.mx, __ldg(curve + k)));
-            sp += per;
-          }
+          /* the reference walks k = k0..k1-1 with sp = sp0 + (k-k0)*per, skips sp <= 0 and stops at sp >= L
+             (psy.c:672-706): clip the k range once instead of testing every step */
+          int ka = jb.k0, kb = jb.k1;
+          if (jb.sp0 <= 0) ka += (-jb.sp0) / per + 1;                      /* first k with sp > 0 */
+          { const int room = (L - 1 - jb.sp0) / per; if (jb.sp0 >= L) kb = ka; else if (jb.k0 + room + 1 < kb) kb = jb.k0 + room + 1; }
+          float *sd = seed + jb.sp0 + (ka - jb.k0) * per;
+          for (int k = ka; k < kb; k++, sd += per) smem_atomic_max(sd, __fadd_rn(jb.mx, __ldg(curve + k)));
         }
         __syncwarp();
         /* move the leftover (< 32 jobs) to the front */
