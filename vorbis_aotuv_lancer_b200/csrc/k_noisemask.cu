@@ -25,55 +25,41 @@ struct NoiseSmem {
                              lanes (one 128-bit access each) on different banks */
   float work[N];
   float noise[N];
-  float held[4];          /* A, B, D of the last fitted bin, reused above the last full window */
   __device__ float *tmp() { return sums[1]; }      /* scratch of the M7 tone fix; the prefix sums are dead by then */
   __device__ float *inm() { return sums[2]; }
 };
 
-/* one regression pass over all bins (the parallel part of bark_noise_hybridmp) */
-template <int N, int T>
-__device__ __forceinline__ void fit_pass(NoiseSmem<N> &sm, const int *__restrict__ bark, int fixed, int pass,
-                                         int b1, int b2, float offset) {
-  const int tid = threadIdx.x;
-  /* bins below b2 have their own window; publish the fit of bin b2-1 for the bins above */
-  for (int i = tid; i < b2; i += T) {
-    int lo, hi;
-    if (pass == 0) { int b = __ldg(bark + i); lo = b >> 16; hi = b & 0xffff; }
-    else { hi = i + fixed / 2; lo = hi - fixed; }
-    float tN, tX, tXX, tY, tXY;
-    if (i < b1) {
-      tN = __fadd_rn(sm.sums[0][hi], sm.sums[0][-lo]); tX = __fsub_rn(sm.sums[1][hi], sm.sums[1][-lo]);
-      tXX = __fadd_rn(sm.sums[2][hi], sm.sums[2][-lo]); tY = __fadd_rn(sm.sums[3][hi], sm.sums[3][-lo]);
-      tXY = __fsub_rn(sm.sums[4][hi], sm.sums[4][-lo]);
-    } else {
-      tN = __fsub_rn(sm.sums[0][hi], sm.sums[0][lo]); tX = __fsub_rn(sm.sums[1][hi], sm.sums[1][lo]);
-      tXX = __fsub_rn(sm.sums[2][hi], sm.sums[2][lo]); tY = __fsub_rn(sm.sums[3][hi], sm.sums[3][lo]);
-      tXY = __fsub_rn(sm.sums[4][hi], sm.sums[4][lo]);
-    }
-    float A = __fsub_rn(__fmul_rn(tY, tXX), __fmul_rn(tX, tXY));
-    float B = __fsub_rn(__fmul_rn(tN, tXY), __fmul_rn(tX, tY));
-    float D = __fsub_rn(__fmul_rn(tN, tXX), __fmul_rn(tX, tX));
-    if (i == b2 - 1) { sm.held[0] = A; sm.held[1] = B; sm.held[2] = D; }
-    float R = __fdiv_rn(__fadd_rn(A, __fmul_rn((float)i, B)), D);
-    if (pass == 0) { if (R < 0.f) R = 0.f; sm.noise[i] = __fsub_rn(R, offset); }
-    else { float v = __fsub_rn(R, offset); if (v < sm.noise[i]) sm.noise[i] = v; }
+/* A, B, D of the regression window of bin ii in pass `pass` (0: the bin's bark window, 1: the fixed window), from the
+   prefix sums (the parallel part of bark_noise_hybridmp) */
+template <int N>
+__device__ __forceinline__ void fit_abd(const NoiseSmem<N> &sm, const int *__restrict__ bark, int fixed, int pass, int b1, int ii,
+                                        float &A, float &B, float &D) {
+  int lo, hi;
+  if (pass == 0) { const int b = __ldg(bark + ii); lo = b >> 16; hi = b & 0xffff; }
+  else { hi = ii + fixed / 2; lo = hi - fixed; }
+  float tN, tX, tXX, tY, tXY;
+  if (ii < b1) {
+    tN = __fadd_rn(sm.sums[0][hi], sm.sums[0][-lo]); tX = __fsub_rn(sm.sums[1][hi], sm.sums[1][-lo]);
+    tXX = __fadd_rn(sm.sums[2][hi], sm.sums[2][-lo]); tY = __fadd_rn(sm.sums[3][hi], sm.sums[3][-lo]);
+    tXY = __fsub_rn(sm.sums[4][hi], sm.sums[4][-lo]);
+  } else {
+    tN = __fsub_rn(sm.sums[0][hi], sm.sums[0][lo]); tX = __fsub_rn(sm.sums[1][hi], sm.sums[1][lo]);
+    tXX = __fsub_rn(sm.sums[2][hi], sm.sums[2][lo]); tY = __fsub_rn(sm.sums[3][hi], sm.sums[3][lo]);
+    tXY = __fsub_rn(sm.sums[4][hi], sm.sums[4][lo]);
   }
-  __syncthreads();
-  {
-    const float A = sm.held[0], B = sm.held[1], D = sm.held[2];
-    for (int i = b2 + tid; i < N; i += T) {
-      float R = __fdiv_rn(__fadd_rn(A, __fmul_rn((float)i, B)), D);
-      if (pass == 0) { if (R < 0.f) R = 0.f; sm.noise[i] = __fsub_rn(R, offset); }
-      else { float v = __fsub_rn(R, offset); if (v < sm.noise[i]) sm.noise[i] = v; }
-    }
-  }
-  __syncthreads();
+  A = __fsub_rn(__fmul_rn(tY, tXX), __fmul_rn(tX, tXY));
+  B = __fsub_rn(__fmul_rn(tN, tXY), __fmul_rn(tX, tY));
+  D = __fsub_rn(__fmul_rn(tN, tXX), __fmul_rn(tX, tX));
 }
 
-/* f (shared or global) -> sm.noise;  both regression passes of one bark_noise_hybridmp call */
-template <int N, int T, typename F>
-__device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f, float offset, int fixed) {
+/* One bark_noise_hybridmp call: f(q, i) -> out(q, i, noise).  Bins keep their owner thread (i = tid + q*T) through the
+   whole kernel, so the only barriers are the ones around the serial prefix chains: a bin above the last full window
+   (i >= b2) recomputes the fit of bin b2-1 itself instead of waiting for it to be published, and the second (fixed
+   window) pass follows the first in the same loop. */
+template <int N, int T, typename F, typename OUT>
+__device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f, float offset, int fixed, OUT out) {
   const int tid = threadIdx.x;
+  __syncthreads();                     /* every reader of the previous prefix sums is done */
 #pragma unroll
   for (int q = 0; q < N / T; q++) {
     const int i = tid + q * T;
@@ -89,7 +75,6 @@ __device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f
       sm.sums[3][i] = __fmul_rn(w, y); sm.sums[4][i] = __fmul_rn(wx, y);
     }
   }
-  if (tid == 0) { sm.held[0] = 0.f; sm.held[1] = 0.f; sm.held[2] = 1.f; }
   __syncthreads();
   if (tid < 5) {                       /* the five serial float32 chains */
     float4 *r = reinterpret_cast<float4 *>(sm.sums[tid]);
@@ -108,8 +93,23 @@ __device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f
     }
   }
   __syncthreads();
-  fit_pass<N, T>(sm, P.bark, fixed, 0, P.nf_b1[0], P.nf_b2[0], offset);
-  if (fixed > 0) fit_pass<N, T>(sm, P.bark, fixed, 1, P.nf_b1[1], P.nf_b2[1], offset);
+  const int b1a = P.nf_b1[0], b2a = P.nf_b2[0], b1f = P.nf_b1[1], b2f = P.nf_b2[1];
+#pragma unroll
+  for (int q = 0; q < N / T; q++) {
+    const int i = tid + q * T;
+    float A = 0.f, B = 0.f, D = 1.f;
+    if (b2a > 0) fit_abd<N>(sm, P.bark, fixed, 0, b1a, i < b2a ? i : b2a - 1, A, B, D);
+    float R = __fdiv_rn(__fadd_rn(A, __fmul_rn((float)i, B)), D);
+    if (R < 0.f) R = 0.f;
+    float nv = __fsub_rn(R, offset);
+    if (fixed > 0) {
+      if (b2f > 0) fit_abd<N>(sm, P.bark, fixed, 1, b1f, i < b2f ? i : b2f - 1, A, B, D);
+      else if (b2a > 0) fit_abd<N>(sm, P.bark, fixed, 0, b1a, b2a - 1, A, B, D);      /* the reference's A, B, D carry over */
+      const float v = __fsub_rn(__fdiv_rn(__fadd_rn(A, __fmul_rn((float)i, B)), D), offset);
+      if (v < nv) nv = v;
+    }
+    out(q, i, nv);
+  }
 }
 
 /* aoTuV M7 (psy.c:3645-3768) on sm.work; short blocks: peak-driven, transition blocks: 8-bin groups.
@@ -197,18 +197,15 @@ k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const 
 #pragma unroll
   for (int q = 0; q < N / T; q++) lastr[q] = (m9 && tid + q * T < P.tonecomp_endp) ? last.at(item, tid + q * T) : 0.f;
 
-  noise_fit<N, T>(sm, P, [&](int q, int) { return lmr[q]; }, 140.f, -1);
-#pragma unroll
-  for (int q = 0; q < N / T; q++) { const int i = tid + q * T; sm.work[i] = __fsub_rn(lmr[q], sm.noise[i]); }
-  __syncthreads();
-  noise_fit<N, T>(sm, P, [&](int, int i) { return sm.work[i]; }, 0.f, P.noisewindowfixed);
-#pragma unroll
-  for (int q = 0; q < N / T; q++) { const int i = tid + q * T; sm.work[i] = __fsub_rn(lmr[q], sm.work[i]); }
-  __syncthreads();
+  noise_fit<N, T>(sm, P, [&](int q, int) { return lmr[q]; }, 140.f, -1,
+                  [&](int q, int i, float nv) { sm.work[i] = __fsub_rn(lmr[q], nv); });
+  noise_fit<N, T>(sm, P, [&](int, int i) { return sm.work[i]; }, 0.f, P.noisewindowfixed,
+                  [&](int q, int i, float nv) { sm.noise[i] = nv; sm.work[i] = __fsub_rn(lmr[q], sm.work[i]); });
   if (mode <= 2 && P.tonefix_end) {
-    if (tid == 0) tone_fix<N>(sm, P, lm, mode);
     __syncthreads();
+    if (tid == 0) tone_fix<N>(sm, P, lm, mode);
   }
+  __syncthreads();                     /* the prefix sums are dead: their rows are reused below */
 
   /* compander (psy.c:3878-4012); epeak staged in sums[0] for M9.  The companded noise and logmdct also go to two
      padded copies (index + index/32: a partition's bins then lie in different banks for every partition), which the
