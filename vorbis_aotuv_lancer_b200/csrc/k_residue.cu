@@ -101,7 +101,8 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
   int *offs = reinterpret_cast<int *>(dyn + ((ent_elems * 2 + 15) & ~(size_t)15));   /* [stages*partvals*rows + 1] */
   __shared__ int rowch[VB200_MAX_CHANNELS];
   __shared__ short tab_bk[64 * 8], tab_nvec[64 * 8];      /* per (class, stage): book and vectors per partition */
-  if (tid == 0) { int r = 0; for (int k = 0; k < ch; k++) if (R.type == 2 || nz[chlist[k]]) rowch[r++] = chlist[k]; }
+  __shared__ int next_pr;
+  if (tid == 0) { next_pr = 0; int r = 0; for (int k = 0; k < ch; k++) if (R.type == 2 || nz[chlist[k]]) rowch[r++] = chlist[k]; }
   for (int i = tid; i < R.partitions * 8; i += RF_WARPS * 32) {
     const int cls = i >> 3, st2 = i & 7;
     int bk = -1, nv = 0;
@@ -115,7 +116,13 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
   /* ---- pass 1: cascade VQ per (partition,row).  A partition holds G/dim <= 16 vectors (often 4 or 8), so a warp
      works on RF_SLOTS partitions at once, RF_LP lanes each; the stage loop is shared, the books differ per slot ---- */
   const int slot = lane / RF_LP, l = lane % RF_LP;
-  for (int pr0 = warp * RF_SLOTS; pr0 < partvals * rows; pr0 += RF_WARPS * RF_SLOTS) {
+  for (;;) {
+    /* partitions cost very different amounts (stages of their class, exhaustive searches): the warps draw the next
+       RF_SLOTS partitions from a counter instead of owning a fixed quarter */
+    int pr0 = 0;
+    if (lane == 0) pr0 = atomicAdd(&next_pr, RF_SLOTS);
+    pr0 = __shfl_sync(FULLMASK, pr0, 0);
+    if (pr0 >= partvals * rows) break;
     const int pr = pr0 + slot;
     const bool valid = pr < partvals * rows;
     const int p = valid ? (rows == 1 ? pr : pr / rows) : 0, row = valid ? (rows == 1 ? 0 : pr % rows) : 0;

@@ -392,5 +392,9 @@ int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int item
     return VB200_OK;
   }
   if (W) return launch_tm<1024, 4>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+  /* short blocks: the chase of the fused kernel runs one lane per ch-block, so more ch-blocks per CTA = more chase lanes */
+  static const int ti = getenv("VB200_TM_ITEMS") ? atoi(getenv("VB200_TM_ITEMS")) : 8;
+  if (ti >= 16) return launch_tm<128, 16>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
+  if (ti >= 8) return launch_tm<128, 8>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
   return launch_tm<128, 4>(s, st, items, psy, logfft, global_ampmax, local_ampmax, tone, Lstride);
 }
