@@ -328,30 +328,41 @@ k_floor_encode(const DevSetup *__restrict__ S, int floor_index, int W, int ch, i
     post[i] = v | (p & 0x8000);
   }
   __syncwarp();
-  if (lane == 0) {
-    vals[0] = post[0]; vals[1] = post[1];
-    for (int i = 2; i < posts; i++) {
+  /* Post prediction (floor1.c:880-920).  The reference walks the posts in index order; a post's prediction reads its
+     two neighbours, which lie on lower levels of the neighbour tree, and only posts on higher levels touch its flag --
+     so the posts of one level go side by side on the lanes, level after level. */
+  if (lane == 0) { vals[0] = post[0]; vals[1] = post[1]; }
+  for (int l = 1; l <= F.nlevels; l++) {
+    for (int k = F.lv_start[l] + lane; k < F.lv_start[l + 1]; k += 32) {
+      const int i = F.lv_order[k];
       const int ln = F.lonb[i - 2], hn = F.hinb[i - 2];
       const int pred = point_at(F.postlist[ln], F.postlist[hn], post[ln], post[hn], F.postlist[i]);
-      if ((post[i] & 0x8000) || pred == post[i]) { post[i] = pred | 0x8000; vals[i] = 0; }
+      const int p = post[i];
+      if ((p & 0x8000) || pred == p) { post[i] = pred | 0x8000; vals[i] = 0; }
       else {
         const int room = (F.quant_q - pred < pred) ? F.quant_q - pred : pred;
-        int d = post[i] - pred;
+        int d = p - pred;
         if (d < 0) d = (d < -room) ? room - d - 1 : -1 - (d << 1);
         else d = (d >= room) ? d + room : d << 1;
         vals[i] = d;
-        post[ln] &= 0x7fff; post[hn] &= 0x7fff;
+        atomicAnd(&post[ln], 0x7fff); atomicAnd(&post[hn], 0x7fff);
       }
     }
-    /* the posts that take part in the rendered curve, in x order */
-    int k = 0;
-    segx[0] = 0; segy[0] = post[0] * F.mult; k = 1;
-    for (int j = 1; j < posts; j++) {
-      const int cur = F.forward[j], hy = post[cur] & 0x7fff;
-      if (hy == post[cur]) { segx[k] = F.postlist[cur]; segy[k] = hy * F.mult; k++; }
+    __syncwarp();
+  }
+  /* the posts that take part in the rendered curve, in x order: a compaction over the sorted posts */
+  {
+    int k = 1;
+    if (lane == 0) { segx[0] = 0; segy[0] = post[0] * F.mult; }
+    for (int j0 = 1; j0 < posts; j0 += 32) {
+      const int j = j0 + lane;
+      int cur = 0, hy = 0; bool in = false;
+      if (j < posts) { cur = F.forward[j]; const int pv = post[cur]; hy = pv & 0x7fff; in = (hy == pv); }
+      const unsigned m = __ballot_sync(FULLMASK, in);
+      if (in) { const int o = k + __popc(m & ((1u << lane) - 1u)); segx[o] = F.postlist[cur]; segy[o] = hy * F.mult; }
+      k += __popc(m);
     }
-    nseg = k;
-    nonzero[item] = 1;
+    if (lane == 0) { nseg = k; nonzero[item] = 1; }
   }
   __syncwarp();
   for (int i = lane; i < posts; i += 32) pio[i] = post[i];

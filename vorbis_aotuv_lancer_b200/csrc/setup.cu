@@ -288,6 +288,22 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
     copy_i(fl.reverse, L.getk("flr%d.reverse", k, VB200_I32, VB200_MAX_POSTS), VB200_MAX_POSTS);
     copy_i(fl.lonb, L.getk("flr%d.lonb", k, VB200_I32, 63), 63);
     copy_i(fl.hinb, L.getk("flr%d.hinb", k, VB200_I32, 63), 63);
+    {
+      int lev[VB200_MAX_POSTS] = {0}, nl = 0;
+      for (int i = 2; i < fl.posts; i++) {
+        const int a = lev[fl.lonb[i - 2]], b = lev[fl.hinb[i - 2]];
+        lev[i] = 1 + (a > b ? a : b);
+        if (lev[i] > nl) nl = lev[i];
+      }
+      fl.nlevels = nl;
+      int n = 0;
+      fl.lv_start[0] = 0; fl.lv_start[1] = 0;
+      for (int l = 1; l <= nl; l++) {
+        fl.lv_start[l] = n;
+        for (int i = 2; i < fl.posts; i++) if (lev[i] == l) fl.lv_order[n++] = i;
+      }
+      fl.lv_start[nl + 1] = n;
+    }
     copy_i(s->hflr[k].partclass, L.getk("flr%d.partclass", k, VB200_I32, 31), 31);
     copy_i(s->hflr[k].class_dim, L.getk("flr%d.class_dim", k, VB200_I32, 16), 16);
     copy_i(s->hflr[k].class_subs, L.getk("flr%d.class_subs", k, VB200_I32, 16), 16);

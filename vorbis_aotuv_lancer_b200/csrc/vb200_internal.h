@@ -47,6 +47,9 @@ struct DevFloor {
   float maxover, maxunder, maxerr, twofitweight, twofitatten;
   int postlist[VB200_MAX_POSTS], sorted[VB200_MAX_POSTS], forward[VB200_MAX_POSTS], reverse[VB200_MAX_POSTS];
   int lonb[VB200_MAX_POSTS], hinb[VB200_MAX_POSTS];
+  /* posts 2.. grouped by their depth in the neighbour tree (a post's prediction reads only posts of lower levels):
+     lv_order[lv_start[l] .. lv_start[l+1]) are the posts of level l = 1..nlevels (setup.cu) */
+  int lv_order[VB200_MAX_POSTS], lv_start[VB200_MAX_POSTS + 2], nlevels;
   /* emission tables (vorbis_info_floor1, backends.h:60-70) for the device bit packer */
   int partitions, partclass[31], class_dim[16], class_subs[16], class_book[16], class_subbook[16 * 8];
 };
