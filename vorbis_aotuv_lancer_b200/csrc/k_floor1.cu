@@ -274,16 +274,23 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     __syncwarp();
   }
   __syncwarp();
-  if (lane == 0) {
-    out[0] = pick(sm.A, sm.B, 0);
-    out[1] = pick(sm.A, sm.B, 1);
-    for (int i = 2; i < posts; i++) {
-      const int ln = F.lonb[i - 2], hn = F.hinb[i - 2];
-      const int pred = point_at(F.postlist[ln], F.postlist[hn], out[ln], out[hn], F.postlist[i]);
-      const int vx = pick(sm.A, sm.B, i);
-      out[i] = (vx >= 0 && pred != vx) ? vx : (pred | 0x8000);
+  /* final posts (floor1.c:728-747): predictions level by level over the neighbour tree, as in k_floor_encode */
+  {
+    unsigned short *o16 = reinterpret_cast<unsigned short *>(sm.lo);      /* lo/hi are dead now */
+    if (lane < 2) { const int v = pick(sm.A, sm.B, lane); o16[lane] = (unsigned short)v; out[lane] = v; }
+    __syncwarp();
+    for (int l = 1; l <= F.nlevels; l++) {
+      for (int k = F.lv_start[l] + lane; k < F.lv_start[l + 1]; k += 32) {
+        const int i = F.lv_order[k];
+        const int ln = F.lonb[i - 2], hn = F.hinb[i - 2];
+        const int pred = point_at(F.postlist[ln], F.postlist[hn], o16[ln], o16[hn], F.postlist[i]);
+        const int vx = pick(sm.A, sm.B, i);
+        const int v = (vx >= 0 && pred != vx) ? vx : (pred | 0x8000);
+        o16[i] = (unsigned short)v; out[i] = v;
+      }
+      __syncwarp();
     }
-    fitted[item] = 1;
+    if (lane == 0) fitted[item] = 1;
   }
 }
 
