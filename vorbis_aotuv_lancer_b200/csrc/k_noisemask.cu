@@ -23,7 +23,6 @@ template <int N>
 struct NoiseSmem {
   float sums[5][N + 4];   /* N, X, XX, Y, XY prefix sums; +4 keeps the rows 16-byte aligned and the five chain
                              lanes (one 128-bit access each) on different banks */
-  float work[N];
   float noise[N];
   __device__ float *tmp() { return sums[1]; }      /* scratch of the M7 tone fix; the prefix sums are dead by then */
   __device__ float *inm() { return sums[2]; }
@@ -112,7 +111,7 @@ __device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f
   }
 }
 
-/* aoTuV M7 (psy.c:3645-3768) on sm.work; short blocks: peak-driven, transition blocks: 8-bin groups.
+/* aoTuV M7 (psy.c:3645-3768) on the staged work vector; short blocks: peak-driven, transition blocks: 8-bin groups.
    Data-dependent and tiny: lane 0 walks it. */
 template <int N>
 __device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restrict__ spec, int block_mode) {
@@ -120,7 +119,7 @@ __device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restr
   if (!nx) return;
   const float *off1 = P.noiseoffset + N;
   const float limit = fabsf(__ldg(off1));
-  float *noise = sm.work;
+  float *noise = sm.sums[3];             /* logmdct - noise fit, staged here by the kernel for this pass */
   float *tmp_ = sm.tmp(), *inm_ = sm.inm();
   constexpr int SCR = N < 256 ? N : 256;
   for (int i = 0; i < SCR; i++) { tmp_[i] = 0.f; inm_[i] = 0.f; }
@@ -175,7 +174,7 @@ __device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restr
 }
 
 template <int N, int T>
-__global__ void __launch_bounds__(T, (T >= 128 ? 7 : 1))
+__global__ void __launch_bounds__(T, (T >= 256 ? 8 : (T >= 128 ? 7 : 1)))
 k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const int *__restrict__ block_mode,
             const float *__restrict__ lowcomp, const float *__restrict__ postev,
             const float *__restrict__ logmdct, LastRef last,
@@ -190,20 +189,26 @@ k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const 
   const int part = P.partition;
 
   /* this thread's bins tid + q*T: logmdct (and, for M9, lastmdct) are read once and stay in registers */
-  float lmr[N / T], lastr[N / T];
+  float lmr[N / T], wk[N / T];
 #pragma unroll
   for (int q = 0; q < N / T; q++) lmr[q] = __ldg(lm + tid + q * T);
   const bool m9 = mode > 1;
-#pragma unroll
-  for (int q = 0; q < N / T; q++) lastr[q] = (m9 && tid + q * T < P.tonecomp_endp) ? last.at(item, tid + q * T) : 0.f;
 
+  /* wk: logmdct minus the first fit, then logmdct minus that -- thread-owned like the bins, so it never needs shared
+     memory (24.6 KB per CTA instead of 28.7: 8 CTAs per SM) */
   noise_fit<N, T>(sm, P, [&](int q, int) { return lmr[q]; }, 140.f, -1,
-                  [&](int q, int i, float nv) { sm.work[i] = __fsub_rn(lmr[q], nv); });
-  noise_fit<N, T>(sm, P, [&](int, int i) { return sm.work[i]; }, 0.f, P.noisewindowfixed,
-                  [&](int q, int i, float nv) { sm.noise[i] = nv; sm.work[i] = __fsub_rn(lmr[q], sm.work[i]); });
-  if (mode <= 2 && P.tonefix_end) {
+                  [&](int q, int, float nv) { wk[q] = __fsub_rn(lmr[q], nv); });
+  noise_fit<N, T>(sm, P, [&](int q, int) { return wk[q]; }, 0.f, P.noisewindowfixed,
+                  [&](int q, int i, float nv) { sm.noise[i] = nv; wk[q] = __fsub_rn(lmr[q], wk[q]); });
+  if (mode <= 2 && P.tonefix_end) {        /* uniform per CTA; rare for long blocks (transitions only) */
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < N / T; q++) sm.sums[3][tid + q * T] = wk[q];
     __syncthreads();
     if (tid == 0) tone_fix<N>(sm, P, lm, mode);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < N / T; q++) wk[q] = sm.sums[3][tid + q * T];
   }
   __syncthreads();                     /* the prefix sums are dead: their rows are reused below */
 
@@ -218,13 +223,17 @@ k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const 
     int dB = (int)((double)sm.noise[i] + .5);
     if (dB >= VB200_COMPAND_LEVELS) dB = VB200_COMPAND_LEVELS - 1;
     if (dB < 0) dB = 0;
-    const float w = sm.work[i], c = P.compand[dB];
+    const float w = wk[q], c = P.compand[dB];
     ep[i] = __fadd_rn(w, (float)S->stn_compand[dB]);
     float v = __fadd_rn(w, c);
     if (level > 0.f && i < P.n33p) v = __fsub_rn(v, __fmul_rn(__fsub_rn(c, P.compand_hi[dB]), level));
     sm.noise[i] = v;
     npad[i + (i >> 5)] = v; lpad[i + (i >> 5)] = lmr[q];
   }
+  /* lastmdct for M9: requested here, consumed after the per-partition pass */
+  float lastr[N / T];
+#pragma unroll
+  for (int q = 0; q < N / T; q++) lastr[q] = (m9 && tid + q * T < P.tonecomp_endp) ? last.at(item, tid + q * T) : 0.f;
   __syncthreads();
 
   /* per-partition work: M2 post-echo cut then M8 npeak (psy.c:4025-4063); one lane per partition */
