@@ -83,7 +83,7 @@ __device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f
       acc = __fadd_rn(acc, v.z); v.z = acc; acc = __fadd_rn(acc, v.w); v.w = acc;
     };
     float4 a0 = r[0], a1 = r[1];
-#pragma unroll 1
+#pragma unroll 2
     for (int i = 0; i < N / 4; i += 4) {      /* two register sets: the next 8 values arrive while 8 are summed */
       float4 b0 = r[i + 2], b1 = r[i + 3];
       run4(a0); r[i] = a0; run4(a1); r[i + 1] = a1;
