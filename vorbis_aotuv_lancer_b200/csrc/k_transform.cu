@@ -103,23 +103,22 @@ k_transform(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm
   const float *src = pcm + (pcm_off ? pcm_off[item] : (long long)item * N);
 
   const float2 *ptw = S->fft_pass_tw[W]; const int r2off = S->fft_r2_off[W];
-  /* ---- stage the block ---- */
-  if ((((uintptr_t)src) & 15) == 0) {
-    for (int i = tid; i < N / 4; i += THREADS) reinterpret_cast<float4 *>(x)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
-  } else {
-    for (int i = tid; i < N; i += THREADS) x[i] = __ldg(src + i);
-  }
-  __syncthreads();
+  /* ---- window geometry (window.c:2137-2261): every boundary is a multiple of 4 samples ---- */
+  const int lW = W ? lWv[item] : 0, nW = W ? nWv[item] : 0;
+  const int ln = S->bs[lW], rn = S->bs[nW];
+  const float *wl = S->win[lW], *wr = S->win[nW];
+  const int leftbegin = N / 4 - ln / 4, leftend = leftbegin + ln / 2;
+  const int rightbegin = N / 2 + N / 4 - rn / 4, rightend = rightbegin + rn / 2;
 
-  /* ---- aoTuV M2 post-echo detector on the un-windowed PCM (psy.c:619-648) ---- */
+  /* ---- aoTuV M2 post-echo detector on the un-windowed PCM (psy.c:619-648), read straight from the timeline ---- */
   if (poste) {
     float ret = -1.f;
     const int mode = block_mode[item], lwm = lW_block_mode[item];
     if (mode == 2 && lwm == 0 && N >= 2048) {   /* uniform per CTA */
       const int sn = N >> 2, mn = sn + sn, en = sn + (N >> 1);
       double up = 0., un = 0.;
-      for (int i = sn + tid; i < mn; i += THREADS) up += (double)fabsf(x[i]);
-      for (int i = mn + tid; i < en; i += THREADS) un += (double)fabsf(x[i]);
+      for (int i = sn + tid; i < mn; i += THREADS) up += (double)fabsf(__ldg(src + i));
+      for (int i = mn + tid; i < en; i += THREADS) un += (double)fabsf(__ldg(src + i));
       up = warp_sum_d(up); un = warp_sum_d(un);
       if ((tid & 31) == 0) { red[0][tid >> 5] = up; red[1][tid >> 5] = un; }
       __syncthreads();
@@ -135,15 +134,25 @@ k_transform(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm
     } else if (tid == 0) poste[item] = ret;
   }
 
-  /* ---- window (window.c:2137-2261) ---- */
-  {
-    const int lW = W ? lWv[item] : 0, nW = W ? nWv[item] : 0;
-    const int ln = S->bs[lW], rn = S->bs[nW];
-    const float *wl = S->win[lW], *wr = S->win[nW];
-    const int leftbegin = N / 4 - ln / 4, leftend = leftbegin + ln / 2;
-    const int rightbegin = N / 2 + N / 4 - rn / 4, rightend = rightbegin + rn / 2;
+  /* ---- stage the block, windowed on the way in: float4 of PCM x float4 of the window table ---- */
+  if ((((uintptr_t)src) & 15) == 0) {
+    for (int c = tid; c < N / 4; c += THREADS) {
+      const int i = c * 4;
+      float4 v = __ldg(reinterpret_cast<const float4 *>(src) + c);
+      if (i < leftbegin || i >= rightend) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      else if (i < leftend) {
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(wl + (i - leftbegin)));
+        v.x = __fmul_rn(v.x, w.x); v.y = __fmul_rn(v.y, w.y); v.z = __fmul_rn(v.z, w.z); v.w = __fmul_rn(v.w, w.w);
+      } else if (i >= rightbegin) {
+        /* the falling half reads the table backwards: sample i+k takes wr[rn/2-1-(i-rightbegin)-k] */
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(wr + (rn / 2 - 4 - (i - rightbegin))));
+        v.x = __fmul_rn(v.x, w.w); v.y = __fmul_rn(v.y, w.z); v.z = __fmul_rn(v.z, w.y); v.w = __fmul_rn(v.w, w.x);
+      }
+      reinterpret_cast<float4 *>(x)[c] = v;
+    }
+  } else {
     for (int i = tid; i < N; i += THREADS) {
-      float v = x[i];
+      float v = __ldg(src + i);
       if (i < leftbegin) v = 0.f;
       else if (i < leftend) v = __fmul_rn(v, __ldg(wl + (i - leftbegin)));
       else if (i >= rightend) v = 0.f;
@@ -190,9 +199,8 @@ k_transform(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm
 
   /* ---- real FFT of the same windowed block via an N2-point complex FFT ---- */
   {
-    for (int m = tid; m < N2; m += THREADS) bufA[m] = make_float2(x[2 * m], x[2 * m + 1]);
-    __syncthreads();
-    float2 *Z = cta_fft<N2, THREADS>(bufA, bufB, ptw, r2off);
+    /* the windowed block read as N2 complex numbers IS the transform's input: no copy, x is the ping buffer */
+    float2 *Z = cta_fft<N2, THREADS>(reinterpret_cast<float2 *>(x), bufA, ptw, r2off);
     const float2 *rt = S->rfft_tw[W];
     const float scale = 4.f / N;
     const float scale_dB = todB_p345(scale);
