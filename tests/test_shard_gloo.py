@@ -62,3 +62,17 @@ def test_two_ranks_cover_all_streams_once():
     for i in range(n_streams):
         blocks, timeline = segment.segment_stream(s, refdata.synth(2, 44100, 1.0, seed=100 + i), stream_index=i)
         assert merged[i] == (len(blocks), int(sum(b.W for b in blocks)), float(np.abs(timeline).sum()))
+
+
+def test_encoder_stream_groups_cover_every_stream_once():
+    """Host logic of Encoder.encode: the ramped stream groups (1, 2, 4, 8, then equal shares) partition the streams."""
+    from vorbis_aotuv_lancer_b200 import encoder
+    for n in (1, 2, 3, 7, 8, 16, 63, 64, 65, 1024):
+        for chunks in (1, 2, 6, 8, 11):
+            groups = encoder.group_cuts(n, encoder.group_weights(chunks))
+            assert groups[0][0] == 0 and groups[-1][1] == n
+            assert all(a < b for a, b in groups)
+            assert all(x[1] == y[0] for x, y in zip(groups[:-1], groups[1:]))
+            assert len(groups) == min(chunks, n)
+    sizes = [b - a for a, b in encoder.group_cuts(64, encoder.group_weights(8))]
+    assert sizes[0] == 1 and sizes == sorted(sizes[:4]) + sizes[4:] and max(sizes) <= 14

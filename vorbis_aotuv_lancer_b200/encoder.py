@@ -93,6 +93,25 @@ class Segmenter:
         return np.ctypeslib.as_array(L.vb200_segmenter_host_pcm(self.h), shape=(elems,))
 
 
+def group_weights(chunks):
+    """Relative sizes of the stream groups one encode() call pipelines: 1, 2, 4, 8, then equal shares."""
+    return [min(2.0 ** g, 12.0) for g in range(max(1, int(chunks)))]
+
+
+def group_cuts(n, weights):
+    """Split streams 0..n-1 into consecutive groups with sizes proportional to `weights` (every group non-empty;
+    fewer groups than weights when there are fewer streams).  -> [(first, last+1)]"""
+    k = min(len(weights), n)
+    w = list(weights[:k])
+    acc, cuts = 0.0, [0]
+    for g in range(k):
+        acc += w[g]
+        cuts.append(max(cuts[-1] + 1, min(n - (k - 1 - g), int(round(n * acc / sum(w))))))
+    if k:
+        cuts[-1] = n
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+
 class Encoder:
     """PCM of many independent streams in, packets out.  The streams are processed in `chunks` groups, each with
     its own segmenter and batch (own CUDA streams): while the kernels of group g run, the host segments group
@@ -105,7 +124,7 @@ class Encoder:
         # group sizes ramp up (1, 2, 4, 8, then equal shares): the device gets its first work after one stream's upload
         # and never starves while the rest arrives; 25 % slack for uneven stream lengths
         env = os.environ.get("VB200_GROUP_WEIGHTS")
-        self.weights = [float(x) for x in env.split(",")] if env else [min(2.0 ** g, 12.0) for g in range(self.chunks)]
+        self.weights = [float(x) for x in env.split(",")] if env else group_weights(self.chunks)
         self.chunks = len(self.weights)
         per = int(1.25 * int(max_blocks) * max(self.weights) / sum(self.weights)) + 64 if self.chunks > 1 else int(max_blocks)
         self.batches = [ops.Batch(setup, per) for _ in range(self.chunks)]
@@ -149,14 +168,7 @@ class Encoder:
         own = streams is None
         if own:
             streams = [ops.Stream(self.setup) for _ in pcms]
-        k = min(self.chunks, n)
-        w = self.weights[:k]
-        acc, cuts = 0.0, [0]
-        for g in range(k):
-            acc += w[g]
-            cuts.append(max(cuts[-1] + 1, min(n - (k - 1 - g), int(round(n * acc / sum(w))))))
-        cuts[-1] = n
-        groups = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        groups = group_cuts(n, self.weights)
         trace = os.environ.get("VB200_TRACE")
         t0 = time.perf_counter()
         marks = []
