@@ -113,6 +113,40 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
   const int pd_mask = (R.phrase_dim & (R.phrase_dim - 1)) == 0 ? R.phrase_dim - 1 : -1;
   __syncthreads();
 
+  /* ---- emission order: symbols per (stage, partition, row) slot and their scan.  The counts depend only on the
+     partition classes, so warp 0 lays the offsets out BEFORE the cascade and then joins it (the partitions are drawn
+     from a counter, so its late start balances out); slots are walked stage by stage so that no index has to be split
+     by division. ---- */
+  const int pd = R.phrase_dim;
+  const int prow = partvals * rows;
+  const int nslots = stages * prow;
+  const int phrase_entries = books[R.groupbook].entries;
+  auto phrase_val = [&](int r2, int p) {
+    int val = pw[r2 * partvals + p];
+    for (int k = 1; k < pd; k++) { val *= R.partitions; if (p + k < partvals) val += pw[r2 * partvals + p + k]; }
+    return val;
+  };
+  if (warp == 0) {
+    int carry = 0;
+    for (int s = 0; s < stages; s++)
+      for (int b0 = 0; b0 < prow; b0 += 32) {
+        const int pr = b0 + lane;
+        int tot = 0;
+        if (pr < prow) {
+          const int p = rows == 1 ? pr : pr / rows, row = rows == 1 ? 0 : pr % rows;
+          tot = tab_nvec[pw[row * partvals + p] * 8 + s];
+          if (s == 0 && row == 0 && (pd_mask >= 0 ? (p & pd_mask) == 0 : (p % pd) == 0))
+            for (int r2 = 0; r2 < rows; r2++) if (phrase_val(r2, p) < phrase_entries) tot++;   /* phrase words lead the group */
+        }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += y; }
+        if (pr < prow) offs[s * prow + pr] = carry + incl - tot;
+        carry += __shfl_sync(FULLMASK, incl, 31);
+      }
+    if (lane == 0) { offs[nslots] = carry; nsyms[blk] = carry < max_syms ? carry : max_syms; }
+  }
+
   /* ---- pass 1: cascade VQ per (partition,row).  A partition holds G/dim <= 16 vectors (often 4 or 8), so a warp
      works on RF_SLOTS partitions at once, RF_LP lanes each; the stage loop is shared, the books differ per slot ---- */
   const int slot = lane / RF_LP, l = lane % RF_LP;
@@ -217,39 +251,7 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
   }
   __syncthreads();
 
-  /* ---- pass 2: emission order.  Count symbols per (stage, partition, row), scan, scatter.  Slots are walked
-     stage by stage so that no index has to be split by division. ---- */
-  const int pd = R.phrase_dim;
-  const int prow = partvals * rows;
-  const int nslots = stages * prow;
-  const int phrase_entries = books[R.groupbook].entries;
-  auto phrase_val = [&](int r2, int p) {
-    int val = pw[r2 * partvals + p];
-    for (int k = 1; k < pd; k++) { val *= R.partitions; if (p + k < partvals) val += pw[r2 * partvals + p + k]; }
-    return val;
-  };
-  if (warp == 0) {
-    int carry = 0;
-    for (int s = 0; s < stages; s++)
-      for (int b0 = 0; b0 < prow; b0 += 32) {
-        const int pr = b0 + lane;
-        int tot = 0;
-        if (pr < prow) {
-          const int p = rows == 1 ? pr : pr / rows, row = rows == 1 ? 0 : pr % rows;
-          tot = tab_nvec[pw[row * partvals + p] * 8 + s];
-          if (s == 0 && row == 0 && (pd_mask >= 0 ? (p & pd_mask) == 0 : (p % pd) == 0))
-            for (int r2 = 0; r2 < rows; r2++) if (phrase_val(r2, p) < phrase_entries) tot++;   /* phrase words lead the group */
-        }
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += y; }
-        if (pr < prow) offs[s * prow + pr] = carry + incl - tot;
-        carry += __shfl_sync(FULLMASK, incl, 31);
-      }
-    if (lane == 0) { offs[nslots] = carry; nsyms[blk] = carry < max_syms ? carry : max_syms; }
-  }
-  __syncthreads();
-  /* scatter: one thread per (stage, partition, row) slot -- most slots hold nothing (the class has no book at that
+  /* ---- pass 2: scatter in emission order, one thread per (stage, partition, row) slot -- most slots hold nothing (the class has no book at that
      stage) and the others 4..16 symbols, too few to give a warp */
   int *out = syms + (size_t)blk * max_syms * 2;
   for (int sl = tid; sl < nslots; sl += RF_WARPS * 32) {
