@@ -24,6 +24,7 @@ struct CoupleSmem {
   int flag[CH][32];
   int out[CH][32];
   int cand[32];
+  __align__(16) float dsum[32];
 };
 
 /* the next partition's inputs are fetched with asynchronous global->shared copies while the current one is
@@ -225,8 +226,23 @@ k_couple(const DevSetup *__restrict__ S, int W, const int *__restrict__ psyv, in
         const int rp = __popc(__ballot_sync(FULLMASK, act && opp));
         const int ap = __popc(am);
         const float d = act ? fabsf(__fsub_rn(fabsf(sm.res[Mi][j]), fabsf(sm.res[Ai][j]))) : 0.f;
+        /* sum of d over the active bins, in bin order (float: the order is part of the result).  d is +0 on the other
+           lanes and the running sum is never negative, so with many active bins the sum simply runs over all 32
+           lanes out of shared memory (8 vector loads + 32 adds) instead of one ffs/shuffle/add round per active bin */
         float def = 0.f;
-        for (unsigned m = am; m; m &= m - 1) def = __fadd_rn(def, __shfl_sync(FULLMASK, d, __ffs(m) - 1));
+        if (ap > 8) {
+          sm.dsum[j] = d;
+          __syncwarp();
+          const float4 *q4 = reinterpret_cast<const float4 *>(sm.dsum);
+#pragma unroll
+          for (int t = 0; t < 8; t++) {
+            const float4 v = q4[t];
+            def = __fadd_rn(def, v.x); def = __fadd_rn(def, v.y); def = __fadd_rn(def, v.z); def = __fadd_rn(def, v.w);
+          }
+          __syncwarp();
+        } else {
+          for (unsigned m = am; m; m &= m - 1) def = __fadd_rn(def, __shfl_sync(FULLMASK, d, __ffs(m) - 1));
+        }
         if (ap != 0) {
           const float cur = __fdiv_rn(def, (float)ap);
           def = cur;
