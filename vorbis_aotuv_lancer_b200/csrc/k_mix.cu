@@ -133,6 +133,7 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
       int local_gate = 0;
 
       for (int i = tid; i < N; i += T) {
+        const float md_in = (sel == 1) ? md[i] : 0.f;      /* M1 scales it at the end of the iteration: request it now */
         float val = __fadd_rn(__ldg(nz + i), __ldg(noff + i));
         float tval = __fadd_rn(__ldg(tn + i), toneatt);
         const float l = __ldg(lm + i);
@@ -186,7 +187,7 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
           float de;
           if (v > coeffi) { de = (float)(1.0 - ((double)__fsub_rn(v, coeffi) * 0.005 * (double)P.m_val)); if (de < 0.f) de = (float)0.0001; }
           else de = (float)(1.0 - ((double)__fsub_rn(v, coeffi) * 0.0003 * (double)P.m_val));
-          md[i] = __fmul_rn(md[i], de);
+          md[i] = __fmul_rn(md_in, de);
           if (nsel > 1 && dbq(out) && __fadd_rn(l, S->flr[floor_index >= 0 ? floor_index : S->floor_of_ch[W][item % ch]].twofitatten) >= out) local_gate = 1;
         }
       }
