@@ -165,13 +165,23 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
     const int off = p * G + R.begin;
     /* stage the partition: res2 reads the channel-interleaved vector work[j*ch+c]=in[c][j] (res0.c:782-787) */
     if (valid)
-      for (int t = l; t < G; t += RF_LP) {
-        if (R.type == 2) {
-          const int w = off + t;
-          const int wc = ch_shift >= 0 ? (w & (ch - 1)) : w % ch, wj = ch_shift >= 0 ? (w >> ch_shift) : w / ch;
-          v[t] = base[(size_t)chlist[wc] * n + wj];
+      for (int t0 = l; t0 < G; t0 += 4 * RF_LP) {          /* four loads in flight per lane, then the stores */
+        int tmp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int t = t0 + u * RF_LP;
+          tmp[u] = 0;
+          if (t < G) {
+            if (R.type == 2) {
+              const int w = off + t;
+              const int wc = ch_shift >= 0 ? (w & (ch - 1)) : w % ch, wj = ch_shift >= 0 ? (w >> ch_shift) : w / ch;
+              tmp[u] = base[(size_t)chlist[wc] * n + wj];
+            }
+            else tmp[u] = base[(size_t)rowch[row] * n + off + t];
+          }
         }
-        else v[t] = base[(size_t)rowch[row] * n + off + t];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int t = t0 + u * RF_LP; if (t < G) v[t] = tmp[u]; }
       }
     __syncwarp();
     for (int s = 0; s < stages; s++) {
