@@ -32,7 +32,7 @@ template <int MODE> __device__ __forceinline__ int swz(int i) {
   if (MODE == 2) return i ^ (((i >> 4) & 3) << 2);
   return i;
 }
-template <int M, int THREADS, int Ns, int RD, int WR>
+template <int M, int THREADS, int Ns, int RD, int WR, bool SYNC = true>
 __device__ __forceinline__ void fft_pass4(const float2 *a, float2 *b, const float2 *__restrict__ ptw) {
   for (int j = threadIdx.x; j < M / 4; j += THREADS) {
     const int k = j & (Ns - 1);
@@ -52,39 +52,40 @@ __device__ __forceinline__ void fft_pass4(const float2 *a, float2 *b, const floa
     b[swz<WR>(o + 2 * Ns)] = make_float2(s02.x - s13.x, s02.y - s13.y);
     b[swz<WR>(o + 3 * Ns)] = make_float2(d02.x - d13.y, d02.y + d13.x);      /* d02 + i*d13 */
   }
-  __syncthreads();
+  if (SYNC) __syncthreads();
 }
-/* M-point complex FFT, forward (exp(-i...)), data in `a`, scratch `b`.  Stockham autosort, radix-4 passes (plus one
-   radix-2 pass when log2 M is odd): a pass reads a[j + r*M/4], multiplies by w^r, w = exp(-2*pi*i*k/(4*Ns)),
-   k = j mod Ns, and writes the 4-point DFT to b[4(j-k) + k + q*Ns].  Returns the buffer holding the result. */
+/* the radix-2 pass that ends a transform whose log2 is odd (Ns == M/2), no barrier */
 template <int M, int THREADS>
-__device__ __forceinline__ float2 *cta_fft(float2 *a, float2 *b, const float2 *__restrict__ ptw, int r2off) {
-  static_assert(M >= 32 && M <= 1024, "sizes of the 256/2048 block pair");
-  fft_pass4<M, THREADS, 1, 0, 1>(a, b, ptw);
-  fft_pass4<M, THREADS, 4, 1, 2>(b, a, ptw);
-  int Ns = 16;
-  if (M >= 64) {
-    fft_pass4<M, THREADS, 16, 2, 0>(a, b, ptw);
-    { float2 *tmp = a; a = b; b = tmp; }
-    Ns = 64;
-    if (M >= 256) { fft_pass4<M, THREADS, 64, 0, 0>(a, b, ptw); float2 *tmp = a; a = b; b = tmp; Ns = 256; }
-    if (M >= 1024) { fft_pass4<M, THREADS, 256, 0, 0>(a, b, ptw); float2 *tmp = a; a = b; b = tmp; Ns = 1024; }
+__device__ __forceinline__ void fft_pass2(const float2 *a, float2 *b, const float2 *__restrict__ ptw, int r2off) {
+  for (int j = threadIdx.x; j < M / 2; j += THREADS) {
+    const float2 w = __ldg(ptw + r2off + j);      /* exp(-2*pi*i*j/M) */
+    const float2 u = a[j], t = cmulf(a[j + M / 2], w);
+    b[j] = make_float2(u.x + t.x, u.y + t.y);
+    b[j + M / 2] = make_float2(u.x - t.x, u.y - t.y);
   }
-  if (Ns < M) {                              /* one radix-2 pass left: Ns == M/2 */
-    for (int j = threadIdx.x; j < M / 2; j += THREADS) {
-      const float2 w = __ldg(ptw + r2off + j);      /* exp(-2*pi*i*j/M) */
-      float2 u, t;
-      if (M == 32) { u = a[swz<2>(j)]; t = cmulf(a[swz<2>(j + M / 2)], w); }       /* straight after the Ns = 4 pass */
-      else { u = a[j]; t = cmulf(a[j + M / 2], w); }
-      b[j] = make_float2(u.x + t.x, u.y + t.y);
-      b[j + M / 2] = make_float2(u.x - t.x, u.y - t.y);
-    }
-    __syncthreads();
-    float2 *tmp = a; a = b; b = tmp;
-  }
-  return a;
 }
-
+/* Both transforms of a block, pass by pass between the same barriers: the N/4-point one of the MDCT (h0 <-> h1) and
+   the N/2-point one of the real FFT (xa <-> xb).  They are independent, have the same number of passes for n = 2048
+   (4 x radix-4 + radix-2, 5 x radix-4) and one pass apart for n = 256; sharing the barriers halves their number and
+   gives the threads the smaller transform leaves idle something to do.  Results: MDCT in h1; real FFT in xb (n = 2048)
+   or xa (n = 256). */
+template <int N, int THREADS>
+__device__ __forceinline__ void cta_fft_pair(float2 *h0, float2 *h1, float2 *xa, float2 *xb, const float2 *__restrict__ ptw, int r2off) {
+  constexpr int M1 = N / 4, M2 = N / 2;
+  static_assert(N == 2048 || N == 256, "block sizes of the built path");
+  fft_pass4<M1, THREADS, 1, 0, 1, false>(h0, h1, ptw); fft_pass4<M2, THREADS, 1, 0, 1, false>(xa, xb, ptw); __syncthreads();
+  fft_pass4<M1, THREADS, 4, 1, 2, false>(h1, h0, ptw); fft_pass4<M2, THREADS, 4, 1, 2, false>(xb, xa, ptw); __syncthreads();
+  fft_pass4<M1, THREADS, 16, 2, 0, false>(h0, h1, ptw); fft_pass4<M2, THREADS, 16, 2, 0, false>(xa, xb, ptw); __syncthreads();
+  if (N == 2048) {
+    fft_pass4<M1, THREADS, 64, 0, 0, false>(h1, h0, ptw); fft_pass4<M2, THREADS, 64, 0, 0, false>(xb, xa, ptw); __syncthreads();
+    fft_pass2<M1, THREADS>(h0, h1, ptw, r2off); fft_pass4<M2, THREADS, 256, 0, 0, false>(xa, xb, ptw); __syncthreads();
+  } else {
+    fft_pass2<M2, THREADS>(xb, xa, ptw, r2off); __syncthreads();
+  }
+}
+/* Complex FFTs, forward (exp(-i...)): Stockham autosort, radix-4 passes (plus one radix-2 pass when log2 M is odd).  A
+   radix-4 pass reads a[j + r*M/4], multiplies by w^r, w = exp(-2*pi*i*k/(4*Ns)), k = j mod Ns, and writes the 4-point
+   DFT to b[4(j-k) + k + q*Ns]. */
 template <int N, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_transform(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm, const long long *__restrict__ pcm_off,
@@ -162,47 +163,38 @@ k_transform(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm
   }
   __syncthreads();
 
-  /* ---- MDCT: fold to N2 reals, pre-twiddle to N4 complex, FFT, post-twiddle ---- */
-  {
-    const float2 *tw = S->mdct_tw[W];
-    for (int m = tid; m < N4; m += THREADS) {
-      /* u[i] = -x[3N2/2-1-i]-x[3N2/2+i]  (i<N2/2);  x[i-N2/2]-x[3N2/2-1-i]  (i>=N2/2) */
-      const int i0 = 2 * m, i1 = N2 - 1 - 2 * m;
-      float u0, u1;
-      if (i0 < N2 / 2) u0 = -x[3 * N2 / 2 - 1 - i0] - x[3 * N2 / 2 + i0];
-      else u0 = x[i0 - N2 / 2] - x[3 * N2 / 2 - 1 - i0];
-      if (i1 < N2 / 2) u1 = -x[3 * N2 / 2 - 1 - i1] - x[3 * N2 / 2 + i1];
-      else u1 = x[i1 - N2 / 2] - x[3 * N2 / 2 - 1 - i1];
-      float2 t = __ldg(tw + m);
-      bufA[m] = make_float2(u0 * t.x - u1 * t.y, u0 * t.y + u1 * t.x);
-    }
-    __syncthreads();
-    float2 *Z = cta_fft<N4, THREADS>(bufA, bufB, ptw, r2off);
-    const float scale = 4.f / N;
-    float *gm = gmdct + (size_t)item * N2, *lm = logmdct + (size_t)item * N2;
-    float2 *Y = (Z == bufA) ? bufB : bufA;   /* stage the interleaved result for coalesced stores */
-    float *out = reinterpret_cast<float *>(Y);
-    for (int k = tid; k < N4; k += THREADS) {
-      float2 t = __ldg(tw + k), z = Z[k];
-      float yr = z.x * t.x - z.y * t.y, yi = z.x * t.y + z.y * t.x;
-      out[2 * k] = yr * scale;
-      out[N2 - 1 - 2 * k] = -yi * scale;
-    }
-    __syncthreads();
-    for (int i = tid; i < N2; i += THREADS) {
-      float v = out[i];
-      gm[i] = v;
-      lm[i] = todB_p345(v);
-    }
-    __syncthreads();
+  /* ---- MDCT: fold to N2 reals, pre-twiddle to N4 complex (into the first half of bufB) ---- */
+  float2 *h0 = bufB, *h1 = bufB + N4;
+  float2 *xa = reinterpret_cast<float2 *>(x), *xb = bufA;      /* the windowed block read as N2 complex numbers IS the
+                                                                  real FFT's input: no copy, x is its ping buffer */
+  const float2 *tw = S->mdct_tw[W];
+  for (int m = tid; m < N4; m += THREADS) {
+    /* u[i] = -x[3N2/2-1-i]-x[3N2/2+i]  (i<N2/2);  x[i-N2/2]-x[3N2/2-1-i]  (i>=N2/2) */
+    const int i0 = 2 * m, i1 = N2 - 1 - 2 * m;
+    float u0, u1;
+    if (i0 < N2 / 2) u0 = -x[3 * N2 / 2 - 1 - i0] - x[3 * N2 / 2 + i0];
+    else u0 = x[i0 - N2 / 2] - x[3 * N2 / 2 - 1 - i0];
+    if (i1 < N2 / 2) u1 = -x[3 * N2 / 2 - 1 - i1] - x[3 * N2 / 2 + i1];
+    else u1 = x[i1 - N2 / 2] - x[3 * N2 / 2 - 1 - i1];
+    float2 t = __ldg(tw + m);
+    h0[m] = make_float2(u0 * t.x - u1 * t.y, u0 * t.y + u1 * t.x);
   }
-
-  /* ---- real FFT of the same windowed block via an N2-point complex FFT ---- */
+  __syncthreads();
+  /* ---- both transforms, pass by pass ---- */
+  cta_fft_pair<N, THREADS>(h0, h1, xa, xb, ptw, r2off);
+  const float scale = 4.f / N;
+  /* ---- MDCT post-twiddle: h1 -> interleaved result staged in h0 for coalesced stores ---- */
+  float *out = reinterpret_cast<float *>(h0);
+  for (int k = tid; k < N4; k += THREADS) {
+    float2 t = __ldg(tw + k), z = h1[k];
+    float yr = z.x * t.x - z.y * t.y, yi = z.x * t.y + z.y * t.x;
+    out[2 * k] = yr * scale;
+    out[N2 - 1 - 2 * k] = -yi * scale;
+  }
+  /* ---- real FFT: split of the N2-point complex transform, dB spectrum, block maximum ---- */
   {
-    /* the windowed block read as N2 complex numbers IS the transform's input: no copy, x is the ping buffer */
-    float2 *Z = cta_fft<N2, THREADS>(reinterpret_cast<float2 *>(x), bufA, ptw, r2off);
+    const float2 *Z = (N == 2048) ? xb : xa;
     const float2 *rt = S->rfft_tw[W];
-    const float scale = 4.f / N;
     const float scale_dB = todB_p345(scale);
     float *lf = logfft + (size_t)item * N2;
     float mx = -3.0e38f;
@@ -228,7 +220,15 @@ k_transform(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm
     }
     mx = warp_max_f(mx);
     if ((tid & 31) == 0) redf[tid >> 5] = mx;
-    __syncthreads();
+  }
+  __syncthreads();                     /* the staged MDCT result and the warp maxima are complete */
+  {
+    float *gm = gmdct + (size_t)item * N2, *lm = logmdct + (size_t)item * N2;
+    for (int i = tid; i < N2; i += THREADS) {
+      float v = out[i];
+      gm[i] = v;
+      lm[i] = todB_p345(v);
+    }
     if (tid == 0) {
       float m = redf[0];
       for (int w = 1; w < THREADS / 32; w++) m = fmaxf(m, redf[w]);
