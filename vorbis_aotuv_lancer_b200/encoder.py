@@ -136,6 +136,7 @@ class Encoder:
         self.batch = self.batches[0]
         self.segmenter = self.segmenters[0]
         self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.begin_pool = ThreadPoolExecutor(max_workers=1)      # one thread: the groups' uploads must be queued in order
 
     def close(self):
         for b in self.batches:
@@ -143,6 +144,7 @@ class Encoder:
         for g in self.segmenters:
             g.close()
         self.pool.shutdown()
+        self.begin_pool.shutdown()
 
     def segment(self, pcms):
         """Host-only segmentation: list of float32 [channels, nsamples] -> (Block array, one timeline buffer, counts)."""
@@ -172,9 +174,12 @@ class Encoder:
         trace = os.environ.get("VB200_TRACE")
         t0 = time.perf_counter()
         marks = []
-        for g, (a, b) in enumerate(groups):            # all uploads and detector kernels are queued first ...
-            self.segmenters[g].begin(pcms[a:b], threads=self.threads)
-        for g, (a, b) in enumerate(groups):            # ... so the copy engine never waits for the host stage of a group
+        # all uploads and detector kernels are queued up front, in group order, so the copy engine never waits for the
+        # host stage of a group -- by a helper thread, so that the first group's host stage does not wait for the
+        # enqueueing of the last one either
+        begun = [self.begin_pool.submit(self.segmenters[g].begin, pcms[a:b], 1024, self.threads) for g, (a, b) in enumerate(groups)]
+        for g, (a, b) in enumerate(groups):
+            begun[g].result()
             blocks, dptr, elems = self.segmenters[g].finish()
             t1 = time.perf_counter()
             self.batches[g].submit(streams[a:b], blocks, dptr, elems)
