@@ -137,6 +137,7 @@ class Encoder:
         self.segmenter = self.segmenters[0]
         self.pool = ThreadPoolExecutor(max_workers=threads)
         self.begin_pool = ThreadPoolExecutor(max_workers=1)      # one thread: the groups' uploads must be queued in order
+        self.submit_pool = ThreadPoolExecutor(max_workers=1)     # one thread: batches are launched in group order
 
     def close(self):
         for b in self.batches:
@@ -145,6 +146,7 @@ class Encoder:
             g.close()
         self.pool.shutdown()
         self.begin_pool.shutdown()
+        self.submit_pool.shutdown()
 
     def segment(self, pcms):
         """Host-only segmentation: list of float32 [channels, nsamples] -> (Block array, one timeline buffer, counts)."""
@@ -178,12 +180,19 @@ class Encoder:
         # host stage of a group -- by a helper thread, so that the first group's host stage does not wait for the
         # enqueueing of the last one either
         begun = [self.begin_pool.submit(self.segmenters[g].begin, pcms[a:b], 1024, self.threads) for g, (a, b) in enumerate(groups)]
+        # the host stage of a group is two halves -- finish (window sequencing, tails) and submit (descriptor pre-pass,
+        # launches); this thread does the finishes, a second one the submits, so group g+1 is sequenced while group g
+        # is being launched
+        subs = []
         for g, (a, b) in enumerate(groups):
             begun[g].result()
             blocks, dptr, elems = self.segmenters[g].finish()
             t1 = time.perf_counter()
-            self.batches[g].submit(streams[a:b], blocks, dptr, elems)
-            marks.append((t1 - t0, time.perf_counter() - t0))
+            subs.append(self.submit_pool.submit(self.batches[g].submit, streams[a:b], blocks, dptr, elems))
+            marks.append((t1 - t0,))
+        for f in subs:
+            f.result()
+        marks.append((time.perf_counter() - t0,))
         out = []
         for g, (a, b) in enumerate(groups):
             self.batches[g].collect()
