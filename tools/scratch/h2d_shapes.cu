@@ -1,3 +1,4 @@
+// build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o tools/scratch/h2d_shapes tools/scratch/h2d_shapes.cu
 // scratch: H2D rate of the segmenter's upload pattern (one 2-row 2D copy per stream) against plain 1D copies
 #include <cstdio>
 #include <cuda_runtime.h>
