@@ -255,21 +255,38 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
       r0 = __shfl_sync(FULLMASK, rr, 0); ly0 = __shfl_sync(FULLMASK, ya, 0); ly1 = __shfl_sync(FULLMASK, yb, 0);
       r1 = __shfl_sync(FULLMASK, rr, 6); hy0 = __shfl_sync(FULLMASK, ya, 6); hy1 = __shfl_sync(FULLMASK, yb, 6);
     }
+    /* every value below is warp-uniform (the solves were broadcast), so the bookkeeping needs no single-lane section */
+    bool relink = false;
+    if (bad) {
+      if (r0) { ly0 = ly; ly1 = hy0; }
+      if (r1) { hy0 = ly1; hy1 = hy; }
+      relink = !(r0 && r1) && (ly1 >= 0 || hy0 >= 0);
+    }
     if (lane == 0) {
-      if (bad) {
-        if (r0) { ly0 = ly; ly1 = hy0; }
-        if (r1) { hy0 = ly1; hy1 = hy; }
-        if (r0 && r1) { sm.A[i] = -200; sm.B[i] = -200; }
-        else {
-          sm.B[ln] = ly0; if (ln == 0) sm.A[ln] = ly0;
-          sm.A[i] = ly1; sm.B[i] = hy0;
-          sm.A[hn] = hy1; if (hn == 1) sm.B[hn] = hy1;
-          if (ly1 >= 0 || hy0 >= 0) {
-            for (int j = sp - 1; j >= 0 && sm.hi[j] == hn; j--) sm.hi[j] = i;
-            for (int j = sp + 1; j < posts && sm.lo[j] == ln; j++) sm.lo[j] = i;
-          }
-        }
+      if (bad && !(r0 && r1)) {
+        sm.B[ln] = ly0; if (ln == 0) sm.A[ln] = ly0;
+        sm.A[i] = ly1; sm.B[i] = hy0;
+        sm.A[hn] = hy1; if (hn == 1) sm.B[hn] = hy1;
       } else { sm.A[i] = -200; sm.B[i] = -200; }
+    }
+    if (relink) {
+      /* the new post becomes the neighbour of the run of sorted positions next to it that pointed past it
+         (floor1.c:703-710: two loops that stop at the first position pointing elsewhere): lane t looks at the t-th
+         position below / above sp, the run is the leading ones of the vote */
+      for (int j0 = sp - 1; j0 >= 0; j0 -= 32) {
+        const int j = j0 - lane;
+        const unsigned m = __ballot_sync(FULLMASK, j >= 0 && sm.hi[j] == hn);
+        const int run = __ffs(~m) - 1;             /* 32 set bits: ffs(0) - 1 = -1 */
+        if (run < 0 || lane < run) { if (j >= 0) sm.hi[j] = i; }
+        if (run >= 0) break;
+      }
+      for (int j0 = sp + 1; j0 < posts; j0 += 32) {
+        const int j = j0 + lane;
+        const unsigned m = __ballot_sync(FULLMASK, j < posts && sm.lo[j] == ln);
+        const int run = __ffs(~m) - 1;
+        if (run < 0 || lane < run) { if (j < posts) sm.lo[j] = i; }
+        if (run >= 0) break;
+      }
     }
     __syncwarp();
   }
