@@ -73,8 +73,11 @@ constexpr int RF_MAXG = 64;     /* largest partition size handled (grouping) */
 constexpr int RF_SLOTS = 4;     /* partitions a warp works on at once */
 constexpr int RF_LP = 32 / RF_SLOTS;
 
+constexpr int RF_SKEW = 9;      /* the four slots of a warp start 9 banks apart: distinct mod 4 (8 lanes at stride dim = 4
+                                   words cover every fourth bank) and nearly disjoint runs at stride 2 -- at a stride of
+                                   RF_MAXG all four slots sat on the same banks (4-way conflicts on every access) */
 struct RfShared {
-  int vec[RF_WARPS][RF_SLOTS][RF_MAXG];
+  int vec[RF_WARPS][RF_SLOTS][RF_MAXG + RF_SKEW];
   int red_d[RF_WARPS], red_i[RF_WARPS];
 };
 
@@ -199,8 +202,12 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
           int *a = v + t * dim;
           int pt[8];
           bool on_lattice = true;          /* the input is exactly a lattice point inside the book's range */
-          for (int i = 0, o = dim; i < dim; i++) {
-            --o;
+          /* components from the last to the first (the index is built most-significant first); the loop is unrolled
+             to the largest dimension so that pt[] is indexed by constants and stays in registers */
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            if (i >= dim) break;
+            const int o = dim - 1 - i;
             int x = a[o] - bmin;
             if (bdelta != 1) {
               /* C division (truncating) by the book's step: exact reciprocal multiply while the value is small */
@@ -210,8 +217,8 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
             }
             const int m = (x < ze) ? ((ze - x) << 1) - 1 : ((x - ze) << 1);
             index = index * qv + (m < 0 ? 0 : (m >= qv ? qv - 1 : m));
-            pt[o] = x * bdelta + bmin;
-            if (m < 0 || m >= qv || pt[o] != a[o]) on_lattice = false;
+            pt[i] = x * bdelta + bmin;
+            if (m < 0 || m >= qv || pt[i] != a[o]) on_lattice = false;
           }
           if (__ldg(B.len + index) == 0) {
             if (B.nearest && on_lattice) {
@@ -221,7 +228,11 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
               for (int i = 0; i < dim; i++) a[i] -= __ldg(ev + i);
               e_out[t] = (short)__ldg(B.used_list + u);
             } else fb = true;
-          } else { for (int i = 0; i < dim; i++) a[i] -= pt[i]; e_out[t] = (short)index; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { if (i >= dim) break; a[dim - 1 - i] -= pt[i]; }
+            e_out[t] = (short)index;
+          }
         }
         /* entries without a codeword: warp-wide exhaustive search over the used entries, one vector at a time */
         unsigned fm = __ballot_sync(FULLMASK, fb);
