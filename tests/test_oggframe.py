@@ -52,6 +52,9 @@ def test_crc_known_answers():
         assert ogg.crc(d) == crc_bitwise(d)
     assert ogg.crc(b"\x00" * 8) == 0                       # initial value 0, no final xor
     assert ogg.crc(b"\x01") == 0x04C11DB7                  # the polynomial itself
+    # published check value: the CRC catalogue lists CRC-32/CKSUM (same polynomial, init 0, unreflected, final
+    # xor 0xFFFFFFFF) with check("123456789") = 0x765E7680; Ogg's variant has no final xor
+    assert ogg.crc(b"123456789") == 0x765E7680 ^ 0xFFFFFFFF == 0x89A1897F
 
 
 def test_pages_round_trip_and_follow_the_paging_rules():
