@@ -60,6 +60,12 @@ void vb200_launch_count_reset(void);
  * INTEGRATION.md) and uploads them to `device`. */
 int  vb200_setup_create(const void *blob, size_t bytes, int device, vb200_setup **out);
 void vb200_setup_destroy(vb200_setup *s);
+/* Front end with operation-exact transforms (off by default; also VB200_EXACT_TRANSFORM=1 at create time).  K1 computes
+ * the MDCT / real FFT in its own formulation, within north_star's 1e-5 of the reference; with this switch on, the
+ * launches that follow perform the reference's own float operations instead (mdct_forward mdct.c:1799-1869, drft_forward
+ * smallft.c:6770 with drftf1/dradf4/dradf2 :5652-6170), so that gmdct, logmdct, logfft and local_ampmax -- and through
+ * them every later stage and the packets -- are bit-identical to the reference's C path. */
+int  vb200_setup_set_exact_transform(vb200_setup *s, int on);
 /* host-side queries (valid without a GPU: pass device = -1 to vb200_setup_create) */
 int  vb200_setup_channels(const vb200_setup *s);
 long vb200_setup_rate(const vb200_setup *s);

@@ -146,6 +146,22 @@ class Oracle:
         self.L.orc_mdct_forward(_fptr(w), _fptr(out), len(w))
         return out
 
+    def mdct_forward_exact(self, windowed):
+        """the reference's own float operations in stage-parallel form: bit-exact against mdct_forward"""
+        w = np.ascontiguousarray(windowed, np.float32)
+        out = np.empty(len(w) // 2, np.float32)
+        self.L.orc_mdct_forward_exact(_fptr(w), _fptr(out), len(w))
+        return out
+
+    def logfft_exact(self, windowed):
+        """spectrum on the operation-by-operation restatement of drft_forward: bit-exact against the reference"""
+        w = np.ascontiguousarray(windowed, np.float32)
+        out = np.empty(len(w) // 2, np.float32)
+        amp = C.c_float()
+        if self.L.orc_logfft_exact(_fptr(w), len(w), _fptr(out), C.byref(amp)):
+            raise ValueError("block size with factors other than 2 and 4")
+        return out, amp.value
+
     def logfft(self, windowed):
         w = np.ascontiguousarray(windowed, np.float32)
         out = np.empty(len(w) // 2, np.float32)

@@ -52,6 +52,11 @@ typedef struct {
 float orc_todB(float x);
 void  orc_window(float *d, int n, int ln, int rn, const float *wl, const float *wr);
 void  orc_mdct_forward(const float *in, float *out, int n);
+void  orc_mdct_forward_exact(const float *in, float *out, int n);   /* the reference's float operations, bit-exact (mdct_exact_port.c) */
+void  orc_mdct_tables(int n, float *T, int *bitrev);
+void  orc_drft_tables(int n, float *wa, int *ifac);
+int   orc_drft_forward_exact(float *data, int n);                   /* smallft.c drft_forward, bit-exact (drft_exact_port.c) */
+int   orc_logfft_exact(const float *w, int n, float *logfft, float *local_ampmax);
 void  orc_logfft(const float *windowed, int n, float *logfft, float *local_ampmax);
 void  orc_logmdct(const float *mdct, int n2, float *logmdct);
 float orc_postnoise(const float *pcm, int n, int mode, int lw_mode);

@@ -56,3 +56,33 @@ def test_transform_matches_reference(config, W):
     assert np.array_equal(out["poste"] > 0, po > 0)
     assert np.allclose(out["poste"], po, rtol=1e-5)
     s.close()
+
+
+@pytest.mark.parametrize("config", ["q4_44k_2ch", "q8_48k_6ch"])
+@pytest.mark.parametrize("W", [1, 0])
+def test_exact_transform_is_bit_identical_to_the_reference(config, W):
+    """K1x (vb200_setup_set_exact_transform): the reference's own float operations in mdct_forward / drft_forward,
+    one thread per butterfly -- MDCT, logmdct, logfft and the block maximum must equal the reference's bit for bit."""
+    from vorbis_aotuv_lancer_b200 import ops
+    cap = refdata.capture(config, 2.0)
+    s = ops.Setup(config).set_exact_transform(True)
+    pcm, lW, nW, bm, lbm, ref_m, ref_lf, ref_lm, ref_amp, ref_po = [], [], [], [], [], [], [], [], [], []
+    for seq in refdata.by_size(cap, W):
+        b = cap["blocks"][seq]
+        blk = b["TAP_BLOCK"][0]["data"]
+        for c in range(s.channels):
+            pcm.append(b["TAP_PCM"][c]["data"]); lW.append(blk[1]); nW.append(blk[2])
+            bm.append(b["TAP_PCM"][c]["a1"]); lbm.append(b["TAP_PCM"][c]["a2"])
+            ref_m.append(b["TAP_MDCT"][c]["data"]); ref_lf.append(b["TAP_TM_LOGFFT"][c]["data"])
+            ref_lm.append(b["TAP_NM_LOGMDCT"][c]["data"]); ref_amp.append(b["TAP_TM_SCAL"][c]["data"][1])
+            ref_po.append(b["TAP_POSTE"][c]["data"][0])
+    assert len(pcm) > 8
+    out = ops.forward_transform(s, W, np.stack(pcm), lW, nW, bm, lbm)
+    bad = int((out["gmdct"] != np.stack(ref_m)).sum())
+    assert bad == 0, "MDCT: %d of %d coefficients differ" % (bad, out["gmdct"].size)
+    assert np.array_equal(out["logmdct"], np.stack(ref_lm))
+    bad = int((out["logfft"] != np.stack(ref_lf)).sum())
+    assert bad == 0, "logfft: %d of %d bins differ" % (bad, out["logfft"].size)
+    assert np.array_equal(out["local_ampmax"], np.array(ref_amp, np.float32))
+    assert np.allclose(out["poste"], np.array(ref_po), rtol=1e-5)
+    s.close()

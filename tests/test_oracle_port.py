@@ -46,12 +46,15 @@ def test_front_end(ctx):
             m = orc.mdct_forward(w)
             rms = np.sqrt((ref.astype(np.float64) ** 2).mean()) + 1e-30
             worst = max(worst, float(np.abs(m - ref).max() / rms))
+            assert np.array_equal(orc.mdct_forward_exact(w), ref)      # the operation-by-operation restatement
             assert np.array_equal(orc.logmdct(ref), b["TAP_NM_LOGMDCT"][c]["data"])
             lf, amp = orc.logfft(w)
             rlf = b["TAP_TM_LOGFFT"][c]["data"]
             good = rlf > rlf.max() - 60
             assert np.abs(lf - rlf)[good].max() < 2e-3
             assert abs(amp - b["TAP_TM_SCAL"][c]["data"][1]) < 2e-3
+            lfx, ampx = orc.logfft_exact(w)                            # the operation-by-operation restatement
+            assert np.array_equal(lfx, rlf) and np.float32(ampx) == b["TAP_TM_SCAL"][c]["data"][1]
             assert orc.postnoise(pcm["data"], pcm["a1"], pcm["a2"]) == pytest.approx(b["TAP_POSTE"][c]["data"][0], rel=1e-6)
             lf_ = b["TAP_LOUDFIX"][c]
             assert orc.loudnoise_fix(b["TAP_NM_LOGMDCT"][c]["a1"], lf_["data"][0], b["TAP_NM_LOGMDCT"][c]["data"],

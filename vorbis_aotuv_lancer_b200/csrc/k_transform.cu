@@ -245,6 +245,8 @@ int vb200_launch_transform(const vb200_setup *s, cudaStream_t st, int W, int ite
                            const int *block_mode, const int *lW_block_mode,
                            float *gmdct, float *logfft, float *logmdct, float *local_ampmax, float *poste) {
   if (items <= 0) return VB200_OK;
+  if (s->exact_transform)          /* opt-in: the reference's own float operations (k_transform_exact.cu) */
+    return vb200_launch_transform_exact(s, st, W, items, pcm, pcm_off, lW, nW, block_mode, lW_block_mode, gmdct, logfft, logmdct, local_ampmax, poste);
   if (W) k_transform<2048, 256><<<items, 256, 0, st>>>(s->d, 1, pcm, pcm_off, lW, nW, block_mode, lW_block_mode, gmdct, logfft, logmdct, local_ampmax, poste);
   else   k_transform<256, 64><<<items, 64, 0, st>>>(s->d, 0, pcm, pcm_off, lW, nW, block_mode, lW_block_mode, gmdct, logfft, logmdct, local_ampmax, poste);
   LAUNCH_CHECK();

@@ -1,0 +1,413 @@
+/* K1x -- the front end with OPERATION-EXACT transforms (opt-in: vb200_setup_set_exact_transform / VB200_EXACT_TRANSFORM=1).
+ *
+ * K1 (k_transform.cu) computes the MDCT and the real FFT with its own radix-4 Stockham formulation; the results agree
+ * with the reference's to ~1e-6 of the block RMS (north_star's tolerance), which is enough to flip a quantiser decision
+ * in a few percent of the packets.  This kernel instead performs the reference's OWN float operations -- same operands,
+ * same order, every product and sum rounded separately -- so that gmdct / logmdct / logfft / local_ampmax, and with them
+ * every later stage, are bit-identical to the reference's C path:
+ *   mdct_forward   mdct.c:1799-1869  (butterflies :1105-1135, :854-895, :1032-1079, :602-659, :495-524, :432-453;
+ *                                     bit reversal :1228-1273; tables mdct_init :54-92)
+ *   drft_forward   smallft.c:6770    (drftf1 :6111-6170, dradf4 :5707-5807, dradf2 :5652-5705; tables drfti1 :5576-5644)
+ *   spectrum loop  mapping0.c:847-888, logmdct :933-951, _postnoise_detection psy.c:619-648, window window.c:2137-2261
+ * The dataflow is the reference's, the form is not: every stage is a set of independent work items with their operand
+ * indices in closed form (validated on the CPU as oracle/port/mdct_exact_port.c and drft_exact_port.c, bit-exact on
+ * every block of every test configuration), one thread per item, one barrier per stage, everything in shared memory.
+ * HBM traffic is K1's: n*4 bytes in, 3*N2*4 bytes out.
+ */
+#include "vb200_internal.h"
+#include "dev_util.cuh"
+#include <math.h>
+
+/* ---- tables (host): the reference's own values, float conversions of double cos/sin (mdct_init) and double cos/sin of
+   float angles (drfti1) ---- */
+void vb200_exact_tables_mdct(int n, float *T, int *bitrev) {
+  const int n2 = n >> 1;
+  int log2n = 0;
+  while ((1 << log2n) < n) log2n++;
+  for (int i = 0; i < n / 4; i++) {
+    T[i * 2] = (float)cos((M_PI / n) * (4 * i));
+    T[i * 2 + 1] = (float)-sin((M_PI / n) * (4 * i));
+    T[n2 + i * 2] = (float)cos((M_PI / (2 * n)) * (2 * i + 1));
+    T[n2 + i * 2 + 1] = (float)sin((M_PI / (2 * n)) * (2 * i + 1));
+  }
+  for (int i = 0; i < n / 8; i++) {
+    T[n + i * 2] = (float)(cos((M_PI / n) * (4 * i + 2)) * .5);
+    T[n + i * 2 + 1] = (float)(-sin((M_PI / n) * (4 * i + 2)) * .5);
+  }
+  const int mask = (1 << (log2n - 1)) - 1, msb = 1 << (log2n - 2);
+  for (int i = 0; i < n / 8; i++) {
+    int acc = 0;
+    for (int j = 0; msb >> j; j++) if ((msb >> j) & i) acc |= 1 << j;
+    bitrev[i * 2] = ((~acc) & mask) - 1;
+    bitrev[i * 2 + 1] = acc;
+  }
+}
+
+/* twiddles of the real FFT for n = 2^k (factors 4...4 and, for an odd k, one 2 that the reference moves to the front);
+   wa must hold 2n floats */
+void vb200_exact_tables_drft(int n, float *wa) {
+  int fac[32], nf = 0, nl = n;
+  while (nl % 4 == 0) { fac[nf++] = 4; nl /= 4; }
+  if (nl == 2) { for (int i = nf; i > 0; i--) fac[i] = fac[i - 1]; fac[0] = 2; nf++; }
+  const float tpi = 6.28318530717958648f;
+  const float argh = tpi / n;
+  int is = 0, l1 = 1;
+  for (int k1 = 0; k1 < nf - 1; k1++) {
+    const int ip = fac[k1], l2 = l1 * ip, ido = n / l2;
+    int ld = 0;
+    for (int j = 0; j < ip - 1; j++) {
+      int w = is;
+      float fi = 0.f;
+      ld += l1;
+      const float argld = (float)ld * argh;
+      for (int ii = 2; ii < ido; ii += 2) {
+        fi += 1.f;
+        const float arg = fi * argld;
+        wa[w++] = (float)cos((double)arg);
+        wa[w++] = (float)sin((double)arg);
+      }
+      is += ido;
+    }
+    l1 = l2;
+  }
+}
+
+namespace {
+
+#define C1_8 .92387953251128675613F
+#define C2_8 .70710678118654752441F
+#define C3_8 .38268343236508977175F
+
+/* a*b + c*d and a*b - c*d with the three roundings of the C expression */
+__device__ __forceinline__ float mad2(float a, float b, float c, float d) { return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+__device__ __forceinline__ float msu2(float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+
+/* the hard-coded 32-point end of the butterfly recursion on registers (mdct.c:602-659 -> :495-524 -> :432-453) */
+__device__ __forceinline__ void bfly8(float *x) {
+  float r0 = add(x[6], x[2]), r1 = sub(x[6], x[2]), r2 = add(x[4], x[0]), r3 = sub(x[4], x[0]);
+  x[6] = add(r0, r2); x[4] = sub(r0, r2);
+  r0 = sub(x[5], x[1]); r2 = sub(x[7], x[3]);
+  x[0] = add(r1, r0); x[2] = sub(r1, r0);
+  r0 = add(x[5], x[1]); r1 = add(x[7], x[3]);
+  x[3] = add(r2, r3); x[1] = sub(r2, r3);
+  x[7] = add(r1, r0); x[5] = sub(r1, r0);
+}
+__device__ __forceinline__ void bfly16(float *x) {
+  float r0 = sub(x[1], x[9]), r1 = sub(x[0], x[8]);
+  x[8] = add(x[8], x[0]); x[9] = add(x[9], x[1]);
+  x[0] = mul(add(r0, r1), C2_8); x[1] = mul(sub(r0, r1), C2_8);
+  r0 = sub(x[3], x[11]); r1 = sub(x[10], x[2]);
+  x[10] = add(x[10], x[2]); x[11] = add(x[11], x[3]);
+  x[2] = r0; x[3] = r1;
+  r0 = sub(x[12], x[4]); r1 = sub(x[13], x[5]);
+  x[12] = add(x[12], x[4]); x[13] = add(x[13], x[5]);
+  x[4] = mul(sub(r0, r1), C2_8); x[5] = mul(add(r0, r1), C2_8);
+  r0 = sub(x[14], x[6]); r1 = sub(x[15], x[7]);
+  x[14] = add(x[14], x[6]); x[15] = add(x[15], x[7]);
+  x[6] = r0; x[7] = r1;
+  bfly8(x); bfly8(x + 8);
+}
+__device__ __forceinline__ void bfly32(float *x) {
+  float r0 = sub(x[30], x[14]), r1 = sub(x[31], x[15]);
+  x[30] = add(x[30], x[14]); x[31] = add(x[31], x[15]); x[14] = r0; x[15] = r1;
+  r0 = sub(x[28], x[12]); r1 = sub(x[29], x[13]);
+  x[28] = add(x[28], x[12]); x[29] = add(x[29], x[13]);
+  x[12] = msu2(r0, C1_8, r1, C3_8); x[13] = mad2(r0, C3_8, r1, C1_8);
+  r0 = sub(x[26], x[10]); r1 = sub(x[27], x[11]);
+  x[26] = add(x[26], x[10]); x[27] = add(x[27], x[11]);
+  x[10] = mul(sub(r0, r1), C2_8); x[11] = mul(add(r0, r1), C2_8);
+  r0 = sub(x[24], x[8]); r1 = sub(x[25], x[9]);
+  x[24] = add(x[24], x[8]); x[25] = add(x[25], x[9]);
+  x[8] = msu2(r0, C3_8, r1, C1_8); x[9] = mad2(r1, C3_8, r0, C1_8);
+  r0 = sub(x[22], x[6]); r1 = sub(x[7], x[23]);
+  x[22] = add(x[22], x[6]); x[23] = add(x[23], x[7]);
+  x[6] = r1; x[7] = r0;
+  r0 = sub(x[4], x[20]); r1 = sub(x[5], x[21]);
+  x[20] = add(x[20], x[4]); x[21] = add(x[21], x[5]);
+  x[4] = mad2(r1, C1_8, r0, C3_8); x[5] = msu2(r1, C3_8, r0, C1_8);
+  r0 = sub(x[2], x[18]); r1 = sub(x[3], x[19]);
+  x[18] = add(x[18], x[2]); x[19] = add(x[19], x[3]);
+  x[2] = mul(add(r1, r0), C2_8); x[3] = mul(sub(r1, r0), C2_8);
+  r0 = sub(x[0], x[16]); r1 = sub(x[1], x[17]);
+  x[16] = add(x[16], x[0]); x[17] = add(x[17], x[1]);
+  x[0] = mad2(r1, C3_8, r0, C1_8); x[1] = msu2(r1, C1_8, r0, C3_8);
+  bfly16(x); bfly16(x + 16);
+}
+
+/* one radix-4 pass of the real FFT, cc -> ch (dradf4): items (k), (k, i), (k) */
+template <int THREADS>
+__device__ __forceinline__ void rpass4(int ido, int l1, const float *cc, float *ch, const float *__restrict__ wa1) {
+  const float *wa2 = wa1 + ido, *wa3 = wa2 + ido;
+  const int t0 = l1 * ido, t6 = ido << 1, tid = threadIdx.x;
+  for (int k = tid; k < l1; k += THREADS) {
+    const int t3 = k * ido, t1 = t0 + t3, t4 = 2 * t0 + t3, t2 = 3 * t0 + t3, t5 = t3 << 2;
+    const float tr1 = add(cc[t1], cc[t2]), tr2 = add(cc[t3], cc[t4]);
+    ch[t5] = add(tr1, tr2);
+    ch[(ido << 2) + t5 - 1] = sub(tr2, tr1);
+    ch[t5 + t6 - 1] = sub(cc[t3], cc[t4]);
+    ch[t5 + t6] = sub(cc[t2], cc[t1]);
+  }
+  if (ido < 2) return;
+  const int per = (ido >> 1) - 1;                 /* i = 2, 4, ... ido-2 */
+  for (int m = tid; m < l1 * per; m += THREADS) {
+    const int k = m / per, i = 2 + 2 * (m - k * per);
+    const int t1 = k * ido, t2 = t1 + i, t4 = (t1 << 2) + i, t5 = t6 + (t1 << 2) - i;
+    int t3 = t2 + t0;
+    const float w1r = __ldg(wa1 + i - 2), w1i = __ldg(wa1 + i - 1), w2r = __ldg(wa2 + i - 2), w2i = __ldg(wa2 + i - 1);
+    const float w3r = __ldg(wa3 + i - 2), w3i = __ldg(wa3 + i - 1);
+    const float cr2 = mad2(w1r, cc[t3 - 1], w1i, cc[t3]), ci2 = msu2(w1r, cc[t3], w1i, cc[t3 - 1]);
+    t3 += t0;
+    const float cr3 = mad2(w2r, cc[t3 - 1], w2i, cc[t3]), ci3 = msu2(w2r, cc[t3], w2i, cc[t3 - 1]);
+    t3 += t0;
+    const float cr4 = mad2(w3r, cc[t3 - 1], w3i, cc[t3]), ci4 = msu2(w3r, cc[t3], w3i, cc[t3 - 1]);
+    const float tr1 = add(cr2, cr4), tr4 = sub(cr4, cr2), ti1 = add(ci2, ci4), ti4 = sub(ci2, ci4);
+    const float ti2 = add(cc[t2], ci3), ti3 = sub(cc[t2], ci3), tr2 = add(cc[t2 - 1], cr3), tr3 = sub(cc[t2 - 1], cr3);
+    ch[t4 - 1] = add(tr1, tr2);      ch[t4] = add(ti1, ti2);
+    ch[t5 - 1] = sub(tr3, ti4);      ch[t5] = sub(tr4, ti3);
+    ch[t4 + t6 - 1] = add(ti4, tr3); ch[t4 + t6] = add(tr4, ti3);
+    ch[t5 + t6 - 1] = sub(tr2, tr1); ch[t5 + t6] = sub(ti1, ti2);
+  }
+  if (ido & 1) return;
+  const float hsqt2 = .70710678118654752f;
+  for (int k = tid; k < l1; k += THREADS) {
+    const int t1 = t0 + ido - 1 + k * ido, t2 = t1 + (t0 << 1), t4 = ido + k * (ido << 2), t5 = ido << 1, t6b = ido + k * ido;
+    const float ti1 = mul(-hsqt2, add(cc[t1], cc[t2])), tr1 = mul(hsqt2, sub(cc[t1], cc[t2]));
+    ch[t4 - 1] = add(tr1, cc[t6b - 1]);
+    ch[t4 + t5 - 1] = sub(cc[t6b - 1], tr1);
+    ch[t4] = sub(ti1, cc[t1 + t0]);
+    ch[t4 + t5] = add(ti1, cc[t1 + t0]);
+  }
+}
+
+/* one radix-2 pass, cc -> ch (dradf2) */
+template <int THREADS>
+__device__ __forceinline__ void rpass2(int ido, int l1, const float *cc, float *ch, const float *__restrict__ wa1) {
+  const int t0 = l1 * ido, tid = threadIdx.x;
+  for (int k = tid; k < l1; k += THREADS) {
+    const int t1 = k * ido, t2 = t0 + k * ido;
+    ch[2 * t1] = add(cc[t1], cc[t2]);
+    ch[2 * t1 + 2 * ido - 1] = sub(cc[t1], cc[t2]);
+  }
+  if (ido < 2) return;
+  const int per = (ido >> 1) - 1;
+  for (int m = tid; m < l1 * per; m += THREADS) {
+    const int k = m / per, i = 2 + 2 * (m - k * per);
+    const int t1 = k * ido, t3 = t0 + t1 + i, t4 = 2 * t1 + 2 * ido - i, t5 = t1 + i, t6 = 2 * t1 + i;
+    const float wr = __ldg(wa1 + i - 2), wi = __ldg(wa1 + i - 1);
+    const float tr2 = mad2(wr, cc[t3 - 1], wi, cc[t3]), ti2 = msu2(wr, cc[t3], wi, cc[t3 - 1]);
+    ch[t6] = add(cc[t5], ti2);
+    ch[t4] = sub(ti2, cc[t5]);
+    ch[t6 - 1] = add(cc[t5 - 1], tr2);
+    ch[t4 - 1] = sub(cc[t5 - 1], tr2);
+  }
+  if (ido & 1) return;
+  for (int k = tid; k < l1; k += THREADS) {
+    const int t1 = ido + 2 * k * ido, t3 = ido - 1 + k * ido, t2 = t3 + t0;
+    ch[t1] = -cc[t2];
+    ch[t1 - 1] = cc[t3];
+  }
+}
+
+template <int N, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm, const long long *__restrict__ pcm_off,
+                  const int *__restrict__ lWv, const int *__restrict__ nWv,
+                  const int *__restrict__ block_mode, const int *__restrict__ lW_block_mode,
+                  float *__restrict__ gmdct, float *__restrict__ logfft, float *__restrict__ logmdct,
+                  float *__restrict__ local_ampmax, float *__restrict__ poste) {
+  constexpr int N2 = N / 2, N4 = N / 4, N8 = N / 8;
+  constexpr int LOG2N = (N == 2048) ? 11 : 8;
+  static_assert(N == 2048 || N == 256, "block sizes of the built path");
+  __shared__ __align__(16) float x[N];        /* the windowed block; later the real FFT's buffer c */
+  __shared__ __align__(16) float w[N];        /* the MDCT's work vector; later the real FFT's buffer ch */
+  __shared__ double red[2][(THREADS + 31) / 32];
+  __shared__ float redf[(THREADS + 31) / 32];
+
+  const int item = blockIdx.x, tid = threadIdx.x;
+  const float *src = pcm + (pcm_off ? pcm_off[item] : (long long)item * N);
+  const int lW = W ? lWv[item] : 0, nW = W ? nWv[item] : 0;
+  const int ln = S->bs[lW], rn = S->bs[nW];
+  const float *wl = S->win[lW], *wr = S->win[nW];
+  const int leftbegin = N / 4 - ln / 4, leftend = leftbegin + ln / 2;
+  const int rightbegin = N / 2 + N / 4 - rn / 4, rightend = rightbegin + rn / 2;
+
+  /* ---- aoTuV M2 post-echo detector on the un-windowed PCM (psy.c:619-648), as in K1 ---- */
+  if (poste) {
+    float ret = -1.f;
+    const int mode = block_mode[item], lwm = lW_block_mode[item];
+    if (mode == 2 && lwm == 0 && N >= 2048) {
+      const int sn = N >> 2, mn = sn + sn, en = sn + (N >> 1);
+      double up = 0., un = 0.;
+      for (int i = sn + tid; i < mn; i += THREADS) up += (double)fabsf(__ldg(src + i));
+      for (int i = mn + tid; i < en; i += THREADS) un += (double)fabsf(__ldg(src + i));
+      up = warp_sum_d(up); un = warp_sum_d(un);
+      if ((tid & 31) == 0) { red[0][tid >> 5] = up; red[1][tid >> 5] = un; }
+      __syncthreads();
+      if (tid == 0) {
+        double upt = 0., unt = 0.;
+        for (int q = 0; q < (THREADS + 31) / 32; q++) { upt += red[0][q]; unt += red[1][q]; }
+        if (!(unt / sn > 0.01)) {
+          upt *= upt; unt *= unt; unt *= 15;
+          if (upt > unt) { ret = (float)(upt - unt); if (ret < 0.1) ret = -1.0f; }
+        }
+        poste[item] = ret;
+      }
+    } else if (tid == 0) poste[item] = ret;
+  }
+
+  /* ---- stage the block, windowed on the way in (window.c:2137-2261) ---- */
+  for (int i = tid; i < N; i += THREADS) {
+    float v = __ldg(src + i);
+    if (i < leftbegin) v = 0.f;
+    else if (i < leftend) v = mul(v, __ldg(wl + (i - leftbegin)));
+    else if (i >= rightend) v = 0.f;
+    else if (i >= rightbegin) v = mul(v, __ldg(wr + (rn / 2 - 1 - (i - rightbegin))));
+    x[i] = v;
+  }
+  __syncthreads();
+
+  const float *T = S->xm_trig[W];
+  const int *bitrev = S->xm_bitrev[W];
+  float *w2 = w + N2;
+
+  /* ---- MDCT, fold + first rotation: pair p of the upper half of w (mdct.c:1817-1846) ---- */
+  for (int p = tid; p < N4; p += THREADS) {
+    const int i = 2 * p;
+    const float t0 = __ldg(T + N2 - 2 - i), t1 = __ldg(T + N2 - 1 - i);
+    float r0, r1;
+    if (i < N8) {
+      const float *x0 = x + N2 + N4 - 4 * (p + 1), *x1 = x + N2 + N4 + 1 + 4 * p;
+      r0 = add(x0[2], x1[0]); r1 = add(x0[0], x1[2]);
+    } else if (i < N2 - N8) {
+      const float *x0 = x + N2 + N4 - 4 * (p + 1), *x1 = x + 1 + 4 * (p - N8 / 2);
+      r0 = sub(x0[2], x1[0]); r1 = sub(x0[0], x1[2]);
+    } else {
+      const float *x0 = x + N - 4 * (p - (N2 - N8) / 2 + 1), *x1 = x + 1 + 4 * (p - N8 / 2);
+      r0 = sub(-x0[2], x1[0]); r1 = sub(-x0[0], x1[2]);
+    }
+    w2[i] = mad2(r1, t1, r0, t0);
+    w2[i + 1] = msu2(r1, t0, r0, t1);
+  }
+  __syncthreads();
+
+  /* ---- butterflies: log2n - 6 radix-2 stages over sub-blocks of N2 >> s floats, one thread per pair ---- */
+#pragma unroll
+  for (int s = 0; s < LOG2N - 6; s++) {
+    const int points = N2 >> s, pairs = points >> 2, trigint = 4 << s;
+    for (int g = tid; g < N8; g += THREADS) {
+      const int j = g / pairs, c = g - j * pairs, cp = pairs - 1 - c;
+      float *lo = w2 + j * points + 2 * cp, *hi = lo + (points >> 1);
+      const float t0 = __ldg(T + c * trigint), t1 = __ldg(T + c * trigint + 1);
+      const float l0 = lo[0], l1 = lo[1], h0 = hi[0], h1 = hi[1];
+      const float r0 = sub(h0, l0), r1 = sub(h1, l1);
+      hi[0] = add(h0, l0);
+      hi[1] = add(h1, l1);
+      lo[0] = mad2(r1, t1, r0, t0);
+      lo[1] = msu2(r1, t0, r0, t1);
+    }
+    __syncthreads();
+  }
+  /* 32-point groups on registers, one thread per group */
+  for (int g = tid; g < N2 / 32; g += THREADS) {
+    float r[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) r[i] = w2[g * 32 + i];
+    bfly32(r);
+#pragma unroll
+    for (int i = 0; i < 32; i++) w2[g * 32 + i] = r[i];
+  }
+  __syncthreads();
+
+  /* ---- bit reversal + rotation into the lower half (mdct.c:1228-1273): item q ---- */
+  for (int q = tid; q < N8; q += THREADS) {
+    const float *x0 = w2 + __ldg(bitrev + 2 * q), *x1 = w2 + __ldg(bitrev + 2 * q + 1);
+    const float tb0 = __ldg(T + N + 2 * q), tb1 = __ldg(T + N + 2 * q + 1);
+    float r0 = sub(x0[1], x1[1]), r1 = add(x0[0], x1[0]);
+    const float r2 = mad2(r1, tb0, r0, tb1), r3 = msu2(r1, tb1, r0, tb0);
+    r0 = mul(add(x0[1], x1[1]), .5f);
+    r1 = mul(sub(x0[0], x1[0]), .5f);
+    w[2 * q] = add(r0, r2);
+    w[N2 - 2 - 2 * q] = sub(r0, r2);
+    w[2 * q + 1] = add(r1, r3);
+    w[N2 - 1 - 2 * q] = sub(r3, r1);
+  }
+  __syncthreads();
+
+  /* ---- final rotation and scale (mdct.c:1855-1868), logmdct (mapping0.c:933-951) ---- */
+  {
+    const float scale = 4.f / N;
+    float *gm = gmdct + (size_t)item * N2, *lm = logmdct + (size_t)item * N2;
+    for (int p = tid; p < N4; p += THREADS) {
+      const float ta = __ldg(T + N2 + 2 * p), tb = __ldg(T + N2 + 2 * p + 1), a = w[2 * p], b = w[2 * p + 1];
+      const float v0 = mul(mad2(a, ta, b, tb), scale), v1 = mul(msu2(a, tb, b, ta), scale);
+      gm[p] = v0; lm[p] = todB_p345(v0);
+      gm[N2 - 1 - p] = v1; lm[N2 - 1 - p] = todB_p345(v1);
+    }
+  }
+  __syncthreads();                    /* w is free again */
+
+  /* ---- real FFT (smallft.c drftf1): factors from the last to the first, ping-pong x <-> w, result in x ---- */
+  {
+    constexpr int NF = (N == 2048) ? 6 : 4;
+    const float *wa = S->xf_wa[W];
+    int l2 = N, iw = N, na = 1;
+#pragma unroll 1
+    for (int k1 = 0; k1 < NF; k1++) {
+      const int ip = (N == 2048 && k1 == NF - 1) ? 2 : 4;
+      const int l1 = l2 / ip, ido = N / l2;
+      iw -= (ip - 1) * ido;
+      na = 1 - na;
+      const float *cc = na ? w : x;
+      float *ch = na ? x : w;
+      if (ip == 4) rpass4<THREADS>(ido, l1, cc, ch, wa + iw - 1);
+      else rpass2<THREADS>(ido, l1, cc, ch, wa + iw - 1);
+      __syncthreads();
+      l2 = l1;
+    }
+  }
+
+  /* ---- dB spectrum and block maximum (mapping0.c:784-795, 847-888) ---- */
+  {
+    const float scale_dB = todB_p345(4.f / N);
+    float *lf = logfft + (size_t)item * N2;
+    float mx = -3.0e38f;
+    for (int k = tid; k < N2; k += THREADS) {
+      float v;
+      if (k == 0) v = (float)((double)add(scale_dB, todB_raw(x[0])) + .345);
+      else {
+        const float xr = x[2 * k - 1], xi = x[2 * k];
+        const float p = add(mul(xr, xr), mul(xi, xi));
+        v = (float)((double)add(scale_dB, mul(.5f, todB_raw(p))) + .345);
+      }
+      lf[k] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max_f(mx);
+    if ((tid & 31) == 0) redf[tid >> 5] = mx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float m = redf[0];
+    for (int q = 1; q < (THREADS + 31) / 32; q++) m = fmaxf(m, redf[q]);
+    if (m > 0.f) m = 0.f;
+    local_ampmax[item] = m;
+  }
+}
+
+}  // namespace
+
+#ifdef __CUDACC__      /* (tests/emu compiles the kernel above as a serial host program to check its index arithmetic) */
+int vb200_launch_transform_exact(const vb200_setup *s, cudaStream_t st, int W, int items,
+                                 const float *pcm, const long long *pcm_off, const int *lW, const int *nW,
+                                 const int *block_mode, const int *lW_block_mode,
+                                 float *gmdct, float *logfft, float *logmdct, float *local_ampmax, float *poste) {
+  if (items <= 0) return VB200_OK;
+  if (W) k_transform_exact<2048, 256><<<items, 256, 0, st>>>(s->d, 1, pcm, pcm_off, lW, nW, block_mode, lW_block_mode, gmdct, logfft, logmdct, local_ampmax, poste);
+  else   k_transform_exact<256, 64><<<items, 64, 0, st>>>(s->d, 0, pcm, pcm_off, lW, nW, block_mode, lW_block_mode, gmdct, logfft, logmdct, local_ampmax, poste);
+  LAUNCH_CHECK();
+  return VB200_OK;
+}
+#endif

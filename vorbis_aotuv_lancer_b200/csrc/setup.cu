@@ -80,6 +80,12 @@ struct Loader {
 static void copy_i(int *dst, const void *src, int n) { if (src) memcpy(dst, src, sizeof(int) * n); }
 }  // namespace
 
+extern "C" int vb200_setup_set_exact_transform(vb200_setup *s, int on) {
+  if (!s) { vb200_set_error("vb200_setup_set_exact_transform: bad arguments"); return VB200_EINVAL; }
+  s->exact_transform = on ? 1 : 0;
+  return VB200_OK;
+}
+
 extern "C" void vb200_setup_destroy(vb200_setup *s) {
   if (!s) return;
   if (s->device >= 0) {
@@ -105,6 +111,7 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
   vb200_setup *s = new vb200_setup();
   memset(s, 0, sizeof(*s));
   s->device = device;
+  { const char *e = getenv("VB200_EXACT_TRANSFORM"); s->exact_transform = (e && *e && *e != '0') ? 1 : 0; }
   s->blob = (unsigned char *)malloc(bytes);
   memcpy(s->blob, blob, bytes);
   s->blob_bytes = bytes;
@@ -165,6 +172,16 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
     for (int k = 0; k < N2; k++) { double a = -2.0 * M_PI * k / (double)n; t[k].x = (float)cos(a); t[k].y = (float)sin(a); }
     h.rfft_tw[w] = (const float2 *)L.up(t, sizeof(float2) * N2);
     free(t);
+    {
+      /* tables of the operation-exact front end (K1x) */
+      std::vector<float> xt((size_t)n + n / 4), xw((size_t)2 * n, 0.f);
+      std::vector<int> xb((size_t)n / 4);
+      vb200_exact_tables_mdct(n, xt.data(), xb.data());
+      vb200_exact_tables_drft(n, xw.data());
+      h.xm_trig[w] = (const float *)L.up(xt.data(), sizeof(float) * xt.size());
+      h.xm_bitrev[w] = (const int *)L.up(xb.data(), sizeof(int) * xb.size());
+      h.xf_wa[w] = (const float *)L.up(xw.data(), sizeof(float) * xw.size());
+    }
   }
 
   { const float *f = (const float *)L.get("psyg.f32", VB200_F32, 4);

@@ -104,6 +104,10 @@ struct DevSetup {
   const float2 *rfft_tw[2];     /* [n/2]  exp(-2*pi*i*k/n) */
   const float2 *fft_pass_tw[2]; /* fft_root regrouped per radix-4 pass (setup.cu), unit-stride reads */
   int fft_r2_off[2];            /* float2 offset of the radix-2 pass's twiddles in fft_pass_tw */
+  /* tables of the operation-exact transforms (k_transform_exact.cu): the reference's own values */
+  const float *xm_trig[2];      /* [n + n/4]  mdct_init, mdct.c:54-92 */
+  const int *xm_bitrev[2];      /* [n/4] */
+  const float *xf_wa[2];        /* [2n]  drfti1, smallft.c:5576-5644 */
 };
 
 /* ---- host-side object behind vb200_setup ---- */
@@ -127,6 +131,7 @@ struct vb200_setup {
   int bi_i32[4]; double bi_f64[2];
   void *stream;               /* cudaStream_t */
   void **allocs; int nallocs, capallocs;
+  int exact_transform;        /* K1x instead of K1 (vb200_setup_set_exact_transform / VB200_EXACT_TRANSFORM=1) */
 };
 
 #ifdef __cplusplus
@@ -134,6 +139,8 @@ extern "C" {
 #endif
 void vb200_set_error(const char *fmt, ...);
 void vb200_count_launch(int n);
+void vb200_exact_tables_mdct(int n, float *T, int *bitrev);      /* k_transform_exact.cu */
+void vb200_exact_tables_drft(int n, float *wa);
 const void *vb200_blob_find(const unsigned char *blob, size_t bytes, const char *name, uint32_t *dtype, uint32_t *count);
 #ifdef __cplusplus
 }
@@ -151,6 +158,10 @@ int vb200_launch_transform(const vb200_setup *s, cudaStream_t st, int W, int ite
                            const float *pcm, const long long *pcm_off, const int *lW, const int *nW,
                            const int *block_mode, const int *lW_block_mode,
                            float *gmdct, float *logfft, float *logmdct, float *local_ampmax, float *poste);
+int vb200_launch_transform_exact(const vb200_setup *s, cudaStream_t st, int W, int items,
+                           const float *pcm, const long long *pcm_off, const int *lW, const int *nW,
+                           const int *block_mode, const int *lW_block_mode,
+                           float *gmdct, float *logfft, float *logmdct, float *local_ampmax, float *poste);   /* K1x, k_transform_exact.cu */
 int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
                            const int *block_mode, const float *lowcomp, const float *poste,
                            const float *logmdct, LastRef last, float *noise, float *epeak, float *npeak, int npeak_stride);

@@ -42,6 +42,12 @@ class Setup:
         self.blocksizes = (L.vb200_setup_blocksize(h, 0), L.vb200_setup_blocksize(h, 1))
         self.managed = L.vb200_setup_managed(h)
 
+    def set_exact_transform(self, on=True):
+        """K1x instead of K1 for the launches that follow: the reference's own float operations in mdct_forward /
+        drft_forward (bit-identical spectra and packets) instead of K1's own formulation (within 1e-5)"""
+        check(L.vb200_setup_set_exact_transform(self.h, int(bool(on))), "vb200_setup_set_exact_transform")
+        return self
+
     def close(self):
         if self.h:
             L.vb200_setup_destroy(self.h)
