@@ -158,6 +158,8 @@ def run_ours(args):
     ch, rate, q, _ = vblob.CATALOGUE[CONFIG]
     S, T = args.streams, args.seconds
     setup = ops.Setup(CONFIG, device=local)
+    if args.exact_transform:
+        setup.set_exact_transform(True)      # K1x: the reference's own float operations, packets byte-identical to the reference's
     pins = [encoder.PinnedArray(ch, int(rate * T)) for _ in range(S)]      # the caller's PCM lives in page-locked memory
     pcms = synth_streams(L, S, T, ch, rate, rank * S, pinned=pins)
     blocks_per_stream = int(T * rate / 700) + 64
@@ -282,6 +284,7 @@ def run_ours(args):
                "config": {"workload": "%d independent %g s q4 44.1 kHz stereo synthetic streams per GPU, all %d blocks "
                                       "(%d long, %d short) batched per step" % (S, T, nblocks, nlong, nshort),
                           "quality": 0.4, "streams_per_gpu": S, "seconds_per_stream": T, "parallelism": "streams sharded i mod G, no collective", "resident_depth": len(fulls),
+                          "front_end": "K1x (operation-exact MDCT/FFT, packets identical to the reference's)" if args.exact_transform else "K1 (own formulation, MDCT within 1e-5)",
                           "l2": "inputs larger than L2 (PCM timeline %.0f MB, per-stage vectors %.0f MB)" % (timeline.nbytes / 1e6, (nlong * 1024 + nshort * 128) * ch * 4 / 1e6)},
                "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(timeline.nbytes), "d2h_bytes_per_step": int(packet_bytes),
                        "steps": e2e_steps, "includes": "host segmentation (LPC head/tail, window sequencing; detector kernels on the GPU), H2D PCM, all kernels, bit packing, D2H packets; %d pipelined stream groups" % args.chunks},
@@ -307,6 +310,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=8, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
     ap.add_argument("--depth", type=int, default=2, help="resident arm: batches in flight (2: host half of step i+1 overlaps device half of step i)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exact-transform", action="store_true", help="front end K1x instead of K1 (DESIGN.md section 4)")
     args = ap.parse_args()
     # stdout carries the one JSON line and nothing else: libraries that write to fd 1 (NCCL's version banner)
     # are sent to stderr while the run lasts
