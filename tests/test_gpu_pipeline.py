@@ -126,11 +126,14 @@ def test_device_bitrate_manager_equals_host_manager_over_many_streams():
     enc.close(); s.close()
 
 
-EXACT_MIN_IDENTICAL = 1.0       # measured on a B200: 204 / 204 and 128 / 128 packets byte-identical (profiles/r01_s4_exact_transform.md)
+# measured on a B200: 204 / 204 and 128 / 128 packets byte-identical (profiles/r01_s4_exact_transform.md).  The other
+# configurations have not been run with K1x yet: they carry K1's bar and print what they reach, to be raised next round.
+EXACT_CASES = [("q4_44k_2ch", 4.0, 1.0), ("q8_48k_6ch", 2.0, 1.0), ("q2_44k_2ch", 3.0, 0.80), ("q10_48k_2ch", 3.0, 0.80),
+               ("q4_48k_6ch", 2.0, 0.80), ("q4_44k_1ch", 3.0, 0.80), ("abr128_44k_2ch", 3.0, 0.80)]
 
 
-@pytest.mark.parametrize("config,seconds", [("q4_44k_2ch", 4.0), ("q8_48k_6ch", 2.0)])
-def test_stream_with_exact_transform(config, seconds):
+@pytest.mark.parametrize("config,seconds,min_identical", EXACT_CASES)
+def test_stream_with_exact_transform(config, seconds, min_identical):
     """Whole path with K1x (operation-exact MDCT / real FFT): every later stage is bit-exact on reference inputs
     (test_gpu_stages), so the packets ARE the reference's: every packet byte-identical."""
     from vorbis_aotuv_lancer_b200 import ops
@@ -148,5 +151,5 @@ def test_stream_with_exact_transform(config, seconds):
     print("\n%s with the exact transform: %d blocks, identical packets %.2f%% (%d differ), bytes gpu %d ref %d"
           % (config, len(ref), 100.0 * same / len(ref), len(ref) - same, gbytes, rbytes))
     assert [a[1] for a in pk] == [r[1] for r in ref]
-    assert same / len(ref) >= EXACT_MIN_IDENTICAL
+    assert same / len(ref) >= min_identical
     st.close(); bt.close(); s.close()
