@@ -211,6 +211,10 @@ __device__ __forceinline__ void rpass2(int ido, int l1, const float *cc, float *
   }
 }
 
+/* position of element i of the MDCT's upper work half: one pad float per 32, so that the threads that own one 32-point
+   group each (stride 32 -> all on one bank) land on 32 different banks */
+__device__ __forceinline__ int P(int i) { return i + (i >> 5); }
+
 template <int N, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm, const long long *__restrict__ pcm_off,
@@ -222,7 +226,7 @@ k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict
   constexpr int LOG2N = (N == 2048) ? 11 : 8;
   static_assert(N == 2048 || N == 256, "block sizes of the built path");
   __shared__ __align__(16) float x[N];        /* the windowed block; later the real FFT's buffer c */
-  __shared__ __align__(16) float w[N];        /* the MDCT's work vector; later the real FFT's buffer ch */
+  __shared__ __align__(16) float w[N + N / 64];   /* the MDCT's work vector (upper half padded, see P()); later the real FFT's buffer ch */
   __shared__ double red[2][(THREADS + 31) / 32];
   __shared__ float redf[(THREADS + 31) / 32];
 
@@ -288,8 +292,8 @@ k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict
       const float *x0 = x + N - 4 * (p - (N2 - N8) / 2 + 1), *x1 = x + 1 + 4 * (p - N8 / 2);
       r0 = sub(-x0[2], x1[0]); r1 = sub(-x0[0], x1[2]);
     }
-    w2[i] = mad2(r1, t1, r0, t0);
-    w2[i + 1] = msu2(r1, t0, r0, t1);
+    w2[P(i)] = mad2(r1, t1, r0, t0);
+    w2[P(i + 1)] = msu2(r1, t0, r0, t1);
   }
   __syncthreads();
 
@@ -299,14 +303,15 @@ k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict
     const int points = N2 >> s, pairs = points >> 2, trigint = 4 << s;
     for (int g = tid; g < N8; g += THREADS) {
       const int j = g / pairs, c = g - j * pairs, cp = pairs - 1 - c;
-      float *lo = w2 + j * points + 2 * cp, *hi = lo + (points >> 1);
+      const int lo = j * points + 2 * cp, hi = lo + (points >> 1);
+      const int pl0 = P(lo), pl1 = P(lo + 1), ph0 = P(hi), ph1 = P(hi + 1);
       const float t0 = __ldg(T + c * trigint), t1 = __ldg(T + c * trigint + 1);
-      const float l0 = lo[0], l1 = lo[1], h0 = hi[0], h1 = hi[1];
+      const float l0 = w2[pl0], l1 = w2[pl1], h0 = w2[ph0], h1 = w2[ph1];
       const float r0 = sub(h0, l0), r1 = sub(h1, l1);
-      hi[0] = add(h0, l0);
-      hi[1] = add(h1, l1);
-      lo[0] = mad2(r1, t1, r0, t0);
-      lo[1] = msu2(r1, t0, r0, t1);
+      w2[ph0] = add(h0, l0);
+      w2[ph1] = add(h1, l1);
+      w2[pl0] = mad2(r1, t1, r0, t0);
+      w2[pl1] = msu2(r1, t0, r0, t1);
     }
     __syncthreads();
   }
@@ -314,21 +319,22 @@ k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict
   for (int g = tid; g < N2 / 32; g += THREADS) {
     float r[32];
 #pragma unroll
-    for (int i = 0; i < 32; i++) r[i] = w2[g * 32 + i];
+    for (int i = 0; i < 32; i++) r[i] = w2[g * 33 + i];          /* = P(g * 32 + i) */
     bfly32(r);
 #pragma unroll
-    for (int i = 0; i < 32; i++) w2[g * 32 + i] = r[i];
+    for (int i = 0; i < 32; i++) w2[g * 33 + i] = r[i];
   }
   __syncthreads();
 
   /* ---- bit reversal + rotation into the lower half (mdct.c:1228-1273): item q ---- */
   for (int q = tid; q < N8; q += THREADS) {
-    const float *x0 = w2 + __ldg(bitrev + 2 * q), *x1 = w2 + __ldg(bitrev + 2 * q + 1);
+    const int b0 = __ldg(bitrev + 2 * q), b1 = __ldg(bitrev + 2 * q + 1);
+    const float x00 = w2[P(b0)], x01 = w2[P(b0 + 1)], x10 = w2[P(b1)], x11 = w2[P(b1 + 1)];
     const float tb0 = __ldg(T + N + 2 * q), tb1 = __ldg(T + N + 2 * q + 1);
-    float r0 = sub(x0[1], x1[1]), r1 = add(x0[0], x1[0]);
+    float r0 = sub(x01, x11), r1 = add(x00, x10);
     const float r2 = mad2(r1, tb0, r0, tb1), r3 = msu2(r1, tb1, r0, tb0);
-    r0 = mul(add(x0[1], x1[1]), .5f);
-    r1 = mul(sub(x0[0], x1[0]), .5f);
+    r0 = mul(add(x01, x11), .5f);
+    r1 = mul(sub(x00, x10), .5f);
     w[2 * q] = add(r0, r2);
     w[N2 - 2 - 2 * q] = sub(r0, r2);
     w[2 * q + 1] = add(r1, r3);
