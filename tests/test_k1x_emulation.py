@@ -1,7 +1,8 @@
-"""K1x (the operation-exact front end, csrc/k_transform_exact.cu) run on the CPU as a serial program -- one "thread"
-executes every work item of every stage in order (tests/emu/k1x_emu.cpp) -- against the reference's own MDCT,
-logmdct, logfft and block maximum, bit for bit.  Covers the kernel's index arithmetic, stage order, tables and buffer
-reuse without a GPU; the `-m gpu` tests (test_gpu_transform.py) cover the real launch."""
+"""K1x (the operation-exact front end, csrc/k_transform_exact.cu) run on the CPU with one OS thread per CUDA thread of
+a block and a pthread barrier for __syncthreads (tests/emu/k1x_emu.cpp) -- against the reference's own MDCT, logmdct,
+logfft and block maximum, bit for bit.  Covers the kernel's index arithmetic, thread-to-item mappings, stage order,
+barrier placement, tables and buffer reuse without a GPU; the `-m gpu` tests (test_gpu_transform.py) cover the real
+launch."""
 import ctypes as C
 import os
 import subprocess
@@ -20,7 +21,7 @@ fp = C.POINTER(C.c_float)
 def emu():
     src = os.path.join(ROOT, "tests", "emu", "k1x_emu.cpp")
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.check_call(["g++", "-O1", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-w",
+    subprocess.check_call(["g++", "-O1", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-w", "-pthread",
                            "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"),
                            "-I" + os.path.join(ROOT, "vorbis_aotuv_lancer_b200", "csrc"), "-o", SO, src])
     return C.CDLL(SO)
@@ -49,3 +50,20 @@ def test_emulated_kernel_equals_the_reference(emu, config):
             assert np.array_equal(lf, b["TAP_TM_LOGFFT"][c]["data"]), (seq, c, "logfft")
             assert np.float32(amp.value) == b["TAP_TM_SCAL"][c]["data"][1], (seq, c, "ampmax")
     assert seen[0] > 0 and seen[1] > 0
+
+
+def test_emulated_kernel_has_no_data_race(tmp_path):
+    """The same emulation under ThreadSanitizer: every shared-memory hand-over between the kernel's stages must be
+    ordered by a barrier."""
+    exe = str(tmp_path / "k1x_tsan")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    r = subprocess.run(["g++", "-O1", "-g", "-fsanitize=thread", "-fno-fast-math", "-ffp-contract=off", "-std=c++17", "-w", "-pthread",
+                        "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "vorbis_aotuv_lancer_b200", "csrc"),
+                        "-o", exe, os.path.join(ROOT, "tests", "emu", "k1x_tsan_main.cpp"), os.path.join(ROOT, "tests", "emu", "k1x_emu.cpp")],
+                       capture_output=True, text=True)
+    if r.returncode != 0 and "tsan" in (r.stderr or "").lower():
+        pytest.skip("ThreadSanitizer runtime not available")
+    assert r.returncode == 0, r.stderr[-2000:]
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and "ThreadSanitizer" not in run.stderr, run.stderr[-3000:]
+    assert "n=2048" in run.stdout and "n=256" in run.stdout

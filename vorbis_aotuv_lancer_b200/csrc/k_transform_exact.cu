@@ -1,4 +1,5 @@
-/* K1x -- the front end with OPERATION-EXACT transforms (opt-in: vb200_setup_set_exact_transform / VB200_EXACT_TRANSFORM=1).
+/* K1x -- the front end with OPERATION-EXACT transforms (the default; vb200_setup_set_exact_transform(s, 0) /
+ * VB200_EXACT_TRANSFORM=0 select K1).
  *
  * K1 (k_transform.cu) computes the MDCT and the real FFT with its own radix-4 Stockham formulation; the results agree
  * with the reference's to ~1e-6 of the block RMS (north_star's tolerance), which is enough to flip a quantiser decision
@@ -9,9 +10,22 @@
  *                                     bit reversal :1228-1273; tables mdct_init :54-92)
  *   drft_forward   smallft.c:6770    (drftf1 :6111-6170, dradf4 :5707-5807, dradf2 :5652-5705; tables drfti1 :5576-5644)
  *   spectrum loop  mapping0.c:847-888, logmdct :933-951, _postnoise_detection psy.c:619-648, window window.c:2137-2261
- * The dataflow is the reference's, the form is not: every stage is a set of independent work items with their operand
+ * The dataflow is the reference's, the form is not.  Every stage is a set of independent work items with their operand
  * indices in closed form (validated on the CPU as oracle/port/mdct_exact_port.c and drft_exact_port.c, bit-exact on
- * every block of every test configuration), one thread per item, one barrier per stage, everything in shared memory.
+ * every block of every test configuration).  B200 mapping, one CTA of n/8 threads per ch-block:
+ *   - the block goes from HBM to registers as float4 quads, windowed on the way; fold item p and its mirror n/4-1-p
+ *     need exactly the same two quads, so one thread folds both straight from registers (and drops the windowed
+ *     quads into shared memory for the real FFT) -- no scalar staging pass, no strided reads of the block;
+ *   - the MDCT's work vector holds complex values as aligned float2 slots, two pad slots per 16: the radix-2
+ *     butterfly stages move 8 bytes per access conflict-free, the 32-point groups (one thread per group, registers)
+ *     move 16; the twiddles of stage s are regrouped at unit stride (vb200_exact_tables_k1x);
+ *   - bit reversal and final rotation are one item: the reversed pair q feeds output pairs q and n/4-1-q directly;
+ *   - the real FFT's passes are compiled per (ido, l1): no index division, the three loops (k), (k, i), (k) of a pass
+ *     are one item space of exactly n/8 items; its buffers store element e at e + 1 + 2*(e / block) -- the (odd, even)
+ *     pairs every pass reads and writes become aligned float2 slots and the block stride becomes odd in slots, so both
+ *     the k-major and the i-major lane orders are conflict-free; the first two passes (ido = 1, 4) are a 16-point
+ *     transform on registers;
+ *   - an MDCT stage and a real-FFT pass share each barrier interval: 8 barriers per long ch-block (was 16).
  * HBM traffic is K1's: n*4 bytes in, 3*N2*4 bytes out.
  */
 #include "vb200_internal.h"
@@ -72,6 +86,25 @@ void vb200_exact_tables_drft(int n, float *wa) {
   }
 }
 
+
+/* per-stage twiddles of the MDCT butterflies at unit stride -- stage s, pair c: (T[c*(4<<s)], T[c*(4<<s)+1]), stages
+   concatenated (n/8 >> s entries each) -- and the bit-reversal targets as padded slot indices (x0 slot, x1 slot).
+   stage_tw must hold n/4 float2, rev n/8 int2. */
+void vb200_exact_tables_k1x(int n, const float *T, const int *bitrev, float2 *stage_tw, int2 *rev) {
+  int log2n = 0;
+  while ((1 << log2n) < n) log2n++;
+  int o = 0;
+  for (int s = 0; s < log2n - 6; s++) {
+    const int pairs = (n / 8) >> s, trigint = 4 << s;
+    for (int c = 0; c < pairs; c++) { stage_tw[o].x = T[c * trigint]; stage_tw[o].y = T[c * trigint + 1]; o++; }
+  }
+  for (int q = 0; q < n / 8; q++) {
+    const int u0 = bitrev[2 * q] >> 1, u1 = bitrev[2 * q + 1] >> 1;      /* complex slots of the upper work half */
+    rev[q].x = u0 + 2 * (u0 >> 4);
+    rev[q].y = u1 + 2 * (u1 >> 4);
+  }
+}
+
 namespace {
 
 #define C1_8 .92387953251128675613F
@@ -84,6 +117,10 @@ __device__ __forceinline__ float msu2(float a, float b, float c, float d) { retu
 __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+
+template <int THREADS> __device__ __forceinline__ void cta_sync() {
+  if (THREADS <= 32) __syncwarp(); else __syncthreads();
+}
 
 /* the hard-coded 32-point end of the butterfly recursion on registers (mdct.c:602-659 -> :495-524 -> :432-453) */
 __device__ __forceinline__ void bfly8(float *x) {
@@ -137,96 +174,178 @@ __device__ __forceinline__ void bfly32(float *x) {
   bfly16(x); bfly16(x + 16);
 }
 
-/* one radix-4 pass of the real FFT, cc -> ch (dradf4): items (k), (k, i), (k) */
-template <int THREADS>
-__device__ __forceinline__ void rpass4(int ido, int l1, const float *cc, float *ch, const float *__restrict__ wa1) {
-  const float *wa2 = wa1 + ido, *wa3 = wa2 + ido;
-  const int t0 = l1 * ido, t6 = ido << 1, tid = threadIdx.x;
-  for (int k = tid; k < l1; k += THREADS) {
-    const int t3 = k * ido, t1 = t0 + t3, t4 = 2 * t0 + t3, t2 = 3 * t0 + t3, t5 = t3 << 2;
-    const float tr1 = add(cc[t1], cc[t2]), tr2 = add(cc[t3], cc[t4]);
-    ch[t5] = add(tr1, tr2);
-    ch[(ido << 2) + t5 - 1] = sub(tr2, tr1);
-    ch[t5 + t6 - 1] = sub(cc[t3], cc[t4]);
-    ch[t5 + t6] = sub(cc[t2], cc[t1]);
+/* slot of complex value u of the MDCT's work vector: two pad slots per 16, so that the threads that own one 32-point
+   group each (stride 16 slots) spread over the banks while every group stays 16-byte aligned and contiguous */
+__device__ __forceinline__ int PS(int u) { return u + 2 * (u >> 4); }
+
+/* float offset of the real FFT's twiddles for the pass with this ido (the reference walks the table backwards,
+   smallft.c:6111-6170): n = 2048 has factors 2,4,4,4,4,4 (the 2 in front: ido 1024, then 256, 64, 16, 4), n = 256 has
+   4,4,4,4 (ido 64, 16, 4); the last factor (ido 1) has no twiddles */
+template <int N> __host__ __device__ constexpr int wa_off(int ido) {
+  int off = 0, l1 = 1, n = N, first = 1;
+  int lg = 0;
+  while ((1 << lg) < N) lg++;
+  while (n > 1) {
+    const int ip = (first && (lg & 1)) ? 2 : 4;
+    first = 0;
+    const int l2 = l1 * ip, id = N / l2;
+    if (id == ido) return off;
+    off += (ip - 1) * id;
+    l1 = l2;
+    n /= ip;
   }
-  if (ido < 2) return;
-  const int per = (ido >> 1) - 1;                 /* i = 2, 4, ... ido-2 */
-  for (int m = tid; m < l1 * per; m += THREADS) {
-    const int k = m / per, i = 2 + 2 * (m - k * per);
-    const int t1 = k * ido, t2 = t1 + i, t4 = (t1 << 2) + i, t5 = t6 + (t1 << 2) - i;
-    int t3 = t2 + t0;
-    const float w1r = __ldg(wa1 + i - 2), w1i = __ldg(wa1 + i - 1), w2r = __ldg(wa2 + i - 2), w2i = __ldg(wa2 + i - 1);
-    const float w3r = __ldg(wa3 + i - 2), w3i = __ldg(wa3 + i - 1);
-    const float cr2 = mad2(w1r, cc[t3 - 1], w1i, cc[t3]), ci2 = msu2(w1r, cc[t3], w1i, cc[t3 - 1]);
-    t3 += t0;
-    const float cr3 = mad2(w2r, cc[t3 - 1], w2i, cc[t3]), ci3 = msu2(w2r, cc[t3], w2i, cc[t3 - 1]);
-    t3 += t0;
-    const float cr4 = mad2(w3r, cc[t3 - 1], w3i, cc[t3]), ci4 = msu2(w3r, cc[t3], w3i, cc[t3 - 1]);
+  return -1;
+}
+
+/* ---- MDCT: one radix-2 butterfly stage over sub-blocks of (N/2 >> S) floats, one thread per pair (mdct.c:854-895,
+   :1032-1079).  Pair c, counted from the top of each half, of sub-block j combines the complex values at slots
+   L = j*points/2 + (pairs-1-c) and L + points/4 with the twiddle T[c*(4<<S)]. ---- */
+template <int N, int S>
+__device__ __forceinline__ void mdct_stage(float2 *wz, const float2 *__restrict__ stw) {
+  constexpr int points = (N / 2) >> S, pairs = points >> 2;
+  int off = 0;
+#pragma unroll
+  for (int q = 0; q < S; q++) off += (N / 8) >> q;
+  const int g = threadIdx.x;
+  const int j = g / pairs, c = g % pairs, cp = pairs - 1 - c;
+  const int L = PS(j * (points / 2) + cp), H = PS(j * (points / 2) + cp + points / 4);
+  const float2 t = __ldg(stw + off + c);
+  const float2 lo = wz[L], hi = wz[H];
+  const float r0 = sub(hi.x, lo.x), r1 = sub(hi.y, lo.y);
+  wz[H] = make_float2(add(hi.x, lo.x), add(hi.y, lo.y));
+  wz[L] = make_float2(mad2(r1, t.y, r0, t.x), msu2(r1, t.x, r0, t.y));
+}
+
+/* ---- real FFT, passes ido = 1 and ido = 4 on registers (smallft.c dradf4 twice): thread k < N/16 reads the 16 block
+   values x[k + m*N/16] and writes elements 16k .. 16k+15 of the next buffer (blocks of 16, see the layout note) ---- */
+template <int N>
+__device__ __forceinline__ void rfft_first16(const float *x, float *ch, const float *__restrict__ wa, int k) {
+  constexpr int Q = N / 16;
+  float y[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const float a0 = x[k + r * Q], a1 = x[k + r * Q + N / 4], a2 = x[k + r * Q + N / 2], a3 = x[k + r * Q + 3 * (N / 4)];
+    const float tr1 = add(a1, a3), tr2 = add(a0, a2);
+    y[r][0] = add(tr1, tr2); y[r][3] = sub(tr2, tr1); y[r][1] = sub(a0, a2); y[r][2] = sub(a3, a1);
+  }
+  const float *wa1 = wa + wa_off<N>(4);
+  const float2 w1 = __ldg(reinterpret_cast<const float2 *>(wa1)), w2 = __ldg(reinterpret_cast<const float2 *>(wa1 + 4)),
+               w3 = __ldg(reinterpret_cast<const float2 *>(wa1 + 8));
+  float o[16];
+  {  /* i = 0 column */
+    const float tr1 = add(y[1][0], y[3][0]), tr2 = add(y[0][0], y[2][0]);
+    o[0] = add(tr1, tr2); o[15] = sub(tr2, tr1); o[7] = sub(y[0][0], y[2][0]); o[8] = sub(y[3][0], y[1][0]);
+  }
+  {  /* i = 2 */
+    const float cr2 = mad2(w1.x, y[1][1], w1.y, y[1][2]), ci2 = msu2(w1.x, y[1][2], w1.y, y[1][1]);
+    const float cr3 = mad2(w2.x, y[2][1], w2.y, y[2][2]), ci3 = msu2(w2.x, y[2][2], w2.y, y[2][1]);
+    const float cr4 = mad2(w3.x, y[3][1], w3.y, y[3][2]), ci4 = msu2(w3.x, y[3][2], w3.y, y[3][1]);
     const float tr1 = add(cr2, cr4), tr4 = sub(cr4, cr2), ti1 = add(ci2, ci4), ti4 = sub(ci2, ci4);
-    const float ti2 = add(cc[t2], ci3), ti3 = sub(cc[t2], ci3), tr2 = add(cc[t2 - 1], cr3), tr3 = sub(cc[t2 - 1], cr3);
-    ch[t4 - 1] = add(tr1, tr2);      ch[t4] = add(ti1, ti2);
-    ch[t5 - 1] = sub(tr3, ti4);      ch[t5] = sub(tr4, ti3);
-    ch[t4 + t6 - 1] = add(ti4, tr3); ch[t4 + t6] = add(tr4, ti3);
-    ch[t5 + t6 - 1] = sub(tr2, tr1); ch[t5 + t6] = sub(ti1, ti2);
+    const float ti2 = add(y[0][2], ci3), ti3 = sub(y[0][2], ci3), tr2 = add(y[0][1], cr3), tr3 = sub(y[0][1], cr3);
+    o[1] = add(tr1, tr2);  o[2] = add(ti1, ti2);
+    o[5] = sub(tr3, ti4);  o[6] = sub(tr4, ti3);
+    o[9] = add(ti4, tr3);  o[10] = add(tr4, ti3);
+    o[13] = sub(tr2, tr1); o[14] = sub(ti1, ti2);
   }
-  if (ido & 1) return;
-  const float hsqt2 = .70710678118654752f;
-  for (int k = tid; k < l1; k += THREADS) {
-    const int t1 = t0 + ido - 1 + k * ido, t2 = t1 + (t0 << 1), t4 = ido + k * (ido << 2), t5 = ido << 1, t6b = ido + k * ido;
-    const float ti1 = mul(-hsqt2, add(cc[t1], cc[t2])), tr1 = mul(hsqt2, sub(cc[t1], cc[t2]));
-    ch[t4 - 1] = add(tr1, cc[t6b - 1]);
-    ch[t4 + t5 - 1] = sub(cc[t6b - 1], tr1);
-    ch[t4] = sub(ti1, cc[t1 + t0]);
-    ch[t4 + t5] = add(ti1, cc[t1 + t0]);
+  {  /* middle column */
+    const float hsqt2 = .70710678118654752f;
+    const float ti1 = mul(-hsqt2, add(y[1][3], y[3][3])), tr1 = mul(hsqt2, sub(y[1][3], y[3][3]));
+    o[3] = add(tr1, y[0][3]); o[11] = sub(y[0][3], tr1); o[4] = sub(ti1, y[2][3]); o[12] = add(ti1, y[2][3]);
+  }
+  float *b = ch + k * 18;               /* element e of the block at b[e + 1] */
+  b[1] = o[0];
+#pragma unroll
+  for (int m = 1; m < 8; m++) *reinterpret_cast<float2 *>(b + 2 * m) = make_float2(o[2 * m - 1], o[2 * m]);
+  b[16] = o[15];
+}
+
+/* ---- real FFT, one radix-4 pass cc -> ch (dradf4, smallft.c:5707-5807) with IDO >= 16.  Buffer layout: element e of a
+   buffer whose blocks have B elements lives at float e + 1 + 2*(e / B); cc has blocks of IDO, ch of 4*IDO.  Item
+   (k, j): j = 0 is the i = 0 column plus the middle column of block k, j >= 1 the pair i = 2j.  KFAST: k is the fast
+   lane index (l1 >= 16), else j. ---- */
+template <int N, int IDO, bool KFAST>
+__device__ __forceinline__ void rfft_pass4(const float *cc, float *ch, const float *__restrict__ wa) {
+  constexpr int L1 = N / (4 * IDO), H = IDO / 2;
+  constexpr int SBI = H + 1, SBO = 2 * IDO + 1;          /* block strides in float2 slots */
+  const float2 *c2 = reinterpret_cast<const float2 *>(cc);
+  float2 *o2 = reinterpret_cast<float2 *>(ch);
+  const int t = threadIdx.x;
+  const int k = KFAST ? t % L1 : t / H, j = KFAST ? t / L1 : t % H;
+  const int ob = k * SBO;
+  if (j == 0) {
+    const float *f0 = cc + k * (IDO + 2), *f1 = f0 + L1 * (IDO + 2), *f2 = f1 + L1 * (IDO + 2), *f3 = f2 + L1 * (IDO + 2);
+    {
+      const float c3 = f0[1], c1 = f1[1], c4 = f2[1], c2v = f3[1];
+      const float tr1 = add(c1, c2v), tr2 = add(c3, c4);
+      ch[2 * ob + 1] = add(tr1, tr2);
+      ch[2 * ob + 4 * IDO] = sub(tr2, tr1);
+      o2[ob + IDO] = make_float2(sub(c3, c4), sub(c2v, c1));
+    }
+    {
+      const float hsqt2 = .70710678118654752f;
+      const float d0 = f0[IDO], d1 = f1[IDO], d2 = f2[IDO], d3 = f3[IDO];
+      const float ti1 = mul(-hsqt2, add(d1, d3)), tr1 = mul(hsqt2, sub(d1, d3));
+      o2[ob + H] = make_float2(add(tr1, d0), sub(ti1, d2));
+      o2[ob + 3 * H] = make_float2(sub(d0, tr1), add(ti1, d2));
+    }
+  } else {
+    const int sb = k * SBI + j;
+    const float2 p0 = c2[sb], p1 = c2[sb + L1 * SBI], p2 = c2[sb + 2 * L1 * SBI], p3 = c2[sb + 3 * L1 * SBI];
+    const float *wa1 = wa + wa_off<N>(IDO) + 2 * (j - 1);
+    const float2 w1 = __ldg(reinterpret_cast<const float2 *>(wa1)), w2 = __ldg(reinterpret_cast<const float2 *>(wa1 + IDO)),
+                 w3 = __ldg(reinterpret_cast<const float2 *>(wa1 + 2 * IDO));
+    const float cr2 = mad2(w1.x, p1.x, w1.y, p1.y), ci2 = msu2(w1.x, p1.y, w1.y, p1.x);
+    const float cr3 = mad2(w2.x, p2.x, w2.y, p2.y), ci3 = msu2(w2.x, p2.y, w2.y, p2.x);
+    const float cr4 = mad2(w3.x, p3.x, w3.y, p3.y), ci4 = msu2(w3.x, p3.y, w3.y, p3.x);
+    const float tr1 = add(cr2, cr4), tr4 = sub(cr4, cr2), ti1 = add(ci2, ci4), ti4 = sub(ci2, ci4);
+    const float ti2 = add(p0.y, ci3), ti3 = sub(p0.y, ci3), tr2 = add(p0.x, cr3), tr3 = sub(p0.x, cr3);
+    o2[ob + j] = make_float2(add(tr1, tr2), add(ti1, ti2));
+    o2[ob + IDO - j] = make_float2(sub(tr3, ti4), sub(tr4, ti3));
+    o2[ob + IDO + j] = make_float2(add(ti4, tr3), add(tr4, ti3));
+    o2[ob + 2 * IDO - j] = make_float2(sub(tr2, tr1), sub(ti1, ti2));
   }
 }
 
-/* one radix-2 pass, cc -> ch (dradf2) */
-template <int THREADS>
-__device__ __forceinline__ void rpass2(int ido, int l1, const float *cc, float *ch, const float *__restrict__ wa1) {
-  const int t0 = l1 * ido, tid = threadIdx.x;
-  for (int k = tid; k < l1; k += THREADS) {
-    const int t1 = k * ido, t2 = t0 + k * ido;
-    ch[2 * t1] = add(cc[t1], cc[t2]);
-    ch[2 * t1 + 2 * ido - 1] = sub(cc[t1], cc[t2]);
-  }
-  if (ido < 2) return;
-  const int per = (ido >> 1) - 1;
-  for (int m = tid; m < l1 * per; m += THREADS) {
-    const int k = m / per, i = 2 + 2 * (m - k * per);
-    const int t1 = k * ido, t3 = t0 + t1 + i, t4 = 2 * t1 + 2 * ido - i, t5 = t1 + i, t6 = 2 * t1 + i;
-    const float wr = __ldg(wa1 + i - 2), wi = __ldg(wa1 + i - 1);
-    const float tr2 = mad2(wr, cc[t3 - 1], wi, cc[t3]), ti2 = msu2(wr, cc[t3], wi, cc[t3 - 1]);
-    ch[t6] = add(cc[t5], ti2);
-    ch[t4] = sub(ti2, cc[t5]);
-    ch[t6 - 1] = add(cc[t5 - 1], tr2);
-    ch[t4 - 1] = sub(cc[t5 - 1], tr2);
-  }
-  if (ido & 1) return;
-  for (int k = tid; k < l1; k += THREADS) {
-    const int t1 = ido + 2 * k * ido, t3 = ido - 1 + k * ido, t2 = t3 + t0;
-    ch[t1] = -cc[t2];
-    ch[t1 - 1] = cc[t3];
+/* ---- real FFT, the radix-2 pass that ends a transform with an odd log2 (dradf2, smallft.c:5652-5705; l1 = 1,
+   ido = N/2): items j < N/4, two per thread ---- */
+template <int N, int THREADS>
+__device__ __forceinline__ void rfft_pass2_last(const float *cc, float *ch, const float *__restrict__ wa) {
+  constexpr int IDO = N / 2, H = IDO / 2;
+  const float2 *c2 = reinterpret_cast<const float2 *>(cc);
+  float2 *o2 = reinterpret_cast<float2 *>(ch);
+#pragma unroll
+  for (int rep = 0; rep < H / THREADS; rep++) {
+    const int j = threadIdx.x + rep * THREADS;
+    if (j == 0) {
+      const float c0 = cc[1], c1 = cc[IDO + 2 + 1];
+      ch[1] = add(c0, c1);
+      ch[2 * IDO] = sub(c0, c1);
+      o2[H] = make_float2(cc[IDO], -cc[IDO + 2 + IDO]);
+    } else {
+      const float2 q0 = c2[j], q1 = c2[H + 1 + j];
+      const float2 w = __ldg(reinterpret_cast<const float2 *>(wa + wa_off<N>(IDO) + 2 * (j - 1)));
+      const float tr2 = mad2(w.x, q1.x, w.y, q1.y), ti2 = msu2(w.x, q1.y, w.y, q1.x);
+      o2[j] = make_float2(add(q0.x, tr2), add(q0.y, ti2));
+      o2[IDO - j] = make_float2(sub(q0.x, tr2), sub(ti2, q0.y));
+    }
   }
 }
-
-/* position of element i of the MDCT's upper work half: one pad float per 32, so that the threads that own one 32-point
-   group each (stride 32 -> all on one bank) land on 32 different banks */
-__device__ __forceinline__ int P(int i) { return i + (i >> 5); }
 
 template <int N, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (N == 2048 ? 6 : 16))
 k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict__ pcm, const long long *__restrict__ pcm_off,
                   const int *__restrict__ lWv, const int *__restrict__ nWv,
                   const int *__restrict__ block_mode, const int *__restrict__ lW_block_mode,
                   float *__restrict__ gmdct, float *__restrict__ logfft, float *__restrict__ logmdct,
                   float *__restrict__ local_ampmax, float *__restrict__ poste) {
-  constexpr int N2 = N / 2, N4 = N / 4, N8 = N / 8;
-  constexpr int LOG2N = (N == 2048) ? 11 : 8;
+  constexpr int N2 = N / 2, N4 = N / 4, N8 = N / 8, N16 = N / 16;
   static_assert(N == 2048 || N == 256, "block sizes of the built path");
-  __shared__ __align__(16) float x[N];        /* the windowed block; later the real FFT's buffer c */
-  __shared__ __align__(16) float w[N + N / 64];   /* the MDCT's work vector (upper half padded, see P()); later the real FFT's buffer ch */
+  static_assert(THREADS == N8, "one thread per fold pair / butterfly / bit-reversal item");
+  /* real FFT ping-pong: A holds the windowed block (natural order), then the buffers with blocks of 64 and 1024;
+     B the buffers with blocks of 16 and 256 and the spectrum */
+  __shared__ __align__(16) float bufA[N + 2 * (N / 64) + 4];
+  __shared__ __align__(16) float bufB[N + 2 * (N / 16) + 4];
+  __shared__ __align__(16) float2 wz[N4 + 2 * (N4 / 16)];       /* the MDCT's upper work half as complex slots, PS() */
   __shared__ double red[2][(THREADS + 31) / 32];
   __shared__ float redf[(THREADS + 31) / 32];
 
@@ -249,7 +368,7 @@ k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict
       for (int i = mn + tid; i < en; i += THREADS) un += (double)fabsf(__ldg(src + i));
       up = warp_sum_d(up); un = warp_sum_d(un);
       if ((tid & 31) == 0) { red[0][tid >> 5] = up; red[1][tid >> 5] = un; }
-      __syncthreads();
+      cta_sync<THREADS>();
       if (tid == 0) {
         double upt = 0., unt = 0.;
         for (int q = 0; q < (THREADS + 31) / 32; q++) { upt += red[0][q]; unt += red[1][q]; }
@@ -262,131 +381,85 @@ k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict
     } else if (tid == 0) poste[item] = ret;
   }
 
-  /* ---- stage the block, windowed on the way in (window.c:2137-2261) ---- */
-  for (int i = tid; i < N; i += THREADS) {
-    float v = __ldg(src + i);
-    if (i < leftbegin) v = 0.f;
-    else if (i < leftend) v = mul(v, __ldg(wl + (i - leftbegin)));
-    else if (i >= rightend) v = 0.f;
-    else if (i >= rightbegin) v = mul(v, __ldg(wr + (rn / 2 - 1 - (i - rightbegin))));
-    x[i] = v;
-  }
-  __syncthreads();
-
   const float *T = S->xm_trig[W];
-  const int *bitrev = S->xm_bitrev[W];
-  float *w2 = w + N2;
+  const float2 *T2 = reinterpret_cast<const float2 *>(T);
+  const float2 *stw = S->xm_stage[W];
+  const float *wa = S->xf_wa[W];
 
-  /* ---- MDCT, fold + first rotation: pair p of the upper half of w (mdct.c:1817-1846) ---- */
-  for (int p = tid; p < N4; p += THREADS) {
-    const int i = 2 * p;
-    const float t0 = __ldg(T + N2 - 2 - i), t1 = __ldg(T + N2 - 1 - i);
-    float r0, r1;
-    if (i < N8) {
-      const float *x0 = x + N2 + N4 - 4 * (p + 1), *x1 = x + N2 + N4 + 1 + 4 * p;
-      r0 = add(x0[2], x1[0]); r1 = add(x0[0], x1[2]);
-    } else if (i < N2 - N8) {
-      const float *x0 = x + N2 + N4 - 4 * (p + 1), *x1 = x + 1 + 4 * (p - N8 / 2);
-      r0 = sub(x0[2], x1[0]); r1 = sub(x0[0], x1[2]);
-    } else {
-      const float *x0 = x + N - 4 * (p - (N2 - N8) / 2 + 1), *x1 = x + 1 + 4 * (p - N8 / 2);
-      r0 = sub(-x0[2], x1[0]); r1 = sub(-x0[0], x1[2]);
-    }
-    w2[P(i)] = mad2(r1, t1, r0, t0);
-    w2[P(i + 1)] = msu2(r1, t0, r0, t1);
+  /* ---- window (window.c:2137-2261) + fold + first rotation (mdct.c:1817-1846).  Pair p and its mirror N/4-1-p read the
+     even / the odd samples of the same two quads qa, qb of the block; every window boundary is a multiple of 4 ---- */
+  {
+    const bool aligned = (((uintptr_t)src) & 15) == 0;
+    auto quad = [&](int q) -> float4 {
+      const int i = 4 * q;
+      float4 v;
+      if (aligned) v = __ldg(reinterpret_cast<const float4 *>(src) + q);
+      else v = make_float4(__ldg(src + i), __ldg(src + i + 1), __ldg(src + i + 2), __ldg(src + i + 3));
+      if (i < leftbegin || i >= rightend) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      else if (i < leftend) {
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(wl + (i - leftbegin)));
+        v.x = mul(v.x, w.x); v.y = mul(v.y, w.y); v.z = mul(v.z, w.z); v.w = mul(v.w, w.w);
+      } else if (i >= rightbegin) {       /* the falling half reads the table backwards */
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(wr + (rn / 2 - 4 - (i - rightbegin))));
+        v.x = mul(v.x, w.w); v.y = mul(v.y, w.z); v.z = mul(v.z, w.y); v.w = mul(v.w, w.x);
+      }
+      return v;
+    };
+    const int p = tid;
+    const bool outer = p < N16;                     /* p in the first segment, its mirror in the third */
+    const int qa = 3 * N16 - 1 - p, qb = outer ? 3 * N16 + p : p - N16;
+    const float4 A = quad(qa), B = quad(qb);
+    reinterpret_cast<float4 *>(bufA)[qa] = A;
+    reinterpret_cast<float4 *>(bufA)[qb] = B;
+    float r0, r1, s0, s1;
+    if (outer) { r0 = add(A.z, B.y); r1 = add(A.x, B.w); s0 = sub(-B.z, A.y); s1 = sub(-B.x, A.w); }
+    else       { r0 = sub(A.z, B.y); r1 = sub(A.x, B.w); s0 = sub(B.z, A.y);  s1 = sub(B.x, A.w); }
+    const float2 t = __ldg(T2 + N4 - 1 - p), u = __ldg(T2 + p);
+    wz[PS(p)] = make_float2(mad2(r1, t.y, r0, t.x), msu2(r1, t.x, r0, t.y));
+    wz[PS(N4 - 1 - p)] = make_float2(mad2(s1, u.y, s0, u.x), msu2(s1, u.x, s0, u.y));
   }
-  __syncthreads();
+  cta_sync<THREADS>();
 
-  /* ---- butterflies: log2n - 6 radix-2 stages over sub-blocks of N2 >> s floats, one thread per pair ---- */
-#pragma unroll
-  for (int s = 0; s < LOG2N - 6; s++) {
-    const int points = N2 >> s, pairs = points >> 2, trigint = 4 << s;
-    for (int g = tid; g < N8; g += THREADS) {
-      const int j = g / pairs, c = g - j * pairs, cp = pairs - 1 - c;
-      const int lo = j * points + 2 * cp, hi = lo + (points >> 1);
-      const int pl0 = P(lo), pl1 = P(lo + 1), ph0 = P(hi), ph1 = P(hi + 1);
-      const float t0 = __ldg(T + c * trigint), t1 = __ldg(T + c * trigint + 1);
-      const float l0 = w2[pl0], l1 = w2[pl1], h0 = w2[ph0], h1 = w2[ph1];
-      const float r0 = sub(h0, l0), r1 = sub(h1, l1);
-      w2[ph0] = add(h0, l0);
-      w2[ph1] = add(h1, l1);
-      w2[pl0] = mad2(r1, t1, r0, t0);
-      w2[pl1] = msu2(r1, t0, r0, t1);
-    }
-    __syncthreads();
+  /* ---- MDCT butterfly stages and real-FFT passes, one of each per barrier interval ---- */
+  if (N == 2048) {
+    mdct_stage<N, 0>(wz, stw); if (tid < N16) rfft_first16<N>(bufA, bufB, wa, tid);   cta_sync<THREADS>();
+    mdct_stage<N, 1>(wz, stw); rfft_pass4<N, 16, true>(bufB, bufA, wa);               cta_sync<THREADS>();
+    mdct_stage<N, 2>(wz, stw); rfft_pass4<N, 64, false>(bufA, bufB, wa);              cta_sync<THREADS>();
+    mdct_stage<N, 3>(wz, stw); rfft_pass4<N, 256, false>(bufB, bufA, wa);             cta_sync<THREADS>();
+    mdct_stage<N, 4>(wz, stw); rfft_pass2_last<N, THREADS>(bufA, bufB, wa);           cta_sync<THREADS>();
+  } else {
+    mdct_stage<N, 0>(wz, stw); if (tid < N16) rfft_first16<N>(bufA, bufB, wa, tid);   cta_sync<THREADS>();
+    mdct_stage<N, 1>(wz, stw); rfft_pass4<N, 16, false>(bufB, bufA, wa);              cta_sync<THREADS>();
+    rfft_pass4<N, 64, false>(bufA, bufB, wa);                                         /* joins the next interval */
   }
-  /* 32-point groups on registers, one thread per group */
-  for (int g = tid; g < N2 / 32; g += THREADS) {
+
+  /* ---- 32-point groups on registers, one thread per group (mdct.c:602-659) ---- */
+  if (tid < N2 / 32) {
+    float4 *g4 = reinterpret_cast<float4 *>(wz + 18 * tid);          /* = PS(16 * tid) */
     float r[32];
 #pragma unroll
-    for (int i = 0; i < 32; i++) r[i] = w2[g * 33 + i];          /* = P(g * 32 + i) */
+    for (int i = 0; i < 8; i++) { const float4 v = g4[i]; r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w; }
     bfly32(r);
 #pragma unroll
-    for (int i = 0; i < 32; i++) w2[g * 33 + i] = r[i];
+    for (int i = 0; i < 8; i++) g4[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
   }
-  __syncthreads();
+  cta_sync<THREADS>();
 
-  /* ---- bit reversal + rotation into the lower half (mdct.c:1228-1273): item q ---- */
-  for (int q = tid; q < N8; q += THREADS) {
-    const int b0 = __ldg(bitrev + 2 * q), b1 = __ldg(bitrev + 2 * q + 1);
-    const float x00 = w2[P(b0)], x01 = w2[P(b0 + 1)], x10 = w2[P(b1)], x11 = w2[P(b1 + 1)];
-    const float tb0 = __ldg(T + N + 2 * q), tb1 = __ldg(T + N + 2 * q + 1);
-    float r0 = sub(x01, x11), r1 = add(x00, x10);
-    const float r2 = mad2(r1, tb0, r0, tb1), r3 = msu2(r1, tb1, r0, tb0);
-    r0 = mul(add(x01, x11), .5f);
-    r1 = mul(sub(x00, x10), .5f);
-    w[2 * q] = add(r0, r2);
-    w[N2 - 2 - 2 * q] = sub(r0, r2);
-    w[2 * q + 1] = add(r1, r3);
-    w[N2 - 1 - 2 * q] = sub(r3, r1);
-  }
-  __syncthreads();
-
-  /* ---- final rotation and scale (mdct.c:1855-1868), logmdct (mapping0.c:933-951) ---- */
-  {
-    const float scale = 4.f / N;
-    float *gm = gmdct + (size_t)item * N2, *lm = logmdct + (size_t)item * N2;
-    for (int p = tid; p < N4; p += THREADS) {
-      const float ta = __ldg(T + N2 + 2 * p), tb = __ldg(T + N2 + 2 * p + 1), a = w[2 * p], b = w[2 * p + 1];
-      const float v0 = mul(mad2(a, ta, b, tb), scale), v1 = mul(msu2(a, tb, b, ta), scale);
-      gm[p] = v0; lm[p] = todB_p345(v0);
-      gm[N2 - 1 - p] = v1; lm[N2 - 1 - p] = todB_p345(v1);
-    }
-  }
-  __syncthreads();                    /* w is free again */
-
-  /* ---- real FFT (smallft.c drftf1): factors from the last to the first, ping-pong x <-> w, result in x ---- */
-  {
-    constexpr int NF = (N == 2048) ? 6 : 4;
-    const float *wa = S->xf_wa[W];
-    int l2 = N, iw = N, na = 1;
-#pragma unroll 1
-    for (int k1 = 0; k1 < NF; k1++) {
-      const int ip = (N == 2048 && k1 == NF - 1) ? 2 : 4;
-      const int l1 = l2 / ip, ido = N / l2;
-      iw -= (ip - 1) * ido;
-      na = 1 - na;
-      const float *cc = na ? w : x;
-      float *ch = na ? x : w;
-      if (ip == 4) rpass4<THREADS>(ido, l1, cc, ch, wa + iw - 1);
-      else rpass2<THREADS>(ido, l1, cc, ch, wa + iw - 1);
-      __syncthreads();
-      l2 = l1;
-    }
-  }
-
-  /* ---- dB spectrum and block maximum (mapping0.c:784-795, 847-888) ---- */
+  /* ---- dB spectrum and block maximum (mapping0.c:784-795, 847-888): the spectrum is in B, element e at B[e + 1] ---- */
   {
     const float scale_dB = todB_p345(4.f / N);
     float *lf = logfft + (size_t)item * N2;
+    const float2 *X = reinterpret_cast<const float2 *>(bufB);
     float mx = -3.0e38f;
-    for (int k = tid; k < N2; k += THREADS) {
+#pragma unroll
+    for (int rep = 0; rep < N2 / THREADS; rep++) {
+      const int k = tid + rep * THREADS;
+      const float2 z = X[k];
       float v;
-      if (k == 0) v = (float)((double)add(scale_dB, todB_raw(x[0])) + .345);
+      if (k == 0) v = (float)((double)add(scale_dB, todB_raw(z.y)) + .345);
       else {
-        const float xr = x[2 * k - 1], xi = x[2 * k];
-        const float p = add(mul(xr, xr), mul(xi, xi));
-        v = (float)((double)add(scale_dB, mul(.5f, todB_raw(p))) + .345);
+        const float pw = add(mul(z.x, z.x), mul(z.y, z.y));
+        v = (float)((double)add(scale_dB, mul(.5f, todB_raw(pw))) + .345);
       }
       lf[k] = v;
       mx = fmaxf(mx, v);
@@ -394,7 +467,31 @@ k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict
     mx = warp_max_f(mx);
     if ((tid & 31) == 0) redf[tid >> 5] = mx;
   }
-  __syncthreads();
+
+  /* ---- bit reversal + rotation (mdct.c:1228-1273) and final rotation + scale (mdct.c:1855-1868), logmdct
+     (mapping0.c:933-951): item q produces the work pairs q and N/4-1-q, i.e. outputs q, N/2-1-q, N/4-1-q, N/4+q ---- */
+  {
+    const int q = tid;
+    const int2 rv = __ldg(S->xm_rev[W] + q);
+    const float2 X0 = wz[rv.x], X1 = wz[rv.y];
+    const float2 tb = __ldg(T2 + N2 + q);                              /* T[N + 2q], T[N + 2q + 1] */
+    float r0 = sub(X0.y, X1.y), r1 = add(X0.x, X1.x);
+    const float r2 = mad2(r1, tb.x, r0, tb.y), r3 = msu2(r1, tb.y, r0, tb.x);
+    r0 = mul(add(X0.y, X1.y), .5f);
+    r1 = mul(sub(X0.x, X1.x), .5f);
+    const float a0 = add(r0, r2), b0 = add(r1, r3);                     /* w[2q], w[2q+1] */
+    const float a1 = sub(r0, r2), b1 = sub(r3, r1);                     /* w[N/2-2-2q], w[N/2-1-2q] */
+    const float2 ta = __ldg(T2 + N4 + q), tc = __ldg(T2 + N4 + N4 - 1 - q);  /* T[N/2 + 2p], p = q and N/4-1-q */
+    const float scale = 4.f / N;
+    float *gm = gmdct + (size_t)item * N2, *lm = logmdct + (size_t)item * N2;
+    const float v0 = mul(mad2(a0, ta.x, b0, ta.y), scale), v1 = mul(msu2(a0, ta.y, b0, ta.x), scale);
+    const float v2 = mul(mad2(a1, tc.x, b1, tc.y), scale), v3 = mul(msu2(a1, tc.y, b1, tc.x), scale);
+    gm[q] = v0;          lm[q] = todB_p345(v0);
+    gm[N2 - 1 - q] = v1; lm[N2 - 1 - q] = todB_p345(v1);
+    gm[N4 - 1 - q] = v2; lm[N4 - 1 - q] = todB_p345(v2);
+    gm[N4 + q] = v3;     lm[N4 + q] = todB_p345(v3);
+  }
+  cta_sync<THREADS>();
   if (tid == 0) {
     float m = redf[0];
     for (int q = 1; q < (THREADS + 31) / 32; q++) m = fmaxf(m, redf[q]);
@@ -405,14 +502,14 @@ k_transform_exact(const DevSetup *__restrict__ S, int W, const float *__restrict
 
 }  // namespace
 
-#ifdef __CUDACC__      /* (tests/emu compiles the kernel above as a serial host program to check its index arithmetic) */
+#ifdef __CUDACC__      /* (tests/emu compiles the kernel above as a host program to check its index arithmetic) */
 int vb200_launch_transform_exact(const vb200_setup *s, cudaStream_t st, int W, int items,
                                  const float *pcm, const long long *pcm_off, const int *lW, const int *nW,
                                  const int *block_mode, const int *lW_block_mode,
                                  float *gmdct, float *logfft, float *logmdct, float *local_ampmax, float *poste) {
   if (items <= 0) return VB200_OK;
   if (W) k_transform_exact<2048, 256><<<items, 256, 0, st>>>(s->d, 1, pcm, pcm_off, lW, nW, block_mode, lW_block_mode, gmdct, logfft, logmdct, local_ampmax, poste);
-  else   k_transform_exact<256, 64><<<items, 64, 0, st>>>(s->d, 0, pcm, pcm_off, lW, nW, block_mode, lW_block_mode, gmdct, logfft, logmdct, local_ampmax, poste);
+  else   k_transform_exact<256, 32><<<items, 32, 0, st>>>(s->d, 0, pcm, pcm_off, lW, nW, block_mode, lW_block_mode, gmdct, logfft, logmdct, local_ampmax, poste);
   LAUNCH_CHECK();
   return VB200_OK;
 }

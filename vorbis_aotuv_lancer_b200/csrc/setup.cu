@@ -181,6 +181,10 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
       h.xm_trig[w] = (const float *)L.up(xt.data(), sizeof(float) * xt.size());
       h.xm_bitrev[w] = (const int *)L.up(xb.data(), sizeof(int) * xb.size());
       h.xf_wa[w] = (const float *)L.up(xw.data(), sizeof(float) * xw.size());
+      std::vector<float2> xs((size_t)n / 4); std::vector<int2> xr((size_t)n / 8);
+      vb200_exact_tables_k1x(n, xt.data(), xb.data(), xs.data(), xr.data());
+      h.xm_stage[w] = (const float2 *)L.up(xs.data(), sizeof(float2) * xs.size());
+      h.xm_rev[w] = (const int2 *)L.up(xr.data(), sizeof(int2) * xr.size());
     }
   }
 

@@ -108,6 +108,8 @@ struct DevSetup {
   const float *xm_trig[2];      /* [n + n/4]  mdct_init, mdct.c:54-92 */
   const int *xm_bitrev[2];      /* [n/4] */
   const float *xf_wa[2];        /* [2n]  drfti1, smallft.c:5576-5644 */
+  const float2 *xm_stage[2];    /* [n/4]  xm_trig regrouped per butterfly stage at unit stride (vb200_exact_tables_k1x) */
+  const int2 *xm_rev[2];        /* [n/8]  xm_bitrev as padded complex-slot indices of K1x's work vector */
 };
 
 /* ---- host-side object behind vb200_setup ---- */
@@ -141,6 +143,7 @@ void vb200_set_error(const char *fmt, ...);
 void vb200_count_launch(int n);
 void vb200_exact_tables_mdct(int n, float *T, int *bitrev);      /* k_transform_exact.cu */
 void vb200_exact_tables_drft(int n, float *wa);
+void vb200_exact_tables_k1x(int n, const float *T, const int *bitrev, float2 *stage_tw, int2 *rev);
 const void *vb200_blob_find(const unsigned char *blob, size_t bytes, const char *name, uint32_t *dtype, uint32_t *count);
 #ifdef __cplusplus
 }
