@@ -60,11 +60,11 @@ void vb200_launch_count_reset(void);
  * INTEGRATION.md) and uploads them to `device`. */
 int  vb200_setup_create(const void *blob, size_t bytes, int device, vb200_setup **out);
 void vb200_setup_destroy(vb200_setup *s);
-/* Front end with operation-exact transforms (off by default; also VB200_EXACT_TRANSFORM=1 at create time).  K1 computes
- * the MDCT / real FFT in its own formulation, within north_star's 1e-5 of the reference; with this switch on, the
- * launches that follow perform the reference's own float operations instead (mdct_forward mdct.c:1799-1869, drft_forward
- * smallft.c:6770 with drftf1/dradf4/dradf2 :5652-6170), so that gmdct, logmdct, logfft and local_ampmax -- and through
- * them every later stage and the packets -- are bit-identical to the reference's C path. */
+/* Front end selection.  The default (on = 1) is K1x, the front end with operation-exact transforms: it performs the
+ * reference's own float operations (mdct_forward mdct.c:1799-1869, drft_forward smallft.c:6770 with drftf1/dradf4/dradf2
+ * :5652-6170), so that gmdct, logmdct, logfft and local_ampmax -- and through them every later stage and the packets --
+ * are bit-identical to the reference's C path.  on = 0 (or VB200_EXACT_TRANSFORM=0 at create time) selects K1, the
+ * same transforms in a radix-4 Stockham formulation, within north_star's 1e-5 of the reference but not bit-identical. */
 int  vb200_setup_set_exact_transform(vb200_setup *s, int on);
 /* host-side queries (valid without a GPU: pass device = -1 to vb200_setup_create) */
 int  vb200_setup_channels(const vb200_setup *s);
@@ -277,7 +277,9 @@ float vb200_batch_kernel_ms(vb200_batch *b);
 int  vb200_batch_kernel_times(vb200_batch *b, const char **names, float *ms, int cap);
 /* intermediate vectors of the last run for the A/B harness (host copies).  what: see VB200_GET_* */
 enum { VB200_GET_GMDCT=0, VB200_GET_LOGFFT, VB200_GET_LOGMDCT, VB200_GET_NOISE, VB200_GET_TONE,
-       VB200_GET_LOGMASK, VB200_GET_EPEAK, VB200_GET_IWORK, VB200_GET_ILOGMASK, VB200_GET_POSTS };
+       VB200_GET_LOGMASK, VB200_GET_EPEAK, VB200_GET_IWORK, VB200_GET_ILOGMASK, VB200_GET_POSTS,
+       VB200_GET_POSTS_LO, VB200_GET_POSTS_HI,   /* managed mode: the low- and the high-rate fit (blobs 0 and 14) */
+       VB200_GET_NPEAK, VB200_GET_BLOB_BYTES };  /* npeak after the last blob; bytes of each packet blob (device packer) */
 int  vb200_batch_get(vb200_batch *b, int what, int block, int ch, void *out, int count);
 
 #ifdef __cplusplus

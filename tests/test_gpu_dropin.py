@@ -34,7 +34,7 @@ def test_reference_encoder_loop_over_the_b200_mapping(config, seconds, batch):
     gb, rb = sum(len(p[0]) for p in pk), sum(len(r[0]) for r in ref)
     same = sum(1 for a, r in zip(pk, ref) if a[0] == r[0]) / len(ref)
     print("\n%s through the reference API: identical packets %.1f%%, bytes %d vs %d" % (config, 100 * same, gb, rb))
-    assert abs(gb - rb) / rb < 0.005 and same > 0.80
+    assert gb == rb and same == 1.0      # the default front end (K1x) performs the reference's own float operations
     # our own public call on the same PCM
     s = ops.Setup(config)
     enc = encoder.Encoder(s, 4096, threads=2, chunks=1)

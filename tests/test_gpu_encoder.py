@@ -69,15 +69,11 @@ def test_encode_decodes_and_matches_reference_bitrate():
     pk = encoder.packets_of(tab, 0)
     ref = cap["packets"]
     assert len(pk) == len(ref)
-    gb, rb = sum(len(p[0]) for p in pk), sum(len(p[0]) for p in ref)
-    assert abs(gb - rb) / rb < 0.005
+    assert [p[0] for p in pk] == [r[0] for r in ref]          # the reference's packets, byte for byte
     R = reflib.RefLib("c")
     dec, _ = R.decode(cap["headers"], pk, cap["pcm"].shape[1] + 8192)
     decr, _ = R.decode(cap["headers"], ref, cap["pcm"].shape[1] + 8192)
-    m = min(dec.shape[1], decr.shape[1])
-    err = (dec[:, :m] - decr[:, :m]).astype(np.float64)
-    snr = 10 * np.log10((decr[:, :m].astype(np.float64) ** 2).sum() / (err ** 2).sum())
-    assert snr > 30, snr
+    assert np.array_equal(dec, decr)
     assert len(encoder.packets_of(tab, 1)) > 20
     enc.close(); s.close()
 
@@ -117,22 +113,18 @@ def test_ragged_batch_of_degenerate_streams():
         same = sum(1 for a, r in zip(pk, ref) if a[0] == r[0]) / len(ref)
         print("stream %d: %d packets, identical %.0f%%, bytes %d vs %d" % (i, len(ref), 100 * same, gb, rb))
         assert abs(gb - rb) <= max(8, 0.005 * rb), (i, gb, rb)
-        if i == 0:
-            assert same == 1.0
-        elif i == 3:
-            # a clipped square wave puts many coefficients exactly on quantiser thresholds: the 1e-5 MDCT tolerance
-            # flips more decisions than on ordinary signal; the stream still has the reference's size
-            assert same > 0.5, (i, same)
-        elif len(ref) > 20:
-            assert same > 0.8, (i, same)
+        # through the GPU segmenter and the default front end (K1x) every stream IS the reference's stream -- also the
+        # clipped square wave (i == 3), whose coefficients sit on quantiser thresholds and which K1's 1e-5 MDCT
+        # tolerance used to leave at 50-60 % identical packets
+        assert same == 1.0 and gb == rb, (i, same, gb, rb)
     enc.close(); s.close()
 
 
 def test_full_length_streams_properties():
     """BASELINE-size streams (60 s, q4 44.1 kHz stereo, the bench's synthetic signal): the result must not depend on
     how the streams are grouped into batches (one group vs three), a second run must reproduce it bit for bit, and
-    the streams must sit where the reference puts them: packet count, granule positions, size within 0.5 %, decodable,
-    > 30 dB SNR against the reference-encoded stream."""
+    the streams must BE the reference's streams: packet count, granule positions, every packet byte-identical,
+    decoding to the same PCM."""
     import ctypes as C
     from oracle import reflib
     from vorbis_aotuv_lancer_b200 import blob as vblob, encoder, ops
@@ -169,13 +161,11 @@ def test_full_length_streams_properties():
         assert len(pk) == len(ref) and [p[1] for p in pk] == [r[1] for r in ref]
         gb, rb = sum(len(p[0]) for p in pk), sum(len(r[0]) for r in ref)
         same = sum(1 for a, r in zip(pk, ref) if a[0] == r[0]) / len(ref)
-        assert abs(gb - rb) / rb < 0.005 and same > 0.8, (i, gb, rb, same)
+        assert gb == rb and same == 1.0, (i, gb, rb, same)
         dec, _ = R.decode(hdr, pk, n + 8192)
         decr, _ = R.decode(hdr, ref, n + 8192)
         m = min(dec.shape[1], decr.shape[1])
         assert m > n - 4096
-        err = (dec[:, :m] - decr[:, :m]).astype(np.float64)
-        snr = 10 * np.log10((decr[:, :m].astype(np.float64) ** 2).sum() / (err ** 2).sum())
-        print("stream %d: %d packets, identical %.1f%%, bytes %d vs %d, SNR vs reference-encoded %.1f dB" % (i, len(ref), 100 * same, gb, rb, snr))
-        assert snr > 30.0
+        assert np.array_equal(dec[:, :m], decr[:, :m])          # identical packets decode to identical PCM
+        print("stream %d: %d packets, identical %.1f%%, bytes %d vs %d" % (i, len(ref), 100 * same, gb, rb))
     s.close()

@@ -688,6 +688,26 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     StreamChains &C = sc[sidx];
     for (int W = 0; W < 2; W++) { C.items[W].reserve((size_t)cnt * ch); C.start[W].reserve((size_t)cnt * ch); C.len[W].reserve((size_t)cnt * ch); }
     for (int k = 0; k < ch; k++) {
+      if (managed) {
+        /* managed mode: the sel = 1 pass of a run's FIRST impulse block reads tempmdct before the sel = 2 pass resets
+           it (mdctbuf_flag == 0, psy.c:4165-4210) -- it sees what the previous run left.  The recurrence therefore
+           runs through every impulse block of the stream: one chain per (stream, channel), the only chain that
+           touches the state slot; every other block is a chain of its own that neither loads nor stores it. */
+        const int start0 = (int)C.items[0].size();
+        for (int j = 0; j < cnt; j++) {
+          const HostBlock &h = b->hb[lst[j]];
+          if (h.W == 0 && h.block_mode == 0) C.items[0].push_back(h.idx * ch + k);
+        }
+        if ((int)C.items[0].size() > start0) { C.start[0].push_back(start0); C.len[0].push_back((int)C.items[0].size() - start0); }
+        for (int j = 0; j < cnt; j++) {
+          const HostBlock &h = b->hb[lst[j]];
+          if (h.W == 0 && h.block_mode == 0) continue;
+          C.start[h.W].push_back((int)C.items[h.W].size());
+          C.items[h.W].push_back(h.idx * ch + k);
+          C.len[h.W].push_back(1 | (1 << 30) | (1 << 29));
+        }
+        continue;
+      }
       int j = 0;
       while (j < cnt) {
         const HostBlock &h = b->hb[lst[j]];
@@ -1192,11 +1212,22 @@ extern "C" int vb200_batch_get(vb200_batch *b, int what, int block, int chn, voi
     case VB200_GET_LOGMDCT: src = c.logmdct + it * c.N2; break;
     case VB200_GET_NOISE: src = c.noise + it * c.N2; break;
     case VB200_GET_TONE: src = c.tone + it * c.N2; break;
-    case VB200_GET_LOGMASK: src = c.logmask + it * c.N2 * (b->s->h.managed ? 3 : 1); break;
+    case VB200_GET_LOGMASK: src = c.logmask + it * c.N2 * (b->s->h.managed ? 3 : 1); n = (size_t)c.N2 * (b->s->h.managed ? 3 : 1); break;
     case VB200_GET_EPEAK: src = c.epeak + it * c.N2; break;
     case VB200_GET_IWORK: src = c.iwork + it * c.N2; break;
     case VB200_GET_ILOGMASK: src = c.iwork + it * c.N2; break;
     case VB200_GET_POSTS: src = c.posts[1] + it * VB200_MAX_POSTS; n = VB200_MAX_POSTS; break;
+    case VB200_GET_POSTS_LO: src = c.posts[0] + it * VB200_MAX_POSTS; n = VB200_MAX_POSTS; break;
+    case VB200_GET_POSTS_HI: src = c.posts[2] + it * VB200_MAX_POSTS; n = VB200_MAX_POSTS; break;
+    case VB200_GET_NPEAK: src = c.npeak + it * c.nps; n = c.nps; break;
+    case VB200_GET_BLOB_BYTES: {      /* sizes of the packet blobs of this block as the device packer left them (one per blob) */
+      const int nblobs = b->s->h.managed ? VB200_PACKETBLOBS : 1;
+      if (count < nblobs || b->host_emit) return VB200_EINVAL;
+      for (int k = 0; k < nblobs; k++)
+        if (cudaMemcpy((int *)out + k, b->d_pk_bytes + ((size_t)k * 2 + h.W) * b->max_blocks + h.idx, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+          vb200_set_error("vb200_batch_get: copy failed"); return VB200_EFAULT; }
+      return nblobs;
+    }
     default: return VB200_EINVAL;
   }
   if ((size_t)count < n) n = count;

@@ -111,7 +111,7 @@ extern "C" int vb200_setup_create(const void *blob, size_t bytes, int device, vb
   vb200_setup *s = new vb200_setup();
   memset(s, 0, sizeof(*s));
   s->device = device;
-  { const char *e = getenv("VB200_EXACT_TRANSFORM"); s->exact_transform = (e && *e && *e != '0') ? 1 : 0; }
+  { const char *e = getenv("VB200_EXACT_TRANSFORM"); s->exact_transform = (e && *e == '0') ? 0 : 1; }      /* K1x unless switched off */
   s->blob = (unsigned char *)malloc(bytes);
   memcpy(s->blob, blob, bytes);
   s->blob_bytes = bytes;
