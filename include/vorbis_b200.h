@@ -273,6 +273,10 @@ int  vb200_batch_packet_table(vb200_batch *b, const unsigned char **base, const 
                               const int64_t **granulepos, const int **eos, const int **stream);
 /* device time (ms) of the kernels of the last run, measured with CUDA events on the batch's stream */
 float vb200_batch_kernel_ms(vb200_batch *b);
+/* managed mode: how many times the last run evaluated the masking stages before the set of ch-blocks that write
+ * lastmdct / tempmdct (those whose nominal floor fit exists, mapping0.c:1097) agreed with the links between blocks
+ * that were derived from it; 1 unless a stream holds digitally silent blocks.  Always 1 in VBR mode. */
+int  vb200_batch_link_rounds(vb200_batch *b);
 /* per-kernel device time of the last run: name[i], ms[i]; returns the number of kernels */
 int  vb200_batch_kernel_times(vb200_batch *b, const char **names, float *ms, int cap);
 /* intermediate vectors of the last run for the A/B harness (host copies).  what: see VB200_GET_* */

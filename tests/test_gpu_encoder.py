@@ -169,3 +169,50 @@ def test_full_length_streams_properties():
         assert np.array_equal(dec[:, :m], decr[:, :m])          # identical packets decode to identical PCM
         print("stream %d: %d packets, identical %.1f%%, bytes %d vs %d" % (i, len(ref), 100 * same, gb, rb))
     s.close()
+
+
+def _silence_streams(ch, rate):
+    """signals with stretches of DIGITAL silence: in managed mode a block whose nominal floor fit is NULL skips the
+    sel = 2 mix (mapping0.c:1097), so lastmdct / tempmdct keep what an OLDER block left"""
+    sig = refdata.synth(ch, rate, 4.0, seed=5)
+    n = sig.shape[1]
+    a = sig.copy(); a[:, :rate] = 0.0                                   # leading silence
+    b = sig.copy(); b[:, rate + 3000:2 * rate + 1234] = 0.0             # a gap in the middle of the track
+    c = sig.copy(); c[:, 3 * rate:] = 0.0                               # trailing silence
+    d = sig.copy()                                                      # clicks out of silence, silence between short blocks
+    d[:, :] = 0.0
+    for k in range(6):
+        p = 9000 + k * 17000
+        d[:, p:p + 300] = sig[:, p:p + 300]
+    e = np.zeros((ch, 3 * rate), np.float32)                            # silence, one burst, silence
+    e[:, rate:rate + 20000] = sig[:, :20000]
+    return [a, b, c, d, e]
+
+
+@pytest.mark.parametrize("config", ["abr128_44k_2ch", "q4_44k_2ch"])
+def test_streams_with_digital_silence_equal_the_reference(config):
+    from oracle import reflib
+    from vorbis_aotuv_lancer_b200 import blob as vblob, encoder, ops
+    if not reflib.available("c"):
+        pytest.skip("oracle/_ref not present")
+    ch, rate, q, abr = vblob.CATALOGUE[config]
+    pcms = _silence_streams(ch, rate)
+    R = reflib.RefLib("c")
+    refs = []
+    for p in pcms:
+        h = R.open(ch, rate, q, abr)
+        R.write(h, p)
+        refs.append(R.packets(h))
+        R.close(h)
+    s = ops.Setup(config)
+    for chunks in (1, 2):
+        enc = encoder.Encoder(s, 4096, threads=4, chunks=chunks)
+        tabs = enc.encode(pcms)
+        for i, ref in enumerate(refs):
+            pk = encoder.packets_of(tabs, i)
+            assert len(pk) == len(ref), i
+            diff = [j for j, (a, r) in enumerate(zip(pk, ref)) if a[0] != r[0]]
+            print("%s stream %d (%d groups): %d packets, %d differ%s" % (config, i, chunks, len(ref), len(diff), (" first at %d" % diff[0]) if diff else ""))
+            assert not diff, (config, i, chunks, len(diff), diff[:8])
+        enc.close()
+    s.close()

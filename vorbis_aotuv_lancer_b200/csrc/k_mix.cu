@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(T)
 k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start, const int *__restrict__ chain_len, const int *__restrict__ chain_items,
       const int *__restrict__ psyv, const int *__restrict__ params, const float *__restrict__ low_compandv,
       const float *__restrict__ noise, const float *__restrict__ tone, const float *__restrict__ logmdct,
-      float *__restrict__ mdct, LastRef last, float *__restrict__ temp_state, const long long *__restrict__ temp_off,
-      float *__restrict__ npeak, int npeak_stride, float *__restrict__ logmask, int nsel, int mask_stride,
+      float *__restrict__ mdct, LastRef last, const float *__restrict__ temp_state, float *__restrict__ temp_state_out,
+      const long long *__restrict__ temp_off, float *__restrict__ npeak, int npeak_stride, float *__restrict__ logmask, int nsel, int mask_stride,
       float *__restrict__ last_out, int *__restrict__ fit_gate, int floor_index, int ch) {
   __shared__ float temp[N > 256 ? 1 : 256];
   __shared__ int pflag[64];
@@ -53,7 +53,7 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
     const float *nz = noise + (size_t)item * N, *tn = tone + (size_t)item * N, *lm = logmdct + (size_t)item * N;
     float *md = mdct + (size_t)item * N;
     float *np = npeak + (size_t)item * npeak_stride;
-    float *tstate = (SHORT && temp_state) ? temp_state + (temp_off ? temp_off[item] : (long long)item * 256) : nullptr;
+    const float *tstate = (SHORT && temp_state) ? temp_state + (temp_off ? temp_off[item] : (long long)item * 256) : nullptr;
 
     if (SHORT && ci == 0 && tstate && t_load) { for (int i = tid; i < N; i += T) temp[i] = tstate[i]; }
     if (tid == 0) gate = 1;
@@ -223,8 +223,9 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
     }
     if (fit_gate && tid == 0) fit_gate[item] = gate;
     if (SHORT && tstate && t_save && ci == clen - 1) {
-      /* leave the chain's tempmdct in the stream's state slot for the next batch */
-      float *dst = temp_state + (temp_off ? temp_off[item] : (long long)item * 256);
+      /* leave the chain's tempmdct in the stream's state slot for the next batch (managed mode: in a staging copy of
+         the slot, committed when the floor-fit gates have settled -- pipeline.cu) */
+      float *dst = temp_state_out + (temp_off ? temp_off[item] : (long long)item * 256);
       for (int i = tid; i < N; i += T) dst[i] = temp[i];
     }
     __syncthreads();
@@ -236,13 +237,13 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
 int vb200_launch_mix(const vb200_setup *s, cudaStream_t st, int W, int nchains, const int *chain_start, const int *chain_len, const int *chain_items,
                      const int *psy, const int *params, const float *low_compand,
                      const float *noise, const float *tone, const float *logmdct, float *mdct, LastRef last,
-                     float *temp_state, const long long *temp_off, float *npeak, int npeak_stride,
+                     const float *temp_state, float *temp_state_out, const long long *temp_off, float *npeak, int npeak_stride,
                      float *logmask, int nsel, int mask_stride, float *last_out, int *fit_gate, int floor_index) {
   if (nchains <= 0) return VB200_OK;
   if (W) k_mix<1024, 256><<<nchains, 256, 0, st>>>(s->d, W, chain_start, chain_len, chain_items, psy, params, low_compand, noise, tone, logmdct, mdct, last,
-                                                   temp_state, temp_off, npeak, npeak_stride, logmask, nsel, mask_stride, last_out, fit_gate, floor_index, s->h.channels);
+                                                   temp_state, temp_state_out, temp_off, npeak, npeak_stride, logmask, nsel, mask_stride, last_out, fit_gate, floor_index, s->h.channels);
   else   k_mix<128, 64><<<nchains, 64, 0, st>>>(s->d, W, chain_start, chain_len, chain_items, psy, params, low_compand, noise, tone, logmdct, mdct, last,
-                                                temp_state, temp_off, npeak, npeak_stride, logmask, nsel, mask_stride, last_out, fit_gate, floor_index, s->h.channels);
+                                                temp_state, temp_state_out, temp_off, npeak, npeak_stride, logmask, nsel, mask_stride, last_out, fit_gate, floor_index, s->h.channels);
   LAUNCH_CHECK();
   return VB200_OK;
 }

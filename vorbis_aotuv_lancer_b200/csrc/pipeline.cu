@@ -37,6 +37,7 @@
 struct StatePool {
   float *last;    /* [slots][ch][2048]  private_state.mblock  */
   float *temp;    /* [slots][ch][256]   private_state.tblock  */
+  float *temp2;   /* managed mode: where K4 leaves tblock until the floor-fit gates of the batch have settled */
   float *scal;    /* [slots][2+ch]      g->ampmax, vbi->ampmax, lownoise_compand_level[ch] */
   unsigned char used[PIPE_MAX_STREAM_SLOTS];
 };
@@ -192,6 +193,12 @@ __global__ void k_save_last(int n, const float *const *__restrict__ src, const i
   }
 }
 
+/* managed mode: copy the tempmdct slots K4 left in the staging pool into the state pool */
+__global__ void k_commit_temp(const long long *__restrict__ off, const float *__restrict__ src, float *__restrict__ dst) {
+  const long long o = off[blockIdx.x];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) dst[o + i] = src[o + i];
+}
+
 __global__ void k_copy_i32(const int *__restrict__ src, int *__restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
@@ -232,7 +239,7 @@ struct ClassBufs {           /* one size class (W) */
   float *npeak_work;
   int *posts[3], *fitted[3], *posts_k, *fitted_k, *vals, *iwork, *nonzero, *fit_gate;
   int *psy_item, *psy_blk, *block_mode, *lW_block_mode, *lW, *nW, *params;
-  long long *pcm_off, *last_addr; int *last_rule;
+  long long *pcm_off, *last_addr, *last_addr2; int *last_rule, *last_rule2;
   int *chain_start, *chain_len, *chain_items; long long *temp_off;
   int *partword, *classified, *syms, *nsyms, *floor_nz;
   int max_syms;
@@ -248,6 +255,7 @@ struct vb200_batch {
   float *d_pcm; size_t pcm_cap;
   ScanBlock *d_scan; int *d_scan_start, *d_slot; float **d_ptrs;
   const float **d_save_src; float **d_save_dst; int *d_save_rule, *d_save_N; int *d_chl;
+  long long *d_commit; int link_rounds;      /* managed mode: tempmdct slots to commit; K2/K4 rounds the last run took */
   /* host staging (pinned) mirrors of the descriptor arrays are carved from `pin` per run */
   std::vector<HostBlock> hb;
   /* results */
@@ -281,6 +289,7 @@ static StatePool *pool_of(vb200_setup *s) {
   const size_t ch = s->h.channels;
   if (cudaMalloc(&p->last, sizeof(float) * PIPE_MAX_STREAM_SLOTS * ch * 2048) != cudaSuccess ||
       cudaMalloc(&p->temp, sizeof(float) * PIPE_MAX_STREAM_SLOTS * ch * 256) != cudaSuccess ||
+      cudaMalloc(&p->temp2, sizeof(float) * PIPE_MAX_STREAM_SLOTS * ch * 256) != cudaSuccess ||
       cudaMalloc(&p->scal, sizeof(float) * PIPE_MAX_STREAM_SLOTS * (2 + VB200_MAX_CHANNELS)) != cudaSuccess) { free(p); return nullptr; }
   g_pool_owner[g_npools] = s; g_pools[g_npools++] = p;
   return p;
@@ -352,6 +361,7 @@ static bool carve_class(vb200_batch *b, int W, int cap_blocks) {
   c.psy_item = a.take<int>(I); c.psy_blk = a.take<int>(cap_blocks); c.block_mode = a.take<int>(I); c.lW_block_mode = a.take<int>(I);
   c.lW = a.take<int>(I); c.nW = a.take<int>(I); c.params = a.take<int>(I * 8);
   c.pcm_off = a.take<long long>(I); c.last_addr = a.take<long long>(I); c.last_rule = a.take<int>(I);
+  c.last_addr2 = a.take<long long>(I); c.last_rule2 = a.take<int>(I);
   c.chain_start = a.take<int>(I); c.chain_len = a.take<int>(I); c.chain_items = a.take<int>(I); c.temp_off = a.take<long long>(I);
   int maxpv = 1;
   for (int r = 0; r < s->h.residues; r++) { const DevResidue &R = s->h.res[r]; const int pv = (R.end - R.begin) / R.grouping; if (pv > maxpv) maxpv = pv; }
@@ -383,13 +393,15 @@ extern "C" int vb200_batch_create(vb200_setup *s, int max_blocks, vb200_batch **
   vb200_batch *b = new vb200_batch();
   b->s = s; b->max_blocks = max_blocks; b->d_pcm = nullptr; b->pcm_cap = 0; b->nev = 0; b->total_ms = 0;
   const size_t bytes = class_bytes(s, 0, max_blocks) + class_bytes(s, 1, max_blocks) + sizeof(ScanBlock) * (size_t)max_blocks
-                     + (size_t)PIPE_MAX_STREAM_SLOTS * (8 + VB200_MAX_CHANNELS * 24) + 65536;
+                     + (size_t)PIPE_MAX_STREAM_SLOTS * (8 + VB200_MAX_CHANNELS * 64) + 65536;
   if (cudaMalloc(&b->dev.base, bytes) != cudaSuccess) { cudaGetLastError(); vb200_set_error("vb200_batch_create: cannot allocate %zu bytes of HBM", bytes); delete b; return VB200_EFAULT; }
   b->dev.cap = bytes;
   b->d_scan = b->dev.take<ScanBlock>(max_blocks); b->d_scan_start = b->dev.take<int>(PIPE_MAX_STREAM_SLOTS + 1); b->d_slot = b->dev.take<int>(PIPE_MAX_STREAM_SLOTS);
   b->d_ptrs = b->dev.take<float *>(8);
-  b->d_save_src = b->dev.take<const float *>((size_t)PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS); b->d_save_dst = b->dev.take<float *>((size_t)PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS);
-  b->d_save_rule = b->dev.take<int>((size_t)PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS); b->d_save_N = b->dev.take<int>((size_t)PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS);
+  /* two groups of state writes per (stream, channel): a 1024-entry writer, then a 128-entry writer on top of it */
+  b->d_save_src = b->dev.take<const float *>((size_t)2 * PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS); b->d_save_dst = b->dev.take<float *>((size_t)2 * PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS);
+  b->d_save_rule = b->dev.take<int>((size_t)2 * PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS); b->d_save_N = b->dev.take<int>((size_t)2 * PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS);
+  b->d_commit = b->dev.take<long long>((size_t)PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS); b->link_rounds = 0;
   b->d_chl = b->dev.take<int>(2 * VB200_MAX_SUBMAPS * VB200_MAX_CHANNELS);
   if (!b->d_chl || !carve_class(b, 0, max_blocks) || !carve_class(b, 1, max_blocks)) { vb200_set_error("vb200_batch_create: arena sizing bug"); cudaFree(b->dev.base); delete b; return VB200_EFAULT; }
   /* pinned staging for descriptors and results */
@@ -602,13 +614,14 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   b->hb.resize(nblocks);
   int nb[2] = {0, 0};
   b->pin.top = 0;
-  struct HostClass { int *psy_item, *psy_blk, *block_mode, *lW_block_mode, *lW, *nW, *params; long long *pcm_off, *last_addr; int *last_rule;
+  struct HostClass { int *psy_item, *psy_blk, *block_mode, *lW_block_mode, *lW, *nW, *params; long long *pcm_off, *last_addr, *last_addr2; int *last_rule, *last_rule2, *gate;
                      int *chain_start, *chain_len, *chain_items; long long *temp_off; int nchains, nchain_items; } hc[2];
   for (int W = 0; W < 2; W++) {
     const size_t I = (size_t)nblocks * ch;
     hc[W].psy_item = b->pin.take<int>(I); hc[W].psy_blk = b->pin.take<int>(nblocks); hc[W].block_mode = b->pin.take<int>(I);
     hc[W].lW_block_mode = b->pin.take<int>(I); hc[W].lW = b->pin.take<int>(I); hc[W].nW = b->pin.take<int>(I); hc[W].params = b->pin.take<int>(I * 8);
     hc[W].pcm_off = b->pin.take<long long>(I); hc[W].last_addr = b->pin.take<long long>(I); hc[W].last_rule = b->pin.take<int>(I);
+    hc[W].last_addr2 = b->pin.take<long long>(I); hc[W].last_rule2 = b->pin.take<int>(I); hc[W].gate = b->pin.take<int>(I);
     hc[W].chain_start = b->pin.take<int>(I); hc[W].chain_len = b->pin.take<int>(I); hc[W].chain_items = b->pin.take<int>(I); hc[W].temp_off = b->pin.take<long long>(I);
     hc[W].nchains = 0; hc[W].nchain_items = 0;
     if (!hc[W].temp_off) { vb200_set_error("vb200_batch_run: pinned staging too small"); return VB200_EFAULT; }
@@ -635,13 +648,60 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   const int flr_of_end[2] = { s->h.flr[s->h.floor_of_ch[0][0]].info_n, s->h.flr[s->h.floor_of_ch[1][0]].info_n };
   const bool hs = s->h.rate >= 26000;
   /* (2) per stream, independent of the other streams (history, lastmdct links, K4 chains, scan list): host threads */
-  struct StreamChains { std::vector<int> start[2], len[2], items[2]; };
+  struct StreamChains { std::vector<int> start[2], len[2], items[2]; bool impulse; };
   std::vector<StreamChains> sc(nstreams);
+  /* Where every ch-block finds lastmdct, and what the stream's state slot must hold after the batch, given which
+     ch-blocks WRITE lastmdct: all of them in VBR mode; in managed mode only those whose nominal floor fit exists
+     (mapping0.c:1097 skips the sel = 2 mix otherwise, and only that call writes, psy.c:4165-4173).  A writer whose
+     next block is short leaves 128 entries (copy of a short block / 8:1 min-pool of a transition block), every other
+     writer 1024 (psy.c:4462-4501); a long reader that finds a 128-entry writer on top takes bins >= 128 from the newest
+     1024-entry writer before it (second source of LastRef).  gate[W] == NULL: every block writes. */
+  struct SaveOp { const float *src; float *dst; int rule, N; };
+  std::vector<std::vector<SaveOp>> saveA(nstreams), saveB(nstreams);
+  const int long_extent = s->h.bs[1] / 2;
+  auto extent_of = [&](const HostBlock &h) { return (h.block_mode == 3 || h.nW) ? long_extent : LAST_SHORT_EXTENT; };
+  auto rule_of = [&](const HostBlock &h) { return h.block_mode <= 1 ? (h.nW ? LAST_EXPAND8 : LAST_COPY) : ((h.block_mode == 2 && !h.nW) ? LAST_MINPOOL8 : LAST_COPY); };
+  auto row_of = [&](const HostBlock &h, int k) -> const float * { const ClassBufs &pc = b->c[h.W]; return pc.logmdct + ((size_t)h.idx * ch + k) * pc.N2; };
+  auto link_stream = [&](int sidx, int *const gate[2]) {
+    vb200_stream *x = streams[sidx];
+    const int *lst = order.data() + sstart[sidx];
+    const int cnt = sstart[sidx + 1] - sstart[sidx];
+    saveA[sidx].clear(); saveB[sidx].clear();
+    for (int k = 0; k < ch; k++) {
+      float *slot = pool->last + ((size_t)x->slot * ch + k) * 2048;
+      int w1 = -1, w2 = -1;          /* newest writer so far; newest writer of 1024 entries (-1: the state slot) */
+      for (int j = 0; j < cnt; j++) {
+        const HostBlock &h = b->hb[lst[j]];
+        HostClass &c = hc[h.W];
+        const int it = h.idx * ch + k;
+        c.last_addr2[it] = 0; c.last_rule2[it] = LAST_NONE;
+        if (!hs) { c.last_addr[it] = (long long)(uintptr_t)slot; c.last_rule[it] = LAST_ZERO; }
+        else if (w1 < 0) { c.last_addr[it] = (long long)(uintptr_t)slot; c.last_rule[it] = LAST_COPY; }
+        else {
+          const HostBlock &p = b->hb[w1];
+          c.last_addr[it] = (long long)(uintptr_t)row_of(p, k); c.last_rule[it] = rule_of(p);
+          if (h.W && extent_of(p) < long_extent) {
+            if (w2 < 0) { c.last_addr2[it] = (long long)(uintptr_t)slot; c.last_rule2[it] = LAST_COPY; }
+            else { const HostBlock &p2 = b->hb[w2]; c.last_addr2[it] = (long long)(uintptr_t)row_of(p2, k); c.last_rule2[it] = rule_of(p2); }
+          }
+        }
+        if (!managed || !gate[h.W] || gate[h.W][it]) { w1 = lst[j]; if (extent_of(h) >= long_extent) w2 = lst[j]; }
+      }
+      if (hs && w1 >= 0) {
+        const HostBlock &p = b->hb[w1];
+        if (extent_of(p) >= long_extent) saveA[sidx].push_back(SaveOp{row_of(p, k), slot, rule_of(p), b->c[p.W].N2});
+        else {
+          if (w2 >= 0) { const HostBlock &p2 = b->hb[w2]; saveA[sidx].push_back(SaveOp{row_of(p2, k), slot, rule_of(p2), b->c[p2.W].N2}); }
+          saveB[sidx].push_back(SaveOp{row_of(p, k), slot, rule_of(p), b->c[p.W].N2});
+        }
+      }
+    }
+  };
+  int *const no_gate[2] = {nullptr, nullptr};
   auto do_stream = [&](int sidx) {
     vb200_stream *x = streams[sidx];
     const int *lst = order.data() + sstart[sidx];
     const int cnt = sstart[sidx + 1] - sstart[sidx];
-    int prev = -1;
     for (int j = 0; j < cnt; j++) {
       const int i = lst[j];
       const vb200_block &q = blocks[i];
@@ -660,18 +720,8 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
         int *pr = c.params + (size_t)it * 8;
         pr[0] = 1; pr[1] = managed; pr[2] = flr_of_end[W]; pr[3] = h.block_mode; pr[4] = h.nW; pr[5] = x->lW_block_mode; pr[6] = x->lW_no; pr[7] = x->impadnum;
         c.pcm_off[it] = q.pcm_offset + (long long)k * q.pcm_stride;
-        /* where this block finds lastmdct */
-        if (!hs) { c.last_addr[it] = (long long)(uintptr_t)(pool->last + ((size_t)x->slot * ch + k) * 2048); c.last_rule[it] = LAST_ZERO; }
-        else if (prev < 0) { c.last_addr[it] = (long long)(uintptr_t)(pool->last + ((size_t)x->slot * ch + k) * 2048); c.last_rule[it] = LAST_COPY; }
-        else {
-          const HostBlock &p = b->hb[prev];
-          const ClassBufs &pc = b->c[p.W];
-          c.last_addr[it] = (long long)(uintptr_t)(pc.logmdct + ((size_t)p.idx * ch + k) * pc.N2);
-          c.last_rule[it] = (p.block_mode <= 1) ? (W ? LAST_EXPAND8 : LAST_COPY) : ((p.block_mode == 2 && !W) ? LAST_MINPOOL8 : LAST_COPY);
-        }
         c.temp_off[it] = ((long long)x->slot * ch + k) * 256;
       }
-      prev = i;
       /* aoTuV history, mapping0.c:1297-1305 -- once per packet blob */
       for (int rep = 0; rep < (managed ? VB200_PACKETBLOBS : 1); rep++) {
         if (h.block_mode >= 2) x->impadnum = 0;
@@ -685,7 +735,10 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     }
     /* chains for K4: runs of consecutive impulse blocks of one stream, per channel; everything else is its own
        chain.  Offsets are local to the stream here and rebased when the streams are concatenated. */
+    link_stream(sidx, no_gate);
     StreamChains &C = sc[sidx];
+    C.impulse = false;
+    for (int j = 0; j < cnt; j++) if (b->hb[lst[j]].W == 0 && b->hb[lst[j]].block_mode == 0) { C.impulse = true; break; }
     for (int W = 0; W < 2; W++) { C.items[W].reserve((size_t)cnt * ch); C.start[W].reserve((size_t)cnt * ch); C.len[W].reserve((size_t)cnt * ch); }
     for (int k = 0; k < ch; k++) {
       if (managed) {
@@ -749,8 +802,6 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     }
   for (int sidx = 0; sidx < nstreams; sidx++) { h_scan_start[sidx] = sstart[sidx]; h_slot[sidx] = streams[sidx]->slot; }
   h_scan_start[nstreams] = nblocks;
-  std::vector<int> last_of_stream(nstreams, -1);          /* the last block every stream has in this batch */
-  for (int sidx = 0; sidx < nstreams; sidx++) if (sstart[sidx + 1] > sstart[sidx]) last_of_stream[sidx] = order[sstart[sidx + 1] - 1];
   b->n_blocks[0] = nb[0]; b->n_blocks[1] = nb[1]; b->n_items[0] = nb[0] * ch; b->n_items[1] = nb[1] * ch;
 
   if (getenv("VB200_TRACE")) fprintf(stderr, "[vb200 batch] host pre-pass %.2f ms for %d blocks (setup %.2f, count %.2f, order %.2f, per-stream %.2f)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_prep0, nblocks, t_prepA - t_prep0, t_prepB - t_prepA, t_prep1 - t_prepB, t_prep2 - t_prep1);
@@ -792,6 +843,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     UP(c.psy_item, h.psy_item, I); UP(c.psy_blk, h.psy_blk, nb[W]); UP(c.block_mode, h.block_mode, I); UP(c.lW_block_mode, h.lW_block_mode, I);
     UP(c.lW, h.lW, I); UP(c.nW, h.nW, I); UP(c.params, h.params, I * 8); UP(c.pcm_off, h.pcm_off, I);
     UP(c.last_addr, h.last_addr, I); UP(c.last_rule, h.last_rule, I);
+    if (managed) { UP(c.last_addr2, h.last_addr2, I); UP(c.last_rule2, h.last_rule2, I); }
     UP(c.chain_start, h.chain_start, h.nchains); UP(c.chain_len, h.chain_len, h.nchains); UP(c.chain_items, h.chain_items, h.nchain_items);
     UP(c.temp_off, h.temp_off, I);
   }
@@ -807,37 +859,90 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   RUN(fetch_flush());
   /* ---- K1: window + MDCT + FFT/dB ---- */
   EV("K1 transform");
-  for (int W = 0; W < 2; W++) {
-    ClassBufs &c = b->c[W];
-    RUN(vb200_launch_transform(s, st, W, nb[W] * ch, d_pcm, c.pcm_off, c.lW, c.nW, c.block_mode, c.lW_block_mode,
-                               c.gmdct, c.logfft, c.logmdct, c.local_ampmax, c.poste));
-  }
+  auto run_k1 = [&]() -> int {
+    for (int W = 0; W < 2; W++) {
+      ClassBufs &c = b->c[W];
+      RUN(vb200_launch_transform(s, st, W, nb[W] * ch, d_pcm, c.pcm_off, c.lW, c.nW, c.block_mode, c.lW_block_mode,
+                                 c.gmdct, c.logfft, c.logmdct, c.local_ampmax, c.poste));
+    }
+    return VB200_OK;
+  };
+  RUN(run_k1());
   EV("scan ampmax");
   k_stream_scan<<<(nstreams + 3) / 4, 128, 0, st>>>(s->d, nstreams, d_slot, d_scan_start, d_scan, pool->scal,
                                                     (const float *const *)d_ptrs, (float *const *)(d_ptrs + 2),
                                                     (const float *const *)(d_ptrs + 4), (float *const *)(d_ptrs + 6));
   LAUNCH_CHECK();
-  /* ---- K2 / K3 ---- */
-  EV("K2 noisemask");
-  for (int W = 0; W < 2; W++) {
-    ClassBufs &c = b->c[W];
-    LastRef last{nullptr, c.last_addr, c.last_rule, 0};
-    RUN(vb200_launch_noisemask(s, st, W, nb[W] * ch, c.psy_item, c.block_mode, c.lowcomp, c.poste, c.logmdct, last, c.noise, c.epeak, c.npeak, c.nps));
+  /* ---- K2 / K3 / K4.  Managed mode at high sampling rates: which ch-blocks write lastmdct / tempmdct depends on
+     their own masks (the nominal-fit gate), so the links assumed by the pre-pass -- every block writes -- are checked
+     against the gates K4 finds and, if a gate is closed (digital silence, mostly), the links are rebuilt and K1
+     (K4 scales gmdct in place), K2 and K4 run again until gates and links agree.  The prefix of every stream up to
+     its first changed gate is final after each round, so this ends; streams without closed gates take one round. ---- */
+  const bool gated = managed && hs;
+  std::vector<int> gate_prev[2];
+  int round = 0;
+  for (;; round++) {
+    if (round > 0) {
+      int *const g[2] = {hc[0].gate, hc[1].gate};
+      for (int sidx = 0; sidx < nstreams; sidx++) link_stream(sidx, g);
+      for (int W = 0; W < 2; W++) {
+        const int I = nb[W] * ch;
+        if (!I) continue;
+        ClassBufs &c = b->c[W]; HostClass &h = hc[W];
+        UP(c.last_addr, h.last_addr, I); UP(c.last_rule, h.last_rule, I); UP(c.last_addr2, h.last_addr2, I); UP(c.last_rule2, h.last_rule2, I);
+      }
+      RUN(fetch_flush());
+      RUN(run_k1());
+    }
+    if (round == 0) EV("K2 noisemask");
+    for (int W = 0; W < 2; W++) {
+      ClassBufs &c = b->c[W];
+      LastRef last{nullptr, c.last_addr, c.last_rule, 0, managed ? c.last_addr2 : nullptr, managed ? c.last_rule2 : nullptr};
+      RUN(vb200_launch_noisemask(s, st, W, nb[W] * ch, c.psy_item, c.block_mode, c.lowcomp, c.poste, c.logmdct, last, c.noise, c.epeak, c.npeak, c.nps));
+    }
+    if (round == 0) {
+      EV("K3 tonemask");
+      for (int W = 0; W < 2; W++) {
+        ClassBufs &c = b->c[W];
+        RUN(vb200_launch_tonemask(s, st, W, nb[W] * ch, c.psy_item, c.logfft, c.global_ampmax, c.local_ampmax, c.tone, c.logmask, c.iwork));   /* logmask / iwork rows are dead until K4 / K5b */
+      }
+      EV("K4 offset_and_mix");
+    }
+    for (int W = 0; W < 2; W++) {
+      ClassBufs &c = b->c[W];
+      if (!nb[W]) continue;
+      LastRef last{nullptr, c.last_addr, c.last_rule, 0, managed ? c.last_addr2 : nullptr, managed ? c.last_rule2 : nullptr};
+      RUN(vb200_launch_mix(s, st, W, hc[W].nchains, c.chain_start, c.chain_len, c.chain_items, c.psy_item, c.params, c.lowcomp,
+                           c.noise, c.tone, c.logmdct, c.gmdct, last, pool->temp, gated ? pool->temp2 : pool->temp, c.temp_off, c.npeak, c.nps,
+                           c.logmask, nsel, c.N2 * nsel, nullptr, managed ? c.fit_gate : nullptr, -1));
+    }
+    if (!gated) break;
+    for (int W = 0; W < 2; W++) if (nb[W]) CUDA_TRY(cudaMemcpyAsync(hc[W].gate, b->c[W].fit_gate, sizeof(int) * (size_t)nb[W] * ch, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    bool same = true;
+    for (int W = 0; W < 2; W++) {
+      const size_t I = (size_t)nb[W] * ch;
+      if (round == 0) { for (size_t q = 0; q < I && same; q++) if (!hc[W].gate[q]) same = false; }
+      else if (memcmp(gate_prev[W].data(), hc[W].gate, sizeof(int) * I)) same = false;
+    }
+    if (same) break;
+    if (round == 15) { vb200_set_error("vb200_batch_submit: the floor-fit gates did not settle in 16 rounds"); return VB200_EFAULT; }
+    for (int W = 0; W < 2; W++) gate_prev[W].assign(hc[W].gate, hc[W].gate + (size_t)nb[W] * ch);
   }
-  EV("K3 tonemask");
-  for (int W = 0; W < 2; W++) {
-    ClassBufs &c = b->c[W];
-    RUN(vb200_launch_tonemask(s, st, W, nb[W] * ch, c.psy_item, c.logfft, c.global_ampmax, c.local_ampmax, c.tone, c.logmask, c.iwork));   /* logmask / iwork rows are dead until K4 / K5b */
-  }
-  /* ---- K4 ---- */
-  EV("K4 offset_and_mix");
-  for (int W = 0; W < 2; W++) {
-    ClassBufs &c = b->c[W];
-    if (!nb[W]) continue;
-    LastRef last{nullptr, c.last_addr, c.last_rule, 0};
-    RUN(vb200_launch_mix(s, st, W, hc[W].nchains, c.chain_start, c.chain_len, c.chain_items, c.psy_item, c.params, c.lowcomp,
-                         c.noise, c.tone, c.logmdct, c.gmdct, last, pool->temp, c.temp_off, c.npeak, c.nps,
-                         c.logmask, nsel, c.N2 * nsel, nullptr, managed ? c.fit_gate : nullptr, -1));
+  b->link_rounds = round + 1;
+  if (gated) {
+    /* tempmdct as the final round left it, for the streams that had an impulse block */
+    long long *h_off = b->pin.take<long long>((size_t)nstreams * ch);
+    int n = 0;
+    for (int sidx = 0; sidx < nstreams; sidx++)
+      if (sc[sidx].impulse) for (int k = 0; k < ch; k++) h_off[n++] = ((long long)streams[sidx]->slot * ch + k) * 256;
+    if (n) {
+      long long *d_off = b->d_commit;
+      UP(d_off, h_off, n);
+      RUN(fetch_flush());
+      k_commit_temp<<<n, 128, 0, st>>>(d_off, pool->temp2, pool->temp);
+      LAUNCH_CHECK();
+    }
   }
   /* ---- K5a ---- */
   EV("K5 floor fit");
@@ -852,29 +957,24 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       RUN(vb200_launch_floor_fit(s, st, W, I, -1, c.logmdct, c.logmask + 2 * c.N2, c.N2, c.N2 * nsel, c.fitted[1], c.posts[0], c.fitted[0]));
     }
   }
-  /* stream state for the next batch: lastmdct of every stream's last block, tempmdct is already in place */
-  {
+  /* stream state for the next batch: lastmdct as the writers of this batch leave it (the newest 1024-entry writer, then
+     a newer 128-entry writer on top of it; link_stream), tempmdct is already in place */
+  for (int pass = 0; pass < 2; pass++) {
+    const std::vector<std::vector<SaveOp>> &ops = pass ? saveB : saveA;
+    size_t total = 0;
+    for (int sidx = 0; sidx < nstreams; sidx++) total += ops[sidx].size();
+    if (!total) continue;
+    const float **h_src = b->pin.take<const float *>(total); float **h_dst = b->pin.take<float *>(total);
+    int *h_rule = b->pin.take<int>(total), *h_N = b->pin.take<int>(total);
     int n = 0;
-    const float **h_src = b->pin.take<const float *>((size_t)nstreams * ch); float **h_dst = b->pin.take<float *>((size_t)nstreams * ch);
-    int *h_rule = b->pin.take<int>((size_t)nstreams * ch), *h_N = b->pin.take<int>((size_t)nstreams * ch);
-    for (int sidx = 0; sidx < nstreams && hs; sidx++) {
-      if (last_of_stream[sidx] < 0) continue;
-      const HostBlock &h = b->hb[last_of_stream[sidx]];
-      const ClassBufs &c = b->c[h.W];
-      for (int k = 0; k < ch; k++) {
-        h_src[n] = c.logmdct + ((size_t)h.idx * ch + k) * c.N2;
-        h_dst[n] = pool->last + ((size_t)streams[sidx]->slot * ch + k) * 2048;
-        h_rule[n] = (h.block_mode <= 1) ? (h.nW ? LAST_EXPAND8 : LAST_COPY) : ((h.block_mode == 2 && !h.nW) ? LAST_MINPOOL8 : LAST_COPY);
-        h_N[n] = c.N2; n++;
-      }
-    }
-    if (n) {
-      const float **d_src = b->d_save_src; float **d_dst = b->d_save_dst; int *d_rule = b->d_save_rule, *d_N = b->d_save_N;
-      UP(d_src, h_src, n); UP(d_dst, h_dst, n); UP(d_rule, h_rule, n); UP(d_N, h_N, n);
-      RUN(fetch_flush());
-      k_save_last<<<n, 128, 0, st>>>(n, d_src, d_rule, d_N, d_dst);
-      LAUNCH_CHECK();
-    }
+    for (int sidx = 0; sidx < nstreams; sidx++)
+      for (const SaveOp &o : ops[sidx]) { h_src[n] = o.src; h_dst[n] = o.dst; h_rule[n] = o.rule; h_N[n] = o.N; n++; }
+    const size_t base = (size_t)pass * PIPE_MAX_STREAM_SLOTS * VB200_MAX_CHANNELS;
+    const float **d_src = b->d_save_src + base; float **d_dst = b->d_save_dst + base; int *d_rule = b->d_save_rule + base, *d_N = b->d_save_N + base;
+    UP(d_src, h_src, n); UP(d_dst, h_dst, n); UP(d_rule, h_rule, n); UP(d_N, h_N, n);
+    RUN(fetch_flush());
+    k_save_last<<<n, 128, 0, st>>>(n, d_src, d_rule, d_N, d_dst);
+    LAUNCH_CHECK();
   }
 
   /* ---- per packet blob: K5b, K6, K7, then the bit packer (device) or the symbol D2H (host emission) ---- */
@@ -1192,6 +1292,7 @@ extern "C" int vb200_batch_packet_table(vb200_batch *b, const unsigned char **ba
 }
 
 extern "C" float vb200_batch_kernel_ms(vb200_batch *b) { return b ? b->total_ms : 0.f; }
+extern "C" int vb200_batch_link_rounds(vb200_batch *b) { return b ? b->link_rounds : 0; }
 
 extern "C" int vb200_batch_kernel_times(vb200_batch *b, const char **names, float *ms, int cap) {
   if (!b) return 0;

@@ -101,7 +101,7 @@ extern "C" int vb200_stage_offset_and_mix(vb200_setup *s, int W, int items, cons
   CHECK_ALLOC(d_md); CHECK_ALLOC(d_last); CHECK_ALLOC(d_lout); CHECK_ALLOC(d_tmp); CHECK_ALLOC(d_np); CHECK_ALLOC(d_mask);
   LastRef last{d_last, nullptr, nullptr, 2048};
   int r = vb200_launch_mix(s, st, W, items, nullptr, nullptr, nullptr, d_psy, d_par, d_lc, d_no, d_to, d_lm, d_md, last,
-                           d_tmp, nullptr, d_np, nps, d_mask, 1, (int)N2, d_lout, nullptr, floor_index);
+                           d_tmp, d_tmp, nullptr, d_np, nps, d_mask, 1, (int)N2, d_lout, nullptr, floor_index);
   if (r) return r;
   CUDA_TRY(d_md.down(mdct, st)); CUDA_TRY(d_lout.down(lastmdct, st)); CUDA_TRY(d_tmp.down(tempmdct, st));
   CUDA_TRY(d_np.down(npeak, st)); CUDA_TRY(d_mask.down(logmask, st));

@@ -174,7 +174,7 @@ int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int item
 int vb200_launch_mix(const vb200_setup *s, cudaStream_t st, int W, int nchains, const int *chain_start, const int *chain_len, const int *chain_items,
                      const int *psy, const int *params, const float *low_compand,
                      const float *noise, const float *tone, const float *logmdct, float *mdct, LastRef last,
-                     float *temp_state, const long long *temp_off, float *npeak, int npeak_stride,
+                     const float *temp_state, float *temp_state_out, const long long *temp_off, float *npeak, int npeak_stride,
                      float *logmask, int nsel, int mask_stride, float *last_out, int *fit_gate, int floor_index);
 int vb200_launch_floor_fit(const vb200_setup *s, cudaStream_t st, int W, int items, int floor_index,
                            const float *logmdct, const float *logmask, int mdct_stride, int mask_stride,
