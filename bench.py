@@ -29,6 +29,23 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # before any CUD
 import numpy as np  # noqa: E402
 
 CONFIG = "q4_44k_2ch"
+QUALITY_NAME = {"q4_44k_2ch": "q4 44.1 kHz stereo", "q5_44k_2ch": "q5 44.1 kHz stereo", "q10_48k_2ch": "q10 48 kHz stereo",
+                "q8_48k_6ch": "q8 48 kHz 5.1", "q2_44k_2ch": "q2 44.1 kHz stereo", "q4_48k_6ch": "q4 48 kHz 5.1",
+                "q4_44k_1ch": "q4 44.1 kHz mono", "abr128_44k_2ch": "128 kbit/s ABR 44.1 kHz stereo"}
+
+
+def workload_config(config, S, T):
+    """The `config` object of the JSON line: the workload and nothing else, identical for both arms (the reference arm
+    times bounded samples of it, see cpu_baseline.sample)."""
+    from vorbis_aotuv_lancer_b200 import blob as vblob
+    ch, rate, q, abr = vblob.CATALOGUE[config]
+    pcm_mb = S * T * rate * ch * 4 / 1e6
+    return {"workload": "%d independent %g s %s synthetic streams per GPU (SURVEY 8d signal, seed per stream), every block of every "
+                        "stream through the whole analysis path per step" % (S, T, QUALITY_NAME.get(config, config)),
+            "setup": config, "quality": q, "managed_bitrate": int(abr), "channels": ch, "rate": rate,
+            "streams_per_gpu": S, "seconds_per_stream": T, "audio_seconds_per_gpu_step": S * T,
+            "parallelism": "streams sharded i mod G, no collective",
+            "l2": "inputs larger than L2: %.0f MB of float PCM per GPU and step (126 MB L2), no flush needed" % pcm_mb}
 # algorithmic HBM bytes per ch-block (long N2=1024 / short N2=128), SURVEY.md section 8(d)
 ALGO_BYTES = {
     "K1 transform": (20480, 2560), "K2 noisemask": (16512, 2112), "K3 tonemask": (8192, 1024),
@@ -86,7 +103,7 @@ def emit(out):
 
 # ------------------------------------------------------------------ reference arm / cpu baseline
 def _ref_worker(args):
-    flavour, channels, rate, quality, seconds, seed_index, reps = args
+    flavour, channels, rate, quality, seconds, seed_index, reps, abr = args
     from oracle import reflib
     from vorbis_aotuv_lancer_b200.lib import L
     pcm = synth_streams(L, 1, seconds, channels, rate, seed_index, threads=1)[0]
@@ -94,23 +111,23 @@ def _ref_worker(args):
     t0 = time.perf_counter()
     nbytes = 0
     for _ in range(reps):
-        h = R.open(channels, rate, quality, 0)
+        h = R.open(channels, rate, quality, abr)
         R.write(h, pcm)
         nbytes += sum(len(p[0]) for p in R.packets(h))
         R.close(h)
     return time.perf_counter() - t0, nbytes
 
 
-def reference_throughput(cores, seconds, reps, flavour="sse"):
+def reference_throughput(cores, seconds, reps, flavour="sse", config=None):
     """The UNMODIFIED reference (oracle/_ref, Lancer SSE path, -O3 -ffast-math) one stream per core."""
     import multiprocessing as mp
     from vorbis_aotuv_lancer_b200 import blob as vblob
-    ch, rate, q, _ = vblob.CATALOGUE[CONFIG]
+    ch, rate, q, abr = vblob.CATALOGUE[config or CONFIG]
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        pool.map(_ref_worker, [(flavour, ch, rate, q, 0.5, i, 1) for i in range(cores)])      # warm the workers
+        pool.map(_ref_worker, [(flavour, ch, rate, q, 0.5, i, 1, abr) for i in range(cores)])      # warm the workers
         t0 = time.perf_counter()
-        res = pool.map(_ref_worker, [(flavour, ch, rate, q, seconds, i, reps) for i in range(cores)])
+        res = pool.map(_ref_worker, [(flavour, ch, rate, q, seconds, i, reps, abr) for i in range(cores)])
         wall = time.perf_counter() - t0
     return cores * reps * seconds / wall, wall, max(r[0] for r in res)
 
@@ -123,21 +140,24 @@ def run_reference(args):
     if not reflib.available("sse"):
         reflib.build()
     cores = os.cpu_count() or 1
-    seconds = 60.0
+    seconds = min(float(args.seconds), 60.0)      # a bounded sample of the workload: streams of the workload's kind, at most 60 s each
     vals = []
     for i in range(args.warmup + args.steps):
-        v, wall, _ = reference_throughput(cores, seconds, 2)
+        v, wall, _ = reference_throughput(cores, seconds, 2, config=args.config)
         if i >= args.warmup:
             vals.append((v, wall))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([w for _, w in vals]) * 1e3)
-    sample = "%d processes x two passes over one 60 s q4 44.1 kHz stereo stream each (reference build oracle/_ref, Lancer SSE, -O3 -ffast-math)" % cores
+    sample = ("each step: %d processes (one per host core) x two passes over one %g s stream of the workload "
+              "(reference build oracle/_ref, Lancer SSE, -O3 -ffast-math, the flags configure.ac:189 ships)" % (cores, seconds))
     out = {"impl": "reference", "metric": "encoded audio-sec/sec @q4 44.1k stereo", "value": value, "unit": "audio-s/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "q4 44.1 kHz stereo, 60 s synthetic streams, one per host core", "quality": 0.4},
+           "config": workload_config(args.config, args.streams, args.seconds),
            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample},
            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.config != CONFIG:
+        out["metric"] = "encoded audio-sec/sec @%s" % QUALITY_NAME.get(args.config, args.config)
     emit(out)
 
 
@@ -155,11 +175,11 @@ def run_ours(args):
     from vorbis_aotuv_lancer_b200.lib import L
     from vorbis_aotuv_lancer_b200 import blob as vblob
 
-    ch, rate, q, _ = vblob.CATALOGUE[CONFIG]
+    ch, rate, q, _ = vblob.CATALOGUE[args.config]
     S, T = args.streams, args.seconds
-    setup = ops.Setup(CONFIG, device=local)
-    if args.exact_transform:
-        setup.set_exact_transform(True)      # K1x: the reference's own float operations, packets byte-identical to the reference's
+    setup = ops.Setup(args.config, device=local)
+    if args.fast_transform:
+        setup.set_exact_transform(False)     # K1: own MDCT/FFT formulation (within 1e-5) instead of the default K1x (bit-identical)
     pins = [encoder.PinnedArray(ch, int(rate * T)) for _ in range(S)]      # the caller's PCM lives in page-locked memory
     pcms = synth_streams(L, S, T, ch, rate, rank * S, pinned=pins)
     blocks_per_stream = int(T * rate / 700) + 64
@@ -219,10 +239,23 @@ def run_ours(args):
     barrier()
     L.vb200_launch_count_reset()
     th.start()
+    # the K timed steps: device time between a CUDA event recorded on the first batch's (idle) stream before the first
+    # submit and one recorded behind the last collect (the packets of the last step are on the host), max over ranks;
+    # the host clock around the same region is reported next to it
+    from vorbis_aotuv_lancer_b200.lib import check
+    check(L.vb200_batch_mark(fulls[0].h), "vb200_batch_mark")          # its stream is idle: the region starts here
     t0 = time.perf_counter()
-    resident(args.warmup, args.steps, True)
+    resident(args.warmup, args.steps, True)                            # returns when every step has been collected
+    if len(fulls) > 1:
+        check(L.vb200_batch_mark(fulls[1].h), "vb200_batch_mark")      # all device work of the region is complete
     barrier()
-    t_dev = maxtime(time.perf_counter() - t0)
+    t_wall = maxtime(time.perf_counter() - t0)
+    if len(fulls) > 1:
+        ev_ms = C.c_float()
+        check(L.vb200_batch_mark_elapsed(fulls[0].h, fulls[1].h, C.byref(ev_ms)), "vb200_batch_mark_elapsed")
+        t_dev = maxtime(ev_ms.value * 1e-3)
+    else:
+        t_dev = t_wall          # a single batch object cannot hold both marks: the synchronised host clock stands in
     launches = L.vb200_launch_count()
     stop.set()
     th.join()
@@ -260,40 +293,50 @@ def run_ours(args):
         whole_gbs = whole / (sum(kern.values()) * 1e-3) / 1e9
         # DRAM traffic of the dominant kernel: from the committed ncu capture of this very workload, else null
         traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if tr["workload"]["streams_per_gpu"] == S and tr["workload"]["seconds_per_stream"] == T:
-                traffic = tr["bytes_per_launch"].get(top)
-        except Exception:
-            pass
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", name)))
+                w = tr["workload"]
+                if w["streams_per_gpu"] == S and w["seconds_per_stream"] == T and w.get("config", CONFIG) == args.config and top in tr["bytes_per_launch"]:
+                    traffic = tr["bytes_per_launch"][top]
+                    break
+            except Exception:
+                pass
         cores = os.cpu_count() or 1
         cpu = None
         if not args.no_cpu_baseline and world == 1:      # reported at N=1 only
             try:
                 from oracle import reflib
                 if reflib.available("sse"):
-                    v, wall, _ = reference_throughput(cores, 60.0, 2)
+                    secs = min(float(T), 60.0)
+                    v, wall, _ = reference_throughput(cores, secs, 2, config=args.config)
                     cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference",
-                           "sample": "%d processes x two passes over one 60 s q4 44.1 kHz stereo stream each, reference build oracle/_ref "
-                                     "(Lancer SSE, -O3 -ffast-math), %.1f s wall" % (cores, wall)}
+                           "sample": "%d processes (one per host core) x two passes over one %g s stream of the workload each, reference build "
+                                     "oracle/_ref (Lancer SSE, -O3 -ffast-math), %.1f s wall" % (cores, secs, wall)}
             except Exception as e:  # the baseline is reported, never required
                 cpu = {"value": None, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
         out = {"metric": "encoded audio-sec/sec @q4 44.1k stereo", "value": value, "unit": "audio-s/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "%d independent %g s q4 44.1 kHz stereo synthetic streams per GPU, all %d blocks "
-                                      "(%d long, %d short) batched per step" % (S, T, nblocks, nlong, nshort),
-                          "quality": 0.4, "streams_per_gpu": S, "seconds_per_stream": T, "parallelism": "streams sharded i mod G, no collective", "resident_depth": len(fulls),
-                          "front_end": "K1x (operation-exact MDCT/FFT, packets identical to the reference's)" if args.exact_transform else "K1 (own formulation, MDCT within 1e-5)",
-                          "l2": "inputs larger than L2 (PCM timeline %.0f MB, per-stage vectors %.0f MB)" % (timeline.nbytes / 1e6, (nlong * 1024 + nshort * 128) * ch * 4 / 1e6)},
+               "config": workload_config(args.config, S, T),
+               "timing": {"ms_per_step": "CUDA events on the batch streams around the K steps (inputs resident in HBM, packets back on the host), max over ranks",
+                          "host_clock_ms_per_step": t_wall / args.steps * 1e3},
+               "detail": {"blocks_per_step": nblocks, "long_blocks": nlong, "short_blocks": nshort, "resident_depth": len(fulls),
+                          "front_end": "K1 (own radix-4 formulation, MDCT within 1e-5 of the reference)" if args.fast_transform
+                                       else "K1x (the reference's own float operations: packets byte-identical to the reference's)",
+                          "resident_bytes": {"pcm_timeline": int(timeline.nbytes), "per_stage_vector": int((nlong * 1024 + nshort * 128) * ch * 4)}},
                "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(timeline.nbytes), "d2h_bytes_per_step": int(packet_bytes),
-                       "steps": e2e_steps, "includes": "host segmentation (LPC head/tail, window sequencing; detector kernels on the GPU), H2D PCM, all kernels, bit packing, D2H packets; %d pipelined stream groups" % args.chunks},
+                       "steps": e2e_steps, "includes": "Encoder.encode from pinned host PCM: host segmentation (LPC head/tail, window sequencing; detector kernels on the GPU), "
+                                                       "H2D of the PCM, all kernels, bit packing, D2H of the packets; %d pipelined stream groups; host clock, max over ranks" % args.chunks},
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": int(algo), "kernel_ms": kern[top],
-                            "all_kernels": {"algorithmic_GBps": whole_gbs, "frac": whole_gbs / peak, "ms": sum(kern.values())}},
+                            "all_kernels": {"algorithmic_GBps": whole_gbs, "frac": whole_gbs / peak, "ms": sum(kern.values()),
+                                            "per_kernel_frac": {k: ((nlong * ALGO_BYTES[k][0] + nshort * ALGO_BYTES[k][1]) * ch / (kern[k] * 1e-3) / 1e9 / peak) for k in kern}}},
                "stage_ms": stage_ms, "clocks": summarize_clocks(samples), "cpu_baseline": cpu,
                "packet_bytes_per_step": int(packet_bytes), "kbps": packet_bytes * 8 / audio / 1000.0}
+        if args.config != CONFIG:
+            out["metric"] = "encoded audio-sec/sec @%s" % QUALITY_NAME.get(args.config, args.config)
         emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -310,7 +353,9 @@ def main():
     ap.add_argument("--chunks", type=int, default=8, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
     ap.add_argument("--depth", type=int, default=2, help="resident arm: batches in flight (2: host half of step i+1 overlaps device half of step i)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exact-transform", action="store_true", help="front end K1x instead of K1 (DESIGN.md section 4)")
+    ap.add_argument("--fast-transform", action="store_true", help="front end K1 (own formulation, within 1e-5) instead of the default K1x (DESIGN.md section 4)")
+    ap.add_argument("--exact-transform", action="store_true", help="(the default since round 2; accepted for old command lines)")
+    ap.add_argument("--config", default=CONFIG, help="setup blob: the metric's q4_44k_2ch, or another BASELINE configuration (q5_44k_2ch, q8_48k_6ch, q10_48k_2ch, abr128_44k_2ch ...)")
     args = ap.parse_args()
     # stdout carries the one JSON line and nothing else: libraries that write to fd 1 (NCCL's version banner)
     # are sent to stderr while the run lasts

@@ -277,6 +277,11 @@ float vb200_batch_kernel_ms(vb200_batch *b);
  * lastmdct / tempmdct (those whose nominal floor fit exists, mapping0.c:1097) agreed with the links between blocks
  * that were derived from it; 1 unless a stream holds digitally silent blocks.  Always 1 in VBR mode. */
 int  vb200_batch_link_rounds(vb200_batch *b);
+/* Device-side timing of a region that spans several runs / batches: vb200_batch_mark records a CUDA event on the
+ * batch's own stream behind everything the batch has been given so far; vb200_batch_mark_elapsed waits for both marks
+ * and returns the device time between them (bench.py times its K steps this way, max over ranks). */
+int  vb200_batch_mark(vb200_batch *b);
+int  vb200_batch_mark_elapsed(vb200_batch *from, vb200_batch *to, float *ms);
 /* per-kernel device time of the last run: name[i], ms[i]; returns the number of kernels */
 int  vb200_batch_kernel_times(vb200_batch *b, const char **names, float *ms, int cap);
 /* intermediate vectors of the last run for the A/B harness (host copies).  what: see VB200_GET_* */

@@ -29,6 +29,11 @@ def test_reference_arm_prints_one_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # `config` is the workload and nothing else: the very object the GPU arm prints for the same command line
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("q4_44k_2ch", 64, 5.0)
+    assert d["config"]["streams_per_gpu"] == 64 and d["config"]["seconds_per_stream"] == 5.0
 
 
 def test_reference_arm_runs_on_rank_0_only():

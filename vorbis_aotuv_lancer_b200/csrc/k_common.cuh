@@ -14,11 +14,6 @@ struct LastRef {
   const long long *off;     /* [items] element offset, or NULL: item*stride */
   const int *rule;          /* [items] LAST_*, or NULL: LAST_COPY */
   long long stride;
-  /* Managed mode only (NULL otherwise).  A block whose nominal floor fit is NULL does not write lastmdct
-     (mapping0.c:1097), so a long block can find the newest writer's 128 entries on top of an OLDER writer's 1024: bins
-     >= LAST_SHORT_EXTENT then come from this second source (absolute addresses; LAST_NONE: one source is enough) */
-  const long long *off2;
-  const int *rule2;
   __device__ __forceinline__ static float fetch(const float *p, int r, int i) {
     if (r == LAST_COPY) return __ldg(p + i);
     if (r == LAST_EXPAND8) return __ldg(p + (i >> 3));
@@ -33,13 +28,25 @@ struct LastRef {
   __device__ __forceinline__ float at(int item, int i) const {
     /* base==NULL: off[] holds absolute device addresses (previous block / stream state live in
        different allocations) */
-    if (off2 && i >= LAST_SHORT_EXTENT) {
-      const int r2 = rule2[item];
-      if (r2 != LAST_NONE) return fetch(reinterpret_cast<const float *>(static_cast<uintptr_t>(off2[item])), r2, i);
-    }
     const float *p = base ? base + (off ? off[item] : (long long)item * stride)
                           : reinterpret_cast<const float *>(static_cast<uintptr_t>(off[item]));
     return fetch(p, rule ? rule[item] : LAST_COPY, i);
+  }
+};
+/* Managed mode.  A block whose nominal floor fit is NULL does not write lastmdct (mapping0.c:1097), so a long block can
+   find the newest writer's 128 entries on top of an OLDER writer's 1024: bins >= LAST_SHORT_EXTENT then come from a
+   second source (absolute addresses; LAST_NONE: one source is enough).  A type of its own, so that the VBR kernels
+   compile exactly as they did without it. */
+struct LastRef2 {
+  LastRef first;
+  const long long *off2;
+  const int *rule2;
+  __device__ __forceinline__ float at(int item, int i) const {
+    if (i >= LAST_SHORT_EXTENT) {
+      const int r2 = rule2[item];
+      if (r2 != LAST_NONE) return LastRef::fetch(reinterpret_cast<const float *>(static_cast<uintptr_t>(off2[item])), r2, i);
+    }
+    return first.at(item, i);
   }
 };
 #endif

@@ -173,11 +173,11 @@ __device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restr
   }
 }
 
-template <int N, int T>
+template <int N, int T, typename LASTREF>
 __global__ void __launch_bounds__(T, (T >= 256 ? 8 : (T >= 128 ? 7 : 1)))
 k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const int *__restrict__ block_mode,
             const float *__restrict__ lowcomp, const float *__restrict__ postev,
-            const float *__restrict__ logmdct, LastRef last,
+            const float *__restrict__ logmdct, LASTREF last,
             float *__restrict__ noise_out, float *__restrict__ epeak_out, float *__restrict__ npeak_out, int npeak_stride) {
   extern __shared__ __align__(16) unsigned char smraw[];
   NoiseSmem<N> &sm = *reinterpret_cast<NoiseSmem<N> *>(smraw);
@@ -286,25 +286,30 @@ k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const 
 
 }  // namespace
 
-int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
-                           const int *block_mode, const float *lowcomp, const float *poste,
-                           const float *logmdct, LastRef last, float *noise, float *epeak, float *npeak, int npeak_stride) {
-  if (items <= 0) return VB200_OK;
-  static const int nmt = getenv("VB200_NM_T") ? atoi(getenv("VB200_NM_T")) : 256;
-  if (W && nmt == 128) {
-    constexpr int N = 1024, T = 128;
-    static bool attr = false;
-    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(k_noisemask<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NoiseSmem<N>))); attr = true; }
-    k_noisemask<N, T><<<items, T, sizeof(NoiseSmem<N>), st>>>(s->d, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
-  } else if (W) {
-    constexpr int N = 1024, T = 256;
-    static bool attr = false;
-    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(k_noisemask<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NoiseSmem<N>))); attr = true; }
-    k_noisemask<N, T><<<items, T, sizeof(NoiseSmem<N>), st>>>(s->d, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
-  } else {
-    constexpr int N = 128, T = 32;
-    k_noisemask<N, T><<<items, T, sizeof(NoiseSmem<N>), st>>>(s->d, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
+template <int N, int T, typename LASTREF>
+static int launch_nm(const vb200_setup *s, cudaStream_t st, int items, const int *psy, const int *block_mode, const float *lowcomp,
+                     const float *poste, const float *logmdct, LASTREF last, float *noise, float *epeak, float *npeak, int npeak_stride) {
+  static bool attr = false;
+  if (!attr && sizeof(NoiseSmem<N>) > 48 * 1024 - 64) {
+    CUDA_TRY(cudaFuncSetAttribute(k_noisemask<N, T, LASTREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NoiseSmem<N>)));
+    attr = true;
   }
+  k_noisemask<N, T, LASTREF><<<items, T, sizeof(NoiseSmem<N>), st>>>(s->d, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
   LAUNCH_CHECK();
   return VB200_OK;
+}
+
+/* off2 / rule2: the second lastmdct source of managed mode (k_common.cuh), or NULL */
+int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
+                           const int *block_mode, const float *lowcomp, const float *poste,
+                           const float *logmdct, LastRef last, const long long *off2, const int *rule2,
+                           float *noise, float *epeak, float *npeak, int npeak_stride) {
+  if (items <= 0) return VB200_OK;
+  if (off2) {
+    LastRef2 l2{last, off2, rule2};
+    if (W) return launch_nm<1024, 256, LastRef2>(s, st, items, psy, block_mode, lowcomp, poste, logmdct, l2, noise, epeak, npeak, npeak_stride);
+    return launch_nm<128, 32, LastRef2>(s, st, items, psy, block_mode, lowcomp, poste, logmdct, l2, noise, epeak, npeak, npeak_stride);
+  }
+  if (W) return launch_nm<1024, 256, LastRef>(s, st, items, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
+  return launch_nm<128, 32, LastRef>(s, st, items, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
 }

@@ -275,6 +275,7 @@ struct vb200_batch {
   std::vector<size_t> pk_off, pk_bytes; std::vector<int64_t> pk_gp; std::vector<int> pk_eos, pk_stream;
   /* timing */
   cudaEvent_t ev[24]; int nev; const char *evname[24]; float ev_ms[24]; float total_ms;
+  cudaEvent_t ev_mark;             /* vb200_batch_mark: a point on this batch's stream for the caller's own timing */
   /* host copies for vb200_batch_get */
   int n_items[2], n_blocks[2];
 };
@@ -436,6 +437,7 @@ extern "C" int vb200_batch_create(vb200_setup *s, int max_blocks, vb200_batch **
     }
   }
   for (int i = 0; i < 24; i++) cudaEventCreate(&b->ev[i]);
+  cudaEventCreate(&b->ev_mark);
   cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming); b->ev_done_set = false; b->after = nullptr;
   b->pending = false;
   if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess) { vb200_set_error("vb200_batch_create: cannot create a stream"); return VB200_EFAULT; }
@@ -447,6 +449,7 @@ extern "C" void vb200_batch_destroy(vb200_batch *b) {
   if (!b) return;
   cudaSetDevice(b->s->device);
   for (int i = 0; i < 24; i++) cudaEventDestroy(b->ev[i]);
+  cudaEventDestroy(b->ev_mark);
   cudaEventDestroy(b->ev_done);
   cudaStreamDestroy(b->st);
   if (b->d_pcm) cudaFree(b->d_pcm);
@@ -897,8 +900,9 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     if (round == 0) EV("K2 noisemask");
     for (int W = 0; W < 2; W++) {
       ClassBufs &c = b->c[W];
-      LastRef last{nullptr, c.last_addr, c.last_rule, 0, managed ? c.last_addr2 : nullptr, managed ? c.last_rule2 : nullptr};
-      RUN(vb200_launch_noisemask(s, st, W, nb[W] * ch, c.psy_item, c.block_mode, c.lowcomp, c.poste, c.logmdct, last, c.noise, c.epeak, c.npeak, c.nps));
+      LastRef last{nullptr, c.last_addr, c.last_rule, 0};
+      RUN(vb200_launch_noisemask(s, st, W, nb[W] * ch, c.psy_item, c.block_mode, c.lowcomp, c.poste, c.logmdct, last,
+                                 gated ? c.last_addr2 : nullptr, gated ? c.last_rule2 : nullptr, c.noise, c.epeak, c.npeak, c.nps));
     }
     if (round == 0) {
       EV("K3 tonemask");
@@ -911,7 +915,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     for (int W = 0; W < 2; W++) {
       ClassBufs &c = b->c[W];
       if (!nb[W]) continue;
-      LastRef last{nullptr, c.last_addr, c.last_rule, 0, managed ? c.last_addr2 : nullptr, managed ? c.last_rule2 : nullptr};
+      LastRef last{nullptr, c.last_addr, c.last_rule, 0};      /* M3 reads lastmdct in short blocks only: one source */
       RUN(vb200_launch_mix(s, st, W, hc[W].nchains, c.chain_start, c.chain_len, c.chain_items, c.psy_item, c.params, c.lowcomp,
                            c.noise, c.tone, c.logmdct, c.gmdct, last, pool->temp, gated ? pool->temp2 : pool->temp, c.temp_off, c.npeak, c.nps,
                            c.logmask, nsel, c.N2 * nsel, nullptr, managed ? c.fit_gate : nullptr, -1));
@@ -1293,6 +1297,22 @@ extern "C" int vb200_batch_packet_table(vb200_batch *b, const unsigned char **ba
 
 extern "C" float vb200_batch_kernel_ms(vb200_batch *b) { return b ? b->total_ms : 0.f; }
 extern "C" int vb200_batch_link_rounds(vb200_batch *b) { return b ? b->link_rounds : 0; }
+/* device-side timing of a region that spans several runs (and several batches): a mark is a CUDA event recorded on the
+   batch's own stream, behind everything the batch has been given so far */
+extern "C" int vb200_batch_mark(vb200_batch *b) {
+  if (!b) { vb200_set_error("vb200_batch_mark: bad arguments"); return VB200_EINVAL; }
+  CUDA_TRY(cudaSetDevice(b->s->device));
+  CUDA_TRY(cudaEventRecord(b->ev_mark, b->st));
+  return VB200_OK;
+}
+extern "C" int vb200_batch_mark_elapsed(vb200_batch *from, vb200_batch *to, float *ms) {
+  if (!from || !to || !ms) { vb200_set_error("vb200_batch_mark_elapsed: bad arguments"); return VB200_EINVAL; }
+  CUDA_TRY(cudaSetDevice(to->s->device));
+  CUDA_TRY(cudaEventSynchronize(from->ev_mark));
+  CUDA_TRY(cudaEventSynchronize(to->ev_mark));
+  CUDA_TRY(cudaEventElapsedTime(ms, from->ev_mark, to->ev_mark));
+  return VB200_OK;
+}
 
 extern "C" int vb200_batch_kernel_times(vb200_batch *b, const char **names, float *ms, int cap) {
   if (!b) return 0;

@@ -55,7 +55,7 @@ extern "C" int vb200_stage_noisemask(vb200_setup *s, int W, int items, const int
   CHECK_ALLOC(d_psy); CHECK_ALLOC(d_bm); CHECK_ALLOC(d_lc); CHECK_ALLOC(d_po); CHECK_ALLOC(d_lm); CHECK_ALLOC(d_last);
   CHECK_ALLOC(d_no); CHECK_ALLOC(d_ep); CHECK_ALLOC(d_np);
   LastRef last{d_last, nullptr, nullptr, (long long)N2};
-  int r = vb200_launch_noisemask(s, st, W, items, d_psy, d_bm, d_lc, d_po, d_lm, last, d_no, d_ep, d_np, nps);
+  int r = vb200_launch_noisemask(s, st, W, items, d_psy, d_bm, d_lc, d_po, d_lm, last, nullptr, nullptr, d_no, d_ep, d_np, nps);
   if (r) return r;
   CUDA_TRY(d_no.down(noise, st)); CUDA_TRY(d_ep.down(epeak, st)); CUDA_TRY(d_np.down(npeak, st));
   CUDA_TRY(cudaStreamSynchronize(st));

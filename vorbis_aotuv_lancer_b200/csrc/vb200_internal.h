@@ -167,7 +167,8 @@ int vb200_launch_transform_exact(const vb200_setup *s, cudaStream_t st, int W, i
                            float *gmdct, float *logfft, float *logmdct, float *local_ampmax, float *poste);   /* K1x, k_transform_exact.cu */
 int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
                            const int *block_mode, const float *lowcomp, const float *poste,
-                           const float *logmdct, LastRef last, float *noise, float *epeak, float *npeak, int npeak_stride);
+                           const float *logmdct, LastRef last, const long long *off2, const int *rule2,
+                           float *noise, float *epeak, float *npeak, int npeak_stride);
 int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
                           const float *logfft, const float *global_ampmax, const float *local_ampmax, float *tone,
                           float *rowA, int *rowB);
