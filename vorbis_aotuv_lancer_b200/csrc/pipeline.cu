@@ -193,15 +193,64 @@ __global__ void k_save_last(int n, const float *const *__restrict__ src, const i
   }
 }
 
+/* What the host says about one block (32 bytes; every per-ch-block descriptor array of the kernels is derived from it
+   on the device by k_expand_desc -- the host used to fill and ship 92 bytes per ch-block) */
+struct BlockDesc {
+  long long pcm_off;            /* channel 0 of the block in the PCM timeline */
+  int pcm_stride;               /* channel stride */
+  int slot;                     /* state slot of the stream */
+  int lW_no;                    /* aoTuV history as the block finds it */
+  int prev;                     /* previous block of the stream in this batch: (W << 30) | index in its size class; -1: none */
+  unsigned char lW, nW, blocktype, lW_block_mode, impadnum, prev_rule, pad0, pad1;
+};
+static_assert(sizeof(BlockDesc) == 32, "BlockDesc layout");
+
+struct ExpandArgs {
+  int *psy_item, *psy_blk, *block_mode, *lW_block_mode, *lW, *nW, *params;
+  long long *pcm_off, *last_addr, *last_addr2, *temp_off; int *last_rule, *last_rule2;
+  const float *logmdct[2]; int N2[2];
+  float *last_pool;
+  int W, ch, managed, hs, flr_end, nblocks;
+};
+__global__ void __launch_bounds__(256) k_expand_desc(const BlockDesc *__restrict__ desc, const ExpandArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.nblocks * a.ch) return;
+  const int idx = t / a.ch, k = t - idx * a.ch;
+  const BlockDesc d = desc[idx];
+  const int block_mode = d.blocktype | (a.W << 1), psy = d.blocktype + (a.W ? 2 : 0);
+  if (k == 0) a.psy_blk[idx] = psy;
+  a.psy_item[t] = psy; a.block_mode[t] = block_mode; a.lW_block_mode[t] = d.lW_block_mode; a.lW[t] = d.lW; a.nW[t] = d.nW;
+  int4 *pr = reinterpret_cast<int4 *>(a.params + (size_t)t * 8);
+  pr[0] = make_int4(1, a.managed, a.flr_end, block_mode);
+  pr[1] = make_int4(d.nW, d.lW_block_mode, d.lW_no, d.impadnum);
+  a.pcm_off[t] = d.pcm_off + (long long)k * d.pcm_stride;
+  a.temp_off[t] = ((long long)d.slot * a.ch + k) * 256;
+  float *slot = a.last_pool + ((size_t)d.slot * a.ch + k) * 2048;
+  if (!a.hs) { a.last_addr[t] = (long long)(uintptr_t)slot; a.last_rule[t] = LAST_ZERO; }
+  else if (d.prev < 0) { a.last_addr[t] = (long long)(uintptr_t)slot; a.last_rule[t] = LAST_COPY; }
+  else {
+    const int pW = d.prev >> 30, pidx = d.prev & 0x3fffffff;
+    a.last_addr[t] = (long long)(uintptr_t)(a.logmdct[pW] + ((size_t)pidx * a.ch + k) * a.N2[pW]);
+    a.last_rule[t] = d.prev_rule;
+  }
+  if (a.last_addr2) { a.last_addr2[t] = 0; a.last_rule2[t] = LAST_NONE; }
+}
+
 /* managed mode: copy the tempmdct slots K4 left in the staging pool into the state pool */
 __global__ void k_commit_temp(const long long *__restrict__ off, const float *__restrict__ src, float *__restrict__ dst) {
   const long long o = off[blockIdx.x];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) dst[o + i] = src[o + i];
 }
 
-__global__ void k_copy_i32(const int *__restrict__ src, int *__restrict__ dst, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+__global__ void __launch_bounds__(256) k_copy_i32(const int *__restrict__ src, int *__restrict__ dst, size_t n) {
+  /* 16 bytes per access (both pointers are 256-byte aligned arena slices), the odd tail by single ints */
+  const size_t n4 = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
+  const int4 *s4 = reinterpret_cast<const int4 *>(src);
+  int4 *d4 = reinterpret_cast<int4 *>(dst);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) d4[i] = s4[i];
+  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
 }
+static inline int copy_grid(size_t n) { const size_t g = (n / 4 + 255) / 256; return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g)); }
 /* Descriptor upload without the copy engine: the arrays of a batch's host pre-pass lie in page-locked (device-visible)
    memory, and a kernel fetches them all in one launch.  A cudaMemcpyAsync would queue behind the PCM uploads of the
    stream groups that follow (the H2D engine is FIFO), holding back this batch's first kernel by milliseconds. */
@@ -215,9 +264,6 @@ __global__ void __launch_bounds__(256) k_fetch(const FetchTable t) {
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) d16[i] = s16[i];
   const int *s4 = reinterpret_cast<const int *>(t.src[e]); int *d4 = reinterpret_cast<int *>(t.dst[e]);
   if (blockIdx.x == 0) for (unsigned i = (n16 << 2) + threadIdx.x; i < (bytes >> 2); i += blockDim.x) d4[i] = s4[i];
-}
-__global__ void k_copy_f32(const float *__restrict__ src, float *__restrict__ dst, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 }  // namespace
@@ -240,6 +286,7 @@ struct ClassBufs {           /* one size class (W) */
   int *posts[3], *fitted[3], *posts_k, *fitted_k, *vals, *iwork, *nonzero, *fit_gate;
   int *psy_item, *psy_blk, *block_mode, *lW_block_mode, *lW, *nW, *params;
   long long *pcm_off, *last_addr, *last_addr2; int *last_rule, *last_rule2;
+  BlockDesc *desc;
   int *chain_start, *chain_len, *chain_items; long long *temp_off;
   int *partword, *classified, *syms, *nsyms, *floor_nz;
   int max_syms;
@@ -363,6 +410,7 @@ static bool carve_class(vb200_batch *b, int W, int cap_blocks) {
   c.lW = a.take<int>(I); c.nW = a.take<int>(I); c.params = a.take<int>(I * 8);
   c.pcm_off = a.take<long long>(I); c.last_addr = a.take<long long>(I); c.last_rule = a.take<int>(I);
   c.last_addr2 = a.take<long long>(I); c.last_rule2 = a.take<int>(I);
+  c.desc = a.take<BlockDesc>(cap_blocks);
   c.chain_start = a.take<int>(I); c.chain_len = a.take<int>(I); c.chain_items = a.take<int>(I); c.temp_off = a.take<long long>(I);
   int maxpv = 1;
   for (int r = 0; r < s->h.residues; r++) { const DevResidue &R = s->h.res[r]; const int pv = (R.end - R.begin) / R.grouping; if (pv > maxpv) maxpv = pv; }
@@ -382,7 +430,7 @@ static size_t class_bytes(const vb200_setup *s, int W, int cap_blocks) {
   size_t maxpv = 1;
   for (int r = 0; r < s->h.residues; r++) { const DevResidue &R = s->h.res[r]; const size_t pv = (R.end - R.begin) / R.grouping; if (pv > maxpv) maxpv = pv; }
   const size_t max_syms = (size_t)(W ? PIPE_SYMS_PER_ITEM_LONG : PIPE_SYMS_PER_ITEM_SHORT) * ch;
-  size_t b = 4 * (V * (7 + nsel) + I * (N2 / 8) * 2 + I * 8 + I * VB200_MAX_POSTS * 5 + I * 32 + cap_blocks * 8)
+  size_t b = 4 * (V * (7 + nsel) + I * (N2 / 8) * 2 + I * 8 + I * VB200_MAX_POSTS * 5 + I * 32 + cap_blocks * 16)
            + 8 * I * 4 + 4 * ((size_t)cap_blocks * s->h.map[s->h.mode_mapping[W]].submaps * (ch * maxpv + 2 + max_syms * 2));
   return b + 64 * 256;
 }
@@ -617,17 +665,23 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   b->hb.resize(nblocks);
   int nb[2] = {0, 0};
   b->pin.top = 0;
-  struct HostClass { int *psy_item, *psy_blk, *block_mode, *lW_block_mode, *lW, *nW, *params; long long *pcm_off, *last_addr, *last_addr2; int *last_rule, *last_rule2, *gate;
-                     int *chain_start, *chain_len, *chain_items; long long *temp_off; int nchains, nchain_items; } hc[2];
+  struct HostClass { BlockDesc *desc; long long *last_addr, *last_addr2; int *last_rule, *last_rule2, *gate;
+                     int *chain_start, *chain_len, *chain_items; int nchains, nchain_items; } hc[2];
+  const bool hs = s->h.rate >= 26000;
+  const bool gated = managed && hs;      /* managed mode at high sampling rates: the lastmdct links may need re-rounds (below) */
   for (int W = 0; W < 2; W++) {
     const size_t I = (size_t)nblocks * ch;
-    hc[W].psy_item = b->pin.take<int>(I); hc[W].psy_blk = b->pin.take<int>(nblocks); hc[W].block_mode = b->pin.take<int>(I);
-    hc[W].lW_block_mode = b->pin.take<int>(I); hc[W].lW = b->pin.take<int>(I); hc[W].nW = b->pin.take<int>(I); hc[W].params = b->pin.take<int>(I * 8);
-    hc[W].pcm_off = b->pin.take<long long>(I); hc[W].last_addr = b->pin.take<long long>(I); hc[W].last_rule = b->pin.take<int>(I);
-    hc[W].last_addr2 = b->pin.take<long long>(I); hc[W].last_rule2 = b->pin.take<int>(I); hc[W].gate = b->pin.take<int>(I);
-    hc[W].chain_start = b->pin.take<int>(I); hc[W].chain_len = b->pin.take<int>(I); hc[W].chain_items = b->pin.take<int>(I); hc[W].temp_off = b->pin.take<long long>(I);
+    memset(&hc[W], 0, sizeof(hc[W]));
+    hc[W].desc = b->pin.take<BlockDesc>(nblocks);
+    if (gated) {        /* per-ch-block link arrays: only a re-round fills and ships them */
+      hc[W].last_addr = b->pin.take<long long>(I); hc[W].last_rule = b->pin.take<int>(I);
+      hc[W].last_addr2 = b->pin.take<long long>(I); hc[W].last_rule2 = b->pin.take<int>(I); hc[W].gate = b->pin.take<int>(I);
+    }
+    if (W == 0) {       /* K4 chains: long blocks are their own chain (no list needed) */
+      hc[W].chain_start = b->pin.take<int>(I); hc[W].chain_len = b->pin.take<int>(I); hc[W].chain_items = b->pin.take<int>(I);
+    }
     hc[W].nchains = 0; hc[W].nchain_items = 0;
-    if (!hc[W].temp_off) { vb200_set_error("vb200_batch_run: pinned staging too small"); return VB200_EFAULT; }
+    if (!hc[W].desc || (gated && !hc[W].gate) || (W == 0 && !hc[W].chain_items)) { vb200_set_error("vb200_batch_run: pinned staging too small"); return VB200_EFAULT; }
   }
   ScanBlock *h_scan = b->pin.take<ScanBlock>(nblocks);
   int *h_scan_start = b->pin.take<int>(nstreams + 1), *h_slot = b->pin.take<int>(nstreams);
@@ -637,7 +691,8 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   std::vector<int> sstart(nstreams + 1, 0), order(nblocks), idx_of(nblocks);      /* compact: this pass is memory-bound */
   for (int i = 0; i < nblocks; i++) {
     const vb200_block &q = blocks[i];
-    if (q.stream < 0 || q.stream >= nstreams || (q.W != 0 && q.W != 1)) { vb200_set_error("vb200_batch_run: block %d malformed", i); return VB200_EINVAL; }
+    if (q.stream < 0 || q.stream >= nstreams || (q.W != 0 && q.W != 1) || q.pcm_stride < 0 || q.pcm_stride > 0x7fffffff || q.blocktype < 0 || q.blocktype > 1) {
+      vb200_set_error("vb200_batch_run: block %d malformed", i); return VB200_EINVAL; }
     sstart[q.stream + 1]++;
     idx_of[i] = nb[q.W]++;
   }
@@ -649,7 +704,6 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   }
   const double t_prep1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   const int flr_of_end[2] = { s->h.flr[s->h.floor_of_ch[0][0]].info_n, s->h.flr[s->h.floor_of_ch[1][0]].info_n };
-  const bool hs = s->h.rate >= 26000;
   /* (2) per stream, independent of the other streams (history, lastmdct links, K4 chains, scan list): host threads */
   struct StreamChains { std::vector<int> start[2], len[2], items[2]; bool impulse; };
   std::vector<StreamChains> sc(nstreams);
@@ -665,7 +719,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   auto extent_of = [&](const HostBlock &h) { return (h.block_mode == 3 || h.nW) ? long_extent : LAST_SHORT_EXTENT; };
   auto rule_of = [&](const HostBlock &h) { return h.block_mode <= 1 ? (h.nW ? LAST_EXPAND8 : LAST_COPY) : ((h.block_mode == 2 && !h.nW) ? LAST_MINPOOL8 : LAST_COPY); };
   auto row_of = [&](const HostBlock &h, int k) -> const float * { const ClassBufs &pc = b->c[h.W]; return pc.logmdct + ((size_t)h.idx * ch + k) * pc.N2; };
-  auto link_stream = [&](int sidx, int *const gate[2]) {
+  auto link_stream = [&](int sidx, int *const gate[2], bool fill_items) {
     vb200_stream *x = streams[sidx];
     const int *lst = order.data() + sstart[sidx];
     const int cnt = sstart[sidx + 1] - sstart[sidx];
@@ -677,10 +731,11 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
         const HostBlock &h = b->hb[lst[j]];
         HostClass &c = hc[h.W];
         const int it = h.idx * ch + k;
-        c.last_addr2[it] = 0; c.last_rule2[it] = LAST_NONE;
-        if (!hs) { c.last_addr[it] = (long long)(uintptr_t)slot; c.last_rule[it] = LAST_ZERO; }
-        else if (w1 < 0) { c.last_addr[it] = (long long)(uintptr_t)slot; c.last_rule[it] = LAST_COPY; }
+        if (!fill_items) { /* first round: every block writes, the links are the device's (k_expand_desc) */ }
+        else if (!hs) { c.last_addr2[it] = 0; c.last_rule2[it] = LAST_NONE; c.last_addr[it] = (long long)(uintptr_t)slot; c.last_rule[it] = LAST_ZERO; }
+        else if (w1 < 0) { c.last_addr2[it] = 0; c.last_rule2[it] = LAST_NONE; c.last_addr[it] = (long long)(uintptr_t)slot; c.last_rule[it] = LAST_COPY; }
         else {
+          c.last_addr2[it] = 0; c.last_rule2[it] = LAST_NONE;
           const HostBlock &p = b->hb[w1];
           c.last_addr[it] = (long long)(uintptr_t)row_of(p, k); c.last_rule[it] = rule_of(p);
           if (h.W && extent_of(p) < long_extent) {
@@ -688,7 +743,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
             else { const HostBlock &p2 = b->hb[w2]; c.last_addr2[it] = (long long)(uintptr_t)row_of(p2, k); c.last_rule2[it] = rule_of(p2); }
           }
         }
-        if (!managed || !gate[h.W] || gate[h.W][it]) { w1 = lst[j]; if (extent_of(h) >= long_extent) w2 = lst[j]; }
+        if (!gated || !gate[h.W] || gate[h.W][it]) { w1 = lst[j]; if (extent_of(h) >= long_extent) w2 = lst[j]; }
       }
       if (hs && w1 >= 0) {
         const HostBlock &p = b->hb[w1];
@@ -714,17 +769,12 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       h.block_mode = q.blocktype | (W << 1); h.psy = q.blocktype + (W ? 2 : 0);
       h.granulepos = q.granulepos; h.eof = q.eofflag; h.idx = idx_of[i];
       h.hist[0] = x->lW_block_mode; h.hist[1] = x->lW_no; h.hist[2] = x->impadnum;
-      HostClass &c = hc[W];
-      c.psy_blk[h.idx] = h.psy;
-      for (int k = 0; k < ch; k++) {
-        const int it = h.idx * ch + k;
-        c.psy_item[it] = h.psy; c.block_mode[it] = h.block_mode; c.lW_block_mode[it] = x->lW_block_mode;
-        c.lW[it] = h.lW; c.nW[it] = h.nW;
-        int *pr = c.params + (size_t)it * 8;
-        pr[0] = 1; pr[1] = managed; pr[2] = flr_of_end[W]; pr[3] = h.block_mode; pr[4] = h.nW; pr[5] = x->lW_block_mode; pr[6] = x->lW_no; pr[7] = x->impadnum;
-        c.pcm_off[it] = q.pcm_offset + (long long)k * q.pcm_stride;
-        c.temp_off[it] = ((long long)x->slot * ch + k) * 256;
-      }
+      BlockDesc &d = hc[W].desc[h.idx];
+      d.pcm_off = q.pcm_offset; d.pcm_stride = (int)q.pcm_stride; d.slot = x->slot; d.lW_no = x->lW_no;
+      d.lW = (unsigned char)h.lW; d.nW = (unsigned char)h.nW; d.blocktype = (unsigned char)q.blocktype;
+      d.lW_block_mode = (unsigned char)x->lW_block_mode; d.impadnum = (unsigned char)x->impadnum; d.pad0 = d.pad1 = 0;
+      if (j == 0) { d.prev = -1; d.prev_rule = LAST_COPY; }
+      else { const HostBlock &p = b->hb[lst[j - 1]]; d.prev = (p.W << 30) | p.idx; d.prev_rule = (unsigned char)rule_of(p); }
       /* aoTuV history, mapping0.c:1297-1305 -- once per packet blob */
       for (int rep = 0; rep < (managed ? VB200_PACKETBLOBS : 1); rep++) {
         if (h.block_mode >= 2) x->impadnum = 0;
@@ -738,11 +788,11 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     }
     /* chains for K4: runs of consecutive impulse blocks of one stream, per channel; everything else is its own
        chain.  Offsets are local to the stream here and rebased when the streams are concatenated. */
-    link_stream(sidx, no_gate);
+    link_stream(sidx, no_gate, false);
     StreamChains &C = sc[sidx];
     C.impulse = false;
     for (int j = 0; j < cnt; j++) if (b->hb[lst[j]].W == 0 && b->hb[lst[j]].block_mode == 0) { C.impulse = true; break; }
-    for (int W = 0; W < 2; W++) { C.items[W].reserve((size_t)cnt * ch); C.start[W].reserve((size_t)cnt * ch); C.len[W].reserve((size_t)cnt * ch); }
+    /* (long blocks: every ch-block is its own chain, K4 needs no list for them) */
     for (int k = 0; k < ch; k++) {
       if (managed) {
         /* managed mode: the sel = 1 pass of a run's FIRST impulse block reads tempmdct before the sel = 2 pass resets
@@ -757,10 +807,10 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
         if ((int)C.items[0].size() > start0) { C.start[0].push_back(start0); C.len[0].push_back((int)C.items[0].size() - start0); }
         for (int j = 0; j < cnt; j++) {
           const HostBlock &h = b->hb[lst[j]];
-          if (h.W == 0 && h.block_mode == 0) continue;
-          C.start[h.W].push_back((int)C.items[h.W].size());
-          C.items[h.W].push_back(h.idx * ch + k);
-          C.len[h.W].push_back(1 | (1 << 30) | (1 << 29));
+          if (h.W || h.block_mode == 0) continue;
+          C.start[0].push_back((int)C.items[0].size());
+          C.items[0].push_back(h.idx * ch + k);
+          C.len[0].push_back(1 | (1 << 30) | (1 << 29));
         }
         continue;
       }
@@ -768,6 +818,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       while (j < cnt) {
         const HostBlock &h = b->hb[lst[j]];
         const int W = h.W;
+        if (W) { j++; continue; }
         const int start = (int)C.items[W].size();
         C.items[W].push_back(h.idx * ch + k);
         int e = j + 1;
@@ -795,7 +846,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   const double t_prep2 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   /* (3) concatenate the chains */
   for (int sidx = 0; sidx < nstreams; sidx++)
-    for (int W = 0; W < 2; W++) {
+    for (int W = 0; W < 1; W++) {
       HostClass &c = hc[W];
       const StreamChains &C = sc[sidx];
       const int base = c.nchain_items;
@@ -827,7 +878,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   FetchTable ft; ft.n = 0;
   auto fetch_flush = [&]() -> int {
     if (!ft.n) return VB200_OK;
-    k_fetch<<<dim3(32, ft.n), 256, 0, st>>>(ft);
+    k_fetch<<<dim3(96, ft.n), 256, 0, st>>>(ft);
     ft.n = 0;
     LAUNCH_CHECK();
     return VB200_OK;
@@ -840,15 +891,10 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   };
 #define UP(dst, src, n) RUN(fetch_add(dst, src, sizeof(*(src)) * (size_t)(n)))
   for (int W = 0; W < 2; W++) {
-    const int I = nb[W] * ch;
-    if (!I) continue;
+    if (!nb[W]) continue;
     ClassBufs &c = b->c[W]; HostClass &h = hc[W];
-    UP(c.psy_item, h.psy_item, I); UP(c.psy_blk, h.psy_blk, nb[W]); UP(c.block_mode, h.block_mode, I); UP(c.lW_block_mode, h.lW_block_mode, I);
-    UP(c.lW, h.lW, I); UP(c.nW, h.nW, I); UP(c.params, h.params, I * 8); UP(c.pcm_off, h.pcm_off, I);
-    UP(c.last_addr, h.last_addr, I); UP(c.last_rule, h.last_rule, I);
-    if (managed) { UP(c.last_addr2, h.last_addr2, I); UP(c.last_rule2, h.last_rule2, I); }
-    UP(c.chain_start, h.chain_start, h.nchains); UP(c.chain_len, h.chain_len, h.nchains); UP(c.chain_items, h.chain_items, h.nchain_items);
-    UP(c.temp_off, h.temp_off, I);
+    UP(c.desc, h.desc, nb[W]);
+    if (W == 0) { UP(c.chain_start, h.chain_start, h.nchains); UP(c.chain_len, h.chain_len, h.nchains); UP(c.chain_items, h.chain_items, h.nchain_items); }
   }
   ScanBlock *d_scan = b->d_scan; int *d_scan_start = b->d_scan_start, *d_slot = b->d_slot; float **d_ptrs = b->d_ptrs;
   {
@@ -860,6 +906,19 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   }
 
   RUN(fetch_flush());
+  /* every per-ch-block descriptor array, from the 32-byte block records */
+  for (int W = 0; W < 2; W++) {
+    if (!nb[W]) continue;
+    ClassBufs &c = b->c[W];
+    ExpandArgs a;
+    a.psy_item = c.psy_item; a.psy_blk = c.psy_blk; a.block_mode = c.block_mode; a.lW_block_mode = c.lW_block_mode; a.lW = c.lW; a.nW = c.nW; a.params = c.params;
+    a.pcm_off = c.pcm_off; a.last_addr = c.last_addr; a.last_addr2 = gated ? c.last_addr2 : nullptr; a.temp_off = c.temp_off;
+    a.last_rule = c.last_rule; a.last_rule2 = gated ? c.last_rule2 : nullptr;
+    a.logmdct[0] = b->c[0].logmdct; a.logmdct[1] = b->c[1].logmdct; a.N2[0] = b->c[0].N2; a.N2[1] = b->c[1].N2;
+    a.last_pool = pool->last; a.W = W; a.ch = ch; a.managed = managed; a.hs = hs ? 1 : 0; a.flr_end = flr_of_end[W]; a.nblocks = nb[W];
+    k_expand_desc<<<(nb[W] * ch + 255) / 256, 256, 0, st>>>(c.desc, a);
+    LAUNCH_CHECK();
+  }
   /* ---- K1: window + MDCT + FFT/dB ---- */
   EV("K1 transform");
   auto run_k1 = [&]() -> int {
@@ -881,13 +940,12 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
      against the gates K4 finds and, if a gate is closed (digital silence, mostly), the links are rebuilt and K1
      (K4 scales gmdct in place), K2 and K4 run again until gates and links agree.  The prefix of every stream up to
      its first changed gate is final after each round, so this ends; streams without closed gates take one round. ---- */
-  const bool gated = managed && hs;
   std::vector<int> gate_prev[2];
   int round = 0;
   for (;; round++) {
     if (round > 0) {
       int *const g[2] = {hc[0].gate, hc[1].gate};
-      for (int sidx = 0; sidx < nstreams; sidx++) link_stream(sidx, g);
+      for (int sidx = 0; sidx < nstreams; sidx++) link_stream(sidx, g, true);
       for (int W = 0; W < 2; W++) {
         const int I = nb[W] * ch;
         if (!I) continue;
@@ -916,7 +974,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       ClassBufs &c = b->c[W];
       if (!nb[W]) continue;
       LastRef last{nullptr, c.last_addr, c.last_rule, 0};      /* M3 reads lastmdct in short blocks only: one source */
-      RUN(vb200_launch_mix(s, st, W, hc[W].nchains, c.chain_start, c.chain_len, c.chain_items, c.psy_item, c.params, c.lowcomp,
+      RUN(vb200_launch_mix(s, st, W, W ? nb[W] * ch : hc[W].nchains, W ? nullptr : c.chain_start, W ? nullptr : c.chain_len, W ? nullptr : c.chain_items, c.psy_item, c.params, c.lowcomp,
                            c.noise, c.tone, c.logmdct, c.gmdct, last, pool->temp, gated ? pool->temp2 : pool->temp, c.temp_off, c.npeak, c.nps,
                            c.logmask, nsel, c.N2 * nsel, nullptr, managed ? c.fit_gate : nullptr, -1));
     }
@@ -1031,14 +1089,14 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       const DevMap &M = s->h.map[s->h.mode_mapping[W]];
       /* posts of blob k (mapping0.c:1090-1181) into posts_k (floor1_encode mutates them) */
       const int H = VB200_PACKETBLOBS / 2;
-      if (!managed || k == H) { k_copy_i32<<<148, 256, 0, st>>>(c.posts[1], c.posts_k, (size_t)I * VB200_MAX_POSTS); k_copy_i32<<<8, 256, 0, st>>>(c.fitted[1], c.fitted_k, I); vb200_count_launch(2); }
-      else if (k == 0) { k_copy_i32<<<148, 256, 0, st>>>(c.posts[0], c.posts_k, (size_t)I * VB200_MAX_POSTS); k_copy_i32<<<8, 256, 0, st>>>(c.fitted[0], c.fitted_k, I); vb200_count_launch(2); }
-      else if (k == VB200_PACKETBLOBS - 1) { k_copy_i32<<<148, 256, 0, st>>>(c.posts[2], c.posts_k, (size_t)I * VB200_MAX_POSTS); k_copy_i32<<<8, 256, 0, st>>>(c.fitted[2], c.fitted_k, I); vb200_count_launch(2); }
+      if (!managed || k == H) { k_copy_i32<<<copy_grid((size_t)I * VB200_MAX_POSTS), 256, 0, st>>>(c.posts[1], c.posts_k, (size_t)I * VB200_MAX_POSTS); k_copy_i32<<<copy_grid((size_t)I), 256, 0, st>>>(c.fitted[1], c.fitted_k, I); vb200_count_launch(2); }
+      else if (k == 0) { k_copy_i32<<<copy_grid((size_t)I * VB200_MAX_POSTS), 256, 0, st>>>(c.posts[0], c.posts_k, (size_t)I * VB200_MAX_POSTS); k_copy_i32<<<copy_grid((size_t)I), 256, 0, st>>>(c.fitted[0], c.fitted_k, I); vb200_count_launch(2); }
+      else if (k == VB200_PACKETBLOBS - 1) { k_copy_i32<<<copy_grid((size_t)I * VB200_MAX_POSTS), 256, 0, st>>>(c.posts[2], c.posts_k, (size_t)I * VB200_MAX_POSTS); k_copy_i32<<<copy_grid((size_t)I), 256, 0, st>>>(c.fitted[2], c.fitted_k, I); vb200_count_launch(2); }
       else if (k < H) RUN(vb200_launch_floor_interp(s, st, W, I, -1, c.posts[0], c.posts[1], c.fitted[0], c.fitted[1], k * 65536 / H, c.posts_k, c.fitted_k));
       else RUN(vb200_launch_floor_interp(s, st, W, I, -1, c.posts[1], c.posts[2], c.fitted[1], c.fitted[2], (k - H) * 65536 / H, c.posts_k, c.fitted_k));
       /* floor1_encode's return value (the pre-coupling nonzero flag) is what the packet carries */
       RUN(vb200_launch_floor_encode(s, st, W, I, -1, c.posts_k, c.fitted_k, c.vals, c.iwork, c.floor_nz));
-      k_copy_i32<<<8, 256, 0, st>>>(c.floor_nz, c.nonzero, I); vb200_count_launch(1);
+      k_copy_i32<<<copy_grid((size_t)I), 256, 0, st>>>(c.floor_nz, c.nonzero, I); vb200_count_launch(1);
       if (host_emit) {
         CUDA_TRY(cudaMemcpyAsync(hr[W].vals, c.vals, sizeof(int) * (size_t)I * VB200_MAX_POSTS, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(hr[W].nonzero, c.floor_nz, sizeof(int) * (size_t)I, cudaMemcpyDeviceToHost, st));
