@@ -187,6 +187,11 @@ typedef struct {
   int64_t  pcm_stride;   /* element distance between channels */
 } vb200_block;
 
+/* A/B hook for the block-size detector: the windowed 128-point forward MDCT _ve_amp takes of one step
+ * (envelope.c:139-186: vec[i] = data[i]*mdct_win[i]; mdct_forward) with the reference's own float operations -- 128
+ * samples in, 64 coefficients out, bit-identical to the reference's.  Host code (the device detector K0 runs the same
+ * function, csrc/ve_mdct128.cuh). */
+int  vb200_stage_detector_mdct(const float *pcm128, float *coef64);
 /* Host-side segmentation of a whole stream into analysis blocks (works without a GPU).  Replaces,
  * for offline encoding, vorbis_analysis_buffer/_wrote (block.c:411-553, incl. the LPC head/tail
  * extrapolation of lpc.c), _ve_envelope_search/_ve_envelope_mark (envelope.c:569-706) and the

@@ -75,6 +75,32 @@ void *ref_enc_open(int channels,long rate,float quality,long managed_bitrate){
   return e;
 }
 
+/* The block-size detector's transform as the reference's own state runs it (envelope.c:139-186, scalar path): the
+   handle's envelope_lookup supplies the window and the 128-point mdct_lookup.  data: 128 samples, out: 64 coefficients.
+   (Any size n the reference can initialise: ref_mdct_forward below.) */
+int ref_envelope_mdct(void *h,const float *data,float *out){
+  ref_enc *e=h;
+  private_state *b=e->vd.backend_state;
+  envelope_lookup *ve=b->ve;
+  float vec[1024];
+  int i,n=ve->winlength;
+  if(n>1024)return -1;
+  for(i=0;i<n;i++)vec[i]=data[i]*ve->mdct_win[i];
+  mdct_forward(&ve->mdct,vec,vec);
+  memcpy(out,vec,sizeof(float)*(n/2));
+  return n;
+}
+void ref_mdct_forward(int n,const float *in,float *out){
+  mdct_lookup m;
+  float *buf=malloc(sizeof(float)*n);
+  memcpy(buf,in,sizeof(float)*n);
+  mdct_init(&m,n);
+  mdct_forward(&m,buf,buf);
+  memcpy(out,buf,sizeof(float)*(n/2));
+  mdct_clear(&m);
+  free(buf);
+}
+
 void ref_enc_close(void *h){
   ref_enc *e=h; int i;
   if(!e)return;

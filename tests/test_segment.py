@@ -80,3 +80,45 @@ def test_degenerate_signals(kind):
     assert [(b.W, b.lW, b.nW, b.blocktype) for b in blocks] == [tuple(int(v) for v in r[:4]) for r in ref]
     assert [b.granulepos for b in blocks] == [p[1] for p in pk]
     s.close()
+
+
+def test_detector_mdct_is_the_references_own_bit_for_bit():
+    """The block-size detector's transform (csrc/ve_mdct128.cuh: window + 128-point forward MDCT with the reference's own
+    float operations; host here, the device detector K0 runs the same function) against the reference's envelope state
+    itself (ref_envelope_mdct: the handle's mdct_win and mdct_lookup, envelope.c:139-186), and the oracle's
+    operation-exact restatement of mdct_forward at n = 128 against the reference's mdct_forward -- all bit for bit."""
+    import ctypes as C
+    from oracle import port, reflib
+    from vorbis_aotuv_lancer_b200 import blob as vblob
+    from vorbis_aotuv_lancer_b200.lib import L
+    fp = C.POINTER(C.c_float)
+    config = "q4_44k_2ch"
+    ch, rate, q, abr = vblob.CATALOGUE[config]
+    R = reflib.RefLib("c")
+    R.lib.ref_envelope_mdct.argtypes = [C.c_void_p, fp, fp]
+    R.lib.ref_mdct_forward.argtypes = [C.c_int, fp, fp]
+    h = R.open(ch, rate, q, abr)
+    OL = C.CDLL(port.LIBPATH)
+    OL.orc_mdct_forward_exact.argtypes = [fp, fp, C.c_int]
+    OL.orc_mdct_forward_exact.restype = None
+    rng = np.random.default_rng(7)
+    sig = refdata.synth(ch, rate, 1.0, seed=11)[0]
+    cases = [sig[k * 64:k * 64 + 128] for k in range(0, 600, 7)]
+    cases += [rng.uniform(-1, 1, 128).astype(np.float32) * np.float32(10.0 ** rng.uniform(-6, 0)) for _ in range(200)]
+    cases += [np.zeros(128, np.float32), np.full(128, 0.99, np.float32), -np.full(128, 0.99, np.float32)]
+    d = np.zeros(128, np.float32); d[77] = 1.0; cases.append(d)
+    for x in cases:
+        x = np.ascontiguousarray(x, np.float32)
+        ref = np.empty(64, np.float32); mine = np.empty(64, np.float32)
+        assert R.lib.ref_envelope_mdct(h, x.ctypes.data_as(fp), ref.ctypes.data_as(fp)) == 128
+        assert L.vb200_stage_detector_mdct(x.ctypes.data_as(fp), mine.ctypes.data_as(fp)) == 0
+        assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+        # the oracle's restatement of mdct_forward, n = 128, on the windowed samples
+        win = (np.sin(np.arange(128) / 127.0 * np.pi).astype(np.float32) ** 2).astype(np.float32)
+        w = (x * win).astype(np.float32)
+        ref2 = np.empty(64, np.float32)
+        R.lib.ref_mdct_forward(128, w.ctypes.data_as(fp), ref2.ctypes.data_as(fp))
+        o = np.empty(64, np.float32)
+        OL.orc_mdct_forward_exact(w.ctypes.data_as(fp), o.ctypes.data_as(fp), 128)
+        assert np.array_equal(o.view(np.uint32), ref2.view(np.uint32))
+    R.close(h)

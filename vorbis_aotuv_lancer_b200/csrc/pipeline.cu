@@ -1153,6 +1153,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     }
   }
   b->run_nb[0] = nb[0]; b->run_nb[1] = nb[1];
+  bool done_marked = false;
   if (!host_emit && managed) {
     /* the bitrate manager runs where the blobs are: only the chosen packets leave the device */
     EV("bitrate manager");
@@ -1167,6 +1168,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       LAUNCH_CHECK();
     }
     EV("d2h packets");
+    CUDA_TRY(cudaEventRecord(b->ev_done, st)); done_marked = true;      /* the kernels end here: a batch ordered behind this one may start */
     CUDA_TRY(cudaMemcpyAsync(b->h_out_top, b->d_out_top, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(b->h_pool_top, b->d_pool_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(b->h_br, b->d_br, sizeof(BitrateState) * nstreams, cudaMemcpyDeviceToHost, st));
@@ -1179,6 +1181,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   } else if (!host_emit) {
     /* first half of the only D2H of the path: packet offsets / sizes and the pool fill level */
     EV("d2h packets");
+    CUDA_TRY(cudaEventRecord(b->ev_done, st)); done_marked = true;
     CUDA_TRY(cudaMemcpyAsync(b->h_pool_top, b->d_pool_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     for (int kk = 0; kk < nblobs; kk++) for (int W = 0; W < 2; W++) if (nb[W]) {
       const size_t o = ((size_t)kk * 2 + W) * b->max_blocks;
@@ -1186,7 +1189,8 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       CUDA_TRY(cudaMemcpyAsync(b->h_pk_bytes + o, b->d_pk_bytes + o, sizeof(int) * nb[W], cudaMemcpyDeviceToHost, st));
     }
   }
-  CUDA_TRY(cudaEventRecord(b->ev_done, st)); b->ev_done_set = true;
+  if (!done_marked) CUDA_TRY(cudaEventRecord(b->ev_done, st));
+  b->ev_done_set = true;
   b->pending = true;
   if (host_emit) return batch_finish(b);
   return VB200_OK;

@@ -28,6 +28,7 @@
 #include <vector>
 #include "vb200_internal.h"
 #include "dev_util.cuh"
+#include "ve_mdct128.cuh"
 
 namespace {
 
@@ -81,13 +82,12 @@ void lpc_predict(const float *coeff, const float *prime, int m, float *data, lon
   }
 }
 
-/* tables of the detector, built once (envelope.c:42-82).  The 128-point MDCT is evaluated as fold (two
-   windowed products per point, summed in double) + 64x64 DCT-IV matrix in double with fused multiply-adds in
-   ascending order, so that host and device evaluate the very same sums */
+/* tables of the detector, built once (envelope.c:42-82).  The 128-point MDCT is the reference's own (ve_mdct128.cuh:
+   mdct_forward for n = 128, operation by operation), on the host and on the device alike. */
 struct Detector {
   float win[VE_N];
   float bandwin[VE_BANDS][8], bandtotal[VE_BANDS];
-  double dct[VE_N / 2][VE_N / 2];      /* [k][n] */
+  float T[VE_N + VE_N / 4];            /* mdct_init(128), mdct.c:54-92 */
   Detector() {
     for (int i = 0; i < VE_N; i++) { const float t = (float)sin(i / (VE_N - 1.) * M_PI); win[i] = t * t; }
     for (int j = 0; j < VE_BANDS; j++) {
@@ -96,8 +96,10 @@ struct Detector {
       for (int i = 0; i < n; i++) { bandwin[j][i] = (float)sin((i + .5) / n * M_PI); tot += bandwin[j][i]; }
       bandtotal[j] = (float)(1. / tot);
     }
-    for (int k = 0; k < VE_N / 2; k++)
-      for (int n = 0; n < VE_N / 2; n++) dct[k][n] = (4.0 / VE_N) * cos(M_PI / (2.0 * VE_N) * (2 * n + 1) * (2 * k + 1));
+    int bitrev[VE_N / 4];
+    vb200_exact_tables_mdct(VE_N, T, bitrev);
+    for (int i = 0; i < VE_N / 8; i++)       /* ve_mdct128.cuh has the bit reversal in closed form */
+      if (bitrev[2 * i] != ve128::rev0(i) || bitrev[2 * i + 1] != ve128::rev1(i)) abort();
   }
 };
 const Detector &detector() { static Detector d; return d; }
@@ -106,30 +108,9 @@ const Detector &detector() { static Detector d; return d; }
 struct NearDC { float ring[VE_NEARDC]; float acc, partial; int ptr; };
 struct BandFilter { float ampbuf[VE_AMP]; int ampptr; };
 
-/* (1) windowed 128-point MDCT, first `nout` coefficients.  Fold: with M = 64, h = 32 and p[t] = data[t]*win[t]
-   (float), u[n] = -p[3h-1-n] - p[3h+n] for n < h, p[n-h] - p[3h-1-n] otherwise; X[k] = sum_n dct[k][n] u[n]. */
-__host__ __device__ inline double ve_fold(const float *data, const float *win, int n) {
-  constexpr int h = VE_N / 4;
-#ifdef __CUDA_ARCH__
-  if (n < h) return -(double)__fmul_rn(data[3 * h - 1 - n], win[3 * h - 1 - n]) - (double)__fmul_rn(data[3 * h + n], win[3 * h + n]);
-  return (double)__fmul_rn(data[n - h], win[n - h]) - (double)__fmul_rn(data[3 * h - 1 - n], win[3 * h - 1 - n]);
-#else
-  if (n < h) { const float a = data[3 * h - 1 - n] * win[3 * h - 1 - n], b = data[3 * h + n] * win[3 * h + n]; return -(double)a - (double)b; }
-  const float a = data[n - h] * win[n - h], b = data[3 * h - 1 - n] * win[3 * h - 1 - n];
-  return (double)a - (double)b;
-#endif
-}
-__attribute__((target("fma"))) void ve_dct_hw(const double (*dct)[VE_N / 2], const double *u, float *vec, int nout) {
-  for (int k = 0; k < nout; k++) { double a = 0; for (int n = 0; n < VE_N / 2; n++) a = __builtin_fma(dct[k][n], u[n], a); vec[k] = (float)a; }
-}
-void ve_dct_sw(const double (*dct)[VE_N / 2], const double *u, float *vec, int nout) {
-  for (int k = 0; k < nout; k++) { double a = 0; for (int n = 0; n < VE_N / 2; n++) a = fma(dct[k][n], u[n], a); vec[k] = (float)a; }
-}
-inline void ve_mdct(const Detector &D, const float *data, float *vec, int nout) {
-  static const bool hw = __builtin_cpu_supports("fma");
-  double u[VE_N / 2];
-  for (int n = 0; n < VE_N / 2; n++) u[n] = ve_fold(data, D.win, n);
-  if (hw) ve_dct_hw(D.dct, u, vec, nout); else ve_dct_sw(D.dct, u, vec, nout);
+/* (1) windowed 128-point MDCT (envelope.c:139-186, scalar path: vec[i] = data[i]*mdct_win[i]; mdct_forward) */
+inline void ve_mdct(const Detector &D, const float *data, float *vec) {
+  ve128::forward([&](int t) { return VE_FM(data[t], D.win[t]); }, vec, D.T);
 }
 __host__ __device__ inline float ve_neartemp(float v0, float v1, float v2) {
   return (float)((double)(v0 * v0) + .7 * (double)v1 * (double)v1 + .2 * (double)v2 * (double)v2);
@@ -297,7 +278,7 @@ struct StreamSeg {
       ve_stretch_params(stretch, env.stretch_penalty, &st, &pen);
       for (int c = 0; c < ch; c++) {
         float vec[VE_N / 2], acc[VE_BANDS];
-        ve_mdct(D, pcm + (size_t)c * T + VE_STEP * j, vec, VE_N / 2);
+        ve_mdct(D, pcm + (size_t)c * T + VE_STEP * j, vec);
         const float decay = ve_neardc(&near[c], ve_neartemp(vec[0], vec[1], vec[2]));
         ve_bands(D, vec, decay, env.minenergy, acc);
         for (int b = 0; b < VE_BANDS; b++) ret |= ve_trigger(&filt[(size_t)c * VE_BANDS + b], acc[b], st, pen, env.pre_th[b], env.post_th[b]);
@@ -409,6 +390,13 @@ extern "C" int vb200_segment_stream(const vb200_setup *s, const float *pcm, long
   return VB200_OK;
 }
 
+/* A/B hook: the detector's windowed 128-point transform of one step (envelope.c:139-186), host code */
+extern "C" int vb200_stage_detector_mdct(const float *pcm128, float *coef64) {
+  if (!pcm128 || !coef64) { vb200_set_error("vb200_stage_detector_mdct: bad arguments"); return VB200_EINVAL; }
+  ve_mdct(detector(), pcm128, coef64);
+  return VB200_OK;
+}
+
 extern "C" void vb200_segments_free(vb200_segments *g) { delete g; }
 extern "C" int vb200_segments_count(const vb200_segments *g) { return g ? (int)g->blocks.size() : VB200_EINVAL; }
 extern "C" const vb200_block *vb200_segments_blocks(const vb200_segments *g) { return g ? g->blocks.data() : nullptr; }
@@ -417,148 +405,90 @@ extern "C" const float *vb200_segments_pcm(const vb200_segments *g, long *elems)
 /* ================================================================ device half of the detector */
 namespace {
 
-struct EnvDev {            /* tables in HBM */
-  const double *dct;       /* [64 k][64 n] */
-  const double *dctt;      /* [64 n][64 k] transposed */
-  const float *win;        /* [128] */
-  float bandwin[VE_BANDS][8], bandtotal[VE_BANDS];
-  int bbegin[VE_BANDS], bend[VE_BANDS];
+struct EnvDev {            /* parameters in HBM */
   float minenergy, stretch_penalty, pre_th[VE_BANDS], post_th[VE_BANDS];
 };
+/* tables every detector thread reads at compile-time indices: constant bank (they depend on nothing but the
+   detector's fixed geometry, so one copy per device serves every setup) */
+__constant__ float c_ve_T[VE_N + VE_N / 4];      /* mdct_init(128) */
+__constant__ float c_ve_win[VE_N];
+__constant__ float c_ve_bandwin[VE_BANDS][8];
+__constant__ float c_ve_bandtotal[VE_BANDS];
+__host__ __device__ constexpr int band_begin(int b) { constexpr int t[VE_BANDS] = {2, 4, 6, 9, 13, 17, 22, 12, 8, 3, 2, 1}; return t[b]; }
+__host__ __device__ constexpr int band_end(int b) { constexpr int t[VE_BANDS] = {4, 5, 6, 8, 8, 8, 8, 4, 4, 3, 2, 4}; return t[b]; }
 
 struct EnvStream { long long pcm_base; long long T; int nsteps; long long out_base; /* step-major output offset */ long long eof; };
 
-constexpr int EV_TILE = 32;      /* steps per CTA */
-constexpr int EV_THREADS = 128;
+constexpr int EV_TILE = 128;     /* steps per CTA */
 constexpr int EV_HALO = 30;      /* the near-DC sum of a step depends on at most the 30 previous steps */
-constexpr int EV_M = VE_N / 2;   /* folded length = number of coefficients */
-constexpr int EV_US = EV_M + 1;  /* row stride of the folded steps in shared memory (doubles) */
+constexpr int EV_THREADS = 160;  /* one thread per transformed step: halo + tile (two spare) */
+constexpr int EV_ROW = EV_THREADS + 1;   /* row stride of the transposed sample tile: odd, conflict-free both ways */
 
-/* K0a: per (stream, channel, tile of 32 steps): fold -> 64x64 DCT-IV in double -> near-DC decay ->
-   spread/limit -> 12 band amplitudes.  Everything here is a pure function of the PCM, so tiles are independent.
-   The matrix product is register-blocked 4 coefficients x 8 steps per thread: thread (kq, sg) owns coefficients
-   kq+16j of steps 8sg..8sg+7, so each pass over n costs 4 matrix loads + 8 broadcast reads for 32 DFMA. */
-__global__ void __launch_bounds__(EV_THREADS, 6)
+/* K0a: per (stream, channel, tile of 128 steps): one thread per step does the whole 128-point MDCT of the reference
+   (ve_mdct128.cuh) on registers -- every sample of the step is read once, from a tile of the timeline that the CTA
+   stages transposed (sample s at row s mod 64, column s div 64: lanes = consecutive steps read consecutive words) --
+   then the near-DC decay (replayed from the 30 halo steps the CTA transforms as well), the spread/limit pass and
+   the 12 band amplitudes, all in the reference's float operations (envelope.c:139-216, scalar path).  Everything
+   here is a pure function of the PCM, so tiles are independent. */
+__global__ void __launch_bounds__(EV_THREADS, 2)
 k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams, int ch, const float *__restrict__ pcm,
             float *__restrict__ acc_out /*[stream][ch][step][12]*/, float *__restrict__ temp_out /*[stream][ch][step]*/) {
-  __shared__ double u[(EV_TILE + EV_HALO) * EV_US];
-  __shared__ float wins[VE_N];
-  __shared__ float temps[EV_TILE + EV_HALO];
-  __shared__ float decay[EV_TILE];
+  __shared__ float tile[VE_STEP * EV_ROW];
+  __shared__ float temps[EV_THREADS];
   const EnvStream S = streams[blockIdx.z];
   const int c = blockIdx.y, tid = threadIdx.x;
   const int j0 = blockIdx.x * EV_TILE;
   if (j0 >= S.nsteps) return;
   const int jn = min(EV_TILE, S.nsteps - j0);
-  const int h0 = max(0, j0 - EV_HALO);                      /* first step that is folded here */
+  const int h0 = max(0, j0 - EV_HALO);                      /* first step that is transformed here */
   const int nh = j0 + jn - h0, toff = j0 - h0;
   const float *src = pcm + S.pcm_base + (long long)c * S.T + (long long)h0 * VE_STEP;
-  for (int i = tid; i < VE_N; i += EV_THREADS) wins[i] = E->win[i];
+  for (int i = tid; i < (nh + 1) * VE_STEP; i += EV_THREADS) tile[(i & (VE_STEP - 1)) * EV_ROW + (i >> 6)] = __ldg(src + i);
   __syncthreads();
-  const float *win = wins;
+  float vec[VE_N / 2];
+  if (tid < nh) {
+    ve128::forward([&](int t) { return __fmul_rn(tile[(t & (VE_STEP - 1)) * EV_ROW + tid + (t >> 6)], c_ve_win[t]); }, vec, c_ve_T);
+    temps[tid] = ve_neartemp(vec[0], vec[1], vec[2]);
+  }
+  __syncthreads();
+  if (tid < toff || tid >= nh) return;
+  const int j = j0 + tid - toff;
+  float dec;
   {
-    /* ve_fold with everything that depends only on n hoisted: EV_THREADS is a multiple of 64, so a thread keeps its n */
-    constexpr int h = VE_N / 4;
-    const int n = tid & 63;
-    const int ia = n < h ? 3 * h - 1 - n : n - h, ib = n < h ? 3 * h + n : 3 * h - 1 - n;
-    const float wa = win[ia], wb = win[ib];
-    const bool neg = n < h;
-    for (int sidx = tid >> 6; sidx < nh; sidx += EV_THREADS / 64) {
-      const float *d = src + sidx * VE_STEP;
-      const double pa = (double)__fmul_rn(d[ia], wa), pb = (double)__fmul_rn(d[ib], wb);
-      u[sidx * EV_US + n] = (neg ? -pa : pa) - pb;
-    }
-  }
-  for (int it = nh * EV_M + tid; it < (EV_TILE + EV_HALO) * EV_M; it += EV_THREADS) u[(it >> 6) * EV_US + (it & 63)] = 0.;
-  __syncthreads();
-  /* near-DC terms of the halo + tile steps: only coefficients 0..2 are needed */
-  for (int sidx = tid; sidx < nh; sidx += EV_THREADS) {
-    const double *us = u + sidx * EV_US;
-    double a0 = 0, a1 = 0, a2 = 0;
-#pragma unroll 4
-    for (int n = 0; n < EV_M; n++) {
-      const double x = us[n];
-      a0 = fma(E->dct[n], x, a0); a1 = fma(E->dct[EV_M + n], x, a1); a2 = fma(E->dct[2 * EV_M + n], x, a2);
-    }
-    temps[sidx] = ve_neartemp((float)a0, (float)a1, (float)a2);
-  }
-  __syncthreads();
-  /* decay of every tile step: replay the refresh cycle it sits in (<= 44 float ops) */
-  for (int q = tid; q < jn; q += EV_THREADS) {
-    const int j = j0 + q, ptr = j % VE_NEARDC, r = j - ptr;      /* r = last refresh step */
+    /* decay: replay the refresh cycle the step sits in (<= 44 float ops) */
+    const int ptr = j % VE_NEARDC, r = j - ptr;      /* r = last refresh step */
     auto T_ = [&](int step) { return step >= 0 ? temps[step - h0] : 0.f; };
     float partial = 0.f;
     if (r >= VE_NEARDC) { partial = T_(r - VE_NEARDC); for (int w = r - VE_NEARDC + 1; w < r; w++) partial = __fadd_rn(partial, T_(w)); }
     float acc = __fadd_rn(partial, T_(r));
-    float dec = acc;
+    dec = acc;
     acc = __fsub_rn(acc, r >= VE_NEARDC ? T_(r - VE_NEARDC) : 0.f);
     for (int w = r + 1; w <= j; w++) {
       acc = __fadd_rn(acc, T_(w)); dec = acc;
       acc = __fsub_rn(acc, w >= VE_NEARDC ? T_(w - VE_NEARDC) : 0.f);
     }
     dec = (float)((double)dec * (1. / (VE_NEARDC + 1)));
-    decay[q] = (float)((double)todB_hd(dec) * .5 - (double)15.f);
-    temp_out[S.out_base * ch + (long long)c * S.nsteps + j] = T_(j);
+    dec = (float)((double)todB_hd(dec) * .5 - (double)15.f);
+    temp_out[S.out_base * ch + (long long)c * S.nsteps + j] = temps[tid];
   }
-  /* results go where the folded steps were: u is dead once every thread has finished its products */
-  float (*vec)[EV_M] = reinterpret_cast<float (*)[EV_M]>(u);
-  float (*v2)[EV_M / 2 + 1] = reinterpret_cast<float (*)[EV_M / 2 + 1]>(reinterpret_cast<float *>(u) + EV_TILE * EV_M);
-  /* the full 64-coefficient transform of the 32 tile steps: thread (kq, sg) owns coefficients kq+16j of the four
-     steps 4sg..4sg+3 */
-  {
-    const int kq = tid & 15, sg = tid >> 4;
-    double a[4][4];
+  /* spread / limit (envelope.c:189-197): pair i of the spectrum -> v2[i], overwriting vec[i] as the reference does */
+  const float minV = E->minenergy;
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-      for (int i = 0; i < 4; i++) a[j][i] = 0.;
-    const double *ub = u + (toff + sg * 4) * EV_US;
-    const double *mt = E->dctt + kq;
-#pragma unroll 4
-    for (int n = 0; n < EV_M; n++) {
-      double m[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) m[j] = mt[n * EV_M + 16 * j];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const double x = ub[i * EV_US + n];
-#pragma unroll
-        for (int j = 0; j < 4; j++) a[j][i] = fma(m[j], x, a[j][i]);
-      }
-    }
-    __syncthreads();                        /* everybody is done reading u */
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) vec[sg * 4 + i][kq + 16 * j] = (float)a[j][i];
+  for (int i = 0; i < VE_N / 4; i++) {
+    float val = __fadd_rn(__fmul_rn(vec[2 * i], vec[2 * i]), __fmul_rn(vec[2 * i + 1], vec[2 * i + 1]));
+    val = __fmul_rn(todB_hd(val), .5f);
+    if (val < dec) val = dec;
+    if (val < minV) val = minV;
+    vec[i] = val;
+    dec = (float)((double)dec - 8.);
   }
-  __syncthreads();
-  /* spread / limit: thread (q, part) walks its share of the 32 coefficient pairs of step q */
-  {
-    constexpr int PER = (EV_M / 2) / (EV_THREADS / 32);       /* coefficient pairs per thread */
-    const int q = tid & 31, part = tid >> 5;
-    if (q < jn) {
-      float dec = decay[q];
-      for (int w = 0; w < part * PER; w++) dec = (float)((double)dec - 8.);
-      const float minV = E->minenergy;
-      for (int i = part * PER; i < part * PER + PER; i++) {
-        const float x0 = vec[q][2 * i], x1 = vec[q][2 * i + 1];
-        float val = __fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1));
-        val = __fmul_rn(todB_hd(val), .5f);
-        if (val < dec) val = dec;
-        if (val < minV) val = minV;
-        v2[q][i] = val;
-        dec = (float)((double)dec - 8.);
-      }
-    }
-  }
-  __syncthreads();
-  for (int it = tid; it < jn * VE_BANDS; it += EV_THREADS) {
-    const int q = it / VE_BANDS, b = it - q * VE_BANDS;
+  float *ao = acc_out + (S.out_base * ch + (long long)c * S.nsteps + j) * VE_BANDS;
+#pragma unroll
+  for (int b = 0; b < VE_BANDS; b++) {
     float acc = 0.f;
-    const int bb = E->bbegin[b], be = E->bend[b];
-    for (int i = 0; i < be; i++) acc = __fadd_rn(acc, __fmul_rn(v2[q][i + bb], E->bandwin[b][i]));
-    acc_out[((S.out_base * ch + (long long)c * S.nsteps + j0) * VE_BANDS) + it] = __fmul_rn(acc, E->bandtotal[b]);
+#pragma unroll
+    for (int i = 0; i < band_end(b); i++) acc = __fadd_rn(acc, __fmul_rn(vec[i + band_begin(b)], c_ve_bandwin[b][i]));
+    ao[b] = __fmul_rn(acc, c_ve_bandtotal[b]);
   }
 }
 
@@ -685,7 +615,7 @@ struct SegRun {            /* what a begun run keeps until it is finished */
 
 struct vb200_segmenter {
   vb200_setup *s; EnvParams env; SegRun *run;
-  EnvDev *d_env; double *d_dct, *d_dctt; float *d_win;
+  EnvDev *d_env;
   float *h_pcm, *d_pcm; size_t pcm_cap;          /* pinned host timeline + device timeline */
   float *d_acc, *d_temp; unsigned *d_flags; size_t step_cap;
   unsigned char *d_marks, *h_marks; size_t mark_cap;
@@ -706,18 +636,15 @@ extern "C" int vb200_segmenter_create(vb200_setup *s, vb200_segmenter **out) {
   if (!env_params(s, &g->env)) { delete g; vb200_set_error("vb200_segmenter_create: setup blob lacks the envelope parameters"); return VB200_EINVAL; }
   const Detector &D = detector();
   EnvDev e;
-  CUDA_TRY(cudaMalloc(&g->d_dct, sizeof(D.dct))); CUDA_TRY(cudaMalloc(&g->d_win, sizeof(D.win))); CUDA_TRY(cudaMalloc(&g->d_env, sizeof(EnvDev)));
-  CUDA_TRY(cudaMemcpy(g->d_dct, D.dct, sizeof(D.dct), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(g->d_win, D.win, sizeof(D.win), cudaMemcpyHostToDevice));
-  {
-    std::vector<double> tr((size_t)(VE_N / 2) * (VE_N / 2));
-    for (int k = 0; k < VE_N / 2; k++) for (int n = 0; n < VE_N / 2; n++) tr[(size_t)n * (VE_N / 2) + k] = D.dct[k][n];
-    CUDA_TRY(cudaMalloc(&g->d_dctt, tr.size() * sizeof(double)));
-    CUDA_TRY(cudaMemcpy(g->d_dctt, tr.data(), tr.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&g->d_env, sizeof(EnvDev)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_ve_T, D.T, sizeof(D.T)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_ve_win, D.win, sizeof(D.win)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_ve_bandwin, D.bandwin, sizeof(D.bandwin)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_ve_bandtotal, D.bandtotal, sizeof(D.bandtotal)));
+  for (int i = 0; i < VE_BANDS; i++) {
+    if (kBandBegin[i] != band_begin(i) || kBandEnd[i] != band_end(i)) { vb200_set_error("vb200_segmenter_create: band tables out of step"); return VB200_EFAULT; }
+    e.pre_th[i] = g->env.pre_th[i]; e.post_th[i] = g->env.post_th[i];
   }
-  e.dct = g->d_dct; e.dctt = g->d_dctt; e.win = g->d_win;
-  memcpy(e.bandwin, D.bandwin, sizeof(e.bandwin)); memcpy(e.bandtotal, D.bandtotal, sizeof(e.bandtotal));
-  for (int i = 0; i < VE_BANDS; i++) { e.bbegin[i] = kBandBegin[i]; e.bend[i] = kBandEnd[i]; e.pre_th[i] = g->env.pre_th[i]; e.post_th[i] = g->env.post_th[i]; }
   e.minenergy = g->env.minenergy; e.stretch_penalty = g->env.stretch_penalty;
   CUDA_TRY(cudaMemcpy(g->d_env, &e, sizeof(e), cudaMemcpyHostToDevice));
   {
@@ -738,7 +665,7 @@ extern "C" void vb200_segmenter_destroy(vb200_segmenter *g) {
   cudaStreamDestroy(g->st);
   cudaEventDestroy(g->ev_h2d);
   delete g->run;
-  cudaFree(g->d_dct); cudaFree(g->d_dctt); cudaFree(g->d_win); cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
+  cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
   cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_flags); cudaFree(g->d_marks); cudaFreeHost(g->h_marks);
   cudaFree(g->d_streams); cudaFreeHost(g->h_streams); cudaFree(g->d_mark_base); cudaFreeHost(g->h_mark_base);
   cudaFree(g->d_stretch); cudaFreeHost(g->h_stretch); cudaFree(g->d_acc_tail); cudaFreeHost(g->h_acc_tail);
