@@ -273,7 +273,7 @@ constexpr int TS_WARPS = 4;
 template <int N>
 __global__ void __launch_bounds__(TS_WARPS * 32)
 k_tone_splat(const DevSetup *__restrict__ S, int items, const int *__restrict__ psyv, const float *__restrict__ logfft,
-             const float *__restrict__ global_ampmax, const float *__restrict__ local_ampmax, float *__restrict__ rowA, int *__restrict__ rowB, int Lstride) {
+             const float *__restrict__ global_ampmax, const float *__restrict__ local_ampmax, float *__restrict__ rowA, int *__restrict__ rowB, int Lstride, int rowN) {
   extern __shared__ __align__(16) unsigned char dyn[];
   float *seed_all = reinterpret_cast<float *>(dyn);
   __shared__ SplatJob queue[TS_WARPS][TM_QCAP];
@@ -286,8 +286,8 @@ k_tone_splat(const DevSetup *__restrict__ S, int items, const int *__restrict__ 
   tm_splat<N>(S, psyv, logfft, global_ampmax, local_ampmax, item, seed, queue, warp, lane);
   __syncwarp();
   const int L = S->psy[psyv[item]].total_octave_lines;
-  float *sg = rowA + (size_t)item * N;
-  unsigned short *cg = reinterpret_cast<unsigned short *>(rowB + (size_t)item * N);
+  float *sg = rowA + (size_t)item * rowN;
+  unsigned short *cg = reinterpret_cast<unsigned short *>(rowB + (size_t)item * rowN);
   for (int p = lane; p < L; p += 32) { sg[p] = seed[p]; cg[p] = (unsigned short)tm_compare_word(seed, p); }
 }
 
@@ -331,7 +331,7 @@ k_tone_chase(int items, int L, int N, int *__restrict__ rowB) {
 template <int N>
 __global__ void __launch_bounds__(TS_WARPS * 32)
 k_tone_fill(const DevSetup *__restrict__ S, int items, const int *__restrict__ psyv, const float *__restrict__ local_ampmax,
-            const float *__restrict__ rowA, const int *__restrict__ rowB, float *__restrict__ tone, int Lstride) {
+            const float *__restrict__ rowA, const int *__restrict__ rowB, float *__restrict__ tone, int Lstride, int rowN) {
   extern __shared__ __align__(16) unsigned char dyn[];
   float *seed_all = reinterpret_cast<float *>(dyn);
   unsigned short *run_all = reinterpret_cast<unsigned short *>(seed_all + TS_WARPS * Lstride);
@@ -342,10 +342,10 @@ k_tone_fill(const DevSetup *__restrict__ S, int items, const int *__restrict__ p
   const DevPsy &P = S->psy[psyv[item]];
   const int L = P.total_octave_lines;
   float *seed = seed_all + warp * Lstride;
-  const float *sg = rowA + (size_t)item * N;
+  const float *sg = rowA + (size_t)item * rowN;
   for (int p = lane; p < L; p += 32) seed[p] = sg[p];
   if (lane < Lstride - L) seed[L + lane] = TM_NEGINF;
-  const unsigned *svg = reinterpret_cast<const unsigned *>(rowB + (size_t)item * N + (N - TM_SVW));
+  const unsigned *svg = reinterpret_cast<const unsigned *>(rowB + (size_t)item * rowN + (rowN - TM_SVW));
   unsigned *sv = surv_all + warp * TM_SVW;
   if (lane < ((L + 31) >> 5)) sv[lane] = svg[lane];
   __syncwarp();
@@ -365,11 +365,12 @@ static int launch_tm(const vb200_setup *s, cudaStream_t st, int items, const int
   return VB200_OK;
 }
 
-/* rowA / rowB: two scratch buffers of `items` rows of N2 floats / ints that are dead while K3 runs (the pipeline
-   lends the logmask and iwork rows); NULL selects the fused kernel */
+/* rowA / rowB: two scratch buffers of `items` rows of rowN floats / ints that are dead while K3 runs (the pipeline
+   lends the logmask and iwork rows of the LONG size class, to the short blocks as well: their own rows are too small
+   for the ~590 seed lines); NULL selects the fused kernel */
 int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
                           const float *logfft, const float *global_ampmax, const float *local_ampmax, float *tone,
-                          float *rowA, int *rowB) {
+                          float *rowA, int *rowB, int rowN) {
   if (items <= 0) return VB200_OK;
   int L = 0, Lmin = 1 << 30;
   for (int k = 0; k < s->h.psys; k++) if (s->h.psy[k].blockflag == W) {
@@ -379,15 +380,17 @@ int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int item
   const int Lstride = (L + 2) | 1;        /* odd: lanes walking equal positions hit different banks */
   const int N = s->h.bs[W] / 2;
   static const bool no_split = getenv("VB200_TM_FUSED") != nullptr;
-  if (W && rowA && rowB && !no_split && L == Lmin && N == 1024 && L <= N && 2 * L <= 4 * (N - TM_SVW)) {
+  if (rowA && rowB && !no_split && L == Lmin && (N == 1024 || N == 128) && L <= rowN && 2 * L <= 4 * (rowN - TM_SVW)) {
     const int grid = (items + TS_WARPS - 1) / TS_WARPS;
     const size_t dynA = (size_t)TS_WARPS * Lstride * sizeof(float);
     const size_t dynC = (size_t)TS_WARPS * Lstride * (sizeof(float) + sizeof(unsigned short));
-    k_tone_splat<1024><<<grid, TS_WARPS * 32, dynA, st>>>(s->d, items, psy, logfft, global_ampmax, local_ampmax, rowA, rowB, Lstride);
+    if (N == 1024) k_tone_splat<1024><<<grid, TS_WARPS * 32, dynA, st>>>(s->d, items, psy, logfft, global_ampmax, local_ampmax, rowA, rowB, Lstride, rowN);
+    else           k_tone_splat<128><<<grid, TS_WARPS * 32, dynA, st>>>(s->d, items, psy, logfft, global_ampmax, local_ampmax, rowA, rowB, Lstride, rowN);
     LAUNCH_CHECK();
-    k_tone_chase<<<(items + TS_WARPS * 32 - 1) / (TS_WARPS * 32), TS_WARPS * 32, 0, st>>>(items, L, N, rowB);
+    k_tone_chase<<<(items + TS_WARPS * 32 - 1) / (TS_WARPS * 32), TS_WARPS * 32, 0, st>>>(items, L, rowN, rowB);
     LAUNCH_CHECK();
-    k_tone_fill<1024><<<grid, TS_WARPS * 32, dynC, st>>>(s->d, items, psy, local_ampmax, rowA, rowB, tone, Lstride);
+    if (N == 1024) k_tone_fill<1024><<<grid, TS_WARPS * 32, dynC, st>>>(s->d, items, psy, local_ampmax, rowA, rowB, tone, Lstride, rowN);
+    else           k_tone_fill<128><<<grid, TS_WARPS * 32, dynC, st>>>(s->d, items, psy, local_ampmax, rowA, rowB, tone, Lstride, rowN);
     LAUNCH_CHECK();
     return VB200_OK;
   }

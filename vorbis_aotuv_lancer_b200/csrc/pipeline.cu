@@ -966,7 +966,8 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
       EV("K3 tonemask");
       for (int W = 0; W < 2; W++) {
         ClassBufs &c = b->c[W];
-        RUN(vb200_launch_tonemask(s, st, W, nb[W] * ch, c.psy_item, c.logfft, c.global_ampmax, c.local_ampmax, c.tone, c.logmask, c.iwork));   /* logmask / iwork rows are dead until K4 / K5b */
+        /* scratch rows: the LONG class's logmask / iwork rows, dead until K4 / K5b, for both size classes (short first) */
+        RUN(vb200_launch_tonemask(s, st, W, nb[W] * ch, c.psy_item, c.logfft, c.global_ampmax, c.local_ampmax, c.tone, b->c[1].logmask, b->c[1].iwork, b->c[1].N2));
       }
       EV("K4 offset_and_mix");
     }

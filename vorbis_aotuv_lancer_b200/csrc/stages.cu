@@ -72,9 +72,10 @@ extern "C" int vb200_stage_tonemask(vb200_setup *s, int W, int items, const int3
   const size_t N2 = s->h.bs[W] / 2;
   DevArr<int> d_psy(psy, items, st);
   DevArr<float> d_lf(logfft, items * N2, st), d_g(global_ampmax, items, st), d_l(local_ampmax, items, st), d_t(items * N2);
-  DevArr<float> d_ra(items * N2); DevArr<int> d_rb(items * N2);       /* scratch rows of the three-kernel path */
+  const size_t RN = s->h.bs[1] / 2;                                   /* scratch rows of the three-kernel path: long-block rows for both sizes */
+  DevArr<float> d_ra(items * RN); DevArr<int> d_rb(items * RN);
   CHECK_ALLOC(d_psy); CHECK_ALLOC(d_lf); CHECK_ALLOC(d_g); CHECK_ALLOC(d_l); CHECK_ALLOC(d_t); CHECK_ALLOC(d_ra); CHECK_ALLOC(d_rb);
-  int r = vb200_launch_tonemask(s, st, W, items, d_psy, d_lf, d_g, d_l, d_t, d_ra, d_rb);
+  int r = vb200_launch_tonemask(s, st, W, items, d_psy, d_lf, d_g, d_l, d_t, d_ra, d_rb, (int)RN);
   if (r) return r;
   CUDA_TRY(d_t.down(tone, st));
   CUDA_TRY(cudaStreamSynchronize(st));

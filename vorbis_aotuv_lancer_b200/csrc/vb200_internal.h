@@ -171,7 +171,7 @@ int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int ite
                            float *noise, float *epeak, float *npeak, int npeak_stride);
 int vb200_launch_tonemask(const vb200_setup *s, cudaStream_t st, int W, int items, const int *psy,
                           const float *logfft, const float *global_ampmax, const float *local_ampmax, float *tone,
-                          float *rowA, int *rowB);
+                          float *rowA, int *rowB, int rowN);
 int vb200_launch_mix(const vb200_setup *s, cudaStream_t st, int W, int nchains, const int *chain_start, const int *chain_len, const int *chain_items,
                      const int *psy, const int *params, const float *low_compand,
                      const float *noise, const float *tone, const float *logmdct, float *mdct, LastRef last,
