@@ -173,8 +173,14 @@ __device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restr
   }
 }
 
+#ifndef NM_T
+#define NM_T 256          /* threads of a long ch-block's CTA */
+#endif
+#ifndef NM_MINB
+#define NM_MINB 8         /* resident CTAs per SM the compiler must leave room for */
+#endif
 template <int N, int T, typename LASTREF>
-__global__ void __launch_bounds__(T, (T >= 256 ? 8 : (T >= 128 ? 7 : 1)))
+__global__ void __launch_bounds__(T, (T >= 128 ? NM_MINB : 1))
 k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const int *__restrict__ block_mode,
             const float *__restrict__ lowcomp, const float *__restrict__ postev,
             const float *__restrict__ logmdct, LASTREF last,
@@ -307,9 +313,9 @@ int vb200_launch_noisemask(const vb200_setup *s, cudaStream_t st, int W, int ite
   if (items <= 0) return VB200_OK;
   if (off2) {
     LastRef2 l2{last, off2, rule2};
-    if (W) return launch_nm<1024, 256, LastRef2>(s, st, items, psy, block_mode, lowcomp, poste, logmdct, l2, noise, epeak, npeak, npeak_stride);
+    if (W) return launch_nm<1024, NM_T, LastRef2>(s, st, items, psy, block_mode, lowcomp, poste, logmdct, l2, noise, epeak, npeak, npeak_stride);
     return launch_nm<128, 32, LastRef2>(s, st, items, psy, block_mode, lowcomp, poste, logmdct, l2, noise, epeak, npeak, npeak_stride);
   }
-  if (W) return launch_nm<1024, 256, LastRef>(s, st, items, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
+  if (W) return launch_nm<1024, NM_T, LastRef>(s, st, items, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
   return launch_nm<128, 32, LastRef>(s, st, items, psy, block_mode, lowcomp, poste, logmdct, last, noise, epeak, npeak, npeak_stride);
 }

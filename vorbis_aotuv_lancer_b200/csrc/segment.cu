@@ -498,6 +498,7 @@ k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams,
    serial walk below only looks its state up.  Word layout: bits 2v / 2v+1 = pre / post trigger of variant v
    (window v+2 steps), OR-ed over channels and bands. */
 constexpr int EV_VARIANTS = VE_MAXSTRETCH - VE_MINSTRETCH + 1;
+constexpr int PIPE_SEG_STREAM_SLACK = 64;      /* spare table rows of the parallel trigger */
 __global__ void __launch_bounds__(128)
 k_env_flags(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams, int ch, const float *__restrict__ acc_in,
             unsigned *__restrict__ flags /*[out_base + step]*/) {
@@ -567,6 +568,99 @@ k_env_trigger(const EnvStream *__restrict__ streams, const unsigned *__restrict_
   }
 }
 
+/* K0c, parallel form.  The counter has 26 states (u = stretch + 1 = 0..25) and a step maps u to u' as a function of the
+   step's flag word only, so a chunk of 32 steps is a 26-entry table and tables compose:
+     k_env_maps   one thread per chunk: the table of its 32 steps (row = 32 bytes: entries 0..25);
+     k_env_walk   one CTA per stream: warps compose 32 tables each into a super-table, thread 0 walks the (few dozen)
+                  super-tables, warps walk their chunks from the states that gives (start state -> byte 31 of the row),
+                  threads replay their chunk's 32 steps for the pre/post-echo hits and write the marks.
+   ~40 us instead of the 1.4 ms a single warp needs to walk a 60 s stream; same marks, same final counter. */
+__device__ __forceinline__ int env_step(int u, unsigned w, unsigned *bits) {
+  const int s1 = u < VE_MAXSTRETCH * 2 ? u : VE_MAXSTRETCH * 2;            /* stretch after the increment */
+  const int v = max(s1 >> 1, VE_MINSTRETCH) - VE_MINSTRETCH;
+  *bits = (w >> (2 * v)) & 3u;
+  return (*bits & 1u) ? 0 : s1 + 1;                                          /* a pre-echo hit sets stretch = -1 */
+}
+__host__ __device__ inline long long env_chunk_base(long long out_base, int stream) { return (out_base >> 5) + stream; }
+
+__global__ void __launch_bounds__(128)
+k_env_maps(const EnvStream *__restrict__ streams, const unsigned *__restrict__ flags, unsigned char *__restrict__ maps) {
+  const EnvStream S = streams[blockIdx.y];
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int nchunks = (S.nsteps + 31) >> 5;
+  if (c >= nchunks) return;
+  const int n = min(32, S.nsteps - c * 32);
+  unsigned w[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) w[k] = k < n ? flags[S.out_base + (long long)c * 32 + k] : 0u;
+  unsigned out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int u0 = 0; u0 <= VE_MAXSTRETCH * 2 + 1; u0++) {
+    int u = u0;
+#pragma unroll
+    for (int k = 0; k < 32; k++) { unsigned b; const int nu = env_step(u, w[k], &b); u = k < n ? nu : u; }
+    out[u0 >> 2] |= (unsigned)u << (8 * (u0 & 3));
+  }
+  uint4 *row = reinterpret_cast<uint4 *>(maps + (env_chunk_base(S.out_base, blockIdx.y) + c) * 32);
+  row[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  row[1] = make_uint4(out[4], out[5], out[6], out[7]);
+}
+
+constexpr int EW_THREADS = 1024, EW_MAXSUPER = 1024;      /* up to 1024 * 32 * 32 steps (~23 min at 48 kHz) per stream; longer streams take the serial walk */
+__global__ void __launch_bounds__(EW_THREADS)
+k_env_walk(const EnvStream *__restrict__ streams, const unsigned *__restrict__ flags, unsigned char *__restrict__ maps,
+           unsigned char *__restrict__ marks, const long long *__restrict__ mark_base, int *__restrict__ stretch_out) {
+  __shared__ unsigned char super[EW_MAXSUPER][32];
+  const EnvStream S = streams[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nchunks = (S.nsteps + 31) >> 5, nsuper = (nchunks + 31) >> 5;
+  unsigned char *rows = maps + env_chunk_base(S.out_base, blockIdx.x) * 32;
+  unsigned char *mk = marks + mark_base[blockIdx.x];
+  for (int sc = warp; sc < nsuper; sc += EW_THREADS / 32) {
+    int x = lane;
+    const int c1 = min(nchunks, sc * 32 + 32);
+    if (lane <= VE_MAXSTRETCH * 2 + 1) for (int c = sc * 32; c < c1; c++) x = rows[(size_t)c * 32 + x];
+    super[sc][lane] = (unsigned char)x;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int u = 1;                                        /* stretch = 0 */
+    for (int sc = 0; sc < nsuper; sc++) { const int nu = super[sc][u]; super[sc][31] = (unsigned char)u; u = nu; }
+    stretch_out[blockIdx.x] = u - 1;
+  }
+  __syncthreads();
+  for (int sc = warp; sc < nsuper; sc += EW_THREADS / 32) {
+    if (lane == 0) {
+      int x = super[sc][31];
+      const int c1 = min(nchunks, sc * 32 + 32);
+      for (int c = sc * 32; c < c1; c++) { const int nx = rows[(size_t)c * 32 + x]; rows[(size_t)c * 32 + 31] = (unsigned char)x; x = nx; }
+    }
+  }
+  __syncthreads();
+  /* replay: pre / post hits of every chunk, left in the first two words of its row (the table is dead by now) */
+  for (int c = tid; c < nchunks; c += EW_THREADS) {
+    int u = rows[(size_t)c * 32 + 31];
+    const int n = min(32, S.nsteps - c * 32);
+    unsigned pre = 0, post = 0;
+    for (int k = 0; k < n; k++) {
+      unsigned b;
+      u = env_step(u, flags[S.out_base + (long long)c * 32 + k], &b);
+      pre |= (b & 1u) << k; post |= (b >> 1) << k;
+    }
+    unsigned *r32 = reinterpret_cast<unsigned *>(rows + (size_t)c * 32);
+    r32[0] = pre; r32[1] = post;
+  }
+  __syncthreads();
+  /* marks (envelope.c:601-614): a hit marks its own step; a pre-echo hit also the next, a post-echo hit the one before */
+  for (int c = tid; c < nchunks; c += EW_THREADS) {
+    const unsigned *r32 = reinterpret_cast<const unsigned *>(rows + (size_t)c * 32);
+    const unsigned pre = r32[0], post = r32[1];
+    const unsigned ppre = c > 0 ? r32[-8] : 0u, npost = c + 1 < nchunks ? r32[9] : 0u;
+    const unsigned m = pre | post | (pre << 1) | (ppre >> 31) | (post >> 1) | (npost << 31);
+    for (unsigned mm = m; mm; mm &= mm - 1) { const int j = c * 32 + __ffs(mm) - 1; if (j <= S.nsteps) mk[j] = 1; }
+    if (c == nchunks - 1 && (S.nsteps & 31) == 0 && (pre >> 31)) mk[S.nsteps] = 1;
+  }
+}
+
 /* direct upload: the caller's samples already sit at [lead, eof) of every channel row; zero the lead-in and
    the tail and apply the setup's pre-amplitude in place */
 __global__ void k_timeline_finish(const EnvStream *__restrict__ streams, int ch, int lead, float pre_amp, float *__restrict__ pcm) {
@@ -617,7 +711,7 @@ struct vb200_segmenter {
   vb200_setup *s; EnvParams env; SegRun *run;
   EnvDev *d_env;
   float *h_pcm, *d_pcm; size_t pcm_cap;          /* pinned host timeline + device timeline */
-  float *d_acc, *d_temp; unsigned *d_flags; size_t step_cap;
+  float *d_acc, *d_temp; unsigned *d_flags; unsigned char *d_maps; size_t step_cap;
   unsigned char *d_marks, *h_marks; size_t mark_cap;
   EnvStream *d_streams, *h_streams; long long *d_mark_base, *h_mark_base; int *d_stretch, *h_stretch;
   float *d_acc_tail, *h_acc_tail, *d_temp_tail, *h_temp_tail; int stream_cap;
@@ -666,7 +760,7 @@ extern "C" void vb200_segmenter_destroy(vb200_segmenter *g) {
   cudaEventDestroy(g->ev_h2d);
   delete g->run;
   cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
-  cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_flags); cudaFree(g->d_marks); cudaFreeHost(g->h_marks);
+  cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_flags); cudaFree(g->d_maps); cudaFree(g->d_marks); cudaFreeHost(g->h_marks);
   cudaFree(g->d_streams); cudaFreeHost(g->h_streams); cudaFree(g->d_mark_base); cudaFreeHost(g->h_mark_base);
   cudaFree(g->d_stretch); cudaFreeHost(g->h_stretch); cudaFree(g->d_acc_tail); cudaFreeHost(g->h_acc_tail);
   cudaFree(g->d_temp_tail); cudaFreeHost(g->h_temp_tail);
@@ -718,9 +812,10 @@ extern "C" int vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const flo
   }
   const size_t nstep_tot = (size_t)step_base[nstreams] * ch;
   if (g->step_cap < nstep_tot) {
-    cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_flags); g->d_acc = g->d_temp = nullptr; g->d_flags = nullptr; g->step_cap = 0;
+    cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_flags); cudaFree(g->d_maps); g->d_acc = g->d_temp = nullptr; g->d_flags = nullptr; g->d_maps = nullptr; g->step_cap = 0;
     SEG_ALLOC(g->d_acc, (nstep_tot + 1) * VE_BANDS * sizeof(float), false); SEG_ALLOC(g->d_temp, (nstep_tot + 1) * sizeof(float), false);
     SEG_ALLOC(g->d_flags, ((size_t)step_base[nstreams] + 1) * sizeof(unsigned), false);
+    SEG_ALLOC(g->d_maps, ((size_t)(step_base[nstreams] >> 5) + nstreams + PIPE_SEG_STREAM_SLACK) * 32, false);
     g->step_cap = nstep_tot;
   }
   const size_t nmark = (size_t)mark_base[nstreams];
@@ -814,8 +909,15 @@ extern "C" int vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const flo
     LAUNCH_CHECK();
     k_env_flags<<<dim3((max_steps + 127) / 128, nstreams), 128, 0, st>>>(g->d_env, g->d_streams, ch, g->d_acc, g->d_flags);
     LAUNCH_CHECK();
-    k_env_trigger<<<nstreams, 32, 0, st>>>(g->d_streams, g->d_flags, g->d_marks, g->d_mark_base, g->d_stretch);
-    LAUNCH_CHECK();
+    if (((max_steps + 31) >> 5) <= EW_MAXSUPER * 32 && getenv("VB200_SEG_SERIAL_TRIGGER") == nullptr) {
+      k_env_maps<<<dim3((((max_steps + 31) >> 5) + 127) / 128, nstreams), 128, 0, st>>>(g->d_streams, g->d_flags, g->d_maps);
+      LAUNCH_CHECK();
+      k_env_walk<<<nstreams, EW_THREADS, 0, st>>>(g->d_streams, g->d_flags, g->d_maps, g->d_marks, g->d_mark_base, g->d_stretch);
+      LAUNCH_CHECK();
+    } else {
+      k_env_trigger<<<nstreams, 32, 0, st>>>(g->d_streams, g->d_flags, g->d_marks, g->d_mark_base, g->d_stretch);
+      LAUNCH_CHECK();
+    }
     k_env_tail<<<dim3(nstreams, ch), 64, 0, st>>>(g->d_streams, ch, g->d_acc, g->d_temp, g->d_acc_tail, g->d_temp_tail);
     LAUNCH_CHECK();
   }
