@@ -159,3 +159,57 @@ def test_stream_with_exact_transform(config, seconds, min_identical):
     assert [a[1] for a in pk] == [r[1] for r in ref]
     assert same / len(ref) >= min_identical
     st.close(); bt.close(); s.close()
+
+
+def _capture_pcm(config, pcm):
+    """like refdata.capture, for a given signal: the reference's blocks (taps) and packets"""
+    from oracle import reflib
+    from vorbis_aotuv_lancer_b200 import blob as vblob
+    ch, rate, q, abr = vblob.CATALOGUE[config]
+    R = reflib.RefLib("c")
+    h = R.open(ch, rate, q, abr)
+    R.tap_all(0, 1 << 30)
+    R.write(h, pcm)
+    out = dict(pcm=pcm, blocks=reflib.group(R.tap_records()), packets=R.packets(h))
+    R.tap_config([], 0, 0)
+    R.close(h)
+    return out
+
+
+@pytest.mark.parametrize("config", ["abr128_44k_2ch", "q4_44k_2ch"])
+def test_time_split_batches_with_digital_silence(config):
+    """A stream with stretches of digital silence analysed in FIVE consecutive batches (what the drop-in does with
+    its block queue): lastmdct / tempmdct and, in managed mode, the floor-fit gates that decide who writes them
+    (mapping0.c:1097) must carry over the batch boundaries exactly -- every packet byte-identical to the reference's."""
+    from vorbis_aotuv_lancer_b200 import blob as vblob, ops
+    from vorbis_aotuv_lancer_b200.lib import L
+    ch, rate, q, abr = vblob.CATALOGUE[config]
+    sig = refdata.synth(ch, rate, 4.0, seed=5)
+    pcm = sig.copy()
+    pcm[:, :20000] = 0.0
+    pcm[:, 60000:90000] = 0.0
+    for k in range(4):                                  # bursts out of silence: short blocks next to silent ones
+        p = 62000 + k * 6000
+        pcm[:, p:p + 250] = sig[:, p:p + 250]
+    pcm[:, 150000:] = 0.0
+    cap = _capture_pcm(config, pcm)
+    s = ops.Setup(config)
+    blocks, flat = build_blocks(cap, s.channels)
+    ref = cap["packets"]
+    st = ops.Stream(s)
+    bt = ops.Batch(s, len(blocks))
+    pk, rounds = [], []
+    cuts = [0, len(blocks) // 7, len(blocks) // 3, len(blocks) // 2, (3 * len(blocks)) // 4, len(blocks)]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        bt.run([st], (ops.Block * (b - a))(*blocks[a:b]), flat)
+        pk += bt.packets()
+        rounds.append(int(L.vb200_batch_link_rounds(bt.h)))
+    assert len(pk) == len(ref)
+    diff = [i for i, (x, r) in enumerate(zip(pk, ref)) if x[0] != r[0]]
+    print("\n%s in 5 batches: %d packets, %d differ, link rounds per batch %s" % (config, len(ref), len(diff), rounds))
+    assert not diff, diff[:10]
+    if s.managed:
+        assert max(rounds) > 1          # the silent blocks did close gates: the links were rebuilt
+    else:
+        assert rounds == [1] * 5
+    st.close(); bt.close(); s.close()
