@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=60.0)
-    ap.add_argument("--chunks", type=int, default=8, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
+    ap.add_argument("--chunks", type=int, default=10, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
     ap.add_argument("--depth", type=int, default=2, help="resident arm: batches in flight (2: host half of step i+1 overlaps device half of step i)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-transform", action="store_true", help="front end K1 (own formulation, within 1e-5) instead of the default K1x (DESIGN.md section 4)")

@@ -65,7 +65,7 @@ def test_two_ranks_cover_all_streams_once():
 
 
 def test_encoder_stream_groups_cover_every_stream_once():
-    """Host logic of Encoder.encode: the ramped stream groups (1, 2, 4, 8, then equal shares) partition the streams."""
+    """Host logic of Encoder.encode: the ramped stream groups (1, 2, 4, 6, then equal shares) partition the streams."""
     from vorbis_aotuv_lancer_b200 import encoder
     for n in (1, 2, 3, 7, 8, 16, 63, 64, 65, 1024):
         for chunks in (1, 2, 6, 8, 11):
