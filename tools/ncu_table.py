@@ -5,7 +5,8 @@ import subprocess
 import sys
 
 rep, title, cmd = sys.argv[1], sys.argv[2], sys.argv[3]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# a report, or its raw page already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv > x_raw.csv`)
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 r = list(csv.reader(raw.splitlines()))
 hdr, units = r[0], r[1]
 col = {k: hdr.index(k) for k in hdr}
