@@ -198,7 +198,15 @@ def run_ours(args):
     d_timeline = torch.from_numpy(timeline).cuda()
     audio = S * T
     total_steps = args.warmup + args.steps
-    streams = [[ops.Stream(setup) for _ in range(S)] for _ in range(2 * total_steps)]
+    # one fresh set of streams per step and arm (a step then always starts from the reference's initial state); a setup
+    # holds 4096 stream slots, so very long runs reuse sets: their streams then simply go on where they stopped
+    n_sets = max(4, min(2 * total_steps, 3500 // max(1, S)))
+    _sets = [[ops.Stream(setup) for _ in range(S)] for _ in range(n_sets)]
+
+    class _Sets:
+        def __getitem__(self, i):
+            return _sets[i % n_sets]
+    streams = _Sets()
 
     def barrier():
         torch.cuda.synchronize()

@@ -239,7 +239,9 @@ int  vb200_pinned_alloc(size_t bytes, void **out);
 void vb200_pinned_free(void *p);
 
 /* Per-stream state: replaces the aoTuV fields of private_state (codec_internal.h:85-92), the
- * ampmax feedback of block.c:649-651 and bitrate_manager_state (bitrate.h:26-38). */
+ * ampmax feedback of block.c:649-651 and bitrate_manager_state (bitrate.h:26-38).  The state lives in HBM inside the
+ * setup (allocated with its first stream, freed by vb200_setup_destroy): destroy a setup's streams, batches and
+ * segmenters before the setup, as vorbis_dsp_clear goes before vorbis_info_clear. */
 int  vb200_stream_create(vb200_setup *s, vb200_stream **out);
 void vb200_stream_destroy(vb200_stream *st);
 

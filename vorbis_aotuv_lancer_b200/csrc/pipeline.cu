@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <mutex>
 #include "vb200_internal.h"
 #include "dev_util.cuh"
 #include "emit.h"
@@ -328,19 +329,30 @@ struct vb200_batch {
 };
 
 /* ------------------------------------------------------------------ streams */
-static StatePool *g_pools[64]; static vb200_setup *g_pool_owner[64]; static int g_npools = 0;
-
+/* the pool lives in the setup it belongs to (created with the first stream, freed by vb200_setup_destroy) */
+static std::mutex g_pool_mutex;
 static StatePool *pool_of(vb200_setup *s) {
-  for (int i = 0; i < g_npools; i++) if (g_pool_owner[i] == s) return g_pools[i];
-  if (g_npools >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (s->state_pool) return (StatePool *)s->state_pool;
   StatePool *p = (StatePool *)calloc(1, sizeof(StatePool));
+  if (!p) return nullptr;
   const size_t ch = s->h.channels;
   if (cudaMalloc(&p->last, sizeof(float) * PIPE_MAX_STREAM_SLOTS * ch * 2048) != cudaSuccess ||
       cudaMalloc(&p->temp, sizeof(float) * PIPE_MAX_STREAM_SLOTS * ch * 256) != cudaSuccess ||
       cudaMalloc(&p->temp2, sizeof(float) * PIPE_MAX_STREAM_SLOTS * ch * 256) != cudaSuccess ||
-      cudaMalloc(&p->scal, sizeof(float) * PIPE_MAX_STREAM_SLOTS * (2 + VB200_MAX_CHANNELS)) != cudaSuccess) { free(p); return nullptr; }
-  g_pool_owner[g_npools] = s; g_pools[g_npools++] = p;
+      cudaMalloc(&p->scal, sizeof(float) * PIPE_MAX_STREAM_SLOTS * (2 + VB200_MAX_CHANNELS)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(p->last); cudaFree(p->temp); cudaFree(p->temp2); cudaFree(p->scal); free(p);
+    return nullptr;
+  }
+  s->state_pool = p;
   return p;
+}
+extern "C" void vb200_state_pool_free(void *pool) {
+  StatePool *p = (StatePool *)pool;
+  if (!p) return;
+  cudaFree(p->last); cudaFree(p->temp); cudaFree(p->temp2); cudaFree(p->scal);
+  free(p);
 }
 
 extern "C" int vb200_stream_create(vb200_setup *s, vb200_stream **out) {
@@ -383,7 +395,7 @@ extern "C" int vb200_stream_create(vb200_setup *s, vb200_stream **out) {
 
 extern "C" void vb200_stream_destroy(vb200_stream *x) {
   if (!x) return;
-  StatePool *p = pool_of(x->s);
+  StatePool *p = (StatePool *)x->s->state_pool;      /* streams go before their setup (as vorbis_dsp_clear goes before vorbis_info_clear) */
   if (p) p->used[x->slot] = 0;
   delete x;
 }

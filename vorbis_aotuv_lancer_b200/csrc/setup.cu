@@ -91,6 +91,7 @@ extern "C" void vb200_setup_destroy(vb200_setup *s) {
   if (s->device >= 0) {
     cudaSetDevice(s->device);
     for (int i = 0; i < s->nallocs; i++) cudaFree(s->allocs[i]);
+    if (s->state_pool) vb200_state_pool_free(s->state_pool);
     if (s->stream) cudaStreamDestroy((cudaStream_t)s->stream);
   }
   free(s->allocs);

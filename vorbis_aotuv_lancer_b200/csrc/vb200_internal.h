@@ -133,7 +133,8 @@ struct vb200_setup {
   int bi_i32[4]; double bi_f64[2];
   void *stream;               /* cudaStream_t */
   void **allocs; int nallocs, capallocs;
-  int exact_transform;        /* K1x instead of K1 (vb200_setup_set_exact_transform / VB200_EXACT_TRANSFORM=1) */
+  int exact_transform;        /* K1x (default) or K1 (vb200_setup_set_exact_transform / VB200_EXACT_TRANSFORM=0) */
+  void *state_pool;           /* per-setup stream state in HBM (pipeline.cu: StatePool), created with the first stream */
 };
 
 #ifdef __cplusplus
@@ -141,6 +142,7 @@ extern "C" {
 #endif
 void vb200_set_error(const char *fmt, ...);
 void vb200_count_launch(int n);
+void vb200_state_pool_free(void *pool);                          /* pipeline.cu */
 void vb200_exact_tables_mdct(int n, float *T, int *bitrev);      /* k_transform_exact.cu */
 void vb200_exact_tables_drft(int n, float *wa);
 void vb200_exact_tables_k1x(int n, const float *T, const int *bitrev, float2 *stage_tw, int2 *rev);
