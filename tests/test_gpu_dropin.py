@@ -11,7 +11,8 @@ from tests import refdata
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("config,seconds,batch", [("q4_44k_2ch", 6.0, 64), ("q8_48k_6ch", 2.0, 37), ("abr128_44k_2ch", 3.0, 256)])
+@pytest.mark.parametrize("config,seconds,batch", [("q4_44k_2ch", 6.0, 64), ("q8_48k_6ch", 2.0, 37), ("abr128_44k_2ch", 3.0, 256),
+                                                  ("q4_32k_2ch", 3.0, 100), ("abr256_48k_6ch", 1.5, 50), ("q0_44k_2ch", 3.0, 4096)])
 def test_reference_encoder_loop_over_the_b200_mapping(config, seconds, batch):
     from oracle import reflib
     from vorbis_aotuv_lancer_b200 import blob as vblob, encoder, ops

@@ -135,7 +135,10 @@ def test_device_bitrate_manager_equals_host_manager_over_many_streams():
 
 # single batch, every configuration: all packets byte-identical (measured on a B200, round 2)
 EXACT_CASES = [("q4_44k_2ch", 4.0, 1.0), ("q8_48k_6ch", 2.0, 1.0), ("q2_44k_2ch", 3.0, 1.0), ("q10_48k_2ch", 3.0, 1.0),
-               ("q4_48k_6ch", 2.0, 1.0), ("q4_44k_1ch", 3.0, 1.0), ("abr128_44k_2ch", 3.0, 1.0), ("q5_44k_2ch", 3.0, 1.0)]
+               ("q4_48k_6ch", 2.0, 1.0), ("q4_44k_1ch", 3.0, 1.0), ("abr128_44k_2ch", 3.0, 1.0), ("q5_44k_2ch", 3.0, 1.0),
+               # round 2: 32 kHz, lowest quality, q6~ branch of M3, managed 5.1, three uncoupled channels
+               ("q4_32k_2ch", 3.0, 1.0), ("q0_44k_2ch", 3.0, 1.0), ("q7_44k_2ch", 3.0, 1.0), ("abr256_48k_6ch", 1.5, 1.0),
+               ("q5_48k_3ch", 2.0, 1.0)]
 
 
 @pytest.mark.parametrize("config,seconds,min_identical", EXACT_CASES)

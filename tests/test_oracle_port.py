@@ -7,8 +7,10 @@ from oracle import port as oport
 from tests import refdata
 from vorbis_aotuv_lancer_b200 import blob as vblob
 
-CONFIGS = ["q4_44k_2ch", "q2_44k_2ch", "q8_48k_6ch", "abr128_44k_2ch", "q4_48k_6ch"]
-SECONDS = {"q4_44k_2ch": 3.0, "q2_44k_2ch": 2.0, "q8_48k_6ch": 1.5, "abr128_44k_2ch": 1.5, "q4_48k_6ch": 1.5}
+CONFIGS = ["q4_44k_2ch", "q2_44k_2ch", "q8_48k_6ch", "abr128_44k_2ch", "q4_48k_6ch",
+           "q4_32k_2ch", "q0_44k_2ch", "q7_44k_2ch", "abr256_48k_6ch", "q5_48k_3ch"]      # second row: round 2
+SECONDS = {"q4_44k_2ch": 3.0, "q2_44k_2ch": 2.0, "q8_48k_6ch": 1.5, "abr128_44k_2ch": 1.5, "q4_48k_6ch": 1.5,
+           "q4_32k_2ch": 1.5, "q0_44k_2ch": 1.5, "q7_44k_2ch": 1.5, "abr256_48k_6ch": 1.0, "q5_48k_3ch": 1.5}
 GOLDEN = ["q4_44k_2ch", "q2_44k_2ch", "q8_48k_6ch", "abr128_44k_2ch"]
 
 

@@ -10,7 +10,8 @@ from vorbis_aotuv_lancer_b200 import ops, segment
 pytestmark = pytest.mark.skipif(not refdata.have_ref("c"), reason="oracle/_ref not built (needs /root/reference)")
 
 
-@pytest.mark.parametrize("config,seconds", [("q4_44k_2ch", 6.0), ("q8_48k_6ch", 2.0), ("q4_44k_1ch", 0.3), ("q10_48k_2ch", 3.0)])
+@pytest.mark.parametrize("config,seconds", [("q4_44k_2ch", 6.0), ("q8_48k_6ch", 2.0), ("q4_44k_1ch", 0.3), ("q10_48k_2ch", 3.0),
+                                            ("q4_32k_2ch", 3.0), ("q0_44k_2ch", 3.0), ("q5_48k_3ch", 2.0)])
 def test_blocks_match_reference(config, seconds):
     cap = refdata.capture(config, seconds)
     s = ops.Setup(config, device=-1)

@@ -19,6 +19,12 @@ CATALOGUE = {
     "q2_44k_2ch": (2, 44100, 0.2, 0),      # aoTuV M4/M5/M8 + noise normalisation live
     "q4_48k_6ch": (6, 48000, 0.4, 0),      # 5.1 with 4 coupling steps
     "q4_44k_1ch": (1, 44100, 0.4, 0),      # mono, no coupling
+    # round 2: the rest of the built scope's corners (parity cases, tests/test_gpu_pipeline.py)
+    "q4_32k_2ch": (2, 32000, 0.4, 0),      # the third sampling-rate family (setup_32.h)
+    "q0_44k_2ch": (2, 44100, 0.0, 0),      # lowest quality with block sizes 256/2048: strongest point stereo, all aoTuV low-rate paths
+    "q7_44k_2ch": (2, 44100, 0.7, 0),      # q6~: the tone-attenuation branch of set_m3p (psy.c:4183), lossless coupling region
+    "abr256_48k_6ch": (6, 48000, 0.4, 256000),  # managed 5.1: 15 blobs x two submaps (residue type 2 + LFE type 1)
+    "q5_48k_3ch": (3, 48000, 0.5, 0),      # three uncoupled channels
 }
 
 
