@@ -271,20 +271,22 @@ def run_ours(args):
     packet_bytes = tab["total"]
 
     # ---- e2e: host PCM -> packets through the public call ----
-    for i in range(min(args.warmup, 1)):
-        enc.encode(pcms, streams[total_steps + i])
-    barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
-    for i in range(e2e_steps):
-        enc.encode(pcms, streams[total_steps + 1 + i])
-    barrier()
-    t_e2e = maxtime(time.perf_counter() - t0)
+    t_e2e = None
+    if not args.no_e2e:
+        for i in range(min(args.warmup, 1)):
+            enc.encode(pcms, streams[total_steps + i])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            enc.encode(pcms, streams[total_steps + 1 + i])
+        barrier()
+        t_e2e = maxtime(time.perf_counter() - t0)
 
     if rank == 0:
         ms_step = t_dev / args.steps * 1e3
         value = world * audio * args.steps / t_dev
-        e2e_value = world * audio * e2e_steps / t_e2e
+        e2e_value = world * audio * e2e_steps / t_e2e if t_e2e else None
         # roofline of the dominant kernel
         peaks = {}
         try:
@@ -361,6 +363,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=10, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
     ap.add_argument("--depth", type=int, default=2, help="resident arm: batches in flight (2: host half of step i+1 overlaps device half of step i)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the e2e arm (the line then carries e2e.value null)")
     ap.add_argument("--fast-transform", action="store_true", help="front end K1 (own formulation, within 1e-5) instead of the default K1x (DESIGN.md section 4)")
     ap.add_argument("--exact-transform", action="store_true", help="(the default since round 2; accepted for old command lines)")
     ap.add_argument("--config", default=CONFIG, help="setup blob: the metric's q4_44k_2ch, or another BASELINE configuration (q5_44k_2ch, q8_48k_6ch, q10_48k_2ch, abr128_44k_2ch ...)")

@@ -78,6 +78,39 @@ def test_encode_decodes_and_matches_reference_bitrate():
     enc.close(); s.close()
 
 
+@pytest.mark.parametrize("config,seconds", [("q4_44k_2ch", 6.0), ("q8_48k_6ch", 2.0), ("abr128_44k_2ch", 4.0)])
+def test_gpu_stream_is_accepted_by_an_independent_decoder(config, seconds):
+    """north_star: "the GPU-encoded stream decodes with stock libvorbis".  Beyond the reference's own decoder
+    (above), the stream goes through csrc/oggframe.c into an .ogg file and FFmpeg -- its own Ogg demultiplexer
+    (CRC-checking) and its own Vorbis decoder, tests/ffcheck.py -- must read it: same packets, the input's length,
+    and PCM equal to the reference decoder's to float rounding.  Headers come from the product (Setup.header)."""
+    from oracle import reflib
+    from tests import ffcheck
+    from vorbis_aotuv_lancer_b200 import encoder, ogg, ops
+    if not ffcheck.available():
+        pytest.skip("no FFmpeg libraries in this image")
+    ch, rate = refdata.vblob.CATALOGUE[config][:2]
+    pcm = refdata.synth(ch, rate, seconds, seed=3)
+    s = ops.Setup(config)
+    enc = encoder.Encoder(s, 2048, threads=2, chunks=1)
+    pk = encoder.packets_of(enc.encode([pcm]), 0)
+    headers = [s.header(i) for i in range(3)]
+    got = ffcheck.read_ogg(ogg.mux(headers, pk), ch)
+    assert [g[0] for g in got["packets"]] == [p[0] for p in pk]
+    assert got["pcm"].shape == pcm.shape
+    order = {6: [0, 2, 1, 5, 3, 4]}.get(ch, list(range(ch)))
+    if reflib.available("c"):
+        ref, _ = reflib.RefLib("c").decode(headers, pk, pcm.shape[1] + 8192)
+        assert ref.shape == pcm.shape
+        assert np.abs(got["pcm"] - ref[order]).max() < 2e-6
+    # and it is the input, lossy-coded: SNR against the PCM that went in, per configuration
+    sig = pcm[order].astype(np.float64)
+    snr = 10 * np.log10((sig ** 2).sum() / ((got["pcm"] - sig) ** 2).sum())
+    print("%s: FFmpeg-decoded GPU stream vs input PCM: %.1f dB" % (config, snr))
+    assert snr > 8.0
+    enc.close(); s.close()
+
+
 def test_ragged_batch_of_degenerate_streams():
     """One call, streams of very different kinds and lengths: digital silence (every floor unused), one sample, less
     than a short block, a clipped square wave, a click train (a transient in every block), ordinary signal.  Each must

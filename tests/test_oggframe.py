@@ -1,9 +1,13 @@
 """Ogg framing (csrc/oggframe.c).  libogg is not in this image and the reference pins nothing
 here, so the check is structural: an independent demultiplexer (written from RFC 3533, bitwise CRC) must get the
-same packets back, and the paging rules the module states must hold."""
+same packets back, and the paging rules the module states must hold.  On top of that FFmpeg's Ogg demultiplexer
+and Vorbis decoder -- third-party implementations that share no code with libogg/libvorbis or with this repository,
+present in this image inside the opencv wheel (tests/ffcheck.py) -- must accept the pages (they verify every CRC),
+return the same packets and timestamps, and decode them to the reference decoder's PCM."""
 import struct
 
 import numpy as np
+import pytest
 
 
 def crc_bitwise(data):
@@ -115,3 +119,58 @@ def test_reference_stream_muxes():
     assert [x[0] for x in got] == headers + [p[0] for p in packets]
     assert pages[-1][1] == packets[-1][1] and pages[-1][0] & 4
     assert len(pages) >= 4
+
+
+@pytest.mark.parametrize("config,seconds", [("q4_44k_2ch", 3.0), ("q8_48k_6ch", 1.0), ("q4_44k_1ch", 1.0),
+                                            ("abr128_44k_2ch", 2.0)])
+def test_ffmpeg_reads_the_pages_and_decodes_the_stream(config, seconds):
+    """csrc/oggframe.c against an independent reader: FFmpeg's demultiplexer (CRC-checking) returns the packets that
+    went in, packet k starts where packet k-1's granule position ends, the stream ends at the input length, and
+    FFmpeg's own Vorbis decoder agrees with the reference's decoder (vorbis_synthesis) to float rounding."""
+    from oracle import reflib
+    from tests import ffcheck, refdata
+    from vorbis_aotuv_lancer_b200 import ogg
+    if not reflib.available("c"):
+        pytest.skip("oracle/_ref not present")
+    if not ffcheck.available():
+        pytest.skip("no FFmpeg libraries in this image")
+    cap = refdata.capture(config, seconds)
+    headers, packets = [bytes(h) for h in cap["headers"]], [(bytes(p[0]), p[1], p[2]) for p in cap["packets"]]
+    ch, n = cap["pcm"].shape
+    got = ffcheck.read_ogg(ogg.mux(headers, packets), ch)
+    assert [g[0] for g in got["packets"]] == [p[0] for p in packets]
+    # timestamps: FFmpeg derives the pts of the first packet of a page from THAT page's granule position (minus the
+    # durations of the page's packets); it must be the granule position the previous packet ended on.  (Inside a
+    # page FFmpeg interpolates with its own duration rule, which is off by design at a long->short transition.)
+    _, mine = demux(ogg.mux(headers, packets))
+    first = [k for k in range(1, len(packets)) if mine[k + 3][1] != mine[k + 2][1]]
+    assert len(first) >= 2
+    assert [got["packets"][k][1] for k in first] == [packets[k - 1][1] for k in first]
+    same = sum(1 for k in range(1, len(packets)) if got["packets"][k][1] == packets[k - 1][1])
+    assert same >= 0.9 * (len(packets) - 1)
+    ref, _ = reflib.RefLib("c").decode(headers, packets, n + 8192)
+    assert got["pcm"].shape == ref.shape == (ch, n)        # the last page's granule position trims the tail
+    # FFmpeg hands 5.1 out in its own channel order (FL FR FC LFE BL BR), Vorbis order is FL FC FR BL BR LFE
+    order = {6: [0, 2, 1, 5, 3, 4]}.get(ch, list(range(ch)))
+    err = np.abs(got["pcm"] - ref[order]).max()
+    assert err < 2e-6, err
+
+
+def test_ffmpeg_rejects_a_damaged_page():
+    """the check above has teeth: one flipped body bit and FFmpeg no longer returns the same packets"""
+    from oracle import reflib
+    from tests import ffcheck, refdata
+    from vorbis_aotuv_lancer_b200 import ogg
+    if not reflib.available("c"):
+        pytest.skip("oracle/_ref not present")
+    if not ffcheck.available():
+        pytest.skip("no FFmpeg libraries in this image")
+    cap = refdata.capture("q4_44k_2ch", 3.0)
+    headers, packets = [bytes(h) for h in cap["headers"]], [(bytes(p[0]), p[1], p[2]) for p in cap["packets"]]
+    stream = bytearray(ogg.mux(headers, packets))
+    stream[len(stream) // 2] ^= 0x10
+    try:
+        got = ffcheck.read_ogg(bytes(stream), 2, decode=False)
+    except AssertionError:
+        return
+    assert [g[0] for g in got["packets"]] != [p[0] for p in packets]
