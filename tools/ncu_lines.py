@@ -4,8 +4,10 @@ import csv, subprocess, sys
 rep, rx = sys.argv[1], sys.argv[2]
 skip = sys.argv[3] if len(sys.argv) > 3 else "0"
 minp = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + rx,
-                      "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
+# a report, or its source page already exported on the GPU box (tools/prof_src.sh: `--page source --csv --print-source cuda,sass`)
+out = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + rx,
+                    "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
 import io
 rows = list(csv.reader(io.StringIO(out)))
 fname, hdr, lines = None, None, []

@@ -151,7 +151,9 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
 
   for (int i = lane; i < n; i += 32) {
     const float m = __ldg(mk + i);
-    sm.q[i] = (unsigned short)(dbq(m) | ((__fadd_rn(__ldg(lm + i), F.twofitatten) >= m) ? 0x8000 : 0));
+    const int qm = dbq(m);
+    const bool loud = __fadd_rn(__ldg(lm + i), F.twofitatten) >= m;
+    sm.q[i] = (unsigned short)(qm | (loud ? (qm ? 0xc000 : 0x8000) : 0));
   }
   __syncwarp();
   /* accumulate_fit: the warp walks the post intervals together; a lane takes every 32nd bin of the interval
@@ -165,8 +167,8 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     const int x0 = F.sorted[j], x1 = F.sorted[j + 1], xe = x1 >= n ? n - 1 : x1;
     int ax = 0, ay = 0, ax2 = 0, ay2 = 0, axy = 0, an = 0, bx = 0, by = 0, bx2 = 0, by2 = 0, bxy = 0, bnn = 0;
     for (int i = x0 + lane; i <= xe; i += 32) {
-      const int qv = sm.q[i], q = qv & 0x7fff;
-      const int on = q != 0, la = on & (qv >> 15), lb = on & (la ^ 1);
+      const int qv = sm.q[i], q = qv & 0x3fff;
+      const int on = q != 0, la = (qv >> 14) & 1, lb = on & (la ^ 1);
       const int ii = i * i, qq = q * q, iq = i * q;
       ax += la * i; ay += la * q; ax2 += la * ii; ay2 += la * qq; axy += la * iq; an += la;
       bx += lb * i; by += lb * q; bx2 += lb * ii; by2 += lb * qq; bxy += lb * iq; bnn += lb;
@@ -216,26 +218,51 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     int viol = 0, mse = 0;
     const LineK LK = line_setup(lx, hx, ly, hy);
     if (int_limits) {
-      /* y, v < 2^10 and the limits are whole numbers: the reference's float comparisons are exact integer ones */
-      for (int x = lx + lane; x < hx; x += 32) {
-        const int qv = sm.q[x];
-        const int y = line_eval(LK, x), v = qv & 0x7fff, d = y - v;
-        mse += d * d;
-        if ((qv >> 15) && (x == lx || v) && (d + imaxover < 0 || d - imaxunder > 0)) viol = 1;
+      /* y, v < 2^10 and the limits are whole numbers: the reference's float comparisons are exact integer ones.
+         A lane evaluates the line once, at its first bin, and then steps it 32 bins at a time: with
+         rem * k = q * adx + r and rem * 32 = a * adx + b, the carry count at k + 32 is q + a + (r + b >= adx).
+         A bin can violate only when it is loud and its mask is not zero (flag bit 14) -- or when it is the first
+         bin of the line, loud, with a zero mask (floor1.c:550-553), which lane 0 tests on its own.  A violation
+         settles the outcome (floor1.c:556,562), so the warp stops at the first 32-bin slice that has one. */
+      const int a32 = div_small(LK.rem * 32, LK.adx), b32 = LK.rem * 32 - a32 * LK.adx;
+      const int ystep = LK.base * 32 + (LK.neg ? -a32 : a32), ycarry = LK.neg ? -1 : 1;
+      const unsigned span = (unsigned)(imaxover + imaxunder);
+      int x = lx + lane, y = 0, r = 0;
+      if (x < hx) {
+        const int k = lane, num = LK.rem * k;
+        int q = (int)((float)num * LK.radx);
+        if (q * LK.adx > num) q--;
+        if ((q + 1) * LK.adx <= num) q++;
+        r = num - q * LK.adx;
+        y = ly + LK.base * k + (LK.neg ? -q : q);
+      }
+      if (lane == 0) {
+        const int qv = sm.q[lx];
+        if ((qv & 0xc000) == 0x8000 && (unsigned)(ly + imaxover) > span) viol = 1;
+      }
+      for (int x0 = lx; x0 < hx; x0 += 32) {         /* uniform trip count */
+        if (x < hx) {
+          const int qv = sm.q[x], d = y - (qv & 0x3fff);
+          mse += d * d;
+          if ((qv & 0x4000) && (unsigned)(d + imaxover) > span) viol = 1;
+          x += 32; y += ystep; r += b32;
+          if (r >= LK.adx) { r -= LK.adx; y += ycarry; }
+        }
+        if (__any_sync(FULLMASK, viol)) { viol = 1; break; }
       }
     } else {
       for (int x = lx + lane; x < hx; x += 32) {
         const int qv = sm.q[x];
-        const int y = line_eval(LK, x), v = qv & 0x7fff;
+        const int y = line_eval(LK, x), v = qv & 0x3fff;
         mse += (y - v) * (y - v);
         if ((qv >> 15) && (x == lx || v)) {
           if (__fadd_rn((float)y, F.maxover) < (float)v) viol = 1;
           if (__fsub_rn((float)y, F.maxunder) > (float)v) viol = 1;
         }
       }
+      viol = __any_sync(FULLMASK, viol);
     }
-    viol = __any_sync(FULLMASK, viol);
-    mse = warp_sum_i(mse);
+    if (!viol) mse = warp_sum_i(mse);
     int bad;
     {
       const int cnt = hx - lx;

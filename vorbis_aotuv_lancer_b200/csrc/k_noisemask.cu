@@ -206,15 +206,60 @@ k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const 
                   [&](int q, int, float nv) { wk[q] = __fsub_rn(lmr[q], nv); });
   noise_fit<N, T>(sm, P, [&](int q, int) { return wk[q]; }, 0.f, P.noisewindowfixed,
                   [&](int q, int i, float nv) { sm.noise[i] = nv; wk[q] = __fsub_rn(lmr[q], wk[q]); });
-  if (mode <= 2 && P.tonefix_end) {        /* uniform per CTA; rare for long blocks (transitions only) */
+  if (mode <= 2 && P.tonefix_end) {        /* uniform per CTA; long blocks: transitions only (one block in ten) */
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < N / T; q++) sm.sums[3][tid + q * T] = wk[q];
-    __syncthreads();
-    if (tid == 0) tone_fix<N>(sm, P, lm, mode);
-    __syncthreads();
+    if constexpr (N >= 256) {
+      /* a long block is a transition block here (block_mode = blocktype | W << 1, mapping0.c:774): psy.c:3735-3766.
+         The group means come from the unmodified vector and every cut depends on the means only, so the walk over the
+         peaks is three parallel steps: means (thread per group), thresholds (thread per candidate peak), and each bin
+         takes the cuts of the <= 7 peaks whose range covers it, in peak order (the order of the float subtractions) */
+      float *tmp_ = sm.sums[1], *th_ = sm.sums[2];
+      int *cut0 = reinterpret_cast<int *>(sm.sums[2] + 256);
+      const int nx = P.tonefix_end, ng = (nx + 7) >> 3, gp = nx >> 3;
+      for (int k = tid; k < 256; k += T) tmp_[k] = 0.f;
+      __syncthreads();
+      for (int k = tid; k < ng; k += T) {
+        double a = 0;
 #pragma unroll
-    for (int q = 0; q < N / T; q++) wk[q] = sm.sums[3][tid + q * T];
+        for (int j = 0; j < 8; j++) a += (double)sm.sums[3][k * 8 + j];
+        tmp_[k] = (float)(a / 8);
+      }
+      __syncthreads();
+      const float *off1 = P.noiseoffset + N;
+      const float limit = fabsf(__ldg(off1));
+      for (int i = tid; i < 256; i += T) {
+        float th = 0.f; int a8 = -1;
+        if (i >= 3 && i < gp && tmp_[i] > tmp_[i - 1] && tmp_[i] > tmp_[i + 1]) {
+          float base; int a;
+          if (tmp_[i - 1] > tmp_[i - 2]) { base = tmp_[i - 2]; a = i - 3; } else { base = tmp_[i - 1]; a = i - 2; }
+          const float t = __fsub_rn(tmp_[i], base);
+          if (t > 2.f) {
+            const float cap = fminf(__ldg(P.ntfix + i * 8), __fadd_rn(__ldg(off1 + i * 8), limit));
+            th = fminf(__fsub_rn(t, 2.f), cap); a8 = a * 8;
+          }
+        }
+        th_[i] = th; cut0[i] = a8;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < N / T; q++) {
+        const int j = tid + q * T, g = j >> 3;
+        float v = wk[q];
+        for (int i = g < 6 ? 3 : g - 3; i <= g + 3 && i < gp; i++) {
+          const int a8 = cut0[i];
+          if (a8 >= 0 && j >= a8 && j <= (i + 3) * 8) v = __fsub_rn(v, th_[i]);
+        }
+        wk[q] = v;
+      }
+    } else {
+      __syncthreads();
+      if (tid == 0) tone_fix<N>(sm, P, lm, mode);
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < N / T; q++) wk[q] = sm.sums[3][tid + q * T];
+    }
   }
   __syncthreads();                     /* the prefix sums are dead: their rows are reused below */
 

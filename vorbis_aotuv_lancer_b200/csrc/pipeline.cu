@@ -175,6 +175,76 @@ k_stream_scan(const DevSetup *__restrict__ S, int nstreams, const int *__restric
   }
 }
 
+/* The same pass for the setups whose lb_loudnoise_fix is switched off for every psy (normal_thresh > .45 or no M
+   value, psy.c:5162: every quality >= q3, i.e. all BASELINE configurations): lownoise_compand_level is -1 throughout,
+   which leaves the ampmax recurrence.  k_stream_scan pays one chain of dependent global loads per 32 blocks (blocks ->
+   local_ampmax), ~2.8 us, 96 times in a 60 s stream.  Here one warp takes a stream in chunks of SC_CHUNK blocks:
+   (A) all lanes fetch the chunk's block maxima and decays into shared memory, every load of the chunk in flight at
+   once; (B) the recurrence walks the chunk out of shared memory, four blocks per 128-bit access (every lane runs it:
+   the values are warp-uniform); (C) all lanes write the results.  0.27 ms -> ~0.05 ms per launch, which an e2e call
+   pays once per stream group. */
+constexpr int SC_CHUNK = 1024;
+__global__ void __launch_bounds__(32)
+k_stream_scan_ampmax(const DevSetup *__restrict__ S, int nstreams, const int *__restrict__ slot,
+                     const int *__restrict__ blk_start, const ScanBlock *__restrict__ blks,
+                     float *__restrict__ scal, const float *const *__restrict__ local_ampmax,
+                     float *const *__restrict__ global_ampmax, float *const *__restrict__ lowcomp) {
+  __shared__ __align__(16) float s_lm[SC_CHUNK], s_d[SC_CHUNK], s_gl[SC_CHUNK];
+  const int lane = threadIdx.x, sidx = blockIdx.x;
+  if (sidx >= nstreams) return;
+  const int ch = S->channels;
+  float *st = scal + (size_t)slot[sidx] * (2 + VB200_MAX_CHANNELS);
+  float g = st[0], vbi = st[1];
+  const float dec0 = __fmul_rn(__fdiv_rn((float)(S->bs[0] / 2), (float)S->rate), S->ampmax_att_per_sec);
+  const float dec1 = __fmul_rn(__fdiv_rn((float)(S->bs[1] / 2), (float)S->rate), S->ampmax_att_per_sec);
+  const float *la[2] = {local_ampmax[0], local_ampmax[1]};
+  float *ga[2] = {global_ampmax[0], global_ampmax[1]}, *lc[2] = {lowcomp[0], lowcomp[1]};
+  const int b_end = blk_start[sidx + 1];
+  for (int c0 = blk_start[sidx]; c0 < b_end; c0 += SC_CHUNK) {
+    const int cnt = min(SC_CHUNK, b_end - c0);
+#pragma unroll 4
+    for (int j = lane; j < cnt; j += 32) {
+      const ScanBlock B = blks[c0 + j];
+      const float *p = la[B.W] + B.first_item;
+      float lmax = -3.0e38f;
+      for (int c = 0; c < ch; c++) { const float v = p[c]; if (v > lmax) lmax = v; }
+      s_lm[j] = lmax; s_d[j] = B.W ? dec1 : dec0;
+    }
+    for (int j = cnt + lane; j < ((cnt + 3) & ~3); j += 32) { s_lm[j] = 0.f; s_d[j] = 0.f; }
+    __syncwarp();
+    auto step = [&](float lm_t, float d_t) {
+      if (vbi > g) g = vbi;
+      g = __fadd_rn(g, d_t);
+      if (g < -9999.f) g = -9999.f;
+      float gl = g;
+      if (lm_t > gl) gl = lm_t;
+      vbi = gl;
+      return gl;
+    };
+    const int full = cnt & ~3;
+    for (int t = 0; t < full; t += 4) {
+      const float4 lm4 = *reinterpret_cast<const float4 *>(s_lm + t), d4 = *reinterpret_cast<const float4 *>(s_d + t);
+      float4 o;
+      o.x = step(lm4.x, d4.x); o.y = step(lm4.y, d4.y); o.z = step(lm4.z, d4.z); o.w = step(lm4.w, d4.w);
+      if (lane == 0) *reinterpret_cast<float4 *>(s_gl + t) = o;
+    }
+    for (int t = full; t < cnt; t++) { const float o = step(s_lm[t], s_d[t]); if (lane == 0) s_gl[t] = o; }
+    __syncwarp();
+#pragma unroll 4
+    for (int j = lane; j < cnt; j += 32) {
+      const ScanBlock B = blks[c0 + j];
+      const float gl = s_gl[j];
+      float *go = ga[B.W] + B.first_item, *lo = lc[B.W] + B.first_item;
+      for (int c = 0; c < ch; c++) { go[c] = gl; lo[c] = -1.f; }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    st[0] = g; st[1] = vbi;
+    for (int c = 0; c < ch; c++) st[2 + c] = -1.f;
+  }
+}
+
 /* end of batch: leave lastmdct in the stream's state slot exactly as the reference leaves
    private_state.mblock (psy.c:4462-4501) */
 __global__ void k_save_last(int n, const float *const *__restrict__ src, const int *__restrict__ rule,
@@ -943,9 +1013,18 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
   };
   RUN(run_k1());
   EV("scan ampmax");
-  k_stream_scan<<<(nstreams + 3) / 4, 128, 0, st>>>(s->d, nstreams, d_slot, d_scan_start, d_scan, pool->scal,
-                                                    (const float *const *)d_ptrs, (float *const *)(d_ptrs + 2),
-                                                    (const float *const *)(d_ptrs + 4), (float *const *)(d_ptrs + 6));
+  {
+    bool loudnoise_off = true;          /* lb_loudnoise_fix returns -1 for every psy of the setup (psy.c:5162) */
+    for (int k = 0; k < s->h.psys; k++) if (!(s->h.psy[k].m_val < 0.5f || s->h.psy[k].normal_thresh > .45)) loudnoise_off = false;
+    static const bool general = getenv("VB200_SCAN_GENERAL") != nullptr;
+    if (loudnoise_off && !general)
+      k_stream_scan_ampmax<<<nstreams, 32, 0, st>>>(s->d, nstreams, d_slot, d_scan_start, d_scan, pool->scal,
+                                                    (const float *const *)d_ptrs, (float *const *)(d_ptrs + 2), (float *const *)(d_ptrs + 6));
+    else
+      k_stream_scan<<<(nstreams + 3) / 4, 128, 0, st>>>(s->d, nstreams, d_slot, d_scan_start, d_scan, pool->scal,
+                                                        (const float *const *)d_ptrs, (float *const *)(d_ptrs + 2),
+                                                        (const float *const *)(d_ptrs + 4), (float *const *)(d_ptrs + 6));
+  }
   LAUNCH_CHECK();
   /* ---- K2 / K3 / K4.  Managed mode at high sampling rates: which ch-blocks write lastmdct / tempmdct depends on
      their own masks (the nominal-fit gate), so the links assumed by the pre-pass -- every block writes -- are checked
