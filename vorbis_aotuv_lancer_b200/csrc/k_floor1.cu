@@ -30,14 +30,8 @@ __device__ __forceinline__ int div_small(int num, int den) {
   if ((q + 1) * den <= num) q++;
   return q;
 }
-/* integer line (x0,y0)-(x1,y1) at x, as render_line0 / inspect_error step it (floor1.c:397-425) */
-__device__ __forceinline__ int line_at(int x0, int x1, int y0, int y1, int x) {
-  const int dy = y1 - y0, adx = x1 - x0, base = dy / adx;
-  const int rem = abs(dy) - abs(base * adx), k = x - x0;
-  const int carry = (rem * k) / adx;
-  return y0 + base * k + (dy < 0 ? -carry : carry);
-}
-/* the same line with its per-line constants hoisted (they are warp-uniform during error inspection) and the
+/* integer line (x0,y0)-(x1,y1) at x, as render_line0 / inspect_error step it (floor1.c:397-425): y0 + base * k +- (rem * k) / adx,
+   with its per-line constants hoisted (they are warp-uniform during error inspection) and the
    per-bin division done as an exact reciprocal-multiply + correction: rem*k < 2^21 is exact in float */
 struct LineK { int x0, y0, base, rem, adx, neg; float radx; };
 __device__ __forceinline__ LineK line_setup(int x0, int x1, int y0, int y1) {
@@ -72,12 +66,18 @@ template <int N>
 struct FitSmem {
   double (*T)[6];                 /* [pcap] weighted sums of a post interval */
   short *A, *B, *lo, *hi, *memo;  /* [pcap] each */
-  unsigned short *q;              /* [N] quantised mask, bit 15 = "loud" (mdct + twofitatten >= mask) */
-  static __host__ __device__ size_t bytes(int pcap) { return ((size_t)pcap * 48 + (size_t)pcap * 10 + (size_t)N * 2 + 15) & ~(size_t)15; }
+  unsigned short *q;              /* [QN] quantised mask, bit 15 = "loud" (mdct + twofitatten >= mask), bit 14 = loud and mask != 0 */
+  unsigned *bm;                   /* [32] posts inside every lane's run of N/32 bins, one bit per bin */
+  /* a lane walks N/32 consecutive bins in accumulate_fit: with 32-bin runs, one pad word per run puts the 32 lanes on
+     32 banks (word 17 * lane + t / 2); the 32-bin slices of the error inspection stay conflict-free */
+  static constexpr int CS = N / 32, QN = (CS == 32) ? N + 2 * (N / 32) : N;
+  static __host__ __device__ constexpr int qi(int i) { return (CS == 32) ? i + ((i >> 5) << 1) : i; }
+  static __host__ __device__ size_t bytes(int pcap) { return ((size_t)pcap * 48 + 128 + (size_t)pcap * 10 + (size_t)QN * 2 + 15) & ~(size_t)15; }
   __device__ FitSmem(unsigned char *base, int pcap) {
     T = reinterpret_cast<double (*)[6]>(base);
-    q = reinterpret_cast<unsigned short *>(base + (size_t)pcap * 48);
-    A = reinterpret_cast<short *>(q + N); B = A + pcap; lo = B + pcap; hi = lo + pcap; memo = hi + pcap;
+    bm = reinterpret_cast<unsigned *>(base + (size_t)pcap * 48);
+    q = reinterpret_cast<unsigned short *>(base + (size_t)pcap * 48 + 128);
+    A = reinterpret_cast<short *>(q + QN); B = A + pcap; lo = B + pcap; hi = lo + pcap; memo = hi + pcap;
   }
 };
 
@@ -153,41 +153,70 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
     const float m = __ldg(mk + i);
     const int qm = dbq(m);
     const bool loud = __fadd_rn(__ldg(lm + i), F.twofitatten) >= m;
-    sm.q[i] = (unsigned short)(qm | (loud ? (qm ? 0xc000 : 0x8000) : 0));
+    sm.q[FitSmem<N>::qi(i)] = (unsigned short)(qm | (loud ? (qm ? 0xc000 : 0x8000) : 0));
   }
+  /* accumulate_fit (floor1.c:427-475) for all post intervals in ONE walk over the bins.  Interval j holds the bins
+     sorted[j] .. min(sorted[j+1], n-1), both ends included: a bin at an inner post belongs to two intervals.  Lane L
+     walks bins L*CS .. L*CS+CS-1 with twelve running integer sums (class a = loud bins, class o = all bins with a
+     quantised mask != 0; class b of the reference is o - a) for the interval it is in; at a post it adds them to the
+     interval's row (shared-memory atomics: integer sums are exact in any order), moves on to the next interval and
+     starts it with the post's own bin; what is left at the end of its run goes to the row of the interval it ends in.
+     The rows are the T rows of the next step, read back as twelve ints and rewritten as six doubles by one lane each.
+     (Was: the whole warp over one interval after the other, 12 warp reductions each -- 17 of the 28 intervals of a
+     long block are narrower than a warp.) */
+  constexpr int CS = FitSmem<N>::CS;
+  int *Ti = reinterpret_cast<int *>(sm.T);
+  for (int i = lane; i < (posts - 1) * 12; i += 32) Ti[i] = 0;
+  sm.bm[lane] = 0;
   __syncwarp();
-  /* accumulate_fit: the warp walks the post intervals together; a lane takes every 32nd bin of the interval
-     and the twelve integer sums are closed with the hardware warp reduction (integer sums are exact in any
-     order).  Branch-free: class a = loud bins, class b = the rest, both only where the quantised mask != 0. */
-  int mine = 0;
-  Seg keep;                                         /* lane j & 31 keeps the sums of interval j; fit_terms runs once per 32 */
+  for (int k = 1 + lane; k < posts - 1; k += 32) { const int x = F.sorted[k]; atomicOr(&sm.bm[x / CS], 1u << (x % CS)); }
+  __syncwarp();
+  int any;
+  {
+    const unsigned mask = sm.bm[lane];
+    int cur = __popc(mask);                         /* -> number of inner posts below this lane's first bin */
+    {
+      int incl = cur;
 #pragma unroll
-  for (int k = 0; k < 6; k++) { keep.s[0][k] = 0; keep.s[1][k] = 0; }
-  for (int j = 0; j < posts - 1; j++) {
-    const int x0 = F.sorted[j], x1 = F.sorted[j + 1], xe = x1 >= n ? n - 1 : x1;
-    int ax = 0, ay = 0, ax2 = 0, ay2 = 0, axy = 0, an = 0, bx = 0, by = 0, bx2 = 0, by2 = 0, bxy = 0, bnn = 0;
-    for (int i = x0 + lane; i <= xe; i += 32) {
-      const int qv = sm.q[i], q = qv & 0x3fff;
-      const int on = q != 0, la = (qv >> 14) & 1, lb = on & (la ^ 1);
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += y; }
+      cur = incl - cur;
+    }
+    int ax = 0, ay = 0, ax2 = 0, ay2 = 0, axy = 0, an = 0, ox = 0, oy = 0, ox2 = 0, oy2 = 0, oxy = 0, on_ = 0, loudbins = 0;
+    const int i0 = lane * CS;
+    auto flush = [&]() {
+      int *row = Ti + cur * 12;
+      atomicAdd(row + 0, ax); atomicAdd(row + 1, ay); atomicAdd(row + 2, ax2); atomicAdd(row + 3, ay2); atomicAdd(row + 4, axy); atomicAdd(row + 5, an);
+      atomicAdd(row + 6, ox); atomicAdd(row + 7, oy); atomicAdd(row + 8, ox2); atomicAdd(row + 9, oy2); atomicAdd(row + 10, oxy); atomicAdd(row + 11, on_);
+    };
+#pragma unroll 4
+    for (int t = 0; t < CS; t++) {
+      const int i = i0 + t;
+      int la = 0, on = 0, q = 0;
+      if (i < n) { const int qv = sm.q[FitSmem<N>::qi(i)]; q = qv & 0x3fff; on = q != 0; la = (qv >> 14) & 1; }
       const int ii = i * i, qq = q * q, iq = i * q;
-      ax += la * i; ay += la * q; ax2 += la * ii; ay2 += la * qq; axy += la * iq; an += la;
-      bx += lb * i; by += lb * q; bx2 += lb * ii; by2 += lb * qq; bxy += lb * iq; bnn += lb;
+      const int cx = on ? i : 0, cx2 = on ? ii : 0, dx = la ? i : 0, dy = la ? q : 0, dx2 = la ? ii : 0, dy2 = la ? qq : 0, dxy = la ? iq : 0;
+      ax += dx; ay += dy; ax2 += dx2; ay2 += dy2; axy += dxy; an += la;
+      ox += cx; oy += q; ox2 += cx2; oy2 += qq; oxy += iq; on_ += on;        /* q == 0 adds nothing to the y sums */
+      loudbins += la;
+      if ((mask >> t) & 1u) {                       /* bin i is the post that ends interval cur and starts cur + 1 */
+        flush();
+        cur++;
+        ax = dx; ay = dy; ax2 = dx2; ay2 = dy2; axy = dxy; an = la;
+        ox = cx; oy = q; ox2 = cx2; oy2 = qq; oxy = iq; on_ = on;
+      }
     }
-    ax = __reduce_add_sync(FULLMASK, ax); ay = __reduce_add_sync(FULLMASK, ay); ax2 = __reduce_add_sync(FULLMASK, ax2);
-    ay2 = __reduce_add_sync(FULLMASK, ay2); axy = __reduce_add_sync(FULLMASK, axy); an = __reduce_add_sync(FULLMASK, an);
-    bx = __reduce_add_sync(FULLMASK, bx); by = __reduce_add_sync(FULLMASK, by); bx2 = __reduce_add_sync(FULLMASK, bx2);
-    by2 = __reduce_add_sync(FULLMASK, by2); bxy = __reduce_add_sync(FULLMASK, bxy); bnn = __reduce_add_sync(FULLMASK, bnn);
-    if (lane == (j & 31)) {
-      keep.s[0][0] = ax; keep.s[0][1] = ay; keep.s[0][2] = ax2; keep.s[0][3] = ay2; keep.s[0][4] = axy; keep.s[0][5] = an;
-      keep.s[1][0] = bx; keep.s[1][1] = by; keep.s[1][2] = bx2; keep.s[1][3] = by2; keep.s[1][4] = bxy; keep.s[1][5] = bnn;
-    }
-    if ((j & 31) == 31 || j == posts - 2) {
-      if (lane <= (j & 31)) fit_terms(keep, F.twofitweight, sm.T[(j & ~31) + lane]);
-    }
-    mine += an;
+    if (i0 < n) flush();
+    any = __any_sync(FULLMASK, loudbins > 0);
   }
   __syncwarp();
-  const int any = mine;
+  for (int j = lane; j < posts - 1; j += 32) {
+    Seg keep;
+    const int *row = Ti + j * 12;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { keep.s[0][k] = row[k]; keep.s[1][k] = row[6 + k] - row[k]; }
+    fit_terms(keep, F.twofitweight, sm.T[j]);       /* in place: the row has been read */
+  }
+  __syncwarp();
 
   if (!any) { if (lane == 0) fitted[item] = 0; return; }
   for (int i = lane; i < posts; i += 32) { sm.A[i] = -200; sm.B[i] = -200; sm.lo[i] = 0; sm.hi[i] = 1; sm.memo[i] = -1; }
@@ -228,6 +257,8 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
       const int ystep = LK.base * 32 + (LK.neg ? -a32 : a32), ycarry = LK.neg ? -1 : 1;
       const unsigned span = (unsigned)(imaxover + imaxunder);
       int x = lx + lane, y = 0, r = 0;
+      int xi = FitSmem<N>::qi(x);                    /* x += 32 is one run further: 32 + its pad */
+      constexpr int XSTEP = FitSmem<N>::qi(32);
       if (x < hx) {
         const int k = lane, num = LK.rem * k;
         int q = (int)((float)num * LK.radx);
@@ -237,22 +268,22 @@ k_floor_fit(const DevSetup *__restrict__ S, int floor_index, int W, int ch, cons
         y = ly + LK.base * k + (LK.neg ? -q : q);
       }
       if (lane == 0) {
-        const int qv = sm.q[lx];
+        const int qv = sm.q[FitSmem<N>::qi(lx)];
         if ((qv & 0xc000) == 0x8000 && (unsigned)(ly + imaxover) > span) viol = 1;
       }
       for (int x0 = lx; x0 < hx; x0 += 32) {         /* uniform trip count */
         if (x < hx) {
-          const int qv = sm.q[x], d = y - (qv & 0x3fff);
+          const int qv = sm.q[xi], d = y - (qv & 0x3fff);
           mse += d * d;
           if ((qv & 0x4000) && (unsigned)(d + imaxover) > span) viol = 1;
-          x += 32; y += ystep; r += b32;
+          x += 32; xi += XSTEP; y += ystep; r += b32;
           if (r >= LK.adx) { r -= LK.adx; y += ycarry; }
         }
         if (__any_sync(FULLMASK, viol)) { viol = 1; break; }
       }
     } else {
       for (int x = lx + lane; x < hx; x += 32) {
-        const int qv = sm.q[x];
+        const int qv = sm.q[FitSmem<N>::qi(x)];
         const int y = line_eval(LK, x), v = qv & 0x3fff;
         mse += (y - v) * (y - v);
         if ((qv >> 15) && (x == lx || v)) {

@@ -183,14 +183,14 @@ k_stream_scan(const DevSetup *__restrict__ S, int nstreams, const int *__restric
    once; (B) the recurrence walks the chunk out of shared memory, four blocks per 128-bit access (every lane runs it:
    the values are warp-uniform); (C) all lanes write the results.  0.27 ms -> ~0.05 ms per launch, which an e2e call
    pays once per stream group. */
-constexpr int SC_CHUNK = 1024;
-__global__ void __launch_bounds__(32)
+constexpr int SC_CHUNK = 1024, SC_T = 128;
+__global__ void __launch_bounds__(SC_T)
 k_stream_scan_ampmax(const DevSetup *__restrict__ S, int nstreams, const int *__restrict__ slot,
                      const int *__restrict__ blk_start, const ScanBlock *__restrict__ blks,
                      float *__restrict__ scal, const float *const *__restrict__ local_ampmax,
                      float *const *__restrict__ global_ampmax, float *const *__restrict__ lowcomp) {
   __shared__ __align__(16) float s_lm[SC_CHUNK], s_d[SC_CHUNK], s_gl[SC_CHUNK];
-  const int lane = threadIdx.x, sidx = blockIdx.x;
+  const int tid = threadIdx.x, sidx = blockIdx.x;
   if (sidx >= nstreams) return;
   const int ch = S->channels;
   float *st = scal + (size_t)slot[sidx] * (2 + VB200_MAX_CHANNELS);
@@ -202,44 +202,46 @@ k_stream_scan_ampmax(const DevSetup *__restrict__ S, int nstreams, const int *__
   const int b_end = blk_start[sidx + 1];
   for (int c0 = blk_start[sidx]; c0 < b_end; c0 += SC_CHUNK) {
     const int cnt = min(SC_CHUNK, b_end - c0);
-#pragma unroll 4
-    for (int j = lane; j < cnt; j += 32) {
+#pragma unroll 8
+    for (int j = tid; j < cnt; j += SC_T) {
       const ScanBlock B = blks[c0 + j];
       const float *p = la[B.W] + B.first_item;
       float lmax = -3.0e38f;
       for (int c = 0; c < ch; c++) { const float v = p[c]; if (v > lmax) lmax = v; }
       s_lm[j] = lmax; s_d[j] = B.W ? dec1 : dec0;
     }
-    for (int j = cnt + lane; j < ((cnt + 3) & ~3); j += 32) { s_lm[j] = 0.f; s_d[j] = 0.f; }
-    __syncwarp();
-    auto step = [&](float lm_t, float d_t) {
-      if (vbi > g) g = vbi;
-      g = __fadd_rn(g, d_t);
-      if (g < -9999.f) g = -9999.f;
-      float gl = g;
-      if (lm_t > gl) gl = lm_t;
-      vbi = gl;
-      return gl;
-    };
-    const int full = cnt & ~3;
-    for (int t = 0; t < full; t += 4) {
-      const float4 lm4 = *reinterpret_cast<const float4 *>(s_lm + t), d4 = *reinterpret_cast<const float4 *>(s_d + t);
-      float4 o;
-      o.x = step(lm4.x, d4.x); o.y = step(lm4.y, d4.y); o.z = step(lm4.z, d4.z); o.w = step(lm4.w, d4.w);
-      if (lane == 0) *reinterpret_cast<float4 *>(s_gl + t) = o;
+    for (int j = cnt + tid; j < ((cnt + 3) & ~3); j += SC_T) { s_lm[j] = 0.f; s_d[j] = 0.f; }
+    __syncthreads();
+    if (tid < 32) {
+      /* block.c:649-651 / mapping0.c:1184 in the reference's order of float operations; fmaxf(vbi, g) is
+         `if (vbi > g) g = vbi` (the sign of a zero does not survive the add that follows) */
+      auto step = [&](float lm_t, float d_t) {
+        g = fmaxf(vbi, g);
+        g = __fadd_rn(g, d_t);
+        g = fmaxf(g, -9999.f);
+        vbi = fmaxf(g, lm_t);
+        return vbi;
+      };
+      const int full = cnt & ~3;
+      for (int t = 0; t < full; t += 4) {
+        const float4 lm4 = *reinterpret_cast<const float4 *>(s_lm + t), d4 = *reinterpret_cast<const float4 *>(s_d + t);
+        float4 o;
+        o.x = step(lm4.x, d4.x); o.y = step(lm4.y, d4.y); o.z = step(lm4.z, d4.z); o.w = step(lm4.w, d4.w);
+        if (tid == 0) *reinterpret_cast<float4 *>(s_gl + t) = o;
+      }
+      for (int t = full; t < cnt; t++) { const float o = step(s_lm[t], s_d[t]); if (tid == 0) s_gl[t] = o; }
     }
-    for (int t = full; t < cnt; t++) { const float o = step(s_lm[t], s_d[t]); if (lane == 0) s_gl[t] = o; }
-    __syncwarp();
-#pragma unroll 4
-    for (int j = lane; j < cnt; j += 32) {
+    __syncthreads();
+#pragma unroll 8
+    for (int j = tid; j < cnt; j += SC_T) {
       const ScanBlock B = blks[c0 + j];
       const float gl = s_gl[j];
       float *go = ga[B.W] + B.first_item, *lo = lc[B.W] + B.first_item;
       for (int c = 0; c < ch; c++) { go[c] = gl; lo[c] = -1.f; }
     }
-    __syncwarp();
+    __syncthreads();
   }
-  if (lane == 0) {
+  if (tid == 0) {
     st[0] = g; st[1] = vbi;
     for (int c = 0; c < ch; c++) st[2 + c] = -1.f;
   }
@@ -1018,7 +1020,7 @@ extern "C" int vb200_batch_submit(vb200_batch *b, vb200_stream **streams, int ns
     for (int k = 0; k < s->h.psys; k++) if (!(s->h.psy[k].m_val < 0.5f || s->h.psy[k].normal_thresh > .45)) loudnoise_off = false;
     static const bool general = getenv("VB200_SCAN_GENERAL") != nullptr;
     if (loudnoise_off && !general)
-      k_stream_scan_ampmax<<<nstreams, 32, 0, st>>>(s->d, nstreams, d_slot, d_scan_start, d_scan, pool->scal,
+      k_stream_scan_ampmax<<<nstreams, SC_T, 0, st>>>(s->d, nstreams, d_slot, d_scan_start, d_scan, pool->scal,
                                                     (const float *const *)d_ptrs, (float *const *)(d_ptrs + 2), (float *const *)(d_ptrs + 6));
     else
       k_stream_scan<<<(nstreams + 3) / 4, 128, 0, st>>>(s->d, nstreams, d_slot, d_scan_start, d_scan, pool->scal,
