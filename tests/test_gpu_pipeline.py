@@ -216,3 +216,19 @@ def test_time_split_batches_with_digital_silence(config):
     else:
         assert rounds == [1] * 5
     st.close(); bt.close(); s.close()
+
+
+def test_bit_packer_second_pass():
+    """K8 packs mono/stereo blocks into a 4 KB shared-memory image first (more CTAs per SM); a block that does not
+    fit is marked and packed again by k_pack_retry with the 16 KB image.  VB200_PACK_LIMIT=64 lets the first pass
+    fill 256 bytes only, so nearly every long block takes the second pass -- the stream must still be the
+    reference's, byte for byte (the variable is read once per process, hence the child process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VB200_PACK_LIMIT="64")
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-1000:], r.stderr[-3000:])
+    assert "100.0% byte-identical" in r.stdout, r.stdout[-1000:]

@@ -87,7 +87,7 @@ __device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f
     for (int i = 0; i < N / 4; i += 4) {      /* two register sets: the next 8 values arrive while 8 are summed */
       float4 b0 = r[i + 2], b1 = r[i + 3];
       run4(a0); r[i] = a0; run4(a1); r[i + 1] = a1;
-      if (i + 4 < N / 4) { a0 = r[i + 4]; a1 = r[i + 5]; }
+      a0 = r[i + 4]; a1 = r[i + 5];            /* last pass: 8 floats past the row, still inside NoiseSmem, never used */
       run4(b0); r[i + 2] = b0; run4(b1); r[i + 3] = b1;
     }
   }

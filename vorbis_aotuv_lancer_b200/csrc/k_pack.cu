@@ -17,26 +17,29 @@
 namespace {
 
 constexpr int PK_T = 128;
-constexpr int PK_WORDS = 4096;        /* 16 KB packet image: far above any block the setups produce */
+constexpr int PK_WORDS_BIG = 4096;    /* 16 KB packet image: far above any block the setups produce */
+constexpr int PK_WORDS_SMALL = 1024;  /* 4 KB image of the first pass over mono/stereo blocks (16 CTAs per SM instead of 11: the kernel is
+                                         latency-bound); a block that does not fit is marked and packed again with the big image */
 constexpr int PK_ZERO0 = 512;         /* words cleared up front; more are cleared on demand as the packet grows */
+constexpr long long PK_RETRY = -2;    /* pk_off of a block the small image could not hold */
 constexpr int PK_PARTS = 31;          /* floor1 partitions (5 bits in the header) */
 constexpr int PK_PSYM = 9;            /* symbols of one floor partition: class word + up to 8 values */
 constexpr int PK_PER = 4;             /* residue symbols per thread and pass */
 
-template <int CH>
+template <int CH, int PK_WORDS>
 struct PackSmem {
   unsigned words[PK_WORDS];
   unsigned pcode[CH][PK_PARTS][PK_PSYM];
   unsigned char plen[CH][PK_PARTS][PK_PSYM + 3];
   int pbits[CH][PK_PARTS], pbase[CH][PK_PARTS];
   int warp_tot[2][PK_T / 32];
-  int base, overflow;
+  int base, overflow, limit_bits;      /* limit_bits: PK_WORDS * 32, or less when a test forces the second pass */
 };
 
-template <int CH>
-__device__ __forceinline__ void put_bits(PackSmem<CH> &sm, int bitpos, unsigned value, int len) {
+template <int CH, int PK_WORDS>
+__device__ __forceinline__ void put_bits(PackSmem<CH, PK_WORDS> &sm, int bitpos, unsigned value, int len) {
   if (len <= 0) return;
-  if (bitpos + len > PK_WORDS * 32) { sm.overflow = 1; return; }
+  if (bitpos + len > sm.limit_bits) { sm.overflow = 1; return; }
   if (len < 32) value &= (1u << len) - 1u;
   const int w = bitpos >> 5, sh = bitpos & 31;
   atomicOr(&sm.words[w], value << sh);
@@ -45,19 +48,19 @@ __device__ __forceinline__ void put_bits(PackSmem<CH> &sm, int bitpos, unsigned 
 
 __device__ __forceinline__ int ilog_(unsigned v) { return 32 - __clz(v); }
 
-template <int CH>
-__global__ void __launch_bounds__(PK_T)
-k_pack(const DevSetup *__restrict__ S, int W, int ch, const int *__restrict__ lWv, const int *__restrict__ nWv,
-       const int *__restrict__ vals, const int *__restrict__ floor_nonzero,
-       int submaps, const int *__restrict__ syms, const int *__restrict__ nsyms, int cap_blocks, int max_syms,
-       unsigned char *__restrict__ pool, unsigned long long pool_cap, unsigned long long *__restrict__ pool_top,
-       long long *__restrict__ pk_off, int *__restrict__ pk_bytes) {
-  __shared__ PackSmem<CH> sm;
-  const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+template <int CH, int PK_WORDS, bool RETRY>
+__device__ __forceinline__ void
+pack_block(const int blk, const DevSetup *__restrict__ S, int W, int ch, const int *__restrict__ lWv, const int *__restrict__ nWv,
+           const int *__restrict__ vals, const int *__restrict__ floor_nonzero,
+           int submaps, const int *__restrict__ syms, const int *__restrict__ nsyms, int cap_blocks, int max_syms,
+           unsigned char *__restrict__ pool, unsigned long long pool_cap, unsigned long long *__restrict__ pool_top,
+           long long *__restrict__ pk_off, int *__restrict__ pk_bytes, int limit_words) {
+  __shared__ PackSmem<CH, PK_WORDS> sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const DevBook *books = S->book;
   for (int i = tid; i < PK_ZERO0; i += PK_T) sm.words[i] = 0;
   int zeroed = PK_ZERO0;               /* uniform: words [0, zeroed) are clear or already carry bits */
-  if (tid == 0) sm.overflow = 0;
+  if (tid == 0) { sm.overflow = 0; sm.limit_bits = (RETRY && limit_words > 0 && limit_words < PK_WORDS ? limit_words : PK_WORDS) * 32; }
   /* make sure the image is clear up to bit `endbit` before anything is OR-ed there; callers are uniform */
   auto ensure = [&](int endbit) {
     int need = (endbit >> 5) + 2;
@@ -192,16 +195,41 @@ k_pack(const DevSetup *__restrict__ S, int W, int ch, const int *__restrict__ lW
   __shared__ unsigned long long s_off;
   const int bits = base, bytes = (bits + 7) >> 3, words = (bytes + 3) >> 2;
   if (tid == 0) {
-    unsigned long long off = atomicAdd(pool_top, (unsigned long long)words * 4ull);
+    unsigned long long off = sm.overflow ? ~0ull : atomicAdd(pool_top, (unsigned long long)words * 4ull);
     if (off + (unsigned long long)words * 4ull > pool_cap || sm.overflow) { off = ~0ull; }
     s_off = off;
-    pk_off[blk] = (off == ~0ull) ? -1ll : (long long)off;
+    pk_off[blk] = (off == ~0ull) ? ((RETRY && sm.overflow) ? PK_RETRY : -1ll) : (long long)off;
     pk_bytes[blk] = bytes;
   }
   __syncthreads();
   if (s_off != ~0ull) {
     unsigned *dst = reinterpret_cast<unsigned *>(pool + s_off);
     for (int i = tid; i < words; i += PK_T) dst[i] = sm.words[i];
+  }
+}
+
+#define PK_PARAMS const DevSetup *__restrict__ S, int W, int ch, const int *__restrict__ lWv, const int *__restrict__ nWv, \
+       const int *__restrict__ vals, const int *__restrict__ floor_nonzero, \
+       int submaps, const int *__restrict__ syms, const int *__restrict__ nsyms, int cap_blocks, int max_syms, \
+       unsigned char *__restrict__ pool, unsigned long long pool_cap, unsigned long long *__restrict__ pool_top, \
+       long long *__restrict__ pk_off, int *__restrict__ pk_bytes, int limit_words
+#define PK_ARGS S, W, ch, lWv, nWv, vals, floor_nonzero, submaps, syms, nsyms, cap_blocks, max_syms, pool, pool_cap, pool_top, pk_off, pk_bytes, limit_words
+
+template <int CH, int PK_WORDS, bool RETRY>
+__global__ void __launch_bounds__(PK_T)
+k_pack(PK_PARAMS) {
+  pack_block<CH, PK_WORDS, RETRY>(blockIdx.x, PK_ARGS);
+}
+
+/* second pass: a CTA looks at 32 blocks and packs the ones the small image could not hold (normally none) */
+template <int CH>
+__global__ void __launch_bounds__(PK_T)
+k_pack_retry(int blocks, PK_PARAMS) {
+  const int b0 = blockIdx.x * 32;
+  for (int k = 0; k < 32 && b0 + k < blocks; k++) {
+    if (pk_off[b0 + k] != PK_RETRY) continue;             /* uniform across the CTA */
+    __syncthreads();                                      /* the previous block's image is no longer read */
+    pack_block<CH, PK_WORDS_BIG, false>(b0 + k, PK_ARGS);
   }
 }
 
@@ -212,12 +240,18 @@ int vb200_launch_pack(const vb200_setup *s, cudaStream_t st, int W, int blocks, 
                       int cap_blocks, int max_syms, unsigned char *pool, unsigned long long pool_cap,
                       unsigned long long *pool_top, long long *pk_off, int *pk_bytes) {
   if (blocks <= 0) return VB200_OK;
-  if (s->h.channels <= 2)
-    k_pack<2><<<blocks, PK_T, 0, st>>>(s->d, W, s->h.channels, lW, nW, vals, floor_nonzero, submaps, syms, nsyms, cap_blocks, max_syms,
-                                       pool, pool_cap, pool_top, pk_off, pk_bytes);
+#define PK_CALL s->d, W, s->h.channels, lW, nW, vals, floor_nonzero, submaps, syms, nsyms, cap_blocks, max_syms, pool, pool_cap, pool_top, pk_off, pk_bytes, limit
+  static const bool big_only = getenv("VB200_PACK_BIG") != nullptr;
+  static const int limit = getenv("VB200_PACK_LIMIT") ? atoi(getenv("VB200_PACK_LIMIT")) : 0;    /* tests: words the first pass may fill */
+  if (s->h.channels <= 2 && !big_only) {
+    k_pack<2, PK_WORDS_SMALL, true><<<blocks, PK_T, 0, st>>>(PK_CALL);
+    LAUNCH_CHECK();
+    k_pack_retry<2><<<(blocks + 31) / 32, PK_T, 0, st>>>(blocks, PK_CALL);
+  } else if (s->h.channels <= 2)
+    k_pack<2, PK_WORDS_BIG, false><<<blocks, PK_T, 0, st>>>(PK_CALL);
   else
-    k_pack<VB200_MAX_CHANNELS><<<blocks, PK_T, 0, st>>>(s->d, W, s->h.channels, lW, nW, vals, floor_nonzero, submaps, syms, nsyms, cap_blocks, max_syms,
-                                                        pool, pool_cap, pool_top, pk_off, pk_bytes);
+    k_pack<VB200_MAX_CHANNELS, PK_WORDS_BIG, false><<<blocks, PK_T, 0, st>>>(PK_CALL);
+#undef PK_CALL
   LAUNCH_CHECK();
   return VB200_OK;
 }
