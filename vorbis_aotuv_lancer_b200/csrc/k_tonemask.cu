@@ -200,26 +200,7 @@ __device__ __forceinline__ void tm_fill(const DevSetup *__restrict__ S, const De
     if (att < P.ath_maxatt) att = P.ath_maxatt;
     float *out = tone + (size_t)item * N;
     const float lim = P.tone_abs_limit;
-    /* max_seeds (psy.c:1053-1070): the minimum over a group's seed span -- the first position clamped to
-       tone_abs_limit, NEGINF entries skipped unless nothing else is there -- is order-free.  The spans of the first
-       few groups are long (148, 54, 34, 26, 20, 17 lines at 44.1 kHz: bins 0..5 are octaves apart), every later one is
-       a handful of lines: the long ones are taken by the whole warp (minimum through an order-preserving integer key
-       and one warp reduction), so that the lane-per-group loop below starts where the spans are short. */
-    int gw = 0;
-    for (; gw < P.n_tone_groups; gw++) {
-      const int4 q = __ldg(P.tone_groups + gw);              /* uniform */
-      if (q.y - q.x < 16) break;
-      unsigned best = 0xffffffffu;
-      for (int p = q.x + lane; p <= q.y; p += 32) {
-        float v = seed[run16[p]];
-        if (p == q.x && v > lim) v = lim;
-        if (v > TM_NEGINF) { const unsigned u = __float_as_uint(v), k = u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u); if (k < best) best = k; }
-      }
-      best = __reduce_min_sync(FULLMASK, best);
-      const float mv = best == 0xffffffffu ? TM_NEGINF : __uint_as_float(best ^ ((best >> 31) ? 0x80000000u : 0xffffffffu));
-      for (int i = q.z + lane; i < q.w; i += 32) { const float fl = __fadd_rn(__ldg(P.ath + i), att); out[i] = fl < mv ? mv : fl; }
-    }
-    for (int g = gw + lane; g < P.n_tone_groups; g += 32) {
+    for (int g = lane; g < P.n_tone_groups; g += 32) {
       const int4 q = __ldg(P.tone_groups + g);
       float mv = seed[run16[q.x]];
       if (mv > lim) mv = lim;
