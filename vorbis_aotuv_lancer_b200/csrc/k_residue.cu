@@ -81,7 +81,10 @@ struct RfShared {
   int red_d[RF_WARPS], red_i[RF_WARPS];
 };
 
-__global__ void __launch_bounds__(RF_WARPS * 32)
+#ifndef RF_MINB
+#define RF_MINB 8          /* 64 registers: 8 CTAs per SM (10, 12, 16: 3.98, 3.98, 4.46 ms against 3.86) */
+#endif
+__global__ void __launch_bounds__(RF_WARPS * 32, RF_MINB)
 k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, const int *__restrict__ chlist, int tot_ch,
                   int *__restrict__ in, const int *__restrict__ nonzero, const int *__restrict__ partword,
                   int maxvec, int *__restrict__ syms, int max_syms, int *__restrict__ nsyms) {

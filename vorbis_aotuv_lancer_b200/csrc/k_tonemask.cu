@@ -291,33 +291,42 @@ k_tone_splat(const DevSetup *__restrict__ S, int items, const int *__restrict__ 
   for (int p = lane; p < L; p += 32) { sg[p] = seed[p]; cg[p] = (unsigned short)tm_compare_word(seed, p); }
 }
 
+/* one lane per ch-block.  A lane reads ITS OWN row of comparison words, 32 positions (64 bytes, four 128-bit loads) at a
+   time, the next 32 requested before the current ones are walked -- every 32-byte sector a lane touches is used in
+   full, and nothing is transposed.  (The first version filled a 32 x 32 shared-memory tile row by row, one 64-byte
+   load per row and iteration, each waiting for the one before it: 32 exposed DRAM latencies per 32 positions -- the
+   kernel took 0.47 ms for 0.29 ms worth of instructions, and as long again for each small stream group of an e2e call.) */
 __global__ void __launch_bounds__(TS_WARPS * 32)
 k_tone_chase(int items, int L, int N, int *__restrict__ rowB) {
-  __shared__ unsigned short tile[TS_WARPS][32][34];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int item0 = (blockIdx.x * TS_WARPS + warp) * 32;
   if (item0 >= items) return;
-  const int nloc = min(32, items - item0);
-  const bool mine = lane < nloc;
-  unsigned *sv = reinterpret_cast<unsigned *>(rowB + (size_t)(item0 + (mine ? lane : 0)) * N + (N - TM_SVW));
+  const bool mine = item0 + lane < items;
+  const int item = mine ? item0 + lane : item0;
+  const uint4 *cg = reinterpret_cast<const uint4 *>(rowB + (size_t)item * N);       /* 8 comparison words per uint4 */
+  unsigned *sv = reinterpret_cast<unsigned *>(rowB + (size_t)item * N + (N - TM_SVW));
   unsigned M = 0, Q = 0, cur = 0;
+  uint4 nx[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) nx[j] = cg[j];
   for (int p0 = 0; p0 < L; p0 += 32) {
-    /* 32 positions of 32 ch-blocks: row r is read with one 64-byte access, then every lane walks its own row */
-    for (int r = 0; r < nloc; r++) {
-      const unsigned short *cg = reinterpret_cast<const unsigned short *>(rowB + (size_t)(item0 + r) * N);
-      tile[warp][r][lane] = (p0 + lane < L) ? cg[p0 + lane] : (unsigned short)0;
+    unsigned w[16];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { w[4 * j] = nx[j].x; w[4 * j + 1] = nx[j].y; w[4 * j + 2] = nx[j].z; w[4 * j + 3] = nx[j].w; }
+    if (p0 + 32 < L) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) nx[j] = cg[(p0 + 32) / 8 + j];
     }
-    __syncwarp();
     const int n = min(32, L - p0);
-    if (mine) {
-#pragma unroll 4
-      for (int k = 0; k < n; k++) {
-        const unsigned m = tm_chase_step(tile[warp][lane][k], M, Q);
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+      if (k < n) {
+        const unsigned c = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+        const unsigned m = tm_chase_step(c, M, Q);
         const int p = p0 + k - 7;
-        if (p >= 0) { cur |= ((m >> 6) & 1u) << (p & 31); if ((p & 31) == 31) { sv[p >> 5] = cur; cur = 0; } }
+        if (p >= 0) { cur |= ((m >> 6) & 1u) << (p & 31); if ((p & 31) == 31) { if (mine) sv[p >> 5] = cur; cur = 0; } }
       }
     }
-    __syncwarp();
   }
   if (mine) {
     for (int k = 7; k >= 1; k--) {
