@@ -51,10 +51,25 @@ __device__ __forceinline__ void tm_splat(const DevSetup *__restrict__ S, const i
       const int r = r0 + lane;
       bool hit = false;
       SplatJob job; job.mx = 0.f; job.sp0 = 0; job.curve = 0; job.k0 = 0; job.k1 = 0;
+      /* maximum of the run: runs are 1 bin long at low frequencies and up to ~11 at the top, so the warp walks as far
+         as its longest run, four bins per lane and iteration with the four loads in flight together (a lane-private
+         loop waited for every load in turn: 40 % of the kernel's stall samples were on this scoreboard) */
+      int2 run = make_int2(0, -1);
+      if (r < nruns) run = __ldg(P.tone_runs + r);        /* first and last bin of the run */
+      float mx = r < nruns ? __ldg(f + run.x) : 0.f;
+      {
+        const int extra = __reduce_max_sync(FULLMASK, run.y - run.x);
+        for (int t = 1; t <= extra; t += 4) {
+          const int j = run.x + t;
+          const float v0 = j <= run.y ? __ldg(f + j) : -INFINITY, v1 = j + 1 <= run.y ? __ldg(f + j + 1) : -INFINITY;
+          const float v2 = j + 2 <= run.y ? __ldg(f + j + 2) : -INFINITY, v3 = j + 3 <= run.y ? __ldg(f + j + 3) : -INFINITY;
+          if (v0 > mx) mx = v0;
+          if (v1 > mx) mx = v1;
+          if (v2 > mx) mx = v2;
+          if (v3 > mx) mx = v3;
+        }
+      }
       if (r < nruns) {
-        const int2 run = __ldg(P.tone_runs + r);          /* first and last bin of the run */
-        float mx = __ldg(f + run.x);
-        for (int j = run.x + 1; j <= run.y; j++) { const float v = __ldg(f + j); if (v > mx) mx = v; }
         const float flr = __fadd_rn(__ldg(P.ath + run.y), att);
         if (__fadd_rn(mx, 6.f) > flr) {
           const int oc = __ldg(P.octave + run.y);
