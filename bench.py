@@ -360,7 +360,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=60.0)
-    ap.add_argument("--chunks", type=int, default=10, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
+    ap.add_argument("--chunks", type=int, default=20, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
     ap.add_argument("--depth", type=int, default=2, help="resident arm: batches in flight (2: host half of step i+1 overlaps device half of step i)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the e2e arm (the line then carries e2e.value null)")

@@ -96,7 +96,8 @@ class Segmenter:
 def group_weights(chunks):
     """Relative sizes of the stream groups one encode() call pipelines: 1, 2, 4, 6, then equal shares of 8 -- a short
     ramp so that the device has work after one stream's upload, then groups small enough that little is left to do
-    when the last upload ends (measured on a B200, 64 streams: 8 groups 83.6 k audio-s/s, 10 groups 86.5 k)."""
+    when the last upload ends (measured on a B200, 64 streams: 8 groups 83.6 k audio-s/s, 10 groups 86.5 k; with the
+    round-2 kernels 8 / 10 / 12 / 16 / 20 / 24 / 32 groups: 86.7 / 87.0 / 88.7 / 88.9 / 89.4 / 89.7 / 87.2 k)."""
     ramp = [1.0, 2.0, 4.0, 6.0]
     return [ramp[g] if g < len(ramp) else 8.0 for g in range(max(1, int(chunks)))]
 
