@@ -12,7 +12,8 @@ ncu --set full --clock-control none --import-source on \
     -s ${SKIP:-14} -c ${CNT:-14} -o /tmp/src_$TAG $CMD > gpurun_out/ncu_src_$TAG.log 2>&1
 tail -n 2 gpurun_out/ncu_src_$TAG.log
 ncu -i /tmp/src_$TAG.ncu-rep --page raw --csv > gpurun_out/raw_src_$TAG.csv 2>/dev/null
-for K in k_floor_fit k_tone_splat k_tone_fill k_couple k_residue_forward k_transform_exact k_pack k_mix k_floor_encode k_tone_chase k_residue_class; do
+KS="${RX:-k_floor_fit|k_tone_splat|k_tone_fill|k_transform_exact|k_mix|k_floor_encode|k_tone_chase}"
+for K in ${KS//|/ }; do
   ncu -i /tmp/src_$TAG.ncu-rep --page source --csv --print-source cuda,sass --kernel-name "regex:$K" --launch-skip ${PICK:-1} --launch-count 1 > gpurun_out/src_${TAG}_$K.csv 2>/dev/null
 done
 ls -la gpurun_out/ | grep "src_$TAG" | head -20

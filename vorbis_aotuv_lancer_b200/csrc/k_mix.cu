@@ -32,6 +32,8 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
       const long long *__restrict__ temp_off, float *__restrict__ npeak, int npeak_stride, float *__restrict__ logmask, int nsel, int mask_stride,
       float *__restrict__ last_out, int *__restrict__ fit_gate, int floor_index, int ch) {
   __shared__ float temp[N > 256 ? 1 : 256];
+  __shared__ float sp_slope[N > 256 ? 1 : 256], sp_lm[N > 256 ? 1 : 256];      /* cross-bin spread of M3 (short blocks) */
+  __shared__ int sp_b[N > 256 ? 1 : 256];
   __shared__ int pflag[64];
   __shared__ int gate;
   const int tid = threadIdx.x;
@@ -104,13 +106,17 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
           /* cross-bin spread (psy.c:4215-4222): bin i raises the bins i+1 .. i+bfn[i]-1.  The reference walks i
              upwards; every target bin t is only ever touched through temp[t], so the updates of one target
              form an independent chain in ascending i -- one thread per target, same order, no race */
+          /* the slope 75 / bfn[i] belongs to the source bin: one division per bin (staged with logmdct and the
+             widths), not one per (source, target) pair -- the same float division, so the same bits */
+          for (int i = tid; i < N; i += T) { const int b = bfn[i]; sp_b[i] = b; sp_slope[i] = 75.f / (float)b; sp_lm[i] = __ldg(lm + i); }
+          __syncthreads();
           for (int t = tid; t < N; t += T) {
             float v = temp[t];
-            const double lift = drop / (double)(float)bfn[t];
+            const double lift = drop / (double)(float)sp_b[t];
             for (int i = (t > 64 ? t - 64 : 0); i < t; i++) {
-              const int b = bfn[i], j = t - i;
-              if (j < b) {
-                const float fb = __fsub_rn(__ldg(lm + i), __fmul_rn(75.f / (float)b, (float)j));
+              const int j = t - i;
+              if (j < sp_b[i]) {
+                const float fb = __fsub_rn(sp_lm[i], __fmul_rn(sp_slope[i], (float)j));
                 if (v < fb) v = (float)((double)v + lift);
               }
             }
