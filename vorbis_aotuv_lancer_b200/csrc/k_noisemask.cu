@@ -111,64 +111,68 @@ __device__ __forceinline__ void noise_fit(NoiseSmem<N> &sm, const DevPsy &P, F f
   }
 }
 
-/* aoTuV M7 (psy.c:3645-3768) on the staged work vector; short blocks: peak-driven, transition blocks: 8-bin groups.
-   Data-dependent and tiny: lane 0 walks it. */
-template <int N>
-__device__ void tone_fix(NoiseSmem<N> &sm, const DevPsy &P, const float *__restrict__ spec, int block_mode) {
+/* aoTuV M7 for short blocks (block_mode <= 1, psy.c:3661-3731) by all threads of the CTA.  The reference walks the
+   bins and jumps to the end of a peak's range after handling it -- but that range is non-increasing, so no strict local
+   maximum is skipped: the peaks are exactly the strict local maxima of [4, nx), each a function of the spectrum
+   alone.  temp[] starts at 0 and only ever takes max(ss, temp) clamped at 0, so the order of the peaks does not matter
+   either: bin j ends with the largest ss of the <= 6 peaks (i in j-3 .. j+2) whose range ps..pe covers it.  Three
+   steps: the compressed spectrum, one thread per candidate peak (ps, pe, ss), one thread per bin (max, cap, subtract).
+   (Lane 0 used to walk all of it: two thirds of the short-block kernel's instructions ran on one lane.) */
+template <int N, int T>
+__device__ __forceinline__ void tone_fix_short(NoiseSmem<N> &sm, const DevPsy &P, const float *__restrict__ spec) {
   int nx = P.tonefix_end;
   if (!nx) return;
+  const int tid = threadIdx.x;
   const float *off1 = P.noiseoffset + N;
   const float limit = fabsf(__ldg(off1));
-  float *noise = sm.sums[3];             /* logmdct - noise fit, staged here by the kernel for this pass */
-  float *tmp_ = sm.tmp(), *inm_ = sm.inm();
-  constexpr int SCR = N < 256 ? N : 256;
-  for (int i = 0; i < SCR; i++) { tmp_[i] = 0.f; inm_[i] = 0.f; }
-  if (block_mode <= 1) {
-    const int up = 3, un = 4;
-    int nxp = nx + un;
-    const float tol = (N == 256) ? 15.f : 9.f, strength = .6f;
-    if (nxp > N) { nx = N; nxp = N - un; }
-    for (int i = 0; i < nxp; i++) {
-      float s = spec[i];
-      inm_[i] = (s < -70.f) ? (float)(-70. + (double)__fadd_rn(s, 70.f) * .1) : s;
-    }
-    for (int i = un; i < nx; i++) {
-      if (!(spec[i] > spec[i - 1] && spec[i] > spec[i + 1])) continue;
+  float *noise = sm.sums[3];             /* logmdct - noise fit, staged here by the kernel */
+  float *ss_ = sm.tmp(), *inm_ = sm.inm();
+  int *rng_ = reinterpret_cast<int *>(sm.sums[0]);       /* ps | pe << 16 of a peak */
+  const int up = 3, un = 4;
+  int nxp = nx + un;
+  const float tol = (N == 256) ? 15.f : 9.f, strength = .6f;
+  if (nxp > N) { nx = N; nxp = N - un; }
+  for (int i = tid; i < N; i += T) {
+    float v = 0.f;
+    if (i < nxp) { const float s = spec[i]; v = (s < -70.f) ? (float)(-70. + (double)__fadd_rn(s, 70.f) * .1) : s; }
+    inm_[i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += T) {
+    float ss = -1.f; int rng = 0;
+    if (i >= un && i < nx && spec[i] > spec[i - 1] && spec[i] > spec[i + 1]) {
       int ps = i - 1, pe = i + 1;
       for (int j = ps; j > i - up; j--) { if (spec[j + 1] < spec[j]) break; ps = j; }
       for (int j = pe; j < i + un; j++) { if (spec[j - 1] < spec[j]) break; pe = j; }
-      float ss = fmaxf(__fsub_rn(inm_[i], inm_[ps]), __fsub_rn(inm_[i], inm_[pe]));
-      if (ss > tol) {
-        if (spec[i] > noise[i]) { ss = __fsub_rn(ss, tol); ss = __fmul_rn(ss, strength); }
-        for (int j = ps; j <= pe; j++) { float t = fmaxf(ss, tmp_[j]); if (t < 0.f) t = 0.f; tmp_[j] = t; }
+      float v = fmaxf(__fsub_rn(inm_[i], inm_[ps]), __fsub_rn(inm_[i], inm_[pe]));
+      if (v > tol) {
+        if (spec[i] > noise[i]) { v = __fsub_rn(v, tol); v = __fmul_rn(v, strength); }
+        ss = v; rng = ps | (pe << 16);
       }
-      i = pe;
     }
-    for (int i = un - 1; i < nx; i++) {
-      float cap = fminf(__ldg(P.ntfix + i), __fadd_rn(__ldg(off1 + i), limit));
-      float t = tmp_[i];
+    ss_[i] = ss; rng_[i] = rng;
+  }
+  __syncthreads();
+  float cut[N / T];
+#pragma unroll
+  for (int q = 0; q < N / T; q++) {
+    const int j = tid + q * T;
+    float t = 0.f;
+    for (int i = (j - 3 < un ? un : j - 3); i <= j + 2 && i < nx; i++) {
+      const float ss = ss_[i];
+      const int rng = rng_[i];
+      if (ss >= 0.f && j >= (rng & 0xffff) && j <= (rng >> 16)) { float m = fmaxf(ss, t); if (m < 0.f) m = 0.f; t = m; }
+    }
+    cut[q] = t;
+  }
+#pragma unroll
+  for (int q = 0; q < N / T; q++) {
+    const int j = tid + q * T;
+    if (j >= un - 1 && j < nx) {
+      const float cap = fminf(__ldg(P.ntfix + j), __fadd_rn(__ldg(off1 + j), limit));
+      float t = cut[q];
       if (t > cap) t = cap;
-      noise[i] = __fsub_rn(noise[i], t);
-    }
-  } else if (block_mode == 2) {
-    int k = 0;
-    for (int i = 0; i < nx; i += 8, k++) {
-      double a = 0;
-      for (int j = 0; j < 8; j++) a += (double)noise[i + j];
-      tmp_[k] = (float)(a / 8);
-    }
-    const int groups = nx / 8;
-    for (int i = 3; i < groups; i++) {
-      if (!(tmp_[i] > tmp_[i - 1] && tmp_[i] > tmp_[i + 1])) continue;
-      float base; int a;
-      if (tmp_[i - 1] > tmp_[i - 2]) { base = tmp_[i - 2]; a = i - 3; } else { base = tmp_[i - 1]; a = i - 2; }
-      const int b = i + 3;
-      float th = __fsub_rn(tmp_[i], base);
-      if (th > 2.f) {
-        float cap = fminf(__ldg(P.ntfix + i * 8), __fadd_rn(__ldg(off1 + i * 8), limit));
-        th = fminf(__fsub_rn(th, 2.f), cap);
-        for (int j = a * 8; j <= b * 8; j++) noise[j] = __fsub_rn(noise[j], th);
-      }
+      noise[j] = __fsub_rn(noise[j], t);
     }
   }
 }
@@ -255,7 +259,7 @@ k_noisemask(const DevSetup *__restrict__ S, const int *__restrict__ psyv, const 
       }
     } else {
       __syncthreads();
-      if (tid == 0) tone_fix<N>(sm, P, lm, mode);
+      tone_fix_short<N, T>(sm, P, lm);
       __syncthreads();
 #pragma unroll
       for (int q = 0; q < N / T; q++) wk[q] = sm.sums[3][tid + q * T];
