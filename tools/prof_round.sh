@@ -11,10 +11,10 @@ python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err || { t
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_$TAG.json 2>/dev/null
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
-# one whole-workload step under --set full: the 27 launches of the warm-up step are skipped, the 27 of the timed step captured
+# one whole-workload step under --set full: the 29 launches of the warm-up step are skipped, the 29 of the timed step captured
 # (the report itself is too large to travel back: its raw page goes home as csv, the report stays on the box)
 ncu --set full --clock-control none -k "regex:k_transform|k_noisemask|k_tone|k_mix|k_floor|k_couple|k_residue|k_pack|k_expand|k_stream_scan" \
-    -s 27 -c 27 -o /tmp/all_$TAG python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_all_$TAG.log 2>&1
+    -s 29 -c 29 -o /tmp/all_$TAG python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_all_$TAG.log 2>&1
 tail -n 2 gpurun_out/ncu_all_$TAG.log
 ncu -i /tmp/all_$TAG.ncu-rep --page raw --csv > gpurun_out/all_${TAG}_raw.csv 2>/dev/null
 # the dominant kernel (K2, long blocks) once more with its source page, at the same workload

@@ -84,8 +84,12 @@ struct RfShared {
 #ifndef RF_MINB
 #define RF_MINB 8          /* 64 registers: 8 CTAs per SM (10, 12, 16: 3.98, 3.98, 4.46 ms against 3.86) */
 #endif
+/* STEREO2: the common case as compile-time facts -- residue type 2 over two channels (one row, interleave by a
+   shift): the row / channel divisions and the type switches fold away (the generic kernel is 3.9 k instructions and
+   spent a fifth of its stall samples waiting for instruction fetch) */
+template <bool STEREO2>
 __global__ void __launch_bounds__(RF_WARPS * 32, RF_MINB)
-k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, const int *__restrict__ chlist, int tot_ch,
+k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch_, const int *__restrict__ chlist, int tot_ch,
                   int *__restrict__ in, const int *__restrict__ nonzero, const int *__restrict__ partword,
                   int maxvec, int *__restrict__ syms, int max_syms, int *__restrict__ nsyms) {
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -93,13 +97,15 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
   const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const DevResidue &R = S->res[resnum];
   const DevBook *books = S->book;
+  const int ch = STEREO2 ? 2 : ch_;
+  const int rtype = STEREO2 ? 2 : R.type;
   const int partvals = (R.end - R.begin) / R.grouping, G = R.grouping, stages = R.stages;
   int *base = in + (size_t)blk * tot_ch * n;
   const int *nz = nonzero + (size_t)blk * tot_ch;
   int used = 0;
   for (int k = 0; k < ch; k++) if (nz[chlist[k]]) used++;
   if (!used) { if (tid == 0) nsyms[blk] = 0; return; }
-  const int rows = (R.type == 2) ? 1 : used;
+  const int rows = STEREO2 ? 1 : ((rtype == 2) ? 1 : used);
   const int *pw = partword + (size_t)blk * ch * partvals;
   /* dynamic shared memory: entry table [stages][partvals][rows][maxvec] (int16) + scan offsets + row->channel map */
   short *ent = reinterpret_cast<short *>(dyn);
@@ -108,14 +114,14 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
   __shared__ int rowch[VB200_MAX_CHANNELS];
   __shared__ short tab_bk[64 * 8], tab_nvec[64 * 8];      /* per (class, stage): book and vectors per partition */
   __shared__ int next_pr;
-  if (tid == 0) { next_pr = 0; int r = 0; for (int k = 0; k < ch; k++) if (R.type == 2 || nz[chlist[k]]) rowch[r++] = chlist[k]; }
+  if (tid == 0) { next_pr = 0; int r = 0; for (int k = 0; k < ch; k++) if (rtype == 2 || nz[chlist[k]]) rowch[r++] = chlist[k]; }
   for (int i = tid; i < R.partitions * 8; i += RF_WARPS * 32) {
     const int cls = i >> 3, st2 = i & 7;
     int bk = -1, nv = 0;
     if (st2 < stages && (R.secondstages[cls] & (1 << st2))) { bk = R.partbooks[i]; if (bk >= 0) nv = G / books[bk].dim; }
     tab_bk[i] = (short)bk; tab_nvec[i] = (short)nv;
   }
-  const int ch_shift = (ch & (ch - 1)) == 0 ? __ffs(ch) - 1 : -1;
+  const int ch_shift = STEREO2 ? 1 : ((ch & (ch - 1)) == 0 ? __ffs(ch) - 1 : -1);
   const int pd_mask = (R.phrase_dim & (R.phrase_dim - 1)) == 0 ? R.phrase_dim - 1 : -1;
   __syncthreads();
 
@@ -178,7 +184,7 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
           const int t = t0 + u * RF_LP;
           tmp[u] = 0;
           if (t < G) {
-            if (R.type == 2) {
+            if (rtype == 2) {
               const int w = off + t;
               const int wc = ch_shift >= 0 ? (w & (ch - 1)) : w % ch, wj = ch_shift >= 0 ? (w >> ch_shift) : w / ch;
               tmp[u] = base[(size_t)chlist[wc] * n + wj];
@@ -270,7 +276,7 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch, con
       __syncwarp();
     }
     /* res1 leaves the cascade residual in place (res2 worked on a private interleaved copy) */
-    if (R.type != 2 && valid) for (int t = l; t < G; t += RF_LP) base[(size_t)rowch[row] * n + off + t] = v[t];
+    if (rtype != 2 && valid) for (int t = l; t < G; t += RF_LP) base[(size_t)rowch[row] * n + off + t] = v[t];
     __syncwarp();
   }
   __syncthreads();
@@ -329,8 +335,13 @@ int vb200_launch_residue_forward(const vb200_setup *s, cudaStream_t st, int W, i
   const size_t ent_bytes = ((size_t)R.stages * partvals * rows * maxvec * 2 + 15) & ~(size_t)15;
   const size_t dyn = ent_bytes + sizeof(int) * ((size_t)R.stages * partvals * rows + 1);
   if (dyn > 200 * 1024) { vb200_set_error("residue %d: symbol table does not fit shared memory", resnum); return VB200_EIMPL; }
-  CUDA_TRY(cudaFuncSetAttribute(k_residue_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  k_residue_forward<<<blocks, RF_WARPS * 32, dyn, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, maxvec, syms, max_syms, nsyms);
+  if (R.type == 2 && ch == 2) {
+    CUDA_TRY(cudaFuncSetAttribute(k_residue_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    k_residue_forward<true><<<blocks, RF_WARPS * 32, dyn, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, maxvec, syms, max_syms, nsyms);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(k_residue_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    k_residue_forward<false><<<blocks, RF_WARPS * 32, dyn, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, maxvec, syms, max_syms, nsyms);
+  }
   LAUNCH_CHECK();
   return VB200_OK;
 }
