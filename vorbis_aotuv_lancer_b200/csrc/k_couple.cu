@@ -127,9 +127,10 @@ __device__ void normalize(CoupleSmem<CH> &sm, const DevPsy &P, int limit, int k,
   __syncwarp();
 }
 
-template <int CH>
+/* STEREO1: two channels, one coupling step -- the channel and step loops unroll and index shared memory statically */
+template <int CH, bool STEREO1>
 __global__ void __launch_bounds__(32)
-k_couple(const DevSetup *__restrict__ S, int W, const int *__restrict__ psyv, int blobno, int n, int ch, int map_index,
+k_couple(const DevSetup *__restrict__ S, int W, const int *__restrict__ psyv, int blobno, int n, int ch_, int map_index,
          const float *__restrict__ mdct, const float *__restrict__ epeak, float *__restrict__ npeak, int npeak_stride,
          int *__restrict__ iwork, int *__restrict__ nonzero) {
   __shared__ CoupleSmem<CH> sm;
@@ -138,7 +139,8 @@ k_couple(const DevSetup *__restrict__ S, int W, const int *__restrict__ psyv, in
   const int blk = blockIdx.x, lane = threadIdx.x;
   const DevPsy &P = S->psy[psyv[blk]];
   const DevMap &M = S->map[map_index];
-  const int part = P.partition, steps = M.coupling_steps;
+  const int ch = STEREO1 ? 2 : ch_;
+  const int part = P.partition, steps = STEREO1 ? 1 : M.coupling_steps;
   const int limit = S->pointlimit[P.blockflag][blobno];
   const float pre = (float)S->stereo_th[S->prepointamp[blobno]], post = (float)S->stereo_th[S->postpointamp[blobno]];
   float pre_x = (float)S->stereo_thx[S->prepointamp[blobno]], post_x = (float)S->stereo_thx[S->postpointamp[blobno]];
@@ -327,10 +329,12 @@ int vb200_launch_couple(const vb200_setup *s, cudaStream_t st, int W, int blocks
   if (blocks <= 0) return VB200_OK;
   if (blobno < 0 || blobno >= VB200_PACKETBLOBS) { vb200_set_error("blob number out of range"); return VB200_EINVAL; }
   const int n = s->h.bs[W] / 2;
-  if (s->h.channels <= 2)
-    k_couple<2><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
+  if (s->h.channels == 2 && s->h.map[s->h.mode_mapping[W]].coupling_steps == 1)
+    k_couple<2, true><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
+  else if (s->h.channels <= 2)
+    k_couple<2, false><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
   else
-    k_couple<VB200_MAX_CHANNELS><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
+    k_couple<VB200_MAX_CHANNELS, false><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
   LAUNCH_CHECK();
   return VB200_OK;
 }

@@ -21,20 +21,22 @@
 namespace {
 
 /* ------------------------------------------------------------------ K7a */
+template <bool STEREO2>          /* residue type 2 over two channels, as in k_residue_forward */
 __global__ void __launch_bounds__(64)
-k_residue_class(const DevSetup *__restrict__ S, int resnum, int n, int ch, const int *__restrict__ chlist, int tot_ch,
+k_residue_class(const DevSetup *__restrict__ S, int resnum, int n, int ch_, const int *__restrict__ chlist, int tot_ch,
                 const int *__restrict__ in, const int *__restrict__ nonzero, int *__restrict__ partword, int *__restrict__ classified) {
   const int blk = blockIdx.x, tid = threadIdx.x;
   const DevResidue &R = S->res[resnum];
+  const int ch = STEREO2 ? 2 : ch_;
   const int partvals = (R.end - R.begin) / R.grouping;
   const int *base = in + (size_t)blk * tot_ch * n;
   const int *nz = nonzero + (size_t)blk * tot_ch;
   int *pw = partword + (size_t)blk * ch * partvals;
   int used = 0;
   for (int k = 0; k < ch; k++) if (nz[chlist[k]]) used++;
-  if (tid == 0) classified[blk] = used ? (R.type == 2 ? 1 : used) : 0;
+  if (tid == 0) classified[blk] = used ? ((STEREO2 || R.type == 2) ? 1 : used) : 0;
   if (!used) return;
-  if (R.type == 2) {
+  if (STEREO2 || R.type == 2) {
     const int per = (R.grouping + ch - 1) / ch;   /* positions per channel per partition (res0.c:498-503) */
     for (int p = tid; p < partvals; p += blockDim.x) {
       int l = R.begin / ch + p * per, mag = 0, ang = 0;
@@ -309,7 +311,8 @@ int vb200_launch_residue_class(const vb200_setup *s, cudaStream_t st, int W, int
                                int tot_ch, const int *in, const int *nonzero, int *partword, int *classified) {
   if (blocks <= 0) return VB200_OK;
   const int n = s->h.bs[W] / 2;
-  k_residue_class<<<blocks, 64, 0, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, classified);
+  if (s->h.res[resnum].type == 2 && ch == 2) k_residue_class<true><<<blocks, 64, 0, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, classified);
+  else k_residue_class<false><<<blocks, 64, 0, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, classified);
   LAUNCH_CHECK();
   return VB200_OK;
 }
