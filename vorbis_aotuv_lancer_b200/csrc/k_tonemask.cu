@@ -25,6 +25,8 @@ namespace {
 #define TM_NEGINF (-9999.f)
 constexpr int TM_SVW = 33;       /* words of the survivor set of one ch-block (<= 1024 octave lines), odd stride */
 constexpr int TM_QCAP = 64;      /* per-warp queue of curves to splat */
+constexpr int TM_PER = 8;        /* eighth_octave_lines: every setup has 8 (vb200_setup_create refuses anything else), so the
+                                    seed-position arithmetic divides and strides by a constant */
 
 __device__ __forceinline__ void smem_atomic_max(float *addr, float v) {
   if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
@@ -41,7 +43,7 @@ __device__ __forceinline__ void tm_splat(const DevSetup *__restrict__ S, const i
                                          int item, float *seed, SplatJob (*queue)[TM_QCAP], int warp, int lane) {
     const DevPsy &P = S->psy[psyv[item]];
     const float *f = logfft + (size_t)item * N;
-    const int L = P.total_octave_lines, per = P.eighth;
+    const int L = P.total_octave_lines; constexpr int per = TM_PER;
     float att = __fadd_rn(local_ampmax[item], P.ath_adjatt);
     if (att < P.ath_maxatt) att = P.ath_maxatt;
     const float dBoffset = __fsub_rn(P.max_curve_dB, global_ampmax[item]);
@@ -155,7 +157,7 @@ __device__ __forceinline__ unsigned tm_chase_step(unsigned c, unsigned &M, unsig
 template <int N>
 __device__ __forceinline__ void tm_fill(const DevSetup *__restrict__ S, const DevPsy &P, int item, float *seed, unsigned short *run16,
                                         const unsigned *sv, const float *__restrict__ local_ampmax, float *__restrict__ tone, int lane) {
-    const int L = P.total_octave_lines, per = P.eighth;
+    const int L = P.total_octave_lines; constexpr int per = TM_PER;
     const int nw = (L + 31) >> 5;
     const unsigned myw = lane < nw ? sv[lane] : 0u;
     /* first survivor after the word this lane holds */
