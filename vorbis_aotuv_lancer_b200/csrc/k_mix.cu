@@ -138,11 +138,10 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
       float *mk = logmask + (size_t)item * mask_stride + (size_t)si * N;
       int local_gate = 0;
 
-      for (int i = tid; i < N; i += T) {
-        const float md_in = (sel == 1) ? md[i] : 0.f;      /* M1 scales it at the end of the iteration: request it now */
-        float val = __fadd_rn(__ldg(nz + i), __ldg(noff + i));
-        float tval = __fadd_rn(__ldg(tn + i), toneatt);
-        const float l = __ldg(lm + i);
+      /* one bin: (noise, noise offset, tone, logmdct, mdct) in, mask and M1-scaled mdct out */
+      auto elem = [&](const int i, const float md_in, const float nz_i, const float noff_i, const float tn_i, const float l, float &mk_o, float &md_o) {
+        float val = __fadd_rn(nz_i, noff_i);
+        float tval = __fadd_rn(tn_i, toneatt);
         if (i <= m4_start) tval = __fsub_rn(tval, low_compand);
         if (val > P.noisemaxsupp) val = P.noisemaxsupp;
         if (SHORT && m3.on && val > tval) {                                       /* aoTuV M3 */
@@ -186,15 +185,39 @@ k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start
           }
           out = tval;
         }
-        mk[i] = out;
+        mk_o = out;
+        md_o = md_in;
         if (sel == 1) {                                                           /* aoTuV M1 */
           const float coeffi = (float)-17.2;
           const float v = __fsub_rn(val, l);
           float de;
           if (v > coeffi) { de = (float)(1.0 - ((double)__fsub_rn(v, coeffi) * 0.005 * (double)P.m_val)); if (de < 0.f) de = (float)0.0001; }
           else de = (float)(1.0 - ((double)__fsub_rn(v, coeffi) * 0.0003 * (double)P.m_val));
-          md[i] = __fmul_rn(md_in, de);
+          md_o = __fmul_rn(md_in, de);
           if (nsel > 1 && dbq(out) && __fadd_rn(l, S->flr[floor_index >= 0 ? floor_index : S->floor_of_ch[W][item % ch]].twofitatten) >= out) local_gate = 1;
+        }
+      };
+      if constexpr (!SHORT && N == 4 * T) {
+        /* long blocks: four consecutive bins per thread, every vector of the block as ONE 128-bit request per thread,
+           all five in flight before the first is used (the stage is HBM-bound: 24 KB per ch-block) */
+        const int i0 = tid * 4;
+        const float4 m4 = (sel == 1) ? *reinterpret_cast<const float4 *>(md + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 n4 = __ldg(reinterpret_cast<const float4 *>(nz + i0)), o4 = __ldg(reinterpret_cast<const float4 *>(noff + i0));
+        const float4 t4 = __ldg(reinterpret_cast<const float4 *>(tn + i0)), l4 = __ldg(reinterpret_cast<const float4 *>(lm + i0));
+        float4 mo, do_;
+        elem(i0, m4.x, n4.x, o4.x, t4.x, l4.x, mo.x, do_.x);
+        elem(i0 + 1, m4.y, n4.y, o4.y, t4.y, l4.y, mo.y, do_.y);
+        elem(i0 + 2, m4.z, n4.z, o4.z, t4.z, l4.z, mo.z, do_.z);
+        elem(i0 + 3, m4.w, n4.w, o4.w, t4.w, l4.w, mo.w, do_.w);
+        *reinterpret_cast<float4 *>(mk + i0) = mo;
+        if (sel == 1) *reinterpret_cast<float4 *>(md + i0) = do_;
+      } else {
+        for (int i = tid; i < N; i += T) {
+          const float md_in = (sel == 1) ? md[i] : 0.f;      /* M1 scales it at the end of the iteration: request it now */
+          float mo, do_;
+          elem(i, md_in, __ldg(nz + i), __ldg(noff + i), __ldg(tn + i), __ldg(lm + i), mo, do_);
+          mk[i] = mo;
+          if (sel == 1) md[i] = do_;
         }
       }
       if (nsel > 1 && si == 0) {

@@ -38,6 +38,27 @@ k_residue_class(const DevSetup *__restrict__ S, int resnum, int n, int ch_, cons
   if (!used) return;
   if (STEREO2 || R.type == 2) {
     const int per = (R.grouping + ch - 1) / ch;   /* positions per channel per partition (res0.c:498-503) */
+    if (STEREO2 && per == 16 && (R.grouping & 1) == 0 && ((R.begin >> 1) & 3) == 0 && (n & 3) == 0) {
+      /* a partition is 16 consecutive values of each channel: four 128-bit loads per channel, all eight requested
+         before the first is used (the scalar walk read a 64-byte run four bytes at a time, lane by lane) */
+      const int4 *r0 = reinterpret_cast<const int4 *>(base + (size_t)chlist[0] * n + (R.begin >> 1));
+      const int4 *r1 = reinterpret_cast<const int4 *>(base + (size_t)chlist[1] * n + (R.begin >> 1));
+      for (int p = tid; p < partvals; p += blockDim.x) {
+        int4 a[4], b[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { a[q] = __ldg(r0 + p * 4 + q); b[q] = __ldg(r1 + p * 4 + q); }
+        int mag = 0, ang = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          mag = max(max(max(mag, abs(a[q].x)), max(abs(a[q].y), abs(a[q].z))), abs(a[q].w));
+          ang = max(max(max(ang, abs(b[q].x)), max(abs(b[q].y), abs(b[q].z))), abs(b[q].w));
+        }
+        int c = 0;
+        for (; c < R.partitions - 1; c++) if (mag <= R.classmetric1[c] && ang <= R.classmetric2[c]) break;
+        pw[p] = c;
+      }
+      return;
+    }
     for (int p = tid; p < partvals; p += blockDim.x) {
       int l = R.begin / ch + p * per, mag = 0, ang = 0;
       for (int j = 0; j < R.grouping; j += ch, l++) {
