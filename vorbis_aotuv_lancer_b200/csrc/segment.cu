@@ -499,38 +499,59 @@ k_env_bands(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams,
    (window v+2 steps), OR-ed over channels and bands. */
 constexpr int EV_VARIANTS = VE_MAXSTRETCH - VE_MINSTRETCH + 1;
 constexpr int PIPE_SEG_STREAM_SLACK = 64;      /* spare table rows of the parallel trigger */
+/* The 14 steps x 12 bands a step looks at are ONE run of 168 consecutive floats of acc ([step][band]), and the next
+   step's run starts 12 floats later: a CTA stages the 141 steps its 128 threads need (coalesced) with a row stride of
+   13 words -- consecutive steps then sit in different banks -- and every thread reads its history from there.
+   (Every one of the 336 history reads per thread used to be a global load whose 32 lanes touched 12 cache lines.) */
+constexpr int EF_HIST = VE_MAXSTRETCH + 1;        /* steps before j that a trigger reads: j-1 .. j-13 */
+constexpr int EF_ROW = VE_BANDS + 1;
 __global__ void __launch_bounds__(128)
 k_env_flags(const EnvDev *__restrict__ E, const EnvStream *__restrict__ streams, int ch, const float *__restrict__ acc_in,
             unsigned *__restrict__ flags /*[out_base + step]*/) {
+  __shared__ float hist[(128 + EF_HIST) * EF_ROW];
   const EnvStream S = streams[blockIdx.y];
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= S.nsteps) return;
+  const int j0 = blockIdx.x * 128, tid = threadIdx.x;
+  if (j0 >= S.nsteps) return;
+  const int j = j0 + tid;
+  const int jn = min(128, S.nsteps - j0);
   float pen[EV_VARIANTS];
 #pragma unroll
   for (int v = 0; v < EV_VARIANTS; v++) { int st; ve_stretch_params(2 * (v + VE_MINSTRETCH), E->stretch_penalty, &st, &pen[v]); }
   unsigned w = 0;
-  for (int c = 0; c < ch; c++)
-    for (int b = 0; b < VE_BANDS; b++) {
-      const float *a = acc_in + (S.out_base * ch + (long long)c * S.nsteps) * VE_BANDS + b;
-      auto A = [&](int step) { return step >= 0 ? a[(long long)step * VE_BANDS] : 0.f; };
-      const float cur = A(j), prev = A(j - 1);
-      const float postmax = cur > prev ? cur : prev, postmin = cur < prev ? cur : prev;
-      const float pre_th = E->pre_th[b], post_th = E->post_th[b];
-      float premax = -99999.f, premin = 99999.f;
+  for (int c = 0; c < ch; c++) {
+    const float *a = acc_in + (S.out_base * ch + (long long)c * S.nsteps) * VE_BANDS;
+    __syncthreads();                                     /* the previous channel's history is no longer read */
+    /* rows r = 0 .. jn + 12 hold steps j0 - 13 + r; steps before the stream's first are zero (envelope.c: the
+       filters start from a zeroed history) */
+    for (int e = tid; e < (jn + EF_HIST) * VE_BANDS; e += 128) {
+      const int r = e / VE_BANDS, bnd = e - r * VE_BANDS, step = j0 - EF_HIST + r;
+      hist[r * EF_ROW + bnd] = step >= 0 ? __ldg(a + (long long)step * VE_BANDS + bnd) : 0.f;
+    }
+    __syncthreads();
+    if (tid < jn) {
+      const float *h = hist + (tid + EF_HIST) * EF_ROW;   /* row of step j; step j - k is k rows up */
 #pragma unroll
-      for (int i = 0; i < VE_MAXSTRETCH; i++) {
-        const float x = A(j - 2 - i);
-        if (x > premax) premax = x;
-        if (x < premin) premin = x;
-        if (i + 1 >= VE_MINSTRETCH) {
-          const int v = i + 1 - VE_MINSTRETCH;
-          const float valmin = __fsub_rn(postmin, premin), valmax = __fsub_rn(postmax, premax);
-          if (valmax > __fadd_rn(pre_th, pen[v])) w |= 1u << (2 * v);
-          if (valmin < __fsub_rn(post_th, pen[v])) w |= 2u << (2 * v);
+      for (int b = 0; b < VE_BANDS; b++) {
+        const float cur = h[b], prev = h[b - EF_ROW];
+        const float postmax = cur > prev ? cur : prev, postmin = cur < prev ? cur : prev;
+        const float pre_th = E->pre_th[b], post_th = E->post_th[b];
+        float premax = -99999.f, premin = 99999.f;
+#pragma unroll
+        for (int i = 0; i < VE_MAXSTRETCH; i++) {
+          const float x = h[b - (2 + i) * EF_ROW];
+          if (x > premax) premax = x;
+          if (x < premin) premin = x;
+          if (i + 1 >= VE_MINSTRETCH) {
+            const int v = i + 1 - VE_MINSTRETCH;
+            const float valmin = __fsub_rn(postmin, premin), valmax = __fsub_rn(postmax, premax);
+            if (valmax > __fadd_rn(pre_th, pen[v])) w |= 1u << (2 * v);
+            if (valmin < __fsub_rn(post_th, pen[v])) w |= 2u << (2 * v);
+          }
         }
       }
     }
-  flags[S.out_base + j] = w;
+  }
+  if (tid < jn) flags[S.out_base + j] = w;
 }
 
 /* K0c: the order-dependent half: the stretch counter, one warp per stream, 32 steps fetched per pass.
