@@ -232,3 +232,19 @@ def test_bit_packer_second_pass():
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, (r.stdout[-1000:], r.stderr[-3000:])
     assert "100.0% byte-identical" in r.stdout, r.stdout[-1000:]
+
+
+def test_general_stream_scan_gives_the_same_stream():
+    """Setups whose loud-noise fix is off (every quality >= q3) take k_stream_scan_ampmax (chunked shared-memory replay
+    of the ampmax recurrence); q <= 2 takes k_stream_scan, which also carries the loud-noise level.  VB200_SCAN_GENERAL
+    sends a q4 stream through the general kernel: it must produce the reference's stream as well (the q2 / q0 cases
+    above pin the general kernel where it is the only choice)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VB200_SCAN_GENERAL="1")
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-1000:], r.stderr[-3000:])
+    assert "100.0% byte-identical" in r.stdout, r.stdout[-1000:]
