@@ -183,7 +183,7 @@ def run_ours(args):
     pins = [encoder.PinnedArray(ch, int(rate * T)) for _ in range(S)]      # the caller's PCM lives in page-locked memory
     pcms = synth_streams(L, S, T, ch, rate, rank * S, pinned=pins)
     blocks_per_stream = int(T * rate / 700) + 64
-    enc = encoder.Encoder(setup, S * blocks_per_stream, threads=max(2, min(32, (os.cpu_count() or 8) // max(1, world))), chunks=args.chunks)
+    enc = encoder.Encoder(setup, S * blocks_per_stream, threads=max(2, min(32, (os.cpu_count() or 8) // max(1, world))), chunks=args.chunks, nstreams=S)
     blocks, timeline, counts = enc.segment(pcms)
     # the resident-input measurement runs the whole workload as one batch per step; two batch objects alternate, so
     # the host half of step i+1 (descriptor pre-pass, launches) overlaps the device half of step i

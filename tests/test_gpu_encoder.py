@@ -111,6 +111,25 @@ def test_gpu_stream_is_accepted_by_an_independent_decoder(config, seconds):
     enc.close(); s.close()
 
 
+def test_a_group_that_outgrows_its_batch_gets_a_larger_one():
+    """Batch capacities are sized from the expected blocks per call; a group with more blocks than that (uneven streams,
+    many groups over few streams) must get a larger batch, not an error -- and the same packets."""
+    from vorbis_aotuv_lancer_b200 import encoder, ops
+    pcm = refdata.synth(2, 44100, 2.0, seed=5)
+    s = ops.Setup("q4_44k_2ch")
+    one = encoder.Encoder(s, 4096, threads=2, chunks=1)
+    want = encoder.packets_of(one.encode([pcm]), 0)
+    one.close()
+    enc = encoder.Encoder(s, 48, threads=2, chunks=3)          # 48 blocks expected in all: every group overflows
+    tabs = enc.encode([pcm, pcm, pcm])
+    for k in range(3):
+        got = encoder.packets_of(tabs, k)
+        assert [p[0] for p in got] == [p[0] for p in want]
+    tabs = enc.encode([pcm, pcm, pcm])                          # and the grown batches serve the next call
+    assert [p[0] for p in encoder.packets_of(tabs, 2)] == [p[0] for p in want]
+    enc.close(); s.close()
+
+
 def test_ragged_batch_of_degenerate_streams():
     """One call, streams of very different kinds and lengths: digital silence (every floor unused), one sample, less
     than a short block, a clipped square wave, a click train (a transient in every block), ordinary signal.  Each must

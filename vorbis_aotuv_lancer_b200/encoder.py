@@ -121,7 +121,11 @@ class Encoder:
     its own segmenter and batch (own CUDA streams): while the kernels of group g run, the host segments group
     g+1 and its PCM goes up -- the host stage and the device stage overlap."""
 
-    def __init__(self, setup, max_blocks, threads=8, chunks=6):
+    def __init__(self, setup, max_blocks, threads=8, chunks=6, nstreams=None):
+        """max_blocks: blocks of one encode() call over all streams; nstreams: how many streams a call will bring, if
+        known -- the groups' batch capacities then follow the actual group sizes (with many groups and few streams a
+        group's share of the streams is far from its share of the weights).  A group that still outgrows its batch
+        gets a larger one on the spot (encode)."""
         self.setup = setup
         self.threads = threads
         self.chunks = max(1, int(chunks))
@@ -130,7 +134,12 @@ class Encoder:
         env = os.environ.get("VB200_GROUP_WEIGHTS")
         self.weights = [float(x) for x in env.split(",")] if env else group_weights(self.chunks)
         self.chunks = len(self.weights)
-        per = int(1.25 * int(max_blocks) * max(self.weights) / sum(self.weights)) + 64 if self.chunks > 1 else int(max_blocks)
+        share = max(self.weights) / sum(self.weights)
+        if nstreams:
+            cuts = group_cuts(int(nstreams), self.weights)
+            share = max(b - a for a, b in cuts) / float(nstreams)
+        per = int(1.25 * int(max_blocks) * share) + 64 if self.chunks > 1 else int(max_blocks)
+        self.capacity = [per] * self.chunks
         self.batches = [ops.Batch(setup, per) for _ in range(self.chunks)]
         for rank, b in enumerate(self.batches):      # earlier groups are served first, so their packets are out first
             check(L.vb200_batch_set_rank(b.h, rank), "vb200_batch_set_rank")
@@ -191,6 +200,13 @@ class Encoder:
         for g, (a, b) in enumerate(groups):
             begun[g].result()
             blocks, dptr, elems = self.segmenters[g].finish()
+            if len(blocks) > self.capacity[g]:          # rare: an uneven group; never silently truncate
+                self.batches[g].close()
+                self.capacity[g] = int(1.25 * len(blocks)) + 64
+                self.batches[g] = ops.Batch(self.setup, self.capacity[g])
+                check(L.vb200_batch_set_rank(self.batches[g].h, g), "vb200_batch_set_rank")
+                if g == 0:
+                    self.batch = self.batches[0]
             t1 = time.perf_counter()
             subs.append(self.submit_pool.submit(self.batches[g].submit, streams[a:b], blocks, dptr, elems))
             marks.append((t1 - t0,))
