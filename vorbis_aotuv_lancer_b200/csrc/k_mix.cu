@@ -27,7 +27,7 @@ __device__ __forceinline__ int dbq(float x) {      /* vorbis_dBquant, floor1.c:2
 #define KM_MINB 6          /* 40 registers: 4 / 5 / 6 CTAs per SM: 2.56 / 2.26 / 2.11 ms */
 #endif
 template <int N, int T>
-__global__ void __launch_bounds__(T, (N > 256 ? KM_MINB : 1))
+__global__ void __launch_bounds__(T, (N > 256 ? KM_MINB : 20))      /* short blocks: 48 registers as before (a bound of 1 let the compiler take 114) */
 k_mix(const DevSetup *__restrict__ S, int W, const int *__restrict__ chain_start, const int *__restrict__ chain_len, const int *__restrict__ chain_items,
       const int *__restrict__ psyv, const int *__restrict__ params, const float *__restrict__ low_compandv,
       const float *__restrict__ noise, const float *__restrict__ tone, const float *__restrict__ logmdct,
