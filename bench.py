@@ -183,6 +183,8 @@ def run_ours(args):
     pins = [encoder.PinnedArray(ch, int(rate * T)) for _ in range(S)]      # the caller's PCM lives in page-locked memory
     pcms = synth_streams(L, S, T, ch, rate, rank * S, pinned=pins)
     blocks_per_stream = int(T * rate / 700) + 64
+    if args.chunks <= 0:
+        args.chunks = max(1, min(20, S // 3))        # 64 streams: 20 groups (sweep in encoder.group_weights); few streams: few groups
     enc = encoder.Encoder(setup, S * blocks_per_stream, threads=max(2, min(32, (os.cpu_count() or 8) // max(1, world))), chunks=args.chunks, nstreams=S)
     blocks, timeline, counts = enc.segment(pcms)
     # the resident-input measurement runs the whole workload as one batch per step; two batch objects alternate, so
@@ -360,7 +362,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=60.0)
-    ap.add_argument("--chunks", type=int, default=20, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g)")
+    ap.add_argument("--chunks", type=int, default=0, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g); 0: one per three streams, at most 20")
     ap.add_argument("--depth", type=int, default=2, help="resident arm: batches in flight (2: host half of step i+1 overlaps device half of step i)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the e2e arm (the line then carries e2e.value null)")

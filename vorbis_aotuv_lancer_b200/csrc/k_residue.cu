@@ -105,7 +105,7 @@ struct RfShared {
 };
 
 #ifndef RF_MINB
-#define RF_MINB 8          /* 64 registers: 8 CTAs per SM (10, 12, 16: 3.98, 3.98, 4.46 ms against 3.86) */
+#define RF_MINB 10         /* 48 registers, 10 CTAs per SM (specialised kernel: 8 / 10 / 12 CTAs: 2.65 / 2.57 / 2.64 ms) */
 #endif
 /* STEREO2: the common case as compile-time facts -- residue type 2 over two channels (one row, interleave by a
    shift): the row / channel divisions and the type switches fold away (the generic kernel is 3.9 k instructions and
