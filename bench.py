@@ -285,6 +285,24 @@ def run_ours(args):
         barrier()
         t_e2e = maxtime(time.perf_counter() - t0)
 
+    # ---- the same call fed with 16-bit PCM (vb200_segmenter_begin_s16): half the host-to-device bytes, the device
+    # converts.  An additional number, not the headline: the reference's own API takes float
+    t_e2e16 = None
+    if not args.no_e2e and not args.no_int16:
+        pins16 = [encoder.PinnedArray(ch, int(rate * T), np.int16) for _ in range(S)]
+        for a16, a in zip(pins16, pcms):
+            a16.array[:] = np.clip(np.rint(a * 32767.0), -32768, 32767).astype(np.int16)
+        pcms16 = [a16.array for a16 in pins16]
+        enc.encode(pcms16, streams[total_steps + 4])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            enc.encode(pcms16, streams[total_steps + 5 + i])
+        barrier()
+        t_e2e16 = maxtime(time.perf_counter() - t0)
+        for a16 in pins16:
+            a16.close()
+
     if rank == 0:
         ms_step = t_dev / args.steps * 1e3
         value = world * audio * args.steps / t_dev
@@ -340,6 +358,11 @@ def run_ours(args):
                "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(timeline.nbytes), "d2h_bytes_per_step": int(packet_bytes),
                        "steps": e2e_steps, "includes": "Encoder.encode from pinned host PCM: host segmentation (LPC head/tail, window sequencing; detector kernels on the GPU), "
                                                        "H2D of the PCM, all kernels, bit packing, D2H of the packets; %d pipelined stream groups; host clock, max over ranks" % args.chunks},
+               "e2e_int16": None if t_e2e16 is None else {
+                   "value": world * audio * e2e_steps / t_e2e16, "unit": "audio-s/s", "h2d_bytes_per_step": int(timeline.nbytes // 2),
+                   "note": "the same Encoder.encode call fed with 16-bit PCM (vb200_segmenter_begin_s16: samples go up as int16, the device converts "
+                           "sample / 32768.f as examples/encoder_example.c:183-190 does on the host); packets identical to the float entry point on the "
+                           "converted samples (tests/test_gpu_encoder.py); an additional number -- the headline e2e is the float API's"},
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": int(algo), "kernel_ms": kern[top],
@@ -365,6 +388,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="stream groups the e2e call pipelines (host stage of group g+1 overlaps kernels of g); 0: one per three streams, at most 20")
     ap.add_argument("--depth", type=int, default=2, help="resident arm: batches in flight (2: host half of step i+1 overlaps device half of step i)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-int16", action="store_true", help="skip the additional e2e measurement with 16-bit PCM input")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the e2e arm (the line then carries e2e.value null)")
     ap.add_argument("--fast-transform", action="store_true", help="front end K1 (own formulation, within 1e-5) instead of the default K1x (DESIGN.md section 4)")
     ap.add_argument("--exact-transform", action="store_true", help="(the default since round 2; accepted for old command lines)")

@@ -219,6 +219,12 @@ int  vb200_segmenter_run(vb200_segmenter *g, int nstreams, const float *const *p
    returns at once; _finish waits for the marks, sequences the windows and uploads the extrapolated tails */
 int  vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const float *const *pcm, const long *nsamples,
                            const long *stride, int chunk, int threads);
+/* the same for 16-bit PCM (planar [channels][nsamples], value = sample / 32768.f: the conversion
+   examples/encoder_example.c:183-190 performs on the host before vorbis_analysis_wrote).  Half the host-to-device
+   bytes; the device converts.  Timeline, blocks and packets are those of vb200_segmenter_begin on the converted
+   samples. */
+int  vb200_segmenter_begin_s16(vb200_segmenter *g, int nstreams, const short *const *pcm, const long *nsamples,
+                               const long *stride, int chunk, int threads);
 int  vb200_segmenter_finish(vb200_segmenter *g);
 /* order g's uploads behind prev's (both begun before either is finished): the first group's PCM arrives first */
 int  vb200_segmenter_after(vb200_segmenter *g, const vb200_segmenter *prev);

@@ -130,6 +130,45 @@ def test_a_group_that_outgrows_its_batch_gets_a_larger_one():
     enc.close(); s.close()
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_sixteen_bit_pcm_gives_the_stream_of_its_float_conversion(pinned):
+    """vb200_segmenter_begin_s16: 16-bit PCM goes up as it is (half the bytes) and the device converts, sample / 32768.f
+    -- what examples/encoder_example.c:183-190 does on the host.  Device timeline, blocks and packets must be exactly
+    those of the float entry point fed with the converted samples; from page-locked memory (direct upload + conversion
+    kernel) and from pageable memory (staged through the host timeline)."""
+    from vorbis_aotuv_lancer_b200 import encoder, ops
+    rng = np.random.default_rng(11)
+    s = ops.Setup("q4_44k_2ch")
+    streams16 = []
+    for k, secs in enumerate((3.0, 1.3, 0.01)):
+        f = refdata.synth(2, 44100, secs, seed=20 + k)
+        q = np.clip(np.rint(f * 32767.0), -32768, 32767).astype(np.int16)
+        if k == 1:
+            q[:, 100:140] = rng.integers(-32768, 32768, (2, 40), dtype=np.int16)       # full-scale values incl. -32768
+        streams16.append(q)
+    as_float = [(q.astype(np.float32) / np.float32(32768.0)) for q in streams16]
+    holders = []
+    if pinned:
+        ins = []
+        for q in streams16:
+            h = encoder.PinnedArray(q.shape[0], q.shape[1], np.int16)
+            h.array[:] = q
+            holders.append(h); ins.append(h.array)
+    else:
+        ins = streams16
+    enc = encoder.Encoder(s, 4096, threads=2, chunks=2)
+    want = enc.encode(as_float)
+    got = enc.encode(ins)
+    if pinned:
+        assert enc.segmenters[0].direct
+    for k in range(len(streams16)):
+        a, b = encoder.packets_of(got, k), encoder.packets_of(want, k)
+        assert len(a) == len(b) and [p[0] for p in a] == [p[0] for p in b] and [p[1] for p in a] == [p[1] for p in b]
+    enc.close(); s.close()
+    for h in holders:
+        h.close()
+
+
 def test_ragged_batch_of_degenerate_streams():
     """One call, streams of very different kinds and lengths: digital silence (every floor unused), one sample, less
     than a short block, a clipped square wave, a click train (a transient in every block), ordinary signal.  Each must

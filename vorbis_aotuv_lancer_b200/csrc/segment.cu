@@ -212,7 +212,12 @@ struct StreamSeg {
 
   /* timeline: lead-in | pre-amplified PCM | tail; head = reverse LPC extrapolation from the signal that
      had arrived when the reference first had more than one long block (block.c:438-471,545-548) */
-  void fill_and_head(const float *src, long stride, int chunk, bool sparse = false) {
+  /* SRC = float (the reference's own input format) or short (16-bit PCM as a WAV file holds it: the value is
+     sample / 32768.f, the conversion examples/encoder_example.c:183-190 does before vorbis_analysis_wrote) */
+  static inline float sample_of(float v) { return v; }
+  static inline float sample_of(short v) { return (float)v / 32768.f; }
+  template <typename SRC>
+  void fill_and_head(const SRC *src, long stride, int chunk, bool sparse = false) {
     /* sparse: the body of the signal goes to the device straight from the caller's (pinned) memory and
        only the two windows the host itself reads are staged: the head the LPC looks at and the tail the
        end-of-stream extrapolation and the last detector steps look at */
@@ -224,10 +229,10 @@ struct StreamSeg {
       if (sn + want_tail < nsamples) { head_n = sn; tail_n = want_tail; }
     }
     for (int c = 0; c < ch; c++) {
-      float *d = pcm + (size_t)c * T; const float *q = src + (size_t)c * stride;
+      float *d = pcm + (size_t)c * T; const SRC *q = src + (size_t)c * stride;
       for (long i = 0; i < lead; i++) d[i] = 0.f;
-      for (long i = 0; i < head_n; i++) d[lead + i] = q[i] * env.pre_amp;
-      for (long i = nsamples - tail_n; i < nsamples; i++) d[lead + i] = q[i] * env.pre_amp;
+      for (long i = 0; i < head_n; i++) d[lead + i] = sample_of(q[i]) * env.pre_amp;
+      for (long i = nsamples - tail_n; i < nsamples; i++) d[lead + i] = sample_of(q[i]) * env.pre_amp;
       for (long i = eof_abs; i < T; i++) d[i] = 0.f;
     }
     long seen = 0;
@@ -417,7 +422,8 @@ __constant__ float c_ve_bandtotal[VE_BANDS];
 __host__ __device__ constexpr int band_begin(int b) { constexpr int t[VE_BANDS] = {2, 4, 6, 9, 13, 17, 22, 12, 8, 3, 2, 1}; return t[b]; }
 __host__ __device__ constexpr int band_end(int b) { constexpr int t[VE_BANDS] = {4, 5, 6, 8, 8, 8, 8, 4, 4, 3, 2, 4}; return t[b]; }
 
-struct EnvStream { long long pcm_base; long long T; int nsteps; long long out_base; /* step-major output offset */ long long eof; };
+struct EnvStream { long long pcm_base; long long T; int nsteps; long long out_base; /* step-major output offset */ long long eof;
+                   long long s16_base; /* 16-bit ingest: the stream's samples in the device staging buffer, [ch][eof - lead] */ };
 
 constexpr int EV_TILE = 128;     /* steps per CTA */
 constexpr int EV_HALO = 30;      /* the near-DC sum of a step depends on at most the 30 previous steps */
@@ -694,6 +700,18 @@ __global__ void k_timeline_finish(const EnvStream *__restrict__ streams, int ch,
   }
 }
 
+/* 16-bit ingest: the caller's samples went up as they are (half the bytes of the float path); this writes them into
+   the timeline as sample / 32768.f -- an exact float operation, the one the reference's caller performs on the host */
+__global__ void k_timeline_from_s16(const EnvStream *__restrict__ streams, int ch, int lead, const short *__restrict__ src, float *__restrict__ pcm) {
+  const EnvStream S = streams[blockIdx.y / ch];
+  const int c = blockIdx.y % ch;
+  const long long n = S.eof - lead;
+  float *d = pcm + S.pcm_base + (long long)c * S.T + lead;
+  const short *q = src + S.s16_base + (long long)c * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = __fdiv_rn((float)q[i], 32768.f);
+}
+
 /* the extrapolated tails (a few thousand samples per channel) are fetched by a kernel straight from the pinned host
    timeline: a copy-engine transfer would queue behind the bulk uploads other segmenters have already issued */
 __global__ void k_tail_upload(const EnvStream *__restrict__ streams, int ch, const float *__restrict__ host_pcm, float *__restrict__ pcm) {
@@ -732,6 +750,7 @@ struct vb200_segmenter {
   vb200_setup *s; EnvParams env; SegRun *run;
   EnvDev *d_env;
   float *h_pcm, *d_pcm; size_t pcm_cap;          /* pinned host timeline + device timeline */
+  short *d_pcm16; size_t pcm16_cap;              /* 16-bit ingest: the samples as uploaded */
   float *d_acc, *d_temp; unsigned *d_flags; unsigned char *d_maps; size_t step_cap;
   unsigned char *d_marks, *h_marks; size_t mark_cap;
   EnvStream *d_streams, *h_streams; long long *d_mark_base, *h_mark_base; int *d_stretch, *h_stretch;
@@ -780,7 +799,7 @@ extern "C" void vb200_segmenter_destroy(vb200_segmenter *g) {
   cudaStreamDestroy(g->st);
   cudaEventDestroy(g->ev_h2d);
   delete g->run;
-  cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFreeHost(g->h_pcm);
+  cudaFree(g->d_env); cudaFree(g->d_pcm); cudaFree(g->d_pcm16); cudaFreeHost(g->h_pcm);
   cudaFree(g->d_acc); cudaFree(g->d_temp); cudaFree(g->d_flags); cudaFree(g->d_maps); cudaFree(g->d_marks); cudaFreeHost(g->h_marks);
   cudaFree(g->d_streams); cudaFreeHost(g->h_streams); cudaFree(g->d_mark_base); cudaFreeHost(g->h_mark_base);
   cudaFree(g->d_stretch); cudaFreeHost(g->h_stretch); cudaFree(g->d_acc_tail); cudaFreeHost(g->h_acc_tail);
@@ -801,8 +820,10 @@ template <typename F> static void parallel_for(int n, int threads, F f) {
 
 /* Segment `nstreams` streams at once.  pcm[i]: planar [channels][nsamples[i]] with stride[i].
    Afterwards the timeline of all streams sits in HBM (vb200_segmenter_device_pcm) and the blocks index it. */
-extern "C" int vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const float *const *pcm, const long *nsamples,
-                                     const long *stride, int chunk, int threads) {
+template <typename SRC>
+static int segmenter_begin_impl(vb200_segmenter *g, int nstreams, const SRC *const *pcm, const long *nsamples,
+                                const long *stride, int chunk, int threads) {
+  constexpr bool S16 = sizeof(SRC) == 2;
   if (!g || nstreams < 1 || !pcm || !nsamples || !stride) { vb200_set_error("vb200_segmenter_begin: bad arguments"); return VB200_EINVAL; }
   vb200_setup *s = g->s;
   CUDA_TRY(cudaSetDevice(s->device));
@@ -868,6 +889,12 @@ extern "C" int vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const flo
     else if (at.type != cudaMemoryTypeHost) direct = false;
   }
   g->direct = direct ? 1 : 0;
+  std::vector<long long> s16_base(nstreams + 1, 0);
+  if (S16 && direct) {
+    for (int i = 0; i < nstreams; i++) s16_base[i + 1] = s16_base[i] + (long long)nsamples[i] * ch;
+    const size_t need = (size_t)s16_base[nstreams] + 8;
+    if (g->pcm16_cap < need) { cudaFree(g->d_pcm16); g->d_pcm16 = nullptr; g->pcm16_cap = 0; SEG_ALLOC(g->d_pcm16, need * sizeof(short), false); g->pcm16_cap = need; }
+  }
   const int lead = s->h.bs[1] / 2;
   int max_steps = 0;
   for (int i = 0; i < nstreams; i++) {
@@ -875,6 +902,7 @@ extern "C" int vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const flo
     const long T = StreamSeg::timeline_len(s, nsamples[i]), eof = lead + nsamples[i];
     const long l = eof / VE_STEP - VE_WIN;
     e.pcm_base = base[i]; e.T = T; e.nsteps = (int)(l > 0 ? l : 0); e.out_base = step_base[i]; e.eof = eof;
+    e.s16_base = s16_base[i];
     g->h_mark_base[i] = mark_base[i];
     if (e.nsteps > max_steps) max_steps = e.nsteps;
   }
@@ -900,9 +928,16 @@ extern "C" int vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const flo
     cudaError_t cerr = cudaSuccess;
     if (direct) {
       for (int i = 0; i < nstreams && cerr == cudaSuccess; i++)
-        if (nsamples[i] > 0)
-          cerr = cudaMemcpy2DAsync(g->d_pcm + base[i] + lead, sizeof(float) * g->h_streams[i].T, pcm[i], sizeof(float) * stride[i],
-                                   sizeof(float) * nsamples[i], ch, cudaMemcpyHostToDevice, st);
+        if (nsamples[i] > 0) {
+          if (S16) cerr = cudaMemcpy2DAsync(g->d_pcm16 + s16_base[i], sizeof(short) * nsamples[i], pcm[i], sizeof(short) * stride[i],
+                                            sizeof(short) * nsamples[i], ch, cudaMemcpyHostToDevice, st);
+          else cerr = cudaMemcpy2DAsync(g->d_pcm + base[i] + lead, sizeof(float) * g->h_streams[i].T, pcm[i], sizeof(float) * stride[i],
+                                        sizeof(float) * nsamples[i], ch, cudaMemcpyHostToDevice, st);
+        }
+      if (S16 && cerr == cudaSuccess) {
+        k_timeline_from_s16<<<dim3(64, nstreams * ch), 256, 0, st>>>(g->d_streams, ch, lead, g->d_pcm16, g->d_pcm);
+        cerr = cudaGetLastError();
+      }
       if (cerr == cudaSuccess) {
         k_timeline_finish<<<dim3(64, nstreams * ch), 256, 0, st>>>(g->d_streams, ch, lead, g->env.pre_amp, g->d_pcm);
         cerr = cudaGetLastError();
@@ -948,6 +983,18 @@ extern "C" int vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const flo
   CUDA_TRY(cudaMemcpyAsync(g->h_temp_tail, g->d_temp_tail, sizeof(float) * nstreams * ch * 45, cudaMemcpyDeviceToHost, st));
   R->t0 = t0; R->t1 = t1; R->nmark = nmark;
   return VB200_OK;
+}
+
+extern "C" int vb200_segmenter_begin(vb200_segmenter *g, int nstreams, const float *const *pcm, const long *nsamples,
+                                     const long *stride, int chunk, int threads) {
+  return segmenter_begin_impl<float>(g, nstreams, pcm, nsamples, stride, chunk, threads);
+}
+/* 16-bit PCM (planar, [channels][nsamples] with stride, as de-interleaved from a WAV file): half the host-to-device
+   bytes of the float entry point; the device converts (sample / 32768.f).  Same timeline, same blocks and the same
+   packets as vb200_segmenter_begin on the converted samples. */
+extern "C" int vb200_segmenter_begin_s16(vb200_segmenter *g, int nstreams, const short *const *pcm, const long *nsamples,
+                                         const long *stride, int chunk, int threads) {
+  return segmenter_begin_impl<short>(g, nstreams, pcm, nsamples, stride, chunk, threads);
 }
 
 /* second half: wait for the marks, sequence the windows, extrapolate and upload the tails */

@@ -26,14 +26,16 @@ L.vb200_segmenter_host_pcm.restype = C.POINTER(C.c_float)
 
 
 class PinnedArray:
-    """float32 [channels, nsamples] in page-locked host memory (vb200_pinned_alloc): PCM held in one of these goes
-    to the device straight from where it lies."""
+    """float32 (or int16) [channels, nsamples] in page-locked host memory (vb200_pinned_alloc): PCM held in one of
+    these goes to the device straight from where it lies."""
 
-    def __init__(self, channels, nsamples):
+    def __init__(self, channels, nsamples, dtype=np.float32):
         p = C.c_void_p()
-        check(L.vb200_pinned_alloc(C.c_size_t(4 * channels * max(1, nsamples)), C.byref(p)), "vb200_pinned_alloc")
+        dt = np.dtype(dtype)
+        check(L.vb200_pinned_alloc(C.c_size_t(dt.itemsize * channels * max(1, nsamples)), C.byref(p)), "vb200_pinned_alloc")
         self.p = p
-        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(channels, nsamples))
+        ctype = C.c_float if dt == np.float32 else C.c_int16
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(channels, nsamples))
 
     def close(self):
         if self.p:
@@ -58,12 +60,17 @@ class Segmenter:
             self.h = None
 
     def begin(self, pcms, chunk=1024, threads=8):
-        """Enqueue the uploads and the detector kernels of these streams; returns at once."""
-        self._pcms = [np.ascontiguousarray(p, np.float32) for p in pcms]       # kept alive until finish()
+        """Enqueue the uploads and the detector kernels of these streams; returns at once.  pcms: float32
+        [channels, nsamples] each -- or int16 each (16-bit PCM, value = sample / 32768: half the upload)."""
+        s16 = len(pcms) > 0 and all(np.asarray(p).dtype == np.int16 for p in pcms)
+        self._pcms = [np.ascontiguousarray(p, np.int16 if s16 else np.float32) for p in pcms]       # kept alive until finish()
         n = len(self._pcms)
         ptrs = (C.c_void_p * n)(*[p.ctypes.data for p in self._pcms])
         ns = (C.c_long * n)(*[p.shape[1] for p in self._pcms])
-        check(L.vb200_segmenter_begin(self.h, n, ptrs, ns, ns, int(chunk), int(threads)), "vb200_segmenter_begin")
+        if s16:
+            check(L.vb200_segmenter_begin_s16(self.h, n, ptrs, ns, ns, int(chunk), int(threads)), "vb200_segmenter_begin_s16")
+        else:
+            check(L.vb200_segmenter_begin(self.h, n, ptrs, ns, ns, int(chunk), int(threads)), "vb200_segmenter_begin")
 
     def finish(self):
         """-> (Block array view, device address, elems)"""
