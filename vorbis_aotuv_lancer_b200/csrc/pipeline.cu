@@ -1297,8 +1297,6 @@ static int batch_finish(vb200_batch *b) {
   cudaStream_t st = b->st;
   const int managed = s->h.managed, nblocks = b->run_nblocks;
   const bool host_emit = b->host_emit != 0;
-  const int k_lo = managed ? 0 : VB200_PACKETBLOBS / 2, k_hi = managed ? VB200_PACKETBLOBS - 1 : VB200_PACKETBLOBS / 2;
-  const int nblobs = k_hi - k_lo + 1;
   std::vector<long> &blob_sizes = b->blob_sizes;
   std::vector<BitWriter> &bws = b->bws; std::vector<std::vector<size_t>> &boff = b->boff;
   vb200_stream **streams = b->run_streams.data();

@@ -1005,7 +1005,7 @@ extern "C" int vb200_segmenter_finish(vb200_segmenter *g) {
   cudaStream_t st = g->st;
   SegRun *R = g->run;
   std::vector<StreamSeg> &seg = R->seg;
-  std::vector<long long> &base = R->base, &mark_base = R->mark_base;
+  std::vector<long long> &mark_base = R->mark_base;
   const int nstreams = R->nstreams, threads = R->threads, ch = s->h.channels;
   const size_t total = R->total;
   const bool trace = getenv("VB200_TRACE") != nullptr;
