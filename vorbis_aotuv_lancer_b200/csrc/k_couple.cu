@@ -127,8 +127,9 @@ __device__ void normalize(CoupleSmem<CH> &sm, const DevPsy &P, int limit, int k,
   __syncwarp();
 }
 
-/* STEREO1: two channels, one coupling step -- the channel and step loops unroll and index shared memory statically */
-template <int CH, bool STEREO1>
+/* CHC > 0 / STEPSC >= 0: channel count and coupling steps as compile-time facts (2, 1: stereo; 6, 0 and 6, 4: the
+   uncoupled and the coupled 5.1 mappings) -- the channel and step loops unroll and index shared memory statically */
+template <int CH, int CHC, int STEPSC>
 __global__ void __launch_bounds__(32)
 k_couple(const DevSetup *__restrict__ S, int W, const int *__restrict__ psyv, int blobno, int n, int ch_, int map_index,
          const float *__restrict__ mdct, const float *__restrict__ epeak, float *__restrict__ npeak, int npeak_stride,
@@ -139,8 +140,8 @@ k_couple(const DevSetup *__restrict__ S, int W, const int *__restrict__ psyv, in
   const int blk = blockIdx.x, lane = threadIdx.x;
   const DevPsy &P = S->psy[psyv[blk]];
   const DevMap &M = S->map[map_index];
-  const int ch = STEREO1 ? 2 : ch_;
-  const int part = P.partition, steps = STEREO1 ? 1 : M.coupling_steps;
+  const int ch = CHC ? CHC : ch_;
+  const int part = P.partition, steps = STEPSC >= 0 ? STEPSC : M.coupling_steps;
   const int limit = S->pointlimit[P.blockflag][blobno];
   const float pre = (float)S->stereo_th[S->prepointamp[blobno]], post = (float)S->stereo_th[S->postpointamp[blobno]];
   float pre_x = (float)S->stereo_thx[S->prepointamp[blobno]], post_x = (float)S->stereo_thx[S->postpointamp[blobno]];
@@ -329,12 +330,14 @@ int vb200_launch_couple(const vb200_setup *s, cudaStream_t st, int W, int blocks
   if (blocks <= 0) return VB200_OK;
   if (blobno < 0 || blobno >= VB200_PACKETBLOBS) { vb200_set_error("blob number out of range"); return VB200_EINVAL; }
   const int n = s->h.bs[W] / 2;
-  if (s->h.channels == 2 && s->h.map[s->h.mode_mapping[W]].coupling_steps == 1)
-    k_couple<2, true><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
-  else if (s->h.channels <= 2)
-    k_couple<2, false><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
-  else
-    k_couple<VB200_MAX_CHANNELS, false><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero);
+  const int steps = s->h.map[s->h.mode_mapping[W]].coupling_steps;
+#define KC_LAUNCH(CAP_, C_, S_) k_couple<CAP_, C_, S_><<<blocks, 32, 0, st>>>(s->d, W, psy, blobno, n, s->h.channels, s->h.mode_mapping[W], mdct, epeak, npeak, npeak_stride, iwork, nonzero)
+  if (s->h.channels == 2 && steps == 1) KC_LAUNCH(2, 2, 1);
+  else if (s->h.channels <= 2) KC_LAUNCH(2, 0, -1);
+  else if (s->h.channels == 6 && steps == 0) KC_LAUNCH(VB200_MAX_CHANNELS, 6, 0);
+  else if (s->h.channels == 6 && steps == 4) KC_LAUNCH(VB200_MAX_CHANNELS, 6, 4);
+  else KC_LAUNCH(VB200_MAX_CHANNELS, 0, -1);
+#undef KC_LAUNCH
   LAUNCH_CHECK();
   return VB200_OK;
 }

@@ -48,7 +48,7 @@ __device__ __forceinline__ void put_bits(PackSmem<CH, PK_WORDS> &sm, int bitpos,
 
 __device__ __forceinline__ int ilog_(unsigned v) { return 32 - __clz(v); }
 
-template <int CH, int PK_WORDS, bool RETRY, bool STEREO1>
+template <int CH, int PK_WORDS, bool RETRY, int CHC, int SUBC>
 __device__ __forceinline__ void
 pack_block(const int blk, const DevSetup *__restrict__ S, int W, int ch_, const int *__restrict__ lWv, const int *__restrict__ nWv,
            const int *__restrict__ vals, const int *__restrict__ floor_nonzero,
@@ -57,7 +57,7 @@ pack_block(const int blk, const DevSetup *__restrict__ S, int W, int ch_, const 
            long long *__restrict__ pk_off, int *__restrict__ pk_bytes, int limit_words) {
   __shared__ PackSmem<CH, PK_WORDS> sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ch = STEREO1 ? 2 : ch_, submaps = STEREO1 ? 1 : submaps_;      /* two channels, one submap: loops unroll */
+  const int ch = CHC ? CHC : ch_, submaps = SUBC ? SUBC : submaps_;      /* channels and submaps as compile-time facts (2, 1: stereo; 6, 2: 5.1): loops unroll */
   const DevBook *books = S->book;
   for (int i = tid; i < PK_ZERO0; i += PK_T) sm.words[i] = 0;
   int zeroed = PK_ZERO0;               /* uniform: words [0, zeroed) are clear or already carry bits */
@@ -216,10 +216,10 @@ pack_block(const int blk, const DevSetup *__restrict__ S, int W, int ch_, const 
        long long *__restrict__ pk_off, int *__restrict__ pk_bytes, int limit_words
 #define PK_ARGS S, W, ch, lWv, nWv, vals, floor_nonzero, submaps, syms, nsyms, cap_blocks, max_syms, pool, pool_cap, pool_top, pk_off, pk_bytes, limit_words
 
-template <int CH, int PK_WORDS, bool RETRY, bool STEREO1>
+template <int CH, int PK_WORDS, bool RETRY, int CHC, int SUBC>
 __global__ void __launch_bounds__(PK_T)
 k_pack(PK_PARAMS) {
-  pack_block<CH, PK_WORDS, RETRY, STEREO1>(blockIdx.x, PK_ARGS);
+  pack_block<CH, PK_WORDS, RETRY, CHC, SUBC>(blockIdx.x, PK_ARGS);
 }
 
 /* second pass: a CTA looks at 32 blocks and packs the ones the small image could not hold (normally none) */
@@ -230,7 +230,7 @@ k_pack_retry(int blocks, PK_PARAMS) {
   for (int k = 0; k < 32 && b0 + k < blocks; k++) {
     if (pk_off[b0 + k] != PK_RETRY) continue;             /* uniform across the CTA */
     __syncthreads();                                      /* the previous block's image is no longer read */
-    pack_block<CH, PK_WORDS_BIG, false, false>(b0 + k, PK_ARGS);
+    pack_block<CH, PK_WORDS_BIG, false, 0, 0>(b0 + k, PK_ARGS);
   }
 }
 
@@ -245,17 +245,19 @@ int vb200_launch_pack(const vb200_setup *s, cudaStream_t st, int W, int blocks, 
   static const bool big_only = getenv("VB200_PACK_BIG") != nullptr;
   static const int limit = getenv("VB200_PACK_LIMIT") ? atoi(getenv("VB200_PACK_LIMIT")) : 0;    /* tests: words the first pass may fill */
   if (s->h.channels == 2 && submaps == 1 && !big_only) {
-    k_pack<2, PK_WORDS_SMALL, true, true><<<blocks, PK_T, 0, st>>>(PK_CALL);
+    k_pack<2, PK_WORDS_SMALL, true, 2, 1><<<blocks, PK_T, 0, st>>>(PK_CALL);
     LAUNCH_CHECK();
     k_pack_retry<2><<<(blocks + 31) / 32, PK_T, 0, st>>>(blocks, PK_CALL);
   } else if (s->h.channels <= 2 && !big_only) {
-    k_pack<2, PK_WORDS_SMALL, true, false><<<blocks, PK_T, 0, st>>>(PK_CALL);
+    k_pack<2, PK_WORDS_SMALL, true, 0, 0><<<blocks, PK_T, 0, st>>>(PK_CALL);
     LAUNCH_CHECK();
     k_pack_retry<2><<<(blocks + 31) / 32, PK_T, 0, st>>>(blocks, PK_CALL);
   } else if (s->h.channels <= 2)
-    k_pack<2, PK_WORDS_BIG, false, false><<<blocks, PK_T, 0, st>>>(PK_CALL);
+    k_pack<2, PK_WORDS_BIG, false, 0, 0><<<blocks, PK_T, 0, st>>>(PK_CALL);
+  else if (s->h.channels == 6 && submaps == 2)
+    k_pack<VB200_MAX_CHANNELS, PK_WORDS_BIG, false, 6, 2><<<blocks, PK_T, 0, st>>>(PK_CALL);
   else
-    k_pack<VB200_MAX_CHANNELS, PK_WORDS_BIG, false, false><<<blocks, PK_T, 0, st>>>(PK_CALL);
+    k_pack<VB200_MAX_CHANNELS, PK_WORDS_BIG, false, 0, 0><<<blocks, PK_T, 0, st>>>(PK_CALL);
 #undef PK_CALL
   LAUNCH_CHECK();
   return VB200_OK;

@@ -21,22 +21,23 @@
 namespace {
 
 /* ------------------------------------------------------------------ K7a */
-template <bool STEREO2>          /* residue type 2 over two channels, as in k_residue_forward */
+template <int CHC>                /* CHC > 0: residue type 2 over CHC channels as a compile-time fact, as in k_residue_forward */
 __global__ void __launch_bounds__(64)
 k_residue_class(const DevSetup *__restrict__ S, int resnum, int n, int ch_, const int *__restrict__ chlist, int tot_ch,
                 const int *__restrict__ in, const int *__restrict__ nonzero, int *__restrict__ partword, int *__restrict__ classified) {
   const int blk = blockIdx.x, tid = threadIdx.x;
   const DevResidue &R = S->res[resnum];
-  const int ch = STEREO2 ? 2 : ch_;
+  constexpr bool STEREO2 = CHC == 2;
+  const int ch = CHC ? CHC : ch_;
   const int partvals = (R.end - R.begin) / R.grouping;
   const int *base = in + (size_t)blk * tot_ch * n;
   const int *nz = nonzero + (size_t)blk * tot_ch;
   int *pw = partword + (size_t)blk * ch * partvals;
   int used = 0;
   for (int k = 0; k < ch; k++) if (nz[chlist[k]]) used++;
-  if (tid == 0) classified[blk] = used ? ((STEREO2 || R.type == 2) ? 1 : used) : 0;
+  if (tid == 0) classified[blk] = used ? ((CHC || R.type == 2) ? 1 : used) : 0;
   if (!used) return;
-  if (STEREO2 || R.type == 2) {
+  if (CHC || R.type == 2) {
     const int per = (R.grouping + ch - 1) / ch;   /* positions per channel per partition (res0.c:498-503) */
     if (STEREO2 && per == 16 && (R.grouping & 1) == 0 && ((R.begin >> 1) & 3) == 0 && (n & 3) == 0) {
       /* a partition is 16 consecutive values of each channel: four 128-bit loads per channel, all eight requested
@@ -107,10 +108,11 @@ struct RfShared {
 #ifndef RF_MINB
 #define RF_MINB 10         /* 48 registers, 10 CTAs per SM (specialised kernel: 8 / 10 / 12 CTAs: 2.65 / 2.57 / 2.64 ms) */
 #endif
-/* STEREO2: the common case as compile-time facts -- residue type 2 over two channels (one row, interleave by a
-   shift): the row / channel divisions and the type switches fold away (the generic kernel is 3.9 k instructions and
-   spent a fifth of its stall samples waiting for instruction fetch) */
-template <bool STEREO2>
+/* CHC > 0: residue type 2 over CHC channels as compile-time facts (2: stereo, interleave by a shift; 5: the five
+   full-band channels of a 5.1 stream, interleave by a constant division): one row, the row / channel divisions and the
+   type switches fold away (the generic kernel is 3.9 k instructions and spent a fifth of its stall samples waiting for
+   instruction fetch) */
+template <int CHC>
 __global__ void __launch_bounds__(RF_WARPS * 32, RF_MINB)
 k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch_, const int *__restrict__ chlist, int tot_ch,
                   int *__restrict__ in, const int *__restrict__ nonzero, const int *__restrict__ partword,
@@ -120,15 +122,16 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch_, co
   const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const DevResidue &R = S->res[resnum];
   const DevBook *books = S->book;
-  const int ch = STEREO2 ? 2 : ch_;
-  const int rtype = STEREO2 ? 2 : R.type;
+  constexpr bool STEREO2 = CHC == 2;
+  const int ch = CHC ? CHC : ch_;
+  const int rtype = CHC ? 2 : R.type;
   const int partvals = (R.end - R.begin) / R.grouping, G = R.grouping, stages = R.stages;
   int *base = in + (size_t)blk * tot_ch * n;
   const int *nz = nonzero + (size_t)blk * tot_ch;
   int used = 0;
   for (int k = 0; k < ch; k++) if (nz[chlist[k]]) used++;
   if (!used) { if (tid == 0) nsyms[blk] = 0; return; }
-  const int rows = STEREO2 ? 1 : ((rtype == 2) ? 1 : used);
+  const int rows = CHC ? 1 : ((rtype == 2) ? 1 : used);
   const int *pw = partword + (size_t)blk * ch * partvals;
   /* dynamic shared memory: entry table [stages][partvals][rows][maxvec] (int16) + scan offsets + row->channel map */
   short *ent = reinterpret_cast<short *>(dyn);
@@ -144,7 +147,7 @@ k_residue_forward(const DevSetup *__restrict__ S, int resnum, int n, int ch_, co
     if (st2 < stages && (R.secondstages[cls] & (1 << st2))) { bk = R.partbooks[i]; if (bk >= 0) nv = G / books[bk].dim; }
     tab_bk[i] = (short)bk; tab_nvec[i] = (short)nv;
   }
-  const int ch_shift = STEREO2 ? 1 : ((ch & (ch - 1)) == 0 ? __ffs(ch) - 1 : -1);
+  const int ch_shift = STEREO2 ? 1 : (CHC ? -1 : ((ch & (ch - 1)) == 0 ? __ffs(ch) - 1 : -1));
   const int pd_mask = (R.phrase_dim & (R.phrase_dim - 1)) == 0 ? R.phrase_dim - 1 : -1;
   __syncthreads();
 
@@ -332,8 +335,9 @@ int vb200_launch_residue_class(const vb200_setup *s, cudaStream_t st, int W, int
                                int tot_ch, const int *in, const int *nonzero, int *partword, int *classified) {
   if (blocks <= 0) return VB200_OK;
   const int n = s->h.bs[W] / 2;
-  if (s->h.res[resnum].type == 2 && ch == 2) k_residue_class<true><<<blocks, 64, 0, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, classified);
-  else k_residue_class<false><<<blocks, 64, 0, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, classified);
+  if (s->h.res[resnum].type == 2 && ch == 2) k_residue_class<2><<<blocks, 64, 0, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, classified);
+  else if (s->h.res[resnum].type == 2 && ch == 5) k_residue_class<5><<<blocks, 64, 0, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, classified);
+  else k_residue_class<0><<<blocks, 64, 0, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, classified);
   LAUNCH_CHECK();
   return VB200_OK;
 }
@@ -359,13 +363,12 @@ int vb200_launch_residue_forward(const vb200_setup *s, cudaStream_t st, int W, i
   const size_t ent_bytes = ((size_t)R.stages * partvals * rows * maxvec * 2 + 15) & ~(size_t)15;
   const size_t dyn = ent_bytes + sizeof(int) * ((size_t)R.stages * partvals * rows + 1);
   if (dyn > 200 * 1024) { vb200_set_error("residue %d: symbol table does not fit shared memory", resnum); return VB200_EIMPL; }
-  if (R.type == 2 && ch == 2) {
-    CUDA_TRY(cudaFuncSetAttribute(k_residue_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    k_residue_forward<true><<<blocks, RF_WARPS * 32, dyn, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, maxvec, syms, max_syms, nsyms);
-  } else {
-    CUDA_TRY(cudaFuncSetAttribute(k_residue_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    k_residue_forward<false><<<blocks, RF_WARPS * 32, dyn, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, maxvec, syms, max_syms, nsyms);
-  }
+#define RF_LAUNCH(C_) do { CUDA_TRY(cudaFuncSetAttribute(k_residue_forward<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    k_residue_forward<C_><<<blocks, RF_WARPS * 32, dyn, st>>>(s->d, resnum, n, ch, chlist, tot_ch, in, nonzero, partword, maxvec, syms, max_syms, nsyms); } while (0)
+  if (R.type == 2 && ch == 2) RF_LAUNCH(2);
+  else if (R.type == 2 && ch == 5) RF_LAUNCH(5);
+  else RF_LAUNCH(0);
+#undef RF_LAUNCH
   LAUNCH_CHECK();
   return VB200_OK;
 }
